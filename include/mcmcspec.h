@@ -1,0 +1,206 @@
+/*
+ * mcmcspec.h -- C ABI of libmcmcspec.so: the B200 (sm_100a) log-posterior engine for
+ * unresolved binary stars.  Drop-in boundary for the per-walker `logposterior` path of
+ * kendallsullivan/mcmc_spec (citations are file:line into that repository's mft6.py).
+ *
+ * The reference has no FFI: its boundary is the Python callable handed to the ensemble sampler,
+ *     emcee.EnsembleSampler(nwalkers, ndim, logposterior, args=[fr, nspec, ndust, data, err,
+ *         broadening, r, specs, ctm, ptm, tmi, tma, vs, tmin, tmax, matrix, ra, dec], kwargs=...)
+ * (mft6.py:1491).  Everything `args` carries is folded once into an `ms_config` and uploaded by
+ * ms_create(); ms_lnprob() then is `logposterior` for a whole batch of walkers.  The binding a
+ * maintainer adds on the reference side is the ctypes stub in INTEGRATION.md (shipped as
+ * mcmc_spec_b200/native.py).
+ *
+ * Conventions: plain pointers and sizes only; all floating point is IEEE binary64; every entry
+ * point returns an int status (MS_OK == 0) and never throws; per-walker domain failures (outside
+ * the prior box, off the isochrone or the grid, NaN chi-square) give lnprob = -inf, never NaN
+ * (mft6.py:1227-1230, :1202-1205, :1465-1466).  Walker vectors theta are
+ * [T1, T2, Av, R1, R2/R1, parallax] (mft6.py:1146), row-major [nw][ndim].
+ * A handle owns one CUDA device and one stream; calls on a handle must be serialised.
+ */
+#ifndef MCMCSPEC_H
+#define MCMCSPEC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_ABI_VERSION 1
+#define MS_TILE 1024            /* model pixels per streaming tile; filter weights are tile padded */
+#define MS_MAX_CONTRAST 4
+#define MS_MAX_PHOT 12
+#define MS_MAX_NDIM 8
+
+enum {
+  MS_OK = 0,
+  MS_ERR_INVALID = 1,           /* bad argument / inconsistent config */
+  MS_ERR_CUDA = 2,              /* CUDA runtime error; see ms_last_error */
+  MS_ERR_UNSUPPORTED = 3,       /* shape outside what the kernels are built for */
+  MS_ERR_NO_DEVICE = 4
+};
+
+/* Where a pointer argument lives. */
+enum { MS_HOST = 0, MS_DEVICE = 1 };
+
+/* Per-walker status bits returned by ms_lnprob_parts (diagnostics; lnprob is -inf if any set). */
+enum {
+  MS_W_PRIOR_BOUNDS = 1,        /* logprior bounds, mft6.py:1227-1230 */
+  MS_W_OFF_ISOCHRONE = 2,       /* Teff outside the isochrone table: interp1d ValueError, mft6.py:76/:95 */
+  MS_W_OFF_GRID = 4,            /* log g outside the grid nodes: get_spec index error, mft6.py:467-477 */
+  MS_W_NONFINITE = 8            /* non-finite theta or NaN chi-square, mft6.py:1202 */
+};
+
+typedef struct ms_handle ms_handle;
+
+/*
+ * All pointers are HOST pointers, read during ms_create() only.
+ *
+ * Replaces (read-only inputs of logposterior):
+ *   grid, *_nodes ........ `specs` dict of pre-broadened rows + 'wl'           mft6.py:342-385, :497-500
+ *   reg_lo, n_reg ........ region cut of get_spec via make_composite           mft6.py:687, :542
+ *   rebin_*, ext_* ....... interp1d(wave1, spec)(wl*1e4) after extinct()       mft6.py:1162, :1169-1170
+ *   data_*, poly_basis ... `data`, `err`, norm_spec's Polynomial.fit           mft6.py:1173-1179, :193-196
+ *   c_* .................. `ctm`, fr[0:2] (contrast filters, mags, errors)     mft6.py:717-741, :1182
+ *   p_* .................. pyphot library filters, fr[3:5], phot_cwl           mft6.py:771-783, :1163, :1188
+ *   iso_* ................ `matrix` rows of log-age 9.0, first 220             mft6.py:70-76, :90-95
+ *   dust_* ............... bayestar(SkyCoord(ra, dec, 1/plx), 'samples')       mft6.py:1233-1239
+ *   prior_*, tmin, tmax .. `prior`, grid extrema                               mft6.py:1241-1260, :1479-1487
+ */
+typedef struct ms_config {
+  int32_t abi_version;          /* MS_ABI_VERSION */
+  int32_t device;               /* CUDA device ordinal */
+
+  /* model grid: rows [n_feh][n_logg][n_teff][row_len], pixels [reg_lo, reg_lo+n_reg) consumed */
+  int32_t n_teff, n_logg, n_feh;
+  int32_t n_reg;
+  int64_t row_len;
+  int64_t reg_lo;
+  const double* teff_nodes;
+  const double* logg_nodes;
+  const double* feh_nodes;
+  const double* grid;
+  double feh;                   /* fixed metallicity of the fit (3-D grids only) */
+
+  /* observed spectrum, ascending wavelength */
+  int32_t n_data;
+  int32_t n_tiles;              /* ceil(n_reg / MS_TILE) */
+  const int32_t* rebin_hi;      /* [n_data] region-relative upper bracketing model pixel, >= 1 */
+  const double* rebin_t;        /* [n_data] (x - wl[hi-1]) / (wl[hi] - wl[hi-1]) */
+  const double* ext_lo;         /* [n_data] -0.4*log2(10)*k(wl[hi-1]);  E = exp2(Av*ext) */
+  const double* ext_hi;         /* [n_data] same at wl[hi] */
+  const double* data_flux;      /* [n_data] */
+  const double* data_err;       /* [n_data] */
+  const double* data_x;         /* [n_data] wavelengths mapped onto [-1, 1] */
+  const int32_t* tile_data_start; /* [n_tiles+1] observed pixels whose rebin_hi lies in each tile */
+  double poly_basis[9];         /* orthonormal quadratic basis, q_k(x) = sum_j B[3k+j] x^j */
+  double data_median;           /* np.median(data_flux) */
+
+  /* contrast filters: per-pixel quadrature weights, whole tiles, zero padded */
+  int32_t n_contrast;
+  int32_t n_phot;
+  const int32_t* c_tile_lo;     /* [n_contrast] */
+  const int32_t* c_tile_hi;
+  const int64_t* c_offset;      /* element offset into c_weights */
+  const double* c_weights;
+  int64_t c_weights_len;
+  const double* c_mag;          /* observed contrasts and errors */
+  const double* c_err;
+
+  /* photometric filters */
+  const int32_t* p_tile_lo;     /* [n_phot] */
+  const int32_t* p_tile_hi;
+  const int64_t* p_offset;
+  const double* p_weights;
+  int64_t p_weights_len;
+  const double* p_norm;         /* 1 / (normalising integral * zero-point flux) */
+  const double* p_ext;          /* CCM89 a+b/Rv at the filter's mean wavelength */
+  const double* p_mag;
+  const double* p_err;
+
+  /* isochrone (sorted by Teff), dust sightline, prior */
+  int32_t n_iso;
+  int32_t n_dm;
+  int32_t n_dust_samples;
+  int32_t nspec;
+  const double* iso_teff;
+  const double* iso_logg;
+  const double* iso_lum;
+  const double* dust_dm_edges;  /* [n_dm] */
+  const double* dust_samples;   /* [n_dust_samples][n_dm] */
+  double tmin, tmax;
+  double prior_mu[MS_MAX_NDIM]; /* 0 -> no Gaussian prior on that parameter */
+  double prior_sig[MS_MAX_NDIM];
+  int32_t ext_flag;             /* `a` / `ext` keyword */
+  int32_t dist_fit;
+  int32_t rad_prior;
+  int32_t reserved;
+} ms_config;
+
+/* sizeof(ms_config) as compiled, so a binding can verify its mirror of the struct. */
+int64_t ms_config_size(void);
+int32_t ms_abi_version(void);
+
+/* Upload all tables; replaces the per-call hand-over of `args` (mft6.py:1491). */
+int ms_create(const ms_config* cfg, ms_handle** out);
+int ms_destroy(ms_handle* h);
+/* Message of the last failing call on this handle (or of the last failing ms_create if h==NULL). */
+const char* ms_last_error(const ms_handle* h);
+/* The handle's CUDA stream (cudaStream_t) and device ordinal, for callers that enqueue around it. */
+void* ms_stream(const ms_handle* h);
+int ms_device(const ms_handle* h);
+
+/*
+ * logposterior for nw walkers (mft6.py:1459-1470).  theta [nw][ndim], lnprob [nw]; `where` says
+ * whether both are MS_HOST (copied through pinned staging, call returns after the result landed)
+ * or MS_DEVICE (enqueued on the handle's stream, asynchronous).
+ */
+int ms_lnprob(ms_handle* h, const double* theta, int64_t nw, double* lnprob, int where);
+
+/*
+ * Same evaluation with the intermediate quantities of loglikelihood exposed (any pointer may be
+ * NULL): chi2_spec [nw] = sum(chisq)/N (mft6.py:1179), contrast [nw][n_contrast] (mft6.py:741),
+ * phot [nw][n_phot] extincted magnitudes (mft6.py:1163), lnprior [nw] (mft6.py:1462),
+ * logg [nw][nspec] (mft6.py:1149), status [nw] MS_W_* bits.
+ */
+int ms_lnprob_parts(ms_handle* h, const double* theta, int64_t nw, double* lnprob, double* chi2_spec,
+                    double* contrast, double* phot, double* lnprior, double* logg, int32_t* status,
+                    int where);
+
+/* Median-scaled model on the observed pixels, out [nw][n_data] (init_cspec after mft6.py:1173). */
+int ms_model_spectrum(ms_handle* h, const double* theta, int64_t nw, double* out, int where);
+
+/*
+ * Instrumental broadening of grid rows in place (host rows [n_rows][row_len]): the operator of
+ * spec_interpolator/broaden, mft6.py:366-383 and :124-130 -- pixels [win_lo, win_lo+win_len) of
+ * every row are convolved with the sum-normalised `taps` (odd n_taps, zero padded 'same'), then
+ * the first 5 and last 10 window samples are patched.  Runs on `device`.
+ */
+int ms_broaden_rows(int device, double* rows, int64_t n_rows, int64_t row_len, int64_t win_lo,
+                    int64_t win_len, const double* taps, int32_t n_taps);
+
+/*
+ * Stretch-move half step on device-resident ensembles (emcee RedBlueMove/StretchMove, a = 2;
+ * the sampler the reference drives at mft6.py:1491-1510).
+ *   ms_stretch_propose: for s < n_s:  z = ((a-1)u+1)^2/a, j = partner in [0,n_c),
+ *       q[s] = c[j] - (c[j] - x[s])*z, logfac[s] = (ndim-1) ln z.
+ *   ms_stretch_accept:  accept where ln u' < logfac + lnp_q - lnp_x; x, lnp_x updated in place,
+ *       accepted[s] incremented.
+ * Random numbers are counter based: stream (seed, iteration, split, gid0 + s), so a sharded
+ * ensemble draws the same numbers as an unsharded one.  All pointers are device pointers.
+ */
+int ms_stretch_propose(ms_handle* h, const double* x, int64_t n_s, const double* c, int64_t n_c,
+                       int32_t ndim, double a, uint64_t seed, uint64_t iteration, int32_t split,
+                       int64_t gid0, double* q, double* logfac);
+int ms_stretch_accept(ms_handle* h, double* x, double* lnp_x, const double* q, const double* lnp_q,
+                      const double* logfac, int64_t n_s, int32_t ndim, uint64_t seed,
+                      uint64_t iteration, int32_t split, int64_t gid0, int32_t* accepted);
+
+/* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
+int64_t ms_launch_count(const ms_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCMCSPEC_H */

@@ -1,0 +1,1128 @@
+// mcmcspec.cu -- sm_100a kernels and C ABI of libmcmcspec.so (see include/mcmcspec.h).
+//
+// One evaluation of mft6.py's logposterior (mft6.py:1459-1470) is split into
+//   walker_prep_kernel   : one thread per walker -- prior (mft6.py:1207-1327), isochrone log g and
+//                          radius (mft6.py:66-98), grid bracket + bilinear/trilinear coefficients
+//                          folded with the (R/d)^2 dilution (mft6.py:439-519, :689-700).
+//   lnprob_stream_kernel : one CTA per walker -- streams the 2*2^D bracketing grid rows once
+//                          (vectorised, coalesced 16-byte loads), forms both component spectra in
+//                          registers, accumulates the contrast and photometric band integrals
+//                          (mft6.py:717-783), extincts and rebins onto the observed pixels through
+//                          a shared-memory tile (mft6.py:1162, :1169-1170), then finishes in shared
+//                          memory: exact median (mft6.py:1173), quadratic renormalisation
+//                          (mft6.py:193-196), chi-square and the final sum (mft6.py:1178-1205).
+// No intermediate spectrum ever goes to HBM.  All arithmetic is binary64.
+//
+// Setup-time operator: broaden_rows_kernel = spec_interpolator's window broadening
+// (mft6.py:124-130, :366-383) as a shared-memory banded stencil.
+// Sampler support: stretch_propose_kernel / stretch_accept_kernel (emcee stretch move, a = 2).
+
+#include "mcmcspec.h"
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int NT = 256;                 // threads per CTA of the streaming kernel
+constexpr int NWARP = NT / 32;
+constexpr int TILE = MS_TILE;           // model pixels per tile (4 per thread)
+constexpr int MAX_STAR = 2;
+constexpr int MAX_CORNER = 8;
+
+constexpr double RSUN_CM = 6.957e10;    // mft6.py:81, :691
+constexpr double PC_CM = 3.086e18;      // mft6.py:691
+constexpr double SIGMA_SB = 5.670374e-5;  // mft6.py:79
+constexpr double LSUN = 3.839e33;       // mft6.py:80
+
+static_assert(TILE == 4 * NT, "each thread owns two pixel pairs per tile");
+
+// ------------------------------------------------------------------------------------------
+// Device-side view of the tables (passed by value as a kernel parameter).
+// ------------------------------------------------------------------------------------------
+struct DevTables {
+  // grid
+  const double* grid;          // [n_rows][stride], region cut, zero padded to whole tiles
+  long long stride;
+  const double* teff_nodes; const double* logg_nodes; const double* feh_nodes;
+  int n_teff, n_logg, n_feh;
+  int n_reg, n_tiles;
+  double feh;
+  // observed spectrum
+  int n_data;
+  const int* rebin_hi; const double* rebin_t; const double* ext_lo; const double* ext_hi;
+  const double* data_flux; const double* data_err; const double* data_x;
+  const int* tile_data_start;
+  const unsigned* tile_cmask; const unsigned* tile_pmask;
+  double basis[9];
+  double data_median;
+  // filters: pointer such that weight of region pixel p is wbase[p]
+  int n_contrast, n_phot;
+  const double* c_wbase[MS_MAX_CONTRAST];
+  const double* p_wbase[MS_MAX_PHOT];
+  double c_mag[MS_MAX_CONTRAST], c_err[MS_MAX_CONTRAST];
+  double p_norm[MS_MAX_PHOT], p_ext[MS_MAX_PHOT], p_mag[MS_MAX_PHOT], p_err[MS_MAX_PHOT];
+  // isochrone, dust, prior
+  const double* iso_teff; const double* iso_logg; const double* iso_lum; int n_iso;
+  const double* dust_dm; const double* dust_samples; int n_dm, n_dust_samples;
+  double tmin, tmax;
+  double prior_mu[MS_MAX_NDIM], prior_sig[MS_MAX_NDIM];
+  int nspec, ndim, ext_flag, dist_fit, rad_prior;
+};
+
+// What walker_prep_kernel hands to the streaming kernel.
+struct __align__(16) WalkerPlan {
+  double coef[MAX_STAR][MAX_CORNER];   // interpolation weight x (R/d)^2, per grid row
+  int row[MAX_STAR][MAX_CORNER];       // grid row index
+  double av;
+  double lp;                           // log prior (finite when status == 0)
+  double logg[MAX_STAR];
+  int status;                          // MS_W_* bits
+  int pad;
+};
+
+struct PartsOut {
+  double* chi2_spec; double* contrast; double* phot; double* lnprior; double* logg; int* status;
+  double* model;                        // [nw][n_data] median-scaled model
+};
+
+// ------------------------------------------------------------------------------------------
+// Small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ldg_stream(const double* p) {
+  // grid rows are streamed once per CTA: keep them out of L1
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum of K per-thread values over the CTA, in a fixed order; result valid in every thread.
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* scratch /* [NWARP*K] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double s = warp_sum(v[k]);
+    if (lane == 0) scratch[warp * K + k] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) s += scratch[w * K + k];
+    v[k] = s;
+  }
+  __syncthreads();
+}
+
+// np.interp / interp1d(kind='linear', bounds_error=True) on an ascending table.
+__device__ bool interp_table(const double* __restrict__ x, const double* __restrict__ y, int n, double v,
+                             double* out) {
+  if (!(v >= x[0] && v <= x[n - 1])) return false;
+  if (v == x[n - 1]) { *out = y[n - 1]; return true; }
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (x[mid] <= v) lo = mid; else hi = mid;
+  }
+  if (x[lo] == v) { *out = y[lo]; return true; }
+  const double slope = (y[lo + 1] - y[lo]) / (x[lo + 1] - x[lo]);
+  *out = slope * (v - x[lo]) + y[lo];
+  return true;
+}
+
+// find_nearest + partner on the far side (mft6.py:100-113, :439-453).  w2 is the weight of node i2.
+__device__ bool bracket_nodes(const double* __restrict__ nodes, int n, double v, int* i1, int* i2, double* w2) {
+  int best = 0;
+  double bd = fabs(nodes[0] - v);
+  for (int i = 1; i < n; ++i) {
+    const double d = fabs(nodes[i] - v);
+    if (d < bd) { bd = d; best = i; }
+  }
+  *i1 = best;
+  if (nodes[best] == v) { *i2 = best; *w2 = 0.0; return true; }
+  const int other = (nodes[best] > v) ? best - 1 : best + 1;
+  if (other < 0 || other >= n) return false;     // reference: wrap-around / IndexError
+  *i2 = other;
+  *w2 = (v - nodes[best]) / (nodes[other] - nodes[best]);
+  return true;
+}
+
+__device__ double stefan_boltzmann_radius(double lum, double teff) {
+  // mft6.py:83
+  return sqrt(lum * LSUN / (4.0 * CUDART_PI * SIGMA_SB * (teff * teff * teff * teff))) / RSUN_CM;
+}
+
+// bayestar(SkyCoord(distance), mode='samples') * 3.1 * 0.884 -> mean, std   (mft6.py:1233-1238)
+__device__ void dust_prior_moments(const DevTables& T, double plx, double* mu, double* sig) {
+  const double d_kpc = (1.0 / plx) / 1.0e3;
+  const double dm = 5.0 * (log10(d_kpc) + 2.0);
+  const int n = T.n_dm, ns = T.n_dust_samples;
+  int c = 0;                                           // np.searchsorted(edges, dm) (side='left')
+  { int lo = 0, hi = n; while (lo < hi) { int mid = (lo + hi) >> 1; if (T.dust_dm[mid] < dm) lo = mid + 1; else hi = mid; } c = lo; }
+  double s[16];
+  double a = 0.0;
+  if (c == 0) a = pow(10.0, 0.2 * (dm - T.dust_dm[0]));
+  else if (c < n) a = (T.dust_dm[c] - dm) / (T.dust_dm[c] - T.dust_dm[c - 1]);
+  double sum = 0.0;
+  for (int k = 0; k < ns; ++k) {
+    double e;
+    if (c == 0) e = a * T.dust_samples[k * n];
+    else if (c == n) e = T.dust_samples[k * n + n - 1];
+    else e = (1.0 - a) * T.dust_samples[k * n + c] + a * T.dust_samples[k * n + c - 1];
+    e = e * 3.1 * 0.884;
+    s[k] = e;
+    sum += e;
+  }
+  const double mean = sum / ns;
+  double var = 0.0;
+  for (int k = 0; k < ns; ++k) { const double d = s[k] - mean; var += d * d; }
+  *mu = mean;
+  *sig = sqrt(var / ns);
+}
+
+// ------------------------------------------------------------------------------------------
+// walker_prep_kernel
+// ------------------------------------------------------------------------------------------
+__global__ void walker_prep_kernel(const DevTables T, const double* __restrict__ theta, long long nw,
+                                   WalkerPlan* __restrict__ plans) {
+  const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  const int ndim = T.ndim, ns = T.nspec;
+  double p[MS_MAX_NDIM];
+  bool finite = true;
+  for (int k = 0; k < ndim; ++k) { p[k] = theta[w * ndim + k]; finite = finite && isfinite(p[k]); }
+
+  WalkerPlan plan;
+  for (int s = 0; s < MAX_STAR; ++s) {
+    plan.logg[s] = CUDART_NAN;
+    for (int c = 0; c < MAX_CORNER; ++c) { plan.coef[s][c] = 0.0; plan.row[s][c] = 0; }
+  }
+  plan.av = 0.0; plan.lp = -CUDART_INF; plan.status = 0; plan.pad = 0;
+  if (!finite) { plan.status = MS_W_NONFINITE; plans[w] = plan; return; }
+
+  // layout mft6.py:1146: T[0..ns), Av, R1, ratios[1..ns), parallax
+  const double* temps = p;
+  const double av = p[ns];
+  const double* rad = p + ns + 1;          // rad[0] = R1, rad[1] = R2/R1
+  const double plx = p[2 * ns + 1];
+
+  // ---- logprior bounds (mft6.py:1227-1230 / :1287-1290)
+  bool out = false;
+  for (int s = 0; s < ns; ++s) out = out || (temps[s] > T.tmax) || (temps[s] < T.tmin);
+  if (T.dist_fit) {
+    for (int s = 0; s < ns; ++s) out = out || (rad[s] < 0.05);
+    out = out || (rad[0] > 1.5) || (plx < 1.0 / 3000.0) || (plx > 1.0 / 4.0);
+  } else {
+    out = out || (rad[1] < 0.05) || (rad[0] < 0.05);
+  }
+  if (T.ext_flag && av < 0.0) out = true;
+  if (out) { plan.status = MS_W_PRIOR_BOUNDS; plans[w] = plan; return; }
+
+  // ---- isochrone: log g and luminosity per star (mft6.py:66-98)
+  double lum[MAX_STAR];
+  for (int s = 0; s < ns; ++s) {
+    double g, l;
+    if (!interp_table(T.iso_teff, T.iso_logg, T.n_iso, temps[s], &g) ||
+        !interp_table(T.iso_teff, T.iso_lum, T.n_iso, temps[s], &l)) {
+      plan.status = MS_W_OFF_ISOCHRONE; plans[w] = plan; return;
+    }
+    plan.logg[s] = g; lum[s] = l;
+  }
+
+  // ---- prior terms, summed in the reference's order
+  double lp = 0.0;
+  if (T.ext_flag) {
+    double mu, sig;
+    dust_prior_moments(T, plx, &mu, &sig);
+    if (sig == 0.0) sig = 0.05;
+    const double z = (av - mu) / sig;
+    lp += -0.5 * (z * z);
+  }
+  const int nprior = T.dist_fit ? ndim : ndim - 2;       // ps has 2*ns+2 or 2*ns entries
+  for (int k = 0; k < nprior; ++k) {
+    if (T.prior_mu[k] != 0.0) {
+      const double z = (p[k] - T.prior_mu[k]) / T.prior_sig[k];
+      lp += -0.5 * (z * z);
+    }
+  }
+  if (T.rad_prior) {
+    const double r1m = stefan_boltzmann_radius(lum[0], temps[0]);
+    const double r2m = stefan_boltzmann_radius(lum[1], temps[1]);
+    const double m0 = r1m, m1 = r2m / r1m;
+    const double z0 = (rad[0] - m0) / (0.02 * m0);
+    const double z1 = (rad[1] - m1) / (0.02 * m1);
+    lp += -0.5 * (z0 * z0);
+    lp += -0.5 * (z1 * z1);
+  }
+  if (!isfinite(lp)) { plan.status = MS_W_NONFINITE; plans[w] = plan; return; }   // mft6.py:1465
+
+  // ---- grid brackets and coefficients
+  int z1 = 0, z2 = 0; double wz = 0.0;
+  if (T.n_feh > 1 && !bracket_nodes(T.feh_nodes, T.n_feh, T.feh, &z1, &z2, &wz)) {
+    plan.status = MS_W_OFF_GRID; plans[w] = plan; return;
+  }
+  const double di = 1.0 / plx;                            // mft6.py:690
+  for (int s = 0; s < ns; ++s) {
+    int t1, t2, g1, g2; double wt, wg;
+    if (!bracket_nodes(T.teff_nodes, T.n_teff, temps[s], &t1, &t2, &wt) ||
+        !bracket_nodes(T.logg_nodes, T.n_logg, plan.logg[s], &g1, &g2, &wg)) {
+      plan.status = MS_W_OFF_GRID; plans[w] = plan; return;
+    }
+    const double base = (s == 0) ? rad[0] * RSUN_CM / (di * PC_CM) : rad[0] * rad[s] * RSUN_CM / (di * PC_CM);
+    const double scale = base * base;                     // mft6.py:691, :700
+    // corners: (t1,g1) (t1,g2) (t2,g1) (t2,g2) [x z1, z2]
+    const double ct[2] = {1.0 - wt, wt}, cg[2] = {1.0 - wg, wg}, cz[2] = {1.0 - wz, wz};
+    const int it[2] = {t1, t2}, ig[2] = {g1, g2}, iz[2] = {z1, z2};
+    const int nz = (T.n_feh > 1) ? 2 : 1;
+    int c = 0;
+    for (int a = 0; a < nz; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int d = 0; d < 2; ++d) {
+          plan.row[s][c] = (iz[a] * T.n_logg + ig[d]) * T.n_teff + it[b];
+          plan.coef[s][c] = ((nz == 2) ? cz[a] : 1.0) * ct[b] * cg[d] * scale;
+          ++c;
+        }
+  }
+  plan.av = (T.ext_flag && av > 0.0) ? av : 0.0;          // mft6.py:1161
+  plan.lp = lp;
+  plans[w] = plan;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact order statistics of sM[0..n) (positive or negative doubles, no NaN) by MSD radix select.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ordered_key(double v) {
+  const long long b = __double_as_longlong(v);
+  return (b < 0) ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_value(unsigned long long k) {
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+struct SelectScratch {
+  unsigned hist[256];
+  unsigned long long kmin[NWARP], kmax[NWARP];
+  unsigned long long bcast[2];
+  int nanflag;
+};
+
+// Returns the median of sM[0..n) as numpy defines it (mean of the two middle order statistics
+// for even n); NaN if any element is NaN.
+__device__ double block_median(const double* sM, int n, SelectScratch* S) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- key range and NaN scan
+  unsigned long long kmin = ~0ull, kmax = 0ull;
+  int has_nan = 0;
+  for (int i = tid; i < n; i += NT) {
+    const double v = sM[i];
+    has_nan |= (v != v);
+    const unsigned long long k = ordered_key(v);
+    kmin = min(kmin, k); kmax = max(kmax, k);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  if (tid == 0) S->nanflag = 0;
+  __syncthreads();
+  if (has_nan) S->nanflag = 1;
+  if (lane == 0) { S->kmin[warp] = kmin; S->kmax[warp] = kmax; }
+  __syncthreads();
+  kmin = S->kmin[0]; kmax = S->kmax[0];
+#pragma unroll
+  for (int w = 1; w < NWARP; ++w) { kmin = min(kmin, S->kmin[w]); kmax = max(kmax, S->kmax[w]); }
+  const int nanflag = S->nanflag;
+  __syncthreads();
+  if (nanflag) return CUDART_NAN;
+  if (kmin == kmax) return key_value(kmin);
+
+  // ---- radix select of rank k1 = (n-1)/2, starting at the first bit where keys differ
+  int bits_done = __clzll((long long)(kmin ^ kmax));
+  unsigned long long prefix = (bits_done == 0) ? 0ull : (kmin & (~0ull << (64 - bits_done)));
+  unsigned rank = (unsigned)((n - 1) >> 1);
+  const int rounds = (n + NT - 1) / NT;
+  while (bits_done < 64) {
+    const int width = min(8, 64 - bits_done);
+    const int shift = 64 - bits_done - width;
+    const unsigned long long himask = (bits_done == 0) ? 0ull : (~0ull << (64 - bits_done));
+    S->hist[tid] = 0;                                    // NT == 256 bins
+    __syncthreads();
+    for (int r = 0; r < rounds; ++r) {
+      const int i = r * NT + tid;
+      unsigned d = 0xffffffffu;
+      if (i < n) {
+        const unsigned long long k = ordered_key(sM[i]);
+        if ((k & himask) == prefix) d = (unsigned)((k >> shift) & ((1u << width) - 1u));
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (d != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&S->hist[d], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // each lane owns 8 consecutive bins; inclusive scan of lane totals across the warp
+      unsigned c[8]; unsigned tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = S->hist[lane * 8 + j]; tot += c[j]; }
+      unsigned incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const unsigned excl = incl - tot;
+      if (rank >= excl && rank < incl) {                 // exactly one lane
+        unsigned run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (rank >= run && rank < run + c[j]) { S->bcast[0] = (unsigned long long)(lane * 8 + j); S->bcast[1] = run; }
+          run += c[j];
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned digit = (unsigned)S->bcast[0];
+    rank -= (unsigned)S->bcast[1];
+    prefix |= ((unsigned long long)digit) << shift;
+    bits_done += width;
+    __syncthreads();
+  }
+  const double v1 = key_value(prefix);
+  if (n & 1) return v1;
+
+  // ---- even n: the next order statistic is v1 again if enough elements are <= v1, else min{v > v1}
+  unsigned cnt_le = 0;
+  unsigned long long kgt = ~0ull;
+  for (int i = tid; i < n; i += NT) {
+    const unsigned long long k = ordered_key(sM[i]);
+    if (k <= prefix) ++cnt_le; else kgt = min(kgt, k);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt_le += __shfl_xor_sync(0xffffffffu, cnt_le, o);
+    kgt = min(kgt, __shfl_xor_sync(0xffffffffu, kgt, o));
+  }
+  if (lane == 0) { S->kmin[warp] = kgt; S->kmax[warp] = cnt_le; }
+  __syncthreads();
+  kgt = S->kmin[0]; unsigned long long tot_le = S->kmax[0];
+#pragma unroll
+  for (int w = 1; w < NWARP; ++w) { kgt = min(kgt, S->kmin[w]); tot_le += S->kmax[w]; }
+  __syncthreads();
+  const unsigned k2 = (unsigned)(n >> 1);                // 0-based rank of the upper middle element
+  const double v2 = (tot_le > k2) ? v1 : key_value(kgt);
+  return (v1 + v2) / 2.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// lnprob_stream_kernel: one CTA per walker.
+//   NR  grid rows per star (4: Teff x log g, 8: with [Fe/H]);  NC / NP compile-time filter caps.
+// ------------------------------------------------------------------------------------------
+template <int NR, int NC, int NP>
+__global__ void __launch_bounds__(NT, 2)
+lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __restrict__ plans,
+                     double* __restrict__ lnprob, const PartsOut parts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int KRED = 2 * NC + NP;
+  double* sF = reinterpret_cast<double*>(smem_raw);                  // [TILE] composite of the current tile
+  double* sRed = sF + TILE;                                          // [NWARP*KRED]
+  SelectScratch* sSel = reinterpret_cast<SelectScratch*>(sRed + NWARP * (KRED > 4 ? KRED : 4));
+  double* sM = reinterpret_cast<double*>(sSel + 1);                  // [n_data] model on observed pixels
+  __shared__ double sCarry;                                          // composite of the last pixel of the previous tile
+  __shared__ WalkerPlan sPlan;
+
+  const int tid = threadIdx.x;
+  const long long w = blockIdx.x;
+  {
+    // cooperative copy of the plan (16-byte chunks)
+    const int4* src = reinterpret_cast<const int4*>(plans + w);
+    int4* dst = reinterpret_cast<int4*>(&sPlan);
+    if (tid < (int)(sizeof(WalkerPlan) / sizeof(int4))) dst[tid] = src[tid];
+  }
+  __syncthreads();
+  const int status = sPlan.status;
+  if (status != 0) {                                                  // mft6.py:1465-1466
+    if (tid == 0) {
+      lnprob[w] = -CUDART_INF;
+      if (parts.status) parts.status[w] = status;
+      if (parts.lnprior) parts.lnprior[w] = -CUDART_INF;
+      if (parts.chi2_spec) parts.chi2_spec[w] = CUDART_NAN;
+      if (parts.logg) for (int s = 0; s < T.nspec; ++s) parts.logg[w * T.nspec + s] = sPlan.logg[s];
+      if (parts.contrast) for (int c = 0; c < T.n_contrast; ++c) parts.contrast[w * T.n_contrast + c] = CUDART_NAN;
+      if (parts.phot) for (int f = 0; f < T.n_phot; ++f) parts.phot[w * T.n_phot + f] = CUDART_NAN;
+    }
+    if (parts.model) for (int i = tid; i < T.n_data; i += NT) parts.model[w * T.n_data + i] = CUDART_NAN;
+    return;
+  }
+
+  double c0[NR], c1[NR];
+  const double* r0[NR];
+  const double* r1[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    c0[r] = sPlan.coef[0][r]; c1[r] = sPlan.coef[1][r];
+    r0[r] = T.grid + (long long)sPlan.row[0][r] * T.stride;
+    r1[r] = T.grid + (long long)sPlan.row[1][r] * T.stride;
+  }
+  const double av = sPlan.av;
+
+  double accC[NC > 0 ? NC : 1][2];
+  double accP[NP > 0 ? NP : 1];
+#pragma unroll
+  for (int f = 0; f < NC; ++f) { accC[f][0] = 0.0; accC[f][1] = 0.0; }
+#pragma unroll
+  for (int f = 0; f < NP; ++f) accP[f] = 0.0;
+
+  // ------------------------------------------------------------------ phase A: stream the rows
+  const int n_tiles = T.n_tiles;
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int base = tile * TILE;
+    const unsigned cmask = T.tile_cmask[tile];
+    const unsigned pmask = T.tile_pmask[tile];
+    const int d0 = T.tile_data_start[tile], d1 = T.tile_data_start[tile + 1];
+    double last = 0.0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int px = base + half * (2 * NT) + 2 * tid;              // first of this thread's pixel pair
+      double2 a[NR], b[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) a[r] = ldg_stream(r0[r] + px);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) b[r] = ldg_stream(r1[r] + px);
+      double2 f1, f2;
+      f1.x = c0[0] * a[0].x; f1.y = c0[0] * a[0].y;
+      f2.x = c1[0] * b[0].x; f2.y = c1[0] * b[0].y;
+#pragma unroll
+      for (int r = 1; r < NR; ++r) {
+        f1.x = fma(c0[r], a[r].x, f1.x); f1.y = fma(c0[r], a[r].y, f1.y);
+        f2.x = fma(c1[r], b[r].x, f2.x); f2.y = fma(c1[r], b[r].y, f2.y);
+      }
+      double2 comp; comp.x = f1.x + f2.x; comp.y = f1.y + f2.y;    // mft6.py:744
+#pragma unroll
+      for (int f = 0; f < NC; ++f) {
+        if ((cmask >> f) & 1u) {                                      // CTA-uniform
+          const double2 wv = __ldg(reinterpret_cast<const double2*>(T.c_wbase[f] + px));
+          accC[f][0] = fma(wv.x, f1.x, accC[f][0]); accC[f][0] = fma(wv.y, f1.y, accC[f][0]);
+          accC[f][1] = fma(wv.x, f2.x, accC[f][1]); accC[f][1] = fma(wv.y, f2.y, accC[f][1]);
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < NP; ++f) {
+        if ((pmask >> f) & 1u) {
+          const double2 wv = __ldg(reinterpret_cast<const double2*>(T.p_wbase[f] + px));
+          accP[f] = fma(wv.x, comp.x, accP[f]); accP[f] = fma(wv.y, comp.y, accP[f]);
+        }
+      }
+      if (d1 > d0) *reinterpret_cast<double2*>(sF + half * (2 * NT) + 2 * tid) = comp;
+      last = comp.y;
+    }
+    if (d1 > d0) {
+      __syncthreads();
+      for (int i = d0 + tid; i < d1; i += NT) {
+        const int h = T.rebin_hi[i] - base;                          // 0 .. TILE-1
+        const double flo = (h == 0) ? sCarry : sF[h - 1];
+        const double fhi = sF[h];
+        const double ylo = flo * exp2(av * T.ext_lo[i]);             // extinct() then interp1d: mft6.py:1162, :1169
+        const double yhi = fhi * exp2(av * T.ext_hi[i]);
+        sM[i] = ylo + (yhi - ylo) * T.rebin_t[i];
+      }
+      __syncthreads();
+    }
+    if (tid == NT - 1) sCarry = last;
+  }
+
+  // ------------------------------------------------------------------ band integrals
+  double red[KRED > 0 ? KRED : 1];
+#pragma unroll
+  for (int f = 0; f < NC; ++f) { red[2 * f] = accC[f][0]; red[2 * f + 1] = accC[f][1]; }
+#pragma unroll
+  for (int f = 0; f < NP; ++f) red[2 * NC + f] = accP[f];
+  block_sum<KRED>(red, sRed);
+
+  // ------------------------------------------------------------------ phase B: spectral chi-square
+  const int n = T.n_data;
+  const double med = block_median(sM, n, sSel);                      // mft6.py:1173
+  const double scale = T.data_median / med;
+  double mom[3] = {0.0, 0.0, 0.0};
+  for (int i = tid; i < n; i += NT) {
+    const double m = sM[i] * scale;
+    sM[i] = m;
+    const double frac = T.data_flux[i] / m;                           // norm_spec: mft6.py:194
+    const double x = T.data_x[i];
+    const double q0 = T.basis[0];
+    const double q1 = fma(T.basis[4], x, T.basis[3]);
+    const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
+    mom[0] = fma(q0, frac, mom[0]); mom[1] = fma(q1, frac, mom[1]); mom[2] = fma(q2, frac, mom[2]);
+  }
+  block_sum<3>(mom, sRed);
+  double chi[1] = {0.0};
+  for (int i = tid; i < n; i += NT) {
+    const double m = sM[i];
+    const double x = T.data_x[i];
+    const double q0 = T.basis[0];
+    const double q1 = fma(T.basis[4], x, T.basis[3]);
+    const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
+    const double pfit = mom[0] * q0 + mom[1] * q1 + mom[2] * q2;
+    const double dn = T.data_flux[i] / pfit;                          // mft6.py:196
+    const double e = T.data_err[i];
+    const double r = m - dn;
+    chi[0] += (r * r) / (e * e);                                      // mft6.py:120
+    if (parts.model) parts.model[w * n + i] = m;
+  }
+  block_sum<1>(chi, sRed);
+
+  // ------------------------------------------------------------------ final sum (mft6.py:1178-1205)
+  if (tid == 0) {
+    const double iic = chi[0] / (double)n;
+    double icontrast = 0.0, iphot = 0.0;
+    for (int f = 0; f < NC; ++f) {
+      if (f < T.n_contrast) {
+        const double m0 = -2.5 * log10(red[2 * f]);
+        const double m1 = -2.5 * log10(red[2 * f + 1]);
+        const double con = m1 - m0;                                   // mft6.py:741
+        const double d = con - T.c_mag[f];
+        icontrast += (d * d) / (T.c_err[f] * T.c_err[f]);
+        if (parts.contrast) parts.contrast[w * T.n_contrast + f] = con;
+      }
+    }
+    for (int f = 0; f < NP; ++f) {
+      if (f < T.n_phot) {
+        double mag = -2.5 * log10(red[2 * NC + f] * T.p_norm[f]);     // mft6.py:780-782
+        mag += av * T.p_ext[f];                                       // mft6.py:1163 (av == 0 when skipped)
+        const double d = mag - T.p_mag[f];
+        iphot += (d * d) / (T.p_err[f] * T.p_err[f]);
+        if (parts.phot) parts.phot[w * T.n_phot + f] = mag;
+      }
+    }
+    const double init_cs = iic * (double)(T.n_contrast + T.n_phot) + icontrast + iphot;   // mft6.py:1191
+    const double lnl = (init_cs != init_cs) ? -CUDART_INF : -0.5 * init_cs;               // mft6.py:1202-1205
+    double out = sPlan.lp + lnl;
+    int st = 0;
+    if (out != out) { out = -CUDART_INF; }
+    if (init_cs != init_cs) st |= MS_W_NONFINITE;
+    lnprob[w] = out;
+    if (parts.status) parts.status[w] = st;
+    if (parts.lnprior) parts.lnprior[w] = sPlan.lp;
+    if (parts.chi2_spec) parts.chi2_spec[w] = iic;
+    if (parts.logg) for (int s = 0; s < T.nspec; ++s) parts.logg[w * T.nspec + s] = sPlan.logg[s];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// broaden_rows_kernel: 'same' zero-padded convolution of the window of each row with `taps`
+// (mft6.py:128; np.convolve semantics), then the 5/10-sample edge patch (mft6.py:129-130).
+// grid = (ceil(win_len / BT), n_rows); dynamic smem = (BT + n_taps - 1) doubles + n_taps doubles.
+// ------------------------------------------------------------------------------------------
+constexpr int BT = 1024;   // output pixels per CTA
+
+__global__ void __launch_bounds__(256)
+broaden_rows_kernel(const double* __restrict__ in, double* __restrict__ out, long long row_len,
+                    long long win_lo, int win_len, const double* __restrict__ taps, int n_taps) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sIn = reinterpret_cast<double*>(smem_raw);        // [BT + n_taps - 1]
+  double* sTap = sIn + (BT + n_taps - 1);                   // [n_taps]
+  const int half = n_taps / 2;                              // odd n_taps: symmetric support
+  const long long row = blockIdx.y;
+  const int o0 = blockIdx.x * BT;
+  const double* src = in + row * row_len + win_lo;
+  for (int i = threadIdx.x; i < BT + n_taps - 1; i += blockDim.x) {
+    const int j = o0 - half + i;                            // window-relative input pixel
+    sIn[i] = (j >= 0 && j < win_len) ? src[j] : 0.0;        // zero padding outside the window
+  }
+  for (int i = threadIdx.x; i < n_taps; i += blockDim.x) sTap[i] = taps[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < BT; i += blockDim.x) {
+    const int o = o0 + i;
+    if (o < win_len) {
+      // np.convolve(y, e, 'same')[o] = sum_k e[k] * y[o + half - k]
+      double acc = 0.0;
+      for (int k = 0; k < n_taps; ++k) acc = fma(sTap[k], sIn[i + n_taps - 1 - k], acc);
+      out[row * row_len + win_lo + o] = acc;
+    }
+  }
+}
+
+__global__ void broaden_patch_kernel(double* __restrict__ rows, long long row_len, long long win_lo, int win_len) {
+  // broad[0:5] = broad[5]; broad[n-10:n] = broad[n-11]        (mft6.py:129-130)
+  const long long row = blockIdx.x;
+  double* b = rows + row * row_len + win_lo;
+  const int t = threadIdx.x;
+  if (win_len < 16) return;
+  const double head = b[5], tail = b[win_len - 11];
+  __syncthreads();
+  if (t < 5) b[t] = head;
+  else if (t < 15) b[win_len - 10 + (t - 5)] = tail;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stretch move (emcee RedBlueMove + StretchMove, a = 2) with a counter-based generator.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// uniform in (0,1): stream (seed, iteration, split, purpose), counter = global walker id
+__host__ __device__ __forceinline__ double counter_uniform(unsigned long long seed, unsigned long long iteration,
+                                                           int split, int purpose, unsigned long long gid) {
+  unsigned long long k = mix64(seed);
+  k = mix64(k ^ iteration);
+  k = mix64(k ^ (unsigned long long)(split * 4 + purpose));
+  const unsigned long long r = mix64(k ^ mix64(gid));
+  return ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void stretch_propose_kernel(const double* __restrict__ x, long long n_s, const double* __restrict__ c,
+                                       long long n_c, int ndim, double a, unsigned long long seed,
+                                       unsigned long long iteration, int split, long long gid0,
+                                       double* __restrict__ q, double* __restrict__ logfac) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= n_s) return;
+  const unsigned long long gid = (unsigned long long)(gid0 + s);
+  const double u = counter_uniform(seed, iteration, split, 0, gid);
+  const double root = (a - 1.0) * u + 1.0;
+  const double z = root * root / a;
+  long long j = (long long)(counter_uniform(seed, iteration, split, 1, gid) * (double)n_c);
+  if (j >= n_c) j = n_c - 1;
+  for (int k = 0; k < ndim; ++k) {
+    const double cj = c[j * ndim + k];
+    q[s * ndim + k] = cj - (cj - x[s * ndim + k]) * z;
+  }
+  logfac[s] = (double)(ndim - 1) * log(z);
+}
+
+__global__ void stretch_accept_kernel(double* __restrict__ x, double* __restrict__ lnp_x, const double* __restrict__ q,
+                                      const double* __restrict__ lnp_q, const double* __restrict__ logfac,
+                                      long long n_s, int ndim, unsigned long long seed, unsigned long long iteration,
+                                      int split, long long gid0, int* __restrict__ accepted) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= n_s) return;
+  const double u = counter_uniform(seed, iteration, split, 2, (unsigned long long)(gid0 + s));
+  const double lnpdiff = logfac[s] + lnp_q[s] - lnp_x[s];
+  if (log(u) < lnpdiff) {                                            // -inf proposals never pass; NaN never passes
+    for (int k = 0; k < ndim; ++k) x[s * ndim + k] = q[s * ndim + k];
+    lnp_x[s] = lnp_q[s];
+    if (accepted) accepted[s] += 1;
+  }
+}
+
+}  // namespace
+
+// ==========================================================================================
+// Host side: handle, uploads, launches
+// ==========================================================================================
+struct ms_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevTables T{};
+  std::vector<void*> allocs;
+  int corners = 4;               // rows per star
+  int variant = 0;               // 0: (NC,NP)=(2,6), 1: (4,12)
+  size_t smem_bytes = 0;
+  // per-call buffers
+  WalkerPlan* plans = nullptr; long long plans_cap = 0;
+  double* d_theta = nullptr; double* d_lnp = nullptr; long long io_cap = 0;
+  double* h_theta = nullptr; double* h_lnp = nullptr; long long pin_cap = 0;
+  long long launches = 0;
+  std::string err;
+};
+
+namespace {
+
+std::string g_create_error;
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      set_err(h, std::string(#call) + ": " + cudaGetErrorString(e__));                \
+      return MS_ERR_CUDA;                                                             \
+    }                                                                                 \
+  } while (0)
+
+void set_err(ms_handle* h, const std::string& m) {
+  if (h) h->err = m; else g_create_error = m;
+}
+
+template <typename Tp>
+int upload(ms_handle* h, const Tp* host, size_t n, const Tp** dev) {
+  void* p = nullptr;
+  const size_t bytes = (n ? n : 1) * sizeof(Tp);
+  CK(cudaMalloc(&p, bytes));
+  h->allocs.push_back(p);
+  if (n) CK(cudaMemcpy(p, host, n * sizeof(Tp), cudaMemcpyHostToDevice));
+  *dev = static_cast<const Tp*>(p);
+  return MS_OK;
+}
+
+template <int NR, int NC, int NP>
+int launch_stream_variant(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts) {
+  auto kern = lnprob_stream_kernel<NR, NC, NP>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, d_lnp, parts);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MS_OK;
+}
+
+size_t stream_smem_bytes(int n_data, int nc, int np) {
+  const int kred = 2 * nc + np;
+  size_t b = (size_t)TILE * 8 + (size_t)NWARP * (kred > 4 ? kred : 4) * 8 + sizeof(SelectScratch);
+  b += (size_t)n_data * 8;
+  return (b + 15) & ~(size_t)15;
+}
+
+int ensure_plans(ms_handle* h, long long nw) {
+  if (nw <= h->plans_cap) return MS_OK;
+  if (h->plans) cudaFree(h->plans);
+  h->plans = nullptr; h->plans_cap = 0;
+  long long cap = nw + nw / 4 + 64;
+  CK(cudaMalloc((void**)&h->plans, (size_t)cap * sizeof(WalkerPlan)));
+  h->plans_cap = cap;
+  return MS_OK;
+}
+
+int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d_lnp, const PartsOut& parts) {
+  if (nw == 0) return MS_OK;
+  int rc = ensure_plans(h, nw);
+  if (rc) return rc;
+  const int pb = 128;
+  walker_prep_kernel<<<(unsigned)((nw + pb - 1) / pb), pb, 0, h->stream>>>(h->T, d_theta, nw, h->plans);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  if (h->corners == 4) {
+    if (h->variant == 0) return launch_stream_variant<4, 2, 6>(h, nw, d_lnp, parts);
+    return launch_stream_variant<4, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts);
+  }
+  if (h->variant == 0) return launch_stream_variant<8, 2, 6>(h, nw, d_lnp, parts);
+  return launch_stream_variant<8, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts);
+}
+
+int ensure_io(ms_handle* h, long long nw) {
+  if (nw > h->io_cap) {
+    if (h->d_theta) cudaFree(h->d_theta);
+    if (h->d_lnp) cudaFree(h->d_lnp);
+    h->d_theta = h->d_lnp = nullptr; h->io_cap = 0;
+    long long cap = nw + nw / 4 + 64;
+    CK(cudaMalloc((void**)&h->d_theta, (size_t)cap * MS_MAX_NDIM * 8));
+    CK(cudaMalloc((void**)&h->d_lnp, (size_t)cap * 8));
+    h->io_cap = cap;
+  }
+  if (nw > h->pin_cap) {
+    if (h->h_theta) cudaFreeHost(h->h_theta);
+    if (h->h_lnp) cudaFreeHost(h->h_lnp);
+    h->h_theta = h->h_lnp = nullptr; h->pin_cap = 0;
+    long long cap = nw + nw / 4 + 64;
+    CK(cudaMallocHost((void**)&h->h_theta, (size_t)cap * MS_MAX_NDIM * 8));
+    CK(cudaMallocHost((void**)&h->h_lnp, (size_t)cap * 8));
+    h->pin_cap = cap;
+  }
+  return MS_OK;
+}
+
+// scratch device buffer for a host-side optional output
+struct HostOut {
+  void* dev = nullptr; void* host = nullptr; size_t bytes = 0;
+};
+
+}  // namespace
+
+extern "C" {
+
+int64_t ms_config_size(void) { return (int64_t)sizeof(ms_config); }
+int32_t ms_abi_version(void) { return MS_ABI_VERSION; }
+
+const char* ms_last_error(const ms_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+void* ms_stream(const ms_handle* h) { return h ? (void*)h->stream : nullptr; }
+int ms_device(const ms_handle* h) { return h ? h->device : -1; }
+int64_t ms_launch_count(const ms_handle* h) { return h ? h->launches : 0; }
+
+int ms_destroy(ms_handle* h) {
+  if (!h) return MS_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->plans) cudaFree(h->plans);
+  if (h->d_theta) cudaFree(h->d_theta);
+  if (h->d_lnp) cudaFree(h->d_lnp);
+  if (h->h_theta) cudaFreeHost(h->h_theta);
+  if (h->h_lnp) cudaFreeHost(h->h_lnp);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MS_OK;
+}
+
+int ms_create(const ms_config* cfg, ms_handle** out) {
+  if (!cfg || !out) { set_err(nullptr, "ms_create: null argument"); return MS_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->abi_version != MS_ABI_VERSION) { set_err(nullptr, "ms_create: ABI version mismatch"); return MS_ERR_INVALID; }
+  if (cfg->nspec != 2) { set_err(nullptr, "ms_create: only nspec == 2 (binaries) is built"); return MS_ERR_UNSUPPORTED; }
+  if (cfg->n_contrast < 0 || cfg->n_contrast > MS_MAX_CONTRAST || cfg->n_phot < 0 || cfg->n_phot > MS_MAX_PHOT) {
+    set_err(nullptr, "ms_create: too many filters"); return MS_ERR_UNSUPPORTED;
+  }
+  if (cfg->n_teff < 1 || cfg->n_logg < 1 || cfg->n_feh < 1 || cfg->n_reg < 2 || cfg->n_data < 1 ||
+      cfg->n_iso < 2 || cfg->n_dm < 1 || cfg->n_dust_samples < 1 || cfg->n_dust_samples > 16 ||
+      cfg->n_tiles != (cfg->n_reg + TILE - 1) / TILE || cfg->reg_lo < 0 || cfg->reg_lo + cfg->n_reg > cfg->row_len) {
+    set_err(nullptr, "ms_create: inconsistent sizes"); return MS_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err(nullptr, "ms_create: no CUDA device"); return MS_ERR_NO_DEVICE; }
+  if (cfg->device < 0 || cfg->device >= ndev) { set_err(nullptr, "ms_create: bad device ordinal"); return MS_ERR_INVALID; }
+
+  ms_handle* h = new (std::nothrow) ms_handle();
+  if (!h) { set_err(nullptr, "ms_create: out of host memory"); return MS_ERR_INVALID; }
+  h->device = cfg->device;
+  auto fail = [&](int rc) { g_create_error = h->err; ms_destroy(h); return rc; };
+#define CKC(expr) do { int rc__ = (expr); if (rc__) return fail(rc__); } while (0)
+#define CKH(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e__); return fail(MS_ERR_CUDA); } } while (0)
+  CKH(cudaSetDevice(h->device));
+  CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+  DevTables& T = h->T;
+  T.n_teff = cfg->n_teff; T.n_logg = cfg->n_logg; T.n_feh = cfg->n_feh;
+  T.n_reg = cfg->n_reg; T.n_tiles = cfg->n_tiles; T.feh = cfg->feh;
+  T.n_data = cfg->n_data;
+  T.n_contrast = cfg->n_contrast; T.n_phot = cfg->n_phot;
+  T.nspec = cfg->nspec; T.ndim = 2 * cfg->nspec + 2;
+  T.ext_flag = cfg->ext_flag; T.dist_fit = cfg->dist_fit; T.rad_prior = cfg->rad_prior;
+  T.tmin = cfg->tmin; T.tmax = cfg->tmax;
+  T.data_median = cfg->data_median;
+  for (int k = 0; k < 9; ++k) T.basis[k] = cfg->poly_basis[k];
+  for (int k = 0; k < MS_MAX_NDIM; ++k) { T.prior_mu[k] = cfg->prior_mu[k]; T.prior_sig[k] = cfg->prior_sig[k]; }
+  T.n_iso = cfg->n_iso; T.n_dm = cfg->n_dm; T.n_dust_samples = cfg->n_dust_samples;
+  h->corners = (cfg->n_feh > 1) ? 8 : 4;
+  h->variant = (cfg->n_contrast <= 2 && cfg->n_phot <= 6) ? 0 : 1;
+
+  // ---- grid: region cut of every row, padded with zeros to whole tiles
+  const long long n_rows = (long long)cfg->n_feh * cfg->n_logg * cfg->n_teff;
+  T.stride = (long long)cfg->n_tiles * TILE;
+  {
+    void* p = nullptr;
+    CKH(cudaMalloc(&p, (size_t)n_rows * T.stride * 8));
+    h->allocs.push_back(p);
+    CKH(cudaMemset(p, 0, (size_t)n_rows * T.stride * 8));
+    CKH(cudaMemcpy2D(p, (size_t)T.stride * 8, cfg->grid + cfg->reg_lo, (size_t)cfg->row_len * 8,
+                     (size_t)cfg->n_reg * 8, (size_t)n_rows, cudaMemcpyHostToDevice));
+    T.grid = static_cast<const double*>(p);
+  }
+  CKC(upload(h, cfg->teff_nodes, cfg->n_teff, &T.teff_nodes));
+  CKC(upload(h, cfg->logg_nodes, cfg->n_logg, &T.logg_nodes));
+  CKC(upload(h, cfg->feh_nodes, cfg->n_feh, &T.feh_nodes));
+
+  // ---- observed spectrum tables
+  for (int i = 0; i < cfg->n_data; ++i) {
+    if (cfg->rebin_hi[i] < 1 || cfg->rebin_hi[i] >= cfg->n_reg || (i && cfg->rebin_hi[i] < cfg->rebin_hi[i - 1])) {
+      h->err = "ms_create: rebin_hi must be ascending and inside the region"; return fail(MS_ERR_INVALID);
+    }
+  }
+  if (cfg->tile_data_start[0] != 0 || cfg->tile_data_start[cfg->n_tiles] != cfg->n_data) {
+    h->err = "ms_create: tile_data_start does not cover the observed pixels"; return fail(MS_ERR_INVALID);
+  }
+  CKC(upload(h, cfg->rebin_hi, cfg->n_data, &T.rebin_hi));
+  CKC(upload(h, cfg->rebin_t, cfg->n_data, &T.rebin_t));
+  CKC(upload(h, cfg->ext_lo, cfg->n_data, &T.ext_lo));
+  CKC(upload(h, cfg->ext_hi, cfg->n_data, &T.ext_hi));
+  CKC(upload(h, cfg->data_flux, cfg->n_data, &T.data_flux));
+  CKC(upload(h, cfg->data_err, cfg->n_data, &T.data_err));
+  CKC(upload(h, cfg->data_x, cfg->n_data, &T.data_x));
+  CKC(upload(h, cfg->tile_data_start, (size_t)cfg->n_tiles + 1, &T.tile_data_start));
+
+  // ---- filters
+  std::vector<unsigned> cmask(cfg->n_tiles, 0u), pmask(cfg->n_tiles, 0u);
+  const double* d_cw = nullptr; const double* d_pw = nullptr;
+  CKC(upload(h, cfg->c_weights, (size_t)cfg->c_weights_len, &d_cw));
+  CKC(upload(h, cfg->p_weights, (size_t)cfg->p_weights_len, &d_pw));
+  for (int f = 0; f < MS_MAX_CONTRAST; ++f) { T.c_wbase[f] = d_cw; T.c_mag[f] = 0; T.c_err[f] = 1; }
+  for (int f = 0; f < MS_MAX_PHOT; ++f) { T.p_wbase[f] = d_pw; T.p_norm[f] = 1; T.p_ext[f] = 0; T.p_mag[f] = 0; T.p_err[f] = 1; }
+  for (int f = 0; f < cfg->n_contrast; ++f) {
+    const int lo = cfg->c_tile_lo[f], hi = cfg->c_tile_hi[f];
+    if (lo < 0 || hi > cfg->n_tiles || hi < lo || cfg->c_offset[f] + (long long)(hi - lo) * TILE > cfg->c_weights_len) {
+      h->err = "ms_create: contrast filter tiles out of range"; return fail(MS_ERR_INVALID);
+    }
+    for (int t = lo; t < hi; ++t) cmask[t] |= 1u << f;
+    T.c_wbase[f] = d_cw + cfg->c_offset[f] - (long long)lo * TILE;
+    T.c_mag[f] = cfg->c_mag[f]; T.c_err[f] = cfg->c_err[f];
+  }
+  for (int f = 0; f < cfg->n_phot; ++f) {
+    const int lo = cfg->p_tile_lo[f], hi = cfg->p_tile_hi[f];
+    if (lo < 0 || hi > cfg->n_tiles || hi < lo || cfg->p_offset[f] + (long long)(hi - lo) * TILE > cfg->p_weights_len) {
+      h->err = "ms_create: photometric filter tiles out of range"; return fail(MS_ERR_INVALID);
+    }
+    for (int t = lo; t < hi; ++t) pmask[t] |= 1u << f;
+    T.p_wbase[f] = d_pw + cfg->p_offset[f] - (long long)lo * TILE;
+    T.p_norm[f] = cfg->p_norm[f]; T.p_ext[f] = cfg->p_ext[f];
+    T.p_mag[f] = cfg->p_mag[f]; T.p_err[f] = cfg->p_err[f];
+  }
+  CKC(upload(h, cmask.data(), cmask.size(), &T.tile_cmask));
+  CKC(upload(h, pmask.data(), pmask.size(), &T.tile_pmask));
+
+  // ---- isochrone, dust
+  CKC(upload(h, cfg->iso_teff, cfg->n_iso, &T.iso_teff));
+  CKC(upload(h, cfg->iso_logg, cfg->n_iso, &T.iso_logg));
+  CKC(upload(h, cfg->iso_lum, cfg->n_iso, &T.iso_lum));
+  CKC(upload(h, cfg->dust_dm_edges, cfg->n_dm, &T.dust_dm));
+  CKC(upload(h, cfg->dust_samples, (size_t)cfg->n_dm * cfg->n_dust_samples, &T.dust_samples));
+
+  // ---- shared memory budget of the streaming kernel
+  const int nc = h->variant == 0 ? 2 : MS_MAX_CONTRAST, np = h->variant == 0 ? 6 : MS_MAX_PHOT;
+  h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np);
+  int max_optin = 0;
+  CKH(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  if (h->smem_bytes + 2048 > (size_t)max_optin) {
+    h->err = "ms_create: n_data too large for the shared-memory resident model spectrum"; return fail(MS_ERR_UNSUPPORTED);
+  }
+  CKH(cudaStreamSynchronize(h->stream));
+#undef CKC
+#undef CKH
+  *out = h;
+  return MS_OK;
+}
+
+int ms_lnprob_parts(ms_handle* h, const double* theta, int64_t nw, double* lnprob, double* chi2_spec,
+                    double* contrast, double* phot, double* lnprior, double* logg, int32_t* status, int where) {
+  if (!h) return MS_ERR_INVALID;
+  if (nw < 0 || (nw > 0 && (!theta || !lnprob))) { set_err(h, "ms_lnprob: null argument"); return MS_ERR_INVALID; }
+  if (nw == 0) return MS_OK;
+  CK(cudaSetDevice(h->device));
+  const int ndim = h->T.ndim;
+  if (where == MS_DEVICE) {
+    PartsOut parts{chi2_spec, contrast, phot, lnprior, logg, status, nullptr};
+    return evaluate_device(h, theta, nw, lnprob, parts);
+  }
+  if (where != MS_HOST) { set_err(h, "ms_lnprob: bad `where`"); return MS_ERR_INVALID; }
+  int rc = ensure_io(h, nw);
+  if (rc) return rc;
+  std::memcpy(h->h_theta, theta, (size_t)nw * ndim * 8);
+  CK(cudaMemcpyAsync(h->d_theta, h->h_theta, (size_t)nw * ndim * 8, cudaMemcpyHostToDevice, h->stream));
+  // optional outputs: device scratch, copied back after the kernel
+  struct Opt { void* host; size_t bytes; void* dev; };
+  Opt opts[6] = {{chi2_spec, (size_t)nw * 8, nullptr}, {contrast, (size_t)nw * h->T.n_contrast * 8, nullptr},
+                 {phot, (size_t)nw * h->T.n_phot * 8, nullptr}, {lnprior, (size_t)nw * 8, nullptr},
+                 {logg, (size_t)nw * h->T.nspec * 8, nullptr}, {status, (size_t)nw * 4, nullptr}};
+  for (auto& o : opts) if (o.host && o.bytes) CK(cudaMalloc(&o.dev, o.bytes));
+  PartsOut parts{(double*)opts[0].dev, (double*)opts[1].dev, (double*)opts[2].dev, (double*)opts[3].dev,
+                 (double*)opts[4].dev, (int*)opts[5].dev, nullptr};
+  rc = evaluate_device(h, h->d_theta, nw, h->d_lnp, parts);
+  if (rc == MS_OK) {
+    cudaError_t e = cudaMemcpyAsync(h->h_lnp, h->d_lnp, (size_t)nw * 8, cudaMemcpyDeviceToHost, h->stream);
+    for (auto& o : opts) if (o.dev && e == cudaSuccess) e = cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { set_err(h, std::string("ms_lnprob: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
+    else std::memcpy(lnprob, h->h_lnp, (size_t)nw * 8);
+  }
+  for (auto& o : opts) if (o.dev) cudaFree(o.dev);
+  return rc;
+}
+
+int ms_lnprob(ms_handle* h, const double* theta, int64_t nw, double* lnprob, int where) {
+  return ms_lnprob_parts(h, theta, nw, lnprob, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, where);
+}
+
+int ms_model_spectrum(ms_handle* h, const double* theta, int64_t nw, double* out, int where) {
+  if (!h) return MS_ERR_INVALID;
+  if (nw < 0 || (nw > 0 && (!theta || !out))) { set_err(h, "ms_model_spectrum: null argument"); return MS_ERR_INVALID; }
+  if (nw == 0) return MS_OK;
+  CK(cudaSetDevice(h->device));
+  const int ndim = h->T.ndim, n = h->T.n_data;
+  int rc = ensure_io(h, nw);
+  if (rc) return rc;
+  const double* d_theta = theta;
+  double* d_out = out;
+  if (where == MS_HOST) {
+    std::memcpy(h->h_theta, theta, (size_t)nw * ndim * 8);
+    CK(cudaMemcpyAsync(h->d_theta, h->h_theta, (size_t)nw * ndim * 8, cudaMemcpyHostToDevice, h->stream));
+    d_theta = h->d_theta;
+    CK(cudaMalloc((void**)&d_out, (size_t)nw * n * 8));
+  }
+  PartsOut parts{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_out};
+  rc = evaluate_device(h, d_theta, nw, h->d_lnp, parts);
+  if (where == MS_HOST) {
+    if (rc == MS_OK) {
+      cudaError_t e = cudaMemcpyAsync(out, d_out, (size_t)nw * n * 8, cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { set_err(h, std::string("ms_model_spectrum: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
+    }
+    cudaFree(d_out);
+  }
+  return rc;
+}
+
+int ms_broaden_rows(int device, double* rows, int64_t n_rows, int64_t row_len, int64_t win_lo, int64_t win_len,
+                    const double* taps, int32_t n_taps) {
+  ms_handle* h = nullptr;   // errors land in the create-error slot
+  if (!rows || !taps || n_rows < 0 || row_len <= 0 || win_lo < 0 || win_len < 0 || win_lo + win_len > row_len ||
+      n_taps < 1 || (n_taps % 2) == 0 || n_taps > 4097 || (win_len > 0 && win_len < n_taps) || win_len > 0x7fffffff) {
+    set_err(h, "ms_broaden_rows: invalid argument (n_taps must be odd and not exceed the window)"); return MS_ERR_INVALID;
+  }
+  if (n_rows == 0 || win_len == 0) return MS_OK;
+  CK(cudaSetDevice(device));
+  double *d_in = nullptr, *d_out = nullptr, *d_taps = nullptr;
+  const long long chunk = std::max<long long>(1, std::min<long long>(n_rows, (1ll << 28) / row_len));   // <= 2 GiB per buffer
+  CK(cudaMalloc((void**)&d_in, (size_t)chunk * row_len * 8));
+  CK(cudaMalloc((void**)&d_out, (size_t)chunk * row_len * 8));
+  CK(cudaMalloc((void**)&d_taps, (size_t)n_taps * 8));
+  int rc = MS_OK;
+  cudaError_t e = cudaMemcpy(d_taps, taps, (size_t)n_taps * 8, cudaMemcpyHostToDevice);
+  const size_t smem = ((size_t)BT + 2 * (size_t)n_taps) * 8;
+  if (e == cudaSuccess && smem > 48 * 1024)
+    e = cudaFuncSetAttribute(broaden_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  for (long long r0 = 0; r0 < n_rows && e == cudaSuccess; r0 += chunk) {
+    const long long nr = std::min<long long>(chunk, n_rows - r0);
+    e = cudaMemcpy(d_in, rows + r0 * row_len, (size_t)nr * row_len * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_out, d_in, (size_t)nr * row_len * 8, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) break;
+    dim3 grid((unsigned)((win_len + BT - 1) / BT), (unsigned)nr);
+    broaden_rows_kernel<<<grid, 256, smem>>>(d_in, d_out, row_len, win_lo, (int)win_len, d_taps, n_taps);
+    broaden_patch_kernel<<<(unsigned)nr, 32>>>(d_out, row_len, win_lo, (int)win_len);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(rows + r0 * row_len, d_out, (size_t)nr * row_len * 8, cudaMemcpyDeviceToHost);
+  }
+  if (e != cudaSuccess) { set_err(h, std::string("ms_broaden_rows: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_taps);
+  return rc;
+}
+
+int ms_stretch_propose(ms_handle* h, const double* x, int64_t n_s, const double* c, int64_t n_c, int32_t ndim,
+                       double a, uint64_t seed, uint64_t iteration, int32_t split, int64_t gid0, double* q,
+                       double* logfac) {
+  if (!h) return MS_ERR_INVALID;
+  if (n_s < 0 || n_c < 1 || ndim < 1 || !x || !c || !q || !logfac) { set_err(h, "ms_stretch_propose: invalid argument"); return MS_ERR_INVALID; }
+  if (n_s == 0) return MS_OK;
+  CK(cudaSetDevice(h->device));
+  stretch_propose_kernel<<<(unsigned)((n_s + 127) / 128), 128, 0, h->stream>>>(x, n_s, c, n_c, ndim, a, seed, iteration,
+                                                                             split, gid0, q, logfac);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MS_OK;
+}
+
+int ms_stretch_accept(ms_handle* h, double* x, double* lnp_x, const double* q, const double* lnp_q,
+                      const double* logfac, int64_t n_s, int32_t ndim, uint64_t seed, uint64_t iteration,
+                      int32_t split, int64_t gid0, int32_t* accepted) {
+  if (!h) return MS_ERR_INVALID;
+  if (n_s < 0 || ndim < 1 || !x || !lnp_x || !q || !lnp_q || !logfac) { set_err(h, "ms_stretch_accept: invalid argument"); return MS_ERR_INVALID; }
+  if (n_s == 0) return MS_OK;
+  CK(cudaSetDevice(h->device));
+  stretch_accept_kernel<<<(unsigned)((n_s + 127) / 128), 128, 0, h->stream>>>(x, lnp_x, q, lnp_q, logfac, n_s, ndim, seed,
+                                                                            iteration, split, gid0, accepted);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MS_OK;
+}
+
+}  // extern "C"

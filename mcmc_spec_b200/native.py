@@ -1,0 +1,258 @@
+"""ctypes binding of libmcmcspec.so (C ABI in include/mcmcspec.h).
+
+This is the stub a maintainer of the reference would add next to mft6.py: it mirrors
+``ms_config`` field for field, loads the in-tree library and fails loudly when the library (or a
+CUDA device) is missing -- there is no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .tables import DeviceTables, TILE
+
+MS_ABI_VERSION = 1
+MS_MAX_CONTRAST, MS_MAX_PHOT, MS_MAX_NDIM = 4, 12, 8
+MS_HOST, MS_DEVICE = 0, 1
+MS_W_PRIOR_BOUNDS, MS_W_OFF_ISOCHRONE, MS_W_OFF_GRID, MS_W_NONFINITE = 1, 2, 4, 8
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmcmcspec.so')
+
+EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_destroy', 'ms_last_error', 'ms_stream',
+           'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_broaden_rows',
+           'ms_stretch_propose', 'ms_stretch_accept', 'ms_launch_count']
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+class MsConfig(C.Structure):
+    _fields_ = [
+        ('abi_version', C.c_int32), ('device', C.c_int32),
+        ('n_teff', C.c_int32), ('n_logg', C.c_int32), ('n_feh', C.c_int32), ('n_reg', C.c_int32),
+        ('row_len', C.c_int64), ('reg_lo', C.c_int64),
+        ('teff_nodes', _dp), ('logg_nodes', _dp), ('feh_nodes', _dp), ('grid', _dp), ('feh', C.c_double),
+        ('n_data', C.c_int32), ('n_tiles', C.c_int32),
+        ('rebin_hi', _ip), ('rebin_t', _dp), ('ext_lo', _dp), ('ext_hi', _dp),
+        ('data_flux', _dp), ('data_err', _dp), ('data_x', _dp), ('tile_data_start', _ip),
+        ('poly_basis', C.c_double * 9), ('data_median', C.c_double),
+        ('n_contrast', C.c_int32), ('n_phot', C.c_int32),
+        ('c_tile_lo', _ip), ('c_tile_hi', _ip), ('c_offset', _lp), ('c_weights', _dp),
+        ('c_weights_len', C.c_int64), ('c_mag', _dp), ('c_err', _dp),
+        ('p_tile_lo', _ip), ('p_tile_hi', _ip), ('p_offset', _lp), ('p_weights', _dp),
+        ('p_weights_len', C.c_int64), ('p_norm', _dp), ('p_ext', _dp), ('p_mag', _dp), ('p_err', _dp),
+        ('n_iso', C.c_int32), ('n_dm', C.c_int32), ('n_dust_samples', C.c_int32), ('nspec', C.c_int32),
+        ('iso_teff', _dp), ('iso_logg', _dp), ('iso_lum', _dp), ('dust_dm_edges', _dp), ('dust_samples', _dp),
+        ('tmin', C.c_double), ('tmax', C.c_double),
+        ('prior_mu', C.c_double * MS_MAX_NDIM), ('prior_sig', C.c_double * MS_MAX_NDIM),
+        ('ext_flag', C.c_int32), ('dist_fit', C.c_int32), ('rad_prior', C.c_int32), ('reserved', C.c_int32),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libmcmcspec.so and declare prototypes.  Raises NativeError if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _LIB_PATH
+    if not os.path.exists(path):
+        raise NativeError(f"{path} is missing: build it with `python -m mcmc_spec_b200.build` "
+                          "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.ms_config_size.restype = C.c_int64
+    lib.ms_abi_version.restype = C.c_int32
+    lib.ms_create.argtypes = [C.POINTER(MsConfig), C.POINTER(vp)]
+    lib.ms_destroy.argtypes = [vp]
+    lib.ms_last_error.argtypes = [vp]
+    lib.ms_last_error.restype = C.c_char_p
+    lib.ms_stream.argtypes = [vp]
+    lib.ms_stream.restype = vp
+    lib.ms_device.argtypes = [vp]
+    lib.ms_lnprob.argtypes = [vp, vp, C.c_int64, vp, C.c_int]
+    lib.ms_lnprob_parts.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+    lib.ms_model_spectrum.argtypes = [vp, vp, C.c_int64, vp, C.c_int]
+    lib.ms_broaden_rows.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32]
+    lib.ms_stretch_propose.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_double, C.c_uint64,
+                                       C.c_uint64, C.c_int32, C.c_int64, vp, vp]
+    lib.ms_stretch_accept.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64,
+                                      C.c_int32, C.c_int64, vp]
+    lib.ms_launch_count.argtypes = [vp]
+    lib.ms_launch_count.restype = C.c_int64
+    for name in EXPORTS:
+        getattr(lib, name)
+    if lib.ms_config_size() != C.sizeof(MsConfig):
+        raise NativeError(f"ms_config layout mismatch: library {lib.ms_config_size()} bytes, "
+                          f"binding {C.sizeof(MsConfig)} bytes")
+    if lib.ms_abi_version() != MS_ABI_VERSION:
+        raise NativeError("libmcmcspec.so ABI version mismatch")
+    if path == _LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _p(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+def make_config(t: DeviceTables, device=0):
+    """DeviceTables -> (MsConfig, keepalive list of the numpy arrays it points into)."""
+    keep = []
+
+    def dbl(a):
+        a = np.ascontiguousarray(a, dtype=np.float64); keep.append(a); return _p(a, C.c_double)
+
+    def i32(a):
+        a = np.ascontiguousarray(a, dtype=np.int32); keep.append(a); return _p(a, C.c_int32)
+
+    def i64(a):
+        a = np.ascontiguousarray(a, dtype=np.int64); keep.append(a); return _p(a, C.c_int64)
+
+    cfg = MsConfig()
+    cfg.abi_version, cfg.device = MS_ABI_VERSION, int(device)
+    cfg.n_teff, cfg.n_logg, cfg.n_feh = len(t.teff_nodes), len(t.logg_nodes), len(t.feh_nodes)
+    cfg.n_reg, cfg.row_len, cfg.reg_lo = t.n_reg, t.row_len, t.reg_lo
+    cfg.teff_nodes, cfg.logg_nodes, cfg.feh_nodes = dbl(t.teff_nodes), dbl(t.logg_nodes), dbl(t.feh_nodes)
+    grid = np.ascontiguousarray(t.grid, dtype=np.float64)
+    if grid.shape[-1] != t.row_len or grid.size != cfg.n_teff * cfg.n_logg * cfg.n_feh * t.row_len:
+        raise ValueError("grid shape does not match the node lists")
+    keep.append(grid)
+    cfg.grid = _p(grid, C.c_double)
+    cfg.feh = t.feh
+    cfg.n_data, cfg.n_tiles = t.n_data, t.n_tiles
+    cfg.rebin_hi, cfg.rebin_t = i32(t.rebin_hi), dbl(t.rebin_t)
+    cfg.ext_lo, cfg.ext_hi = dbl(t.ext_lo), dbl(t.ext_hi)
+    cfg.data_flux, cfg.data_err, cfg.data_x = dbl(t.data_flux), dbl(t.data_err), dbl(t.data_x)
+    cfg.tile_data_start = i32(t.tile_data_start)
+    cfg.poly_basis = (C.c_double * 9)(*np.asarray(t.poly_basis, dtype=np.float64).ravel())
+    cfg.data_median = t.data_median
+    cfg.n_contrast, cfg.n_phot = t.contrast.n, t.phot.n
+    if cfg.n_contrast > MS_MAX_CONTRAST or cfg.n_phot > MS_MAX_PHOT:
+        raise ValueError("too many filters for the compiled kernels")
+    cfg.c_tile_lo, cfg.c_tile_hi, cfg.c_offset = i32(t.contrast.tile_lo), i32(t.contrast.tile_hi), i64(t.contrast.offset)
+    cfg.c_weights, cfg.c_weights_len = dbl(t.contrast.weights), int(t.contrast.weights.size)
+    cfg.c_mag, cfg.c_err = dbl(t.c_mag), dbl(t.c_err)
+    cfg.p_tile_lo, cfg.p_tile_hi, cfg.p_offset = i32(t.phot.tile_lo), i32(t.phot.tile_hi), i64(t.phot.offset)
+    cfg.p_weights, cfg.p_weights_len = dbl(t.phot.weights), int(t.phot.weights.size)
+    cfg.p_norm, cfg.p_ext, cfg.p_mag, cfg.p_err = dbl(t.p_norm), dbl(t.p_ext), dbl(t.p_mag), dbl(t.p_err)
+    cfg.n_iso, cfg.n_dm, cfg.n_dust_samples, cfg.nspec = len(t.iso_teff), len(t.dust_dm_edges), t.dust_samples.shape[0], t.nspec
+    cfg.iso_teff, cfg.iso_logg, cfg.iso_lum = dbl(t.iso_teff), dbl(t.iso_logg), dbl(t.iso_lum)
+    cfg.dust_dm_edges, cfg.dust_samples = dbl(t.dust_dm_edges), dbl(t.dust_samples)
+    cfg.tmin, cfg.tmax = t.tmin, t.tmax
+    mu = np.zeros(MS_MAX_NDIM); sig = np.ones(MS_MAX_NDIM)
+    mu[:len(t.prior_mu)] = t.prior_mu; sig[:len(t.prior_sig)] = t.prior_sig
+    cfg.prior_mu = (C.c_double * MS_MAX_NDIM)(*mu)
+    cfg.prior_sig = (C.c_double * MS_MAX_NDIM)(*sig)
+    cfg.ext_flag, cfg.dist_fit, cfg.rad_prior = t.ext_flag, t.dist_fit, t.rad_prior
+    assert TILE == 1024
+    return cfg, keep
+
+
+class Engine:
+    """Owns one ``ms_handle`` (one GPU, one stream).  Thin, typed wrapper over the C ABI."""
+
+    def __init__(self, tables: DeviceTables, device=0, lib=None):
+        self.lib = lib or load_library()
+        self.tables = tables
+        self.ndim = 2 * tables.nspec + 2
+        self.n_data, self.n_contrast, self.n_phot, self.nspec = tables.n_data, tables.contrast.n, tables.phot.n, tables.nspec
+        cfg, keep = make_config(tables, device)
+        h = C.c_void_p()
+        rc = self.lib.ms_create(C.byref(cfg), C.byref(h))
+        del keep
+        if rc != 0:
+            raise NativeError(f"ms_create failed ({rc}): {self.lib.ms_last_error(None).decode()}")
+        self._h = h
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.ms_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise NativeError(f"{what} failed ({rc}): {self.lib.ms_last_error(self._h).decode()}")
+
+    @property
+    def stream(self):
+        return self.lib.ms_stream(self._h)
+
+    @property
+    def device(self):
+        return self.lib.ms_device(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.ms_launch_count(self._h))
+
+    # -- host-buffer calls (numpy in, numpy out)
+    def lnprob_host(self, theta):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if theta.ndim != 2 or theta.shape[1] != self.ndim:
+            raise ValueError(f"theta must be [nw, {self.ndim}]")
+        out = np.empty(theta.shape[0], dtype=np.float64)
+        self._check(self.lib.ms_lnprob(self._h, theta.ctypes.data, theta.shape[0], out.ctypes.data, MS_HOST), 'ms_lnprob')
+        return out
+
+    def lnprob_parts_host(self, theta):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        nw = theta.shape[0]
+        out = dict(lnprob=np.empty(nw), chi2_spec=np.empty(nw), contrast=np.empty((nw, self.n_contrast)),
+                   phot=np.empty((nw, self.n_phot)), lnprior=np.empty(nw), logg=np.empty((nw, self.nspec)),
+                   status=np.empty(nw, dtype=np.int32))
+        self._check(self.lib.ms_lnprob_parts(
+            self._h, theta.ctypes.data, nw, out['lnprob'].ctypes.data, out['chi2_spec'].ctypes.data,
+            out['contrast'].ctypes.data, out['phot'].ctypes.data, out['lnprior'].ctypes.data,
+            out['logg'].ctypes.data, out['status'].ctypes.data, MS_HOST), 'ms_lnprob_parts')
+        return out
+
+    def model_spectrum_host(self, theta):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        out = np.empty((theta.shape[0], self.n_data), dtype=np.float64)
+        self._check(self.lib.ms_model_spectrum(self._h, theta.ctypes.data, theta.shape[0], out.ctypes.data, MS_HOST),
+                    'ms_model_spectrum')
+        return out
+
+    # -- device-pointer calls (asynchronous on the handle's stream)
+    def lnprob_device(self, theta_ptr, nw, lnprob_ptr):
+        self._check(self.lib.ms_lnprob(self._h, theta_ptr, nw, lnprob_ptr, MS_DEVICE), 'ms_lnprob')
+
+    def stretch_propose(self, x_ptr, n_s, c_ptr, n_c, a, seed, iteration, split, gid0, q_ptr, logfac_ptr):
+        self._check(self.lib.ms_stretch_propose(self._h, x_ptr, n_s, c_ptr, n_c, self.ndim, a, seed, iteration,
+                                                split, gid0, q_ptr, logfac_ptr), 'ms_stretch_propose')
+
+    def stretch_accept(self, x_ptr, lnp_x_ptr, q_ptr, lnp_q_ptr, logfac_ptr, n_s, seed, iteration, split, gid0,
+                       accepted_ptr):
+        self._check(self.lib.ms_stretch_accept(self._h, x_ptr, lnp_x_ptr, q_ptr, lnp_q_ptr, logfac_ptr, n_s,
+                                               self.ndim, seed, iteration, split, gid0, accepted_ptr),
+                    'ms_stretch_accept')
+
+
+def broaden_rows(rows, win_lo, win_len, taps, device=0, lib=None):
+    """In-place window broadening of host rows [n_rows, row_len] on the GPU (ms_broaden_rows)."""
+    lib = lib or load_library()
+    if rows.dtype != np.float64 or not rows.flags.c_contiguous or rows.ndim != 2:
+        raise ValueError("rows must be a C-contiguous float64 [n_rows, row_len] array")
+    taps = np.ascontiguousarray(taps, dtype=np.float64)
+    rc = lib.ms_broaden_rows(int(device), rows.ctypes.data, rows.shape[0], rows.shape[1], int(win_lo),
+                             int(win_len), taps.ctypes.data, int(taps.size))
+    if rc != 0:
+        raise NativeError(f"ms_broaden_rows failed ({rc}): {lib.ms_last_error(None).decode()}")
+    return rows
