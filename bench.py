@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- walker log-likelihood evaluations/s on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # product arm (CUDA, C ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (oracle port, all host cores)
+
+Workload (config C4): a 65 536-walker ensemble on an 8192-pixel observed
+spectrum, 32 768-pixel model rows, 26 x 4 (Teff, log g) grid, 2 contrast + 6 photometric bands,
+synthetic tables (seed 2298).  One *step* is one ensemble iteration of the stretch move: two half
+steps, each proposing for half of the walkers, evaluating `logposterior` for the proposals
+(walker_prep_kernel + lnprob_stream_kernel), accepting, and all-gathering the updated half over
+NCCL when N > 1 -- i.e. 65 536 evaluations per step, sharded by walker across the N ranks (strong
+scaling: the ensemble size is fixed by the config).
+
+`value`   whole-job evaluations/s, ensemble resident in HBM, timed with CUDA events around each
+          step on the launching stream (L2 flushed between steps), max over ranks.
+`e2e`     the same count through the public host-buffer call (`LogPosterior(theta_host)` ->
+          ms_lnprob(MS_HOST)): host->device copy of the proposals and device->host copy of the
+          log-probabilities inside the timed region.
+`roofline` lnprob_stream_kernel: algorithmic bytes (n_star * 2^D * P_reg * 8 + 8*ndim + 8 per
+          evaluation) / event-timed kernel duration, against the measured HBM peak.
+`cpu_baseline` the numpy/scipy oracle (a port: the reference itself cannot be imported offline)
+          on the host cores, bounded sample, rank 0 at N = 1 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'tests')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "walker log-likelihood evals/sec"
+UNIT = "evals/s"
+NWALKERS = 65536
+SEED = 2298
+
+
+# ------------------------------------------------------------------------------------------ workload
+def make_workload():
+    from mcmc_spec_b200 import synthetic
+    return synthetic.make_problem_c4(seed=SEED)
+
+
+def initial_ensemble(prob, nw, seed=1):
+    """Walkers uniform in the central third of the prior box: every stretch proposal
+    (z <= 2) stays inside the box, so no evaluation is short-circuited by the prior bounds."""
+    rng = np.random.default_rng(seed)
+    lo = np.array([min(prob.temps), min(prob.temps), 0.0, 0.1, 0.1, 1 / 3000.0])
+    hi = np.array([max(prob.temps), max(prob.temps), 1.0, 1.2, 1.0, 1 / 100.0])
+    a, b = lo + (hi - lo) / 3.0, hi - (hi - lo) / 3.0
+    return a + (b - a) * rng.random((nw, 6))
+
+
+def workload_config(prob, tables, extra=None):
+    cfg = {"workload": "C4: 65536-walker ensemble, 8192-px observed spectrum, 32768-px model rows, 26x4 grid, "
+                       "2 contrast + 6 photometric bands (synthetic, seed 2298)",
+           "walkers": NWALKERS, "n_data": int(tables.n_data), "p_reg": int(tables.n_reg),
+           "grid_nodes": [len(prob.lgs), len(prob.temps)], "bytes_per_eval": int(tables.bytes_per_eval()),
+           "step": "one stretch-move iteration = 2 half steps = 65536 logposterior evaluations",
+           "walker_init": "uniform in the central third of the prior box (no prior-rejected proposals)",
+           "l2": "flushed between timed steps (256 MiB write); the 27 MB grid is re-read ~32768x within a step and is "
+                 "L2-resident by nature"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+_ORACLE = None
+
+
+def _oracle_init():
+    global _ORACLE
+    os.environ['OMP_NUM_THREADS'] = '1'
+    from oracle_adapter import to_oracle
+    _ORACLE = to_oracle(make_workload())
+
+
+def _oracle_eval(theta):
+    return float(_ORACLE.lnprob(theta))
+
+
+def cpu_pool(cores):
+    ctx = mp.get_context('spawn')           # no fork after CUDA / torch threads
+    return ctx.Pool(cores, initializer=_oracle_init)
+
+
+def time_cpu_sample(pool, theta):
+    t0 = time.perf_counter()
+    out = pool.map(_oracle_eval, list(theta), chunksize=max(1, len(theta) // (4 * pool._processes)))
+    return time.perf_counter() - t0, np.array(out)
+
+
+def cpu_baseline(prob, target_s=15.0):
+    """Oracle throughput on all host cores over a bounded sample of the C4 ensemble."""
+    cores = os.cpu_count() or 1
+    theta = initial_ensemble(prob, 65536, seed=2)
+    with cpu_pool(cores) as pool:
+        dt, _ = time_cpu_sample(pool, theta[:cores * 2])                  # warm-up + per-eval estimate
+        dt, _ = time_cpu_sample(pool, theta[:cores * 2])
+        per = dt / (cores * 2)
+        n = int(min(len(theta), max(cores * 4, target_s / max(per, 1e-6))))
+        dt, out = time_cpu_sample(pool, theta[:n])
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} evaluations of the C4 workload (walkers drawn like the GPU ensemble) through the numpy/scipy "
+                      f"oracle, multiprocessing.Pool({cores}), {dt:.1f} s; optimistic w.r.t. the reference (no glob / "
+                      f"pyphot / astropy / dustmaps overhead)"}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return 0
+    prob = make_workload()
+    from mcmc_spec_b200.tables import build_tables
+    tables = build_tables(prob)
+    cores = os.cpu_count() or 1
+    per_step = cores * 8
+    theta = initial_ensemble(prob, per_step * (args.steps + args.warmup), seed=3)
+    times = []
+    with cpu_pool(cores) as pool:
+        time_cpu_sample(pool, theta[:cores])                                  # workers up
+        for k in range(args.warmup + args.steps):
+            dt, _ = time_cpu_sample(pool, theta[k * per_step:(k + 1) * per_step])
+            if k >= args.warmup:
+                times.append(dt)
+    total = float(np.sum(times))
+    value = per_step * args.steps / total
+    sample = (f"each step = {per_step} logposterior evaluations of the C4 workload through the numpy/scipy oracle on "
+              f"multiprocessing.Pool({cores})")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(prob, tables, {"reference_note": "mft6.py cannot be imported offline (emcee, pyphot, "
+                                                     "extinction, dustmaps ... absent); this arm times the oracle port"}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), [s.strip() for s in line.split(',')]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.samples if t0 <= t <= t1 + 0.15 and len(r) >= 7]
+        if not rows:
+            rows = [r for _, r in self.samples if len(r) >= 7][-3:]
+        if not rows:
+            return None
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[2]) for r in rows)}
+
+
+# ------------------------------------------------------------------------------------------ product arm
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def recorded_traffic():
+    """DRAM bytes per launch of lnprob_stream_kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def run_product_arm(args, rank, local_rank, world):
+    cpu = None
+    prob = make_workload()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(prob, target_s=args.cpu_seconds)          # before CUDA is initialised
+
+    import torch
+    import torch.distributed as dist
+    from mcmc_spec_b200.ensemble import CudaBackend, EnsembleSampler
+    from mcmc_spec_b200.posterior import LogPosterior
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    lp = LogPosterior(prob, device=local_rank)
+    tables = lp.tables
+    nw = args.walkers
+    work_stream = torch.cuda.Stream(device=dev)                     # everything of the step runs on this stream
+    torch.cuda.set_stream(work_stream)
+    sampler = EnsembleSampler(nw, 6, CudaBackend(lp.engine), seed=SEED, rank=rank, world_size=world)
+    sampler.initialize(initial_ensemble(prob, nw))
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+
+    for _ in range(args.warmup):
+        sampler.step()
+    torch.cuda.synchronize(); barrier()
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    lp.engine.set_timing(True)
+    lp.engine.kernel_time()
+    launches0 = lp.engine.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.time()
+    for k in range(args.steps):
+        flush.zero_()                                               # evict L2 between timed steps
+        ev[k][0].record()
+        sampler.step()
+        ev[k][1].record()
+    torch.cuda.synchronize(); barrier()
+    t_wall1 = time.time()
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = torch.tensor([float(step_ms.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) / 1e3
+    k_ms, k_launches, k_walkers = lp.engine.kernel_time()
+    lp.engine.set_timing(False)
+    launches = lp.engine.launch_count - launches0
+    clock_summary = None
+    if clocks:
+        time.sleep(0.12)
+        clocks.stop()
+        clock_summary = clocks.summary(t_wall0, t_wall1)
+    acc_frac = float(sampler.acceptance_fraction.mean())
+    finite_frac = float(torch.isfinite(sampler.log_prob).double().mean().item())
+
+    # ---- end-to-end through the host-buffer API (pinned staging + H2D + kernels + D2H per call)
+    lp.engine.use_own_stream()
+    per_rank = nw // world
+    host_theta = initial_ensemble(prob, per_rank, seed=100 + rank)
+    halves = [np.ascontiguousarray(host_theta[:per_rank // 2]), np.ascontiguousarray(host_theta[per_rank // 2:])]
+    for _ in range(2):
+        for h in halves:
+            lp(h)
+    lp.engine.use_own_stream()
+    torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for _ in range(args.e2e_steps):
+        for h in halves:
+            checksum += float(lp(h)[0])
+    torch.cuda.synchronize(); barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = nw * args.e2e_steps / float(e2e_s.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bpe = tables.bytes_per_eval()
+        achieved = (k_walkers * bpe / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0
+        traffic = recorded_traffic()
+        roofline = {"bound": "hbm", "kernel": "lnprob_stream_kernel<4,2,6>", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "traffic": None if not traffic else traffic.get("dram_bytes_per_launch"),
+                    "avg_launch_ms": k_ms / max(k_launches, 1), "launches_timed": int(k_launches),
+                    "walkers_per_launch": k_walkers / max(k_launches, 1),
+                    "algorithmic_bytes_per_launch": bpe * k_walkers / max(k_launches, 1),
+                    "kernel_share_of_step": k_ms / float(step_ms.sum()),
+                    "note": "algorithmic bytes are grid-row bytes consumed; the 27 MB grid is L2-resident, so DRAM traffic "
+                            "is far below algorithmic bytes (see profiles/)"}
+        line = {"metric": METRIC, "value": nw * args.steps / total_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(prob, tables, {"parallelism": f"walker-sharded x{world}, 1 all-gather per half step",
+                                                         "acceptance_fraction": acc_frac, "finite_lnprob_frac": finite_frac}),
+                "roofline": roofline,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nw * 6 * 8),
+                        "d2h_bytes_per_step": int(nw * 8), "steps": args.e2e_steps,
+                        "api": "LogPosterior.__call__(theta_host[nw/2/N, 6]) -> ms_lnprob(MS_HOST), two calls per step per rank"},
+                "gpu_launches": int(launches), "clocks": clock_summary}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    lp.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=60)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--walkers', type=int, default=NWALKERS)
+    ap.add_argument('--e2e-steps', type=int, default=10)
+    ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        return run_reference_arm(args, rank)
+    if world != args.gpus:
+        if args.gpus > 1:
+            raise SystemExit(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    return run_product_arm(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

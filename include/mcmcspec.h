@@ -197,8 +197,25 @@ int ms_stretch_accept(ms_handle* h, double* x, double* lnp_x, const double* q, c
                       const double* logfac, int64_t n_s, int32_t ndim, uint64_t seed,
                       uint64_t iteration, int32_t split, int64_t gid0, int32_t* accepted);
 
+/*
+ * Enqueue on the caller's stream (a cudaStream_t, taken literally: 0 is the CUDA legacy default
+ * stream) instead of the handle's own, e.g. the stream a collective library runs on.  The caller
+ * keeps ownership.  ms_use_own_stream() goes back to the stream the handle created.
+ */
+int ms_set_stream(ms_handle* h, void* stream);
+int ms_use_own_stream(ms_handle* h);
+
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 int64_t ms_launch_count(const ms_handle* h);
+
+/*
+ * Device-side timing of the streaming kernel: after ms_set_timing(h, 1) every launch of
+ * lnprob_stream_kernel is bracketed by CUDA events on its stream.  ms_kernel_time() synchronises
+ * those events, returns their summed duration in milliseconds and the launch / walker counts they
+ * cover, and resets the accumulation.
+ */
+int ms_set_timing(ms_handle* h, int enabled);
+int ms_kernel_time(ms_handle* h, double* total_ms, int64_t* n_launches, int64_t* n_walkers);
 
 #ifdef __cplusplus
 }

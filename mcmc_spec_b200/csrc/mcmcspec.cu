@@ -739,6 +739,12 @@ struct ms_handle {
   double* d_theta = nullptr; double* d_lnp = nullptr; long long io_cap = 0;
   double* h_theta = nullptr; double* h_lnp = nullptr; long long pin_cap = 0;
   long long launches = 0;
+  cudaStream_t own_stream = nullptr;
+  // optional device-side timing of the streaming kernel
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;      // start/stop pairs, reused
+  size_t ev_used = 0;
+  long long timed_walkers = 0;
   std::string err;
 };
 
@@ -774,8 +780,18 @@ template <int NR, int NC, int NP>
 int launch_stream_variant(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts) {
   auto kern = lnprob_stream_kernel<NR, NC, NP>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing) {
+    if (h->ev_used + 2 > h->ev_pool.size()) {
+      for (int k = 0; k < 2; ++k) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
+    }
+    e0 = h->ev_pool[h->ev_used]; e1 = h->ev_pool[h->ev_used + 1];
+    h->ev_used += 2; h->timed_walkers += nw;
+    CK(cudaEventRecord(e0, h->stream));
+  }
   kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, d_lnp, parts);
   CK(cudaGetLastError());
+  if (h->timing) CK(cudaEventRecord(e1, h->stream));
   h->launches += 1;
   return MS_OK;
 }
@@ -855,14 +871,15 @@ int64_t ms_launch_count(const ms_handle* h) { return h ? h->launches : 0; }
 int ms_destroy(ms_handle* h) {
   if (!h) return MS_OK;
   cudaSetDevice(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->stream);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   if (h->plans) cudaFree(h->plans);
   if (h->d_theta) cudaFree(h->d_theta);
   if (h->d_lnp) cudaFree(h->d_lnp);
   if (h->h_theta) cudaFreeHost(h->h_theta);
   if (h->h_lnp) cudaFreeHost(h->h_lnp);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return MS_OK;
 }
@@ -891,7 +908,8 @@ int ms_create(const ms_config* cfg, ms_handle** out) {
 #define CKC(expr) do { int rc__ = (expr); if (rc__) return fail(rc__); } while (0)
 #define CKH(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e__); return fail(MS_ERR_CUDA); } } while (0)
   CKH(cudaSetDevice(h->device));
-  CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
 
   DevTables& T = h->T;
   T.n_teff = cfg->n_teff; T.n_logg = cfg->n_logg; T.n_feh = cfg->n_feh;
@@ -990,6 +1008,41 @@ int ms_create(const ms_config* cfg, ms_handle** out) {
 #undef CKC
 #undef CKH
   *out = h;
+  return MS_OK;
+}
+
+int ms_set_stream(ms_handle* h, void* stream) {
+  if (!h) return MS_ERR_INVALID;
+  h->stream = (cudaStream_t)stream;
+  return MS_OK;
+}
+
+int ms_use_own_stream(ms_handle* h) {
+  if (!h) return MS_ERR_INVALID;
+  h->stream = h->own_stream;
+  return MS_OK;
+}
+
+int ms_set_timing(ms_handle* h, int enabled) {
+  if (!h) return MS_ERR_INVALID;
+  h->timing = enabled != 0;
+  return MS_OK;
+}
+
+int ms_kernel_time(ms_handle* h, double* total_ms, int64_t* n_launches, int64_t* n_walkers) {
+  if (!h) return MS_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  double tot = 0.0;
+  for (size_t k = 0; k + 1 < h->ev_used; k += 2) {
+    CK(cudaEventSynchronize(h->ev_pool[k + 1]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev_pool[k], h->ev_pool[k + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (n_launches) *n_launches = (int64_t)(h->ev_used / 2);
+  if (n_walkers) *n_walkers = h->timed_walkers;
+  h->ev_used = 0; h->timed_walkers = 0;
   return MS_OK;
 }
 

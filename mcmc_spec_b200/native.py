@@ -22,7 +22,8 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmcmcspe
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_destroy', 'ms_last_error', 'ms_stream',
            'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_broaden_rows',
-           'ms_stretch_propose', 'ms_stretch_accept', 'ms_launch_count']
+           'ms_stretch_propose', 'ms_stretch_accept', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_timing',
+           'ms_kernel_time']
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -89,6 +90,10 @@ def load_library(path=None):
                                       C.c_int32, C.c_int64, vp]
     lib.ms_launch_count.argtypes = [vp]
     lib.ms_launch_count.restype = C.c_int64
+    lib.ms_set_stream.argtypes = [vp, vp]
+    lib.ms_use_own_stream.argtypes = [vp]
+    lib.ms_set_timing.argtypes = [vp, C.c_int]
+    lib.ms_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.ms_config_size() != C.sizeof(MsConfig):
@@ -201,6 +206,22 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.ms_launch_count(self._h))
+
+    def set_stream(self, stream_ptr):
+        """Enqueue on a caller-owned cudaStream_t (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        self._check(self.lib.ms_set_stream(self._h, stream_ptr), 'ms_set_stream')
+
+    def use_own_stream(self):
+        self._check(self.lib.ms_use_own_stream(self._h), 'ms_use_own_stream')
+
+    def set_timing(self, enabled):
+        self._check(self.lib.ms_set_timing(self._h, int(bool(enabled))), 'ms_set_timing')
+
+    def kernel_time(self):
+        """(total ms, launches, walkers) of the streaming kernel since the last call; resets."""
+        ms, nl, nw = C.c_double(), C.c_int64(), C.c_int64()
+        self._check(self.lib.ms_kernel_time(self._h, C.byref(ms), C.byref(nl), C.byref(nw)), 'ms_kernel_time')
+        return ms.value, nl.value, nw.value
 
     # -- host-buffer calls (numpy in, numpy out)
     def lnprob_host(self, theta):

@@ -225,13 +225,16 @@ def make_problem(*, temps=None, lgs=None, specmin=3000.0, specmax=30000.0, dlam=
                  contrast_curves=None, contrast_names=None, phot_bands=None, phot_curves=None,
                  phot_names=None, truth=None, plx=2.0732e-3, plx_err=0.0277e-3, snr=150.0,
                  seed=2298, fehs=None, feh=0.0, rad_prior=True, dist_fit=True,
-                 data_flux=None, data_err=None, cmag=None, cerr=None, pmag=None, perr=None):
+                 data_flux=None, data_err=None, cmag=None, cerr=None, pmag=None, perr=None,
+                 ctm=None, ptm=None, pfilt_names=None):
     """Assemble a synthetic ``Problem``.
 
     Defaults give the reference's koi2298 shapes (26 x 4 nodes, 135 000-pixel rows at 0.2 A,
     window 6450-8400 A at R = 1700) with synthetic passbands; pass ``contrast_curves`` /
     ``phot_bands`` read from ``bps/`` (see ``passbands``) for the real filter set, and
-    ``data_wl_um`` / ``data_flux`` / ``data_err`` for a real observed spectrum.
+    ``data_wl_um`` / ``data_flux`` / ``data_err`` for a real observed spectrum.  ``ctm`` / ``ptm``
+    given explicitly (as ``passbands.assemble_filter_tables`` returns them) override the tables
+    derived from the curves, so reference quirks such as float32 FITS columns survive.
     """
     rng = np.random.default_rng(seed + 7)
     temps = list(range(3000, 5501, 100)) if temps is None else [int(t) for t in temps]
@@ -273,10 +276,14 @@ def make_problem(*, temps=None, lgs=None, specmin=3000.0, specmax=30000.0, dlam=
             phot_bands.append(band)
     if contrast_names is None:
         contrast_names = [f'c{k}' for k in range(len(contrast_curves))]
-    ctm = _filter_table(contrast_curves, res)
+    if ctm is None:
+        ctm = _filter_table(contrast_curves, res)
+    else:
+        contrast_curves = list(zip(ctm[0], ctm[1]))
     # ptm: the reference carries the bps/ curves of the photometric filters only for the region
     # span and the central wavelengths (mft6.py:3588-3595); here they coincide with the library.
-    ptm = _filter_table([(b.wavelength, b.transmit) for b in phot_bands], res)
+    if ptm is None:
+        ptm = _filter_table([(b.wavelength, b.transmit) for b in phot_bands], res)
     tmi = min(min(min(w) for w in ctm[0]), min(min(w) for w in ptm[0]))
     tma = max(max(max(w) for w in ctm[0]), max(max(w) for w in ptm[0]))
 
@@ -324,7 +331,7 @@ def make_problem(*, temps=None, lgs=None, specmin=3000.0, specmax=30000.0, dlam=
             m = -2.5 * np.log10(band_flux(b, wl, comp) / b.zero_flux) + truth[2] * float(_ccm89_k(np.mean(b.wavelength)))
             perr.append(0.03)
             pmag.append(float(m + rng.normal(0, 0.02)))
-    phot_names_fr = [b.name for b in phot_bands]
+    phot_names_fr = list(pfilt_names) if pfilt_names is not None else [b.name for b in phot_bands]
     fr = [list(cmag), list(cerr), np.array(contrast_names), np.array(pmag, dtype=float), list(perr),
           np.array(phot_names_fr)]
     ndim = 6
@@ -352,8 +359,13 @@ def make_problem_c4(seed=2298, **kw):
     model range at 4x coarser sampling; broadened at R = 1700 over
     that window; 2 contrast + 6 photometric synthetic passbands inside the model range.
     """
-    args = dict(specmin=5300.0, dlam=0.57, n_pix=32768, window_um=(0.5310, 2.3960), n_data=8192,
-                res=1700, seed=seed)
+    rng = np.random.default_rng(seed + 11)
+    n_data = int(kw.pop('n_data', 8192))
+    step = (2.39765 - 0.53003) / (n_data - 1)
+    data_wl = 0.53003 + step * np.arange(n_data)
+    data_wl[1:-1] += rng.uniform(-0.2, 0.2, n_data - 2) * step          # slightly irregular sampling
+    args = dict(specmin=5300.0, dlam=0.57, n_pix=32768, window_um=(0.5300, 2.3978), n_data=n_data,
+                data_wl_um=data_wl, res=1700, seed=seed)
     args.update(kw)
     return make_problem(**args)
 

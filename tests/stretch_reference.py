@@ -1,0 +1,68 @@
+"""numpy mirror of the device stretch-move kernels and their counter-based generator (TEST code).
+
+Restates emcee's StretchMove arithmetic (emcee/moves/stretch.py, not vendored by the reference):
+zz = ((a - 1) * u + 1)**2 / a;  factors = (ndim - 1) * log(zz);  q = c[j] - (c[j] - s) * zz;
+accept where log(u') < factors + lnp(q) - lnp(s).
+"""
+import numpy as np
+import torch
+
+M = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def mix64(x):
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over='ignore'):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def counter_uniform(seed, iteration, split, purpose, gid):
+    k = mix64(np.uint64(seed))
+    k = mix64(k ^ np.uint64(iteration))
+    k = mix64(k ^ np.uint64(split * 4 + purpose))
+    r = mix64(k ^ mix64(np.asarray(gid, dtype=np.uint64)))
+    return ((r >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def propose(x, c, a, seed, iteration, split, gid0):
+    n_s, ndim = x.shape
+    gid = gid0 + np.arange(n_s)
+    u = counter_uniform(seed, iteration, split, 0, gid)
+    root = (a - 1.0) * u + 1.0
+    z = root * root / a
+    j = np.minimum((counter_uniform(seed, iteration, split, 1, gid) * c.shape[0]).astype(np.int64), c.shape[0] - 1)
+    cj = c[j]
+    q = cj - (cj - x) * z[:, None]
+    return q, (ndim - 1) * np.log(z)
+
+
+def accept_mask(lnp_x, lnp_q, logfac, seed, iteration, split, gid0):
+    gid = gid0 + np.arange(lnp_x.shape[0])
+    u = counter_uniform(seed, iteration, split, 2, gid)
+    with np.errstate(invalid='ignore'):
+        return np.log(u) < logfac + lnp_q - lnp_x
+
+
+class NumpyBackend:
+    """EnsembleSampler backend on CPU tensors with a user lnprob(theta[n, ndim]) -> [n] (numpy)."""
+
+    def __init__(self, lnprob_fn, ndim):
+        self.fn, self.ndim = lnprob_fn, ndim
+        self.device = torch.device('cpu')
+
+    def lnprob(self, theta):
+        return torch.from_numpy(np.asarray(self.fn(theta.numpy()), dtype=np.float64))
+
+    def propose(self, x, c, a, seed, iteration, split, gid0):
+        q, lf = propose(x.numpy(), c.numpy(), a, seed, iteration, split, gid0)
+        return torch.from_numpy(q), torch.from_numpy(lf)
+
+    def accept(self, x, lnp_x, q, lnp_q, logfac, seed, iteration, split, gid0, accepted):
+        m = accept_mask(lnp_x.numpy(), lnp_q.numpy(), logfac.numpy(), seed, iteration, split, gid0)
+        mt = torch.from_numpy(m)
+        x[mt] = q[mt]
+        lnp_x[mt] = lnp_q[mt]
+        accepted += mt.to(torch.int32)

@@ -1,0 +1,26 @@
+"""The oracle reproduces the committed golden vectors (CPU).  See tests/golden/make_fixtures.py."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_io
+from oracle_adapter import to_oracle
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+@pytest.mark.parametrize('name,n_data', [('c2_koi2298', 1945), ('c1_synth_3850_3425', 2183)])
+def test_oracle_matches_golden(name, n_data):
+    path = os.path.join(GOLD, name + '.npz')
+    fx = np.load(path)
+    prob = golden_io.problem_from_fixture(path)
+    assert prob.n_data == n_data                      # N after mask + cut
+    assert prob.grid.shape == (4, 26, 135000)
+    orc = to_oracle(prob)
+    idx = list(range(0, 64, 3))                       # a third of the vectors keeps the CPU suite short
+    got = orc.lnprob_batch(fx['theta'][idx])
+    want = fx['oracle_lnprob'][idx]
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    f = np.isfinite(want)
+    assert np.allclose(got[f], want[f], rtol=1e-12, atol=0)

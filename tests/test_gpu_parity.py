@@ -1,0 +1,190 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle and the golden vectors.
+
+Bar (BASELINE.json north_star): |lnp_gpu - lnp_oracle| <= 1e-9 * |lnp_oracle| per walker, identical
+-inf sets.  Nothing here reads /root/reference.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9          # the tolerance north_star states
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _compare(got, want, rtol=RTOL):
+    assert not np.any(np.isnan(got))                       # emcee raises on NaN log-prob
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    assert np.all(got[~np.isfinite(want)] == -np.inf)
+    f = np.isfinite(want)
+    rel = np.abs(got[f] - want[f]) / np.abs(want[f])
+    assert rel.max() <= rtol, f"max rel err {rel.max():.3e}"
+    return rel.max()
+
+
+@pytest.fixture(scope='module')
+def small_gpu(small_problem, native_lib):
+    from mcmc_spec_b200.posterior import LogPosterior
+    lp = LogPosterior(small_problem)
+    yield lp
+    lp.close()
+
+
+def test_small_problem_2048_walkers(small_problem, small_oracle, small_gpu):
+    from mcmc_spec_b200 import synthetic
+    theta = synthetic.sample_prior_box(small_problem, 2048, seed=101)
+    worst = _compare(small_gpu(theta), small_oracle.lnprob_batch(theta))
+    assert worst < 1e-12                                    # in practice rounding level
+
+
+def test_scalar_and_vector_forms_agree(small_problem, small_gpu):
+    from mcmc_spec_b200 import synthetic
+    theta = synthetic.sample_prior_box(small_problem, 32, seed=7)
+    vec = small_gpu(theta)
+    for k in (0, 5, 8, 20):
+        s = small_gpu(theta[k])
+        assert isinstance(s, float) and (s == vec[k] or (np.isinf(s) and np.isinf(vec[k])))
+    with pytest.raises(ValueError):
+        small_gpu(np.zeros(5))
+
+
+def test_parts_match_oracle(small_problem, small_oracle, small_gpu):
+    from mcmc_spec_b200 import synthetic
+    theta = synthetic.sample_prior_box(small_problem, 64, seed=9, edge_cases=False)
+    parts = small_gpu.parts(theta)
+    model = small_gpu.model_spectrum(theta[:8])
+    for k in range(64):
+        ref = {}
+        small_oracle.lnprob(theta[k], ref)
+        assert parts['lnprior'][k] == pytest.approx(ref['lp'], rel=1e-12)
+        assert parts['chi2_spec'][k] == pytest.approx(ref['chi2_spec'], rel=1e-11)
+        assert np.allclose(parts['contrast'][k], ref['contrast'], rtol=1e-12)
+        assert np.allclose(parts['phot'][k], ref['phot'], rtol=1e-13)
+        assert np.allclose(parts['logg'][k], ref['logg'], rtol=1e-14)
+        assert parts['status'][k] == 0
+        if k < 8:
+            assert np.allclose(model[k], ref['model'], rtol=1e-13)
+
+
+def test_status_bits_and_domain_failures(small_problem, small_gpu):
+    from mcmc_spec_b200 import native
+    t = small_problem.truth
+    bad = np.array([t, t, t, t, t])
+    bad[1, 2] = -0.1            # Av < 0
+    bad[2, 0] = 9000.0          # above tmax
+    bad[3, 3] = np.nan          # non-finite theta
+    bad[4, 5] = 0.3             # parallax > 1/4
+    p = small_gpu.parts(bad)
+    assert np.isfinite(p['lnprob'][0]) and np.all(p['lnprob'][1:] == -np.inf)
+    assert p['status'][1] == native.MS_W_PRIOR_BOUNDS and p['status'][2] == native.MS_W_PRIOR_BOUNDS
+    assert p['status'][3] == native.MS_W_NONFINITE and p['status'][4] == native.MS_W_PRIOR_BOUNDS
+
+
+def test_batch_split_and_permutation_are_bit_identical(small_problem, small_gpu):
+    from mcmc_spec_b200 import synthetic
+    theta = synthetic.sample_prior_box(small_problem, 600, seed=33)
+    full = small_gpu(theta)
+    parts = np.concatenate([small_gpu(theta[:77]), small_gpu(theta[77:301]), small_gpu(theta[301:])])
+    assert np.array_equal(full, parts)
+    perm = np.random.default_rng(0).permutation(600)
+    assert np.array_equal(small_gpu(theta[perm]), full[perm])
+    assert small_gpu(theta[:0]).shape == (0,)               # empty batch
+
+
+@pytest.mark.parametrize('n_data', [7, 255, 256, 300, 301, 1025])
+def test_ragged_and_odd_even_sizes(n_data):
+    """median over odd/even N, N not a multiple of the CTA width, N < one warp."""
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    p = synthetic.make_problem_small(n_data=n_data, seed=40 + n_data)
+    lp = LogPosterior(p)
+    theta = synthetic.sample_prior_box(p, 48, seed=n_data)
+    _compare(lp(theta), to_oracle(p).lnprob_batch(theta))
+    lp.close()
+
+
+def test_duplicate_model_values_in_median():
+    """Flat model spectrum -> many equal keys in the radix select."""
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    p = synthetic.make_problem_small(n_data=200, seed=77)
+    p.grid[...] = 1.0e6                                     # every row flat: model on data pixels is constant x extinction
+    lp = LogPosterior(p)
+    theta = synthetic.sample_prior_box(p, 32, seed=5)
+    theta[:8, 2] = 0.0                                      # Av = 0: exactly constant model
+    _compare(lp(theta), to_oracle(p).lnprob_batch(theta))
+    lp.close()
+
+
+@pytest.mark.parametrize('name', ['c2_koi2298', 'c1_synth_3850_3425'])
+def test_golden_fixtures_full_size(name, native_lib):
+    """BASELINE configs C1/C2: committed observed data + passbands, 135 000-pixel rows, 64 fixed theta."""
+    import golden_io
+    from mcmc_spec_b200.posterior import LogPosterior
+    path = os.path.join(GOLD, name + '.npz')
+    fx = np.load(path)
+    lp = LogPosterior(golden_io.problem_from_fixture(path))
+    _compare(lp(fx['theta']), fx['oracle_lnprob'])
+    parts = lp.parts(fx['theta'])
+    f = np.isfinite(fx['oracle_lnprob'])
+    assert np.allclose(parts['chi2_spec'][f], fx['oracle_chi2_spec'][f], rtol=1e-10)
+    assert np.allclose(parts['contrast'][f], fx['oracle_contrast'][f], rtol=1e-11)
+    assert np.allclose(parts['phot'][f], fx['oracle_phot'][f], rtol=1e-12)
+    lp.close()
+
+
+def test_c4_shape_against_oracle_and_properties(native_lib):
+    """BASELINE config C4 (8192 observed pixels, 32 768-pixel rows): oracle on a sample + size-independent
+    properties on the full batch."""
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    p = synthetic.make_problem_c4()
+    lp = LogPosterior(p)
+    theta = synthetic.sample_prior_box(p, 8192, seed=55)
+    got = lp(theta)
+    _compare(got[:96], to_oracle(p).lnprob_batch(theta[:96]))
+    # (i) the median-scaled model has the data's median (mft6.py:1173)
+    model = lp.model_spectrum(theta[100:132])
+    assert np.allclose(np.median(model, axis=1), np.median(p.data[1]), rtol=1e-14)
+    # (ii) spectral chi-square and contrasts do not depend on the overall flux scale: R1 -> 1.3 R1
+    a = lp.parts(theta[200:264]); th2 = theta[200:264].copy(); th2[:, 3] *= 1.3
+    b = lp.parts(th2)
+    ok = (a['status'] == 0) & (b['status'] == 0)
+    assert ok.sum() > 20
+    assert np.allclose(a['chi2_spec'][ok], b['chi2_spec'][ok], rtol=1e-10)
+    assert np.allclose(a['contrast'][ok], b['contrast'][ok], rtol=1e-12, atol=1e-12)
+    assert np.allclose(b['phot'][ok] - a['phot'][ok], -5 * np.log10(1.3), rtol=1e-10)
+    # (iii) determinism
+    assert np.array_equal(lp(theta), got)
+    lp.close()
+
+
+def test_broaden_rows_matches_oracle_splice(native_lib):
+    from mcmc_spec_b200 import native, synthetic
+    from oracle import mft6_oracle as mo
+    wl = np.arange(5000.0, 9000.0, 0.2)
+    rows = synthetic.make_native_grid([3000, 3100, 3200], [4.5, 5.0], wl, seed=3).reshape(6, -1).copy()
+    window = [6450.0, 8400.0]
+    natives = {'{}, {}'.format(k, 0.0): rows[k].copy() for k in range(6)}
+    want = mo.splice_broadened_grid(natives, wl, window, 1700)
+    inw = np.where((wl >= window[0]) & (wl <= window[1]))[0]
+    _, taps = synthetic.gauss_taps(wl[inw][1] - wl[inw][0], np.mean(wl[inw]), 1700)
+    native.broaden_rows(rows, inw[0], inw.size, taps)
+    for k in range(6):
+        ref = want['{}, {}'.format(k, 0.0)]
+        assert np.allclose(rows[k], ref, rtol=1e-13, atol=0)
+        assert np.array_equal(rows[k][:inw[0]], ref[:inw[0]])       # outside the window untouched
+
+
+def test_config_errors_surface_as_exceptions(small_problem, native_lib):
+    from mcmc_spec_b200 import native
+    from mcmc_spec_b200.tables import build_tables
+    t = build_tables(small_problem)
+    t.rebin_hi = t.rebin_hi[::-1].copy()                    # not ascending
+    with pytest.raises(native.NativeError):
+        native.Engine(t)
