@@ -60,7 +60,7 @@ struct DevTables {
   // observed spectrum
   int n_data;
   const int* rebin_hi; const double* rebin_t; const double* ext_lo; const double* ext_hi;
-  const double* data_flux; const double* data_err; const double* data_x;
+  const double* data_flux; const double* data_inv_e2; const double* data_x;
   const int* tile_data_start;
   const unsigned* tile_cmask; const unsigned* tile_pmask;
   double basis[9];
@@ -306,7 +306,13 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// Exact order statistics of sM[0..n) (positive or negative doubles, no NaN) by MSD radix select.
+// Exact median of sM[0..n) (np.median: mean of the two middle order statistics for even n) by an
+// MSD radix select, fused with the chi-square pass.
+//
+// Because norm_spec's fit is linear in data/model and the median scaling is a common factor
+// (mft6.py:1173-1179),  chi2 = s^2 * sum_i ((m_i - d_i / p0(x_i))^2 / e_i^2)  with m the
+// *unscaled* model, p0 the quadratic fitted to d/m and s = median(d)/median(m): the chi-square
+// sum does not need the median and shares the first histogram pass over sM.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ordered_key(double v) {
   const long long b = __double_as_longlong(v);
@@ -317,114 +323,175 @@ __device__ __forceinline__ double key_value(unsigned long long k) {
   return __longlong_as_double((long long)b);
 }
 
+constexpr int LIST_CAP = 256;            // finish by counting once the bin holds at most this many keys
+static_assert(LIST_CAP <= TILE, "the candidate list lives in the (idle) composite tile buffer");
+
 struct SelectScratch {
   unsigned hist[256];
   unsigned long long kmin[NWARP], kmax[NWARP];
-  unsigned long long bcast[2];
+  unsigned long long bcast[4];
+  unsigned count;
   int nanflag;
 };
 
-// Returns the median of sM[0..n) as numpy defines it (mean of the two middle order statistics
-// for even n); NaN if any element is NaN.
-__device__ double block_median(const double* sM, int n, SelectScratch* S) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // ---- key range and NaN scan
-  unsigned long long kmin = ~0ull, kmax = 0ull;
-  int has_nan = 0;
-  for (int i = tid; i < n; i += NT) {
-    const double v = sM[i];
-    has_nan |= (v != v);
-    const unsigned long long k = ordered_key(v);
-    kmin = min(kmin, k); kmax = max(kmax, k);
-  }
+// Locate the bin holding `rank` in S->hist (256 bins).  Warp 0 only; writes
+// bcast[0] = bin, bcast[1] = elements below the bin, bcast[2] = elements in the bin.
+__device__ __forceinline__ void locate_rank_bin(SelectScratch* S, unsigned rank, int lane) {
+  unsigned c[8]; unsigned tot = 0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-  }
-  if (tid == 0) S->nanflag = 0;
-  __syncthreads();
-  if (has_nan) S->nanflag = 1;
-  if (lane == 0) { S->kmin[warp] = kmin; S->kmax[warp] = kmax; }
-  __syncthreads();
-  kmin = S->kmin[0]; kmax = S->kmax[0];
+  for (int j = 0; j < 8; ++j) { c[j] = S->hist[lane * 8 + j]; tot += c[j]; }
+  unsigned incl = tot;
 #pragma unroll
-  for (int w = 1; w < NWARP; ++w) { kmin = min(kmin, S->kmin[w]); kmax = max(kmax, S->kmax[w]); }
-  const int nanflag = S->nanflag;
-  __syncthreads();
-  if (nanflag) return CUDART_NAN;
-  if (kmin == kmax) return key_value(kmin);
-
-  // ---- radix select of rank k1 = (n-1)/2, starting at the first bit where keys differ
-  int bits_done = __clzll((long long)(kmin ^ kmax));
-  unsigned long long prefix = (bits_done == 0) ? 0ull : (kmin & (~0ull << (64 - bits_done)));
-  unsigned rank = (unsigned)((n - 1) >> 1);
-  const int rounds = (n + NT - 1) / NT;
-  while (bits_done < 64) {
-    const int width = min(8, 64 - bits_done);
-    const int shift = 64 - bits_done - width;
-    const unsigned long long himask = (bits_done == 0) ? 0ull : (~0ull << (64 - bits_done));
-    S->hist[tid] = 0;                                    // NT == 256 bins
-    __syncthreads();
-    for (int r = 0; r < rounds; ++r) {
-      const int i = r * NT + tid;
-      unsigned d = 0xffffffffu;
-      if (i < n) {
-        const unsigned long long k = ordered_key(sM[i]);
-        if ((k & himask) == prefix) d = (unsigned)((k >> shift) & ((1u << width) - 1u));
+  for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  const unsigned excl = incl - tot;
+  if (rank >= excl && rank < incl) {                   // exactly one lane
+    unsigned run = excl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (rank >= run && rank < run + c[j]) {
+        S->bcast[0] = (unsigned long long)(lane * 8 + j); S->bcast[1] = run; S->bcast[2] = c[j];
       }
+      run += c[j];
+    }
+  }
+}
+
+// One histogram pass over the elements whose key matches `prefix` on its top `bits_done` bits.
+// Warp-aggregated shared-memory atomics (neighbouring pixels of a smooth spectrum share a bin).
+__device__ __forceinline__ void histogram_pass(const double* sM, int n, SelectScratch* S, unsigned long long prefix,
+                                               int bits_done, int shift, int width) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned long long himask = (bits_done == 0) ? 0ull : (~0ull << (64 - bits_done));
+  const int rounds = (n + NT - 1) / NT;
+  for (int r = 0; r < rounds; ++r) {
+    const int i = r * NT + tid;
+    unsigned d = 0xffffffffu;
+    if (i < n) {
+      const unsigned long long k = ordered_key(sM[i]);
+      if ((k & himask) == prefix) d = (unsigned)((k >> shift) & ((1u << width) - 1u));
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (d != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&S->hist[d], (unsigned)__popc(peers));
+  }
+}
+
+// Median of sM[0..n) given the block-wide key range [kmin, kmax]; also returns, through *chi_out,
+// sum_i (m_i - d_i/p0(x_i))^2 * inv_e2_i with p0 = a[0] q0 + a[1] q1 + a[2] q2.
+// `list` is scratch for LIST_CAP keys.
+__device__ double block_median_chi(const double* sM, int n, SelectScratch* S, unsigned long long* list,
+                                   unsigned long long kmin, unsigned long long kmax, const DevTables& T,
+                                   const double (&a)[3], double* chi_out, double* red_scratch) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rounds = (n + NT - 1) / NT;
+  unsigned rank = (unsigned)((n - 1) >> 1);
+  const bool flat = (kmin == kmax);
+  int bits_done = flat ? 64 : __clzll((long long)(kmin ^ kmax));
+  unsigned long long prefix = (bits_done == 0) ? 0ull : (bits_done == 64 ? kmin : (kmin & (~0ull << (64 - bits_done))));
+  const int width0 = flat ? 0 : min(8, 64 - bits_done);
+  const int shift0 = 64 - bits_done - width0;
+
+  // ---- pass 1: chi-square terms + histogram of the first 8 differing key bits
+  S->hist[tid] = 0;                                      // NT == 256 bins
+  if (tid == 0) S->count = 0;
+  __syncthreads();
+  double chi = 0.0;
+  for (int r = 0; r < rounds; ++r) {
+    const int i = r * NT + tid;
+    unsigned d = 0xffffffffu;
+    if (i < n) {
+      const double m = sM[i];
+      const double x = T.data_x[i];
+      const double q1 = fma(T.basis[4], x, T.basis[3]);
+      const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
+      const double pfit = a[0] * T.basis[0] + a[1] * q1 + a[2] * q2;
+      const double res = m - T.data_flux[i] / pfit;                     // mft6.py:196, :120 (unscaled)
+      chi = fma(res * res, T.data_inv_e2[i], chi);
+      if (!flat) d = (unsigned)((ordered_key(m) >> shift0) & ((1u << width0) - 1u));
+    }
+    if (!flat) {
       const unsigned peers = __match_any_sync(0xffffffffu, d);
       if (d != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&S->hist[d], (unsigned)__popc(peers));
     }
-    __syncthreads();
-    if (warp == 0) {
-      // each lane owns 8 consecutive bins; inclusive scan of lane totals across the warp
-      unsigned c[8]; unsigned tot = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { c[j] = S->hist[lane * 8 + j]; tot += c[j]; }
-      unsigned incl = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      const unsigned excl = incl - tot;
-      if (rank >= excl && rank < incl) {                 // exactly one lane
-        unsigned run = excl;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (rank >= run && rank < run + c[j]) { S->bcast[0] = (unsigned long long)(lane * 8 + j); S->bcast[1] = run; }
-          run += c[j];
-        }
-      }
-    }
+  }
+  {
+    double c1[1] = {chi};
+    block_sum<1>(c1, red_scratch);                        // includes the barriers that publish hist
+    *chi_out = c1[0];
+  }
+  if (flat) return key_value(kmin);
+
+  // ---- narrow down to a bin small enough to finish by counting
+  int width = width0, shift = shift0;
+  unsigned in_bin = 0;
+  while (true) {
+    if (warp == 0) locate_rank_bin(S, rank, lane);
     __syncthreads();
     const unsigned digit = (unsigned)S->bcast[0];
     rank -= (unsigned)S->bcast[1];
+    in_bin = (unsigned)S->bcast[2];
     prefix |= ((unsigned long long)digit) << shift;
     bits_done += width;
     __syncthreads();
+    if (in_bin <= (unsigned)LIST_CAP || bits_done >= 64) break;
+    width = min(8, 64 - bits_done);
+    shift = 64 - bits_done - width;
+    S->hist[tid] = 0;
+    __syncthreads();
+    histogram_pass(sM, n, S, prefix, bits_done, shift, width);
+    __syncthreads();
   }
-  const double v1 = key_value(prefix);
-  if (n & 1) return v1;
 
-  // ---- even n: the next order statistic is v1 again if enough elements are <= v1, else min{v > v1}
-  unsigned cnt_le = 0;
-  unsigned long long kgt = ~0ull;
-  for (int i = tid; i < n; i += NT) {
-    const unsigned long long k = ordered_key(sM[i]);
-    if (k <= prefix) ++cnt_le; else kgt = min(kgt, k);
+  double v1, v2;
+  bool need_next = false;                                 // upper middle element lies beyond this bin
+  if (bits_done >= 64) {
+    // all 64 bits fixed: `in_bin` copies of one value
+    v1 = key_value(prefix);
+    v2 = v1;
+    need_next = (rank + 1 >= in_bin);
+  } else {
+    // ---- compact the bin's keys, then rank them by counting
+    const unsigned long long himask = ~0ull << (64 - bits_done);
+    for (int i = tid; i < n; i += NT) {
+      const unsigned long long k = ordered_key(sM[i]);
+      if ((k & himask) == prefix) list[atomicAdd(&S->count, 1u)] = k;
+    }
+    __syncthreads();
+    const unsigned cnt = S->count;                         // == in_bin
+    for (unsigned t = tid; t < cnt; t += NT) {
+      const unsigned long long mine = list[t];
+      unsigned below = 0;
+      for (unsigned j = 0; j < cnt; ++j) {
+        const unsigned long long o = list[j];
+        below += (o < mine) || (o == mine && j < t);
+      }
+      if (below == rank) S->bcast[0] = mine;
+      if (below == rank + 1) S->bcast[1] = mine;
+    }
+    __syncthreads();
+    v1 = key_value(S->bcast[0]);
+    v2 = key_value(S->bcast[1]);
+    need_next = (rank + 1 >= cnt);
+    __syncthreads();
   }
+  if (n & 1) return v1;
+  if (need_next) {
+    // rare: the lower median is the largest element of its bin -> upper median = min{key > v1}
+    const unsigned long long k1 = ordered_key(v1);
+    unsigned long long kgt = ~0ull;
+    for (int i = tid; i < n; i += NT) {
+      const unsigned long long k = ordered_key(sM[i]);
+      if (k > k1) kgt = min(kgt, k);
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    cnt_le += __shfl_xor_sync(0xffffffffu, cnt_le, o);
-    kgt = min(kgt, __shfl_xor_sync(0xffffffffu, kgt, o));
+    for (int o = 16; o > 0; o >>= 1) kgt = min(kgt, __shfl_xor_sync(0xffffffffu, kgt, o));
+    if (lane == 0) S->kmin[warp] = kgt;
+    __syncthreads();
+    kgt = S->kmin[0];
+#pragma unroll
+    for (int w = 1; w < NWARP; ++w) kgt = min(kgt, S->kmin[w]);
+    __syncthreads();
+    v2 = key_value(kgt);
   }
-  if (lane == 0) { S->kmin[warp] = kgt; S->kmax[warp] = cnt_le; }
-  __syncthreads();
-  kgt = S->kmin[0]; unsigned long long tot_le = S->kmax[0];
-#pragma unroll
-  for (int w = 1; w < NWARP; ++w) { kgt = min(kgt, S->kmin[w]); tot_le += S->kmax[w]; }
-  __syncthreads();
-  const unsigned k2 = (unsigned)(n >> 1);                // 0-based rank of the upper middle element
-  const double v2 = (tot_le > k2) ? v1 : key_value(kgt);
   return (v1 + v2) / 2.0;
 }
 
@@ -487,6 +554,10 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
 #pragma unroll
   for (int f = 0; f < NP; ++f) accP[f] = 0.0;
 
+  double mom[3] = {0.0, 0.0, 0.0};                                   // sum_i q_k(x_i) d_i / m_i
+  unsigned long long kmin = ~0ull, kmax = 0ull;                      // key range of the model, for the median
+  int has_nan = 0;
+
   // ------------------------------------------------------------------ phase A: stream the rows
   const int n_tiles = T.n_tiles;
   for (int tile = 0; tile < n_tiles; ++tile) {
@@ -538,7 +609,17 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         const double fhi = sF[h];
         const double ylo = flo * exp2(av * T.ext_lo[i]);             // extinct() then interp1d: mft6.py:1162, :1169
         const double yhi = fhi * exp2(av * T.ext_hi[i]);
-        sM[i] = ylo + (yhi - ylo) * T.rebin_t[i];
+        const double m = ylo + (yhi - ylo) * T.rebin_t[i];
+        sM[i] = m;
+        // norm_spec's normal equations in the orthonormal basis, on the unscaled model (mft6.py:194-195)
+        const double frac = T.data_flux[i] / m;
+        const double x = T.data_x[i];
+        const double q1 = fma(T.basis[4], x, T.basis[3]);
+        const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
+        mom[0] = fma(T.basis[0], frac, mom[0]); mom[1] = fma(q1, frac, mom[1]); mom[2] = fma(q2, frac, mom[2]);
+        has_nan |= (m != m);
+        const unsigned long long k = ordered_key(m);
+        kmin = min(kmin, k); kmax = max(kmax, k);
       }
       __syncthreads();
     }
@@ -555,39 +636,33 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
 
   // ------------------------------------------------------------------ phase B: spectral chi-square
   const int n = T.n_data;
-  const double med = block_median(sM, n, sSel);                      // mft6.py:1173
-  const double scale = T.data_median / med;
-  double mom[3] = {0.0, 0.0, 0.0};
-  for (int i = tid; i < n; i += NT) {
-    const double m = sM[i] * scale;
-    sM[i] = m;
-    const double frac = T.data_flux[i] / m;                           // norm_spec: mft6.py:194
-    const double x = T.data_x[i];
-    const double q0 = T.basis[0];
-    const double q1 = fma(T.basis[4], x, T.basis[3]);
-    const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
-    mom[0] = fma(q0, frac, mom[0]); mom[1] = fma(q1, frac, mom[1]); mom[2] = fma(q2, frac, mom[2]);
-  }
   block_sum<3>(mom, sRed);
-  double chi[1] = {0.0};
-  for (int i = tid; i < n; i += NT) {
-    const double m = sM[i];
-    const double x = T.data_x[i];
-    const double q0 = T.basis[0];
-    const double q1 = fma(T.basis[4], x, T.basis[3]);
-    const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
-    const double pfit = mom[0] * q0 + mom[1] * q1 + mom[2] * q2;
-    const double dn = T.data_flux[i] / pfit;                          // mft6.py:196
-    const double e = T.data_err[i];
-    const double r = m - dn;
-    chi[0] += (r * r) / (e * e);                                      // mft6.py:120
-    if (parts.model) parts.model[w * n + i] = m;
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+      kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+      has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, o);
+    }
+    if (tid == 0) sSel->nanflag = 0;
+    __syncthreads();
+    if (lane == 0) { sSel->kmin[warp] = kmin; sSel->kmax[warp] = kmax; if (has_nan) sSel->nanflag = 1; }
+    __syncthreads();
+    kmin = sSel->kmin[0]; kmax = sSel->kmax[0];
+#pragma unroll
+    for (int w = 1; w < NWARP; ++w) { kmin = min(kmin, sSel->kmin[w]); kmax = max(kmax, sSel->kmax[w]); }
+    has_nan = sSel->nanflag;
+    __syncthreads();
   }
-  block_sum<1>(chi, sRed);
+  double chi_un = CUDART_NAN, med = CUDART_NAN;
+  if (!has_nan) med = block_median_chi(sM, n, sSel, reinterpret_cast<unsigned long long*>(sF), kmin, kmax, T, mom, &chi_un, sRed);  // mft6.py:1173
+  const double scale = T.data_median / med;
+  if (parts.model) for (int i = tid; i < n; i += NT) parts.model[w * n + i] = sM[i] * scale;
 
   // ------------------------------------------------------------------ final sum (mft6.py:1178-1205)
   if (tid == 0) {
-    const double iic = chi[0] / (double)n;
+    const double iic = (scale * scale) * chi_un / (double)n;             // mft6.py:1173-1179
     double icontrast = 0.0, iphot = 0.0;
     for (int f = 0; f < NC; ++f) {
       if (f < T.n_contrast) {
@@ -956,7 +1031,11 @@ int ms_create(const ms_config* cfg, ms_handle** out) {
   CKC(upload(h, cfg->ext_lo, cfg->n_data, &T.ext_lo));
   CKC(upload(h, cfg->ext_hi, cfg->n_data, &T.ext_hi));
   CKC(upload(h, cfg->data_flux, cfg->n_data, &T.data_flux));
-  CKC(upload(h, cfg->data_err, cfg->n_data, &T.data_err));
+  {
+    std::vector<double> inv_e2(cfg->n_data);
+    for (int i = 0; i < cfg->n_data; ++i) inv_e2[i] = 1.0 / (cfg->data_err[i] * cfg->data_err[i]);   // mft6.py:120
+    CKC(upload(h, inv_e2.data(), inv_e2.size(), &T.data_inv_e2));
+  }
   CKC(upload(h, cfg->data_x, cfg->n_data, &T.data_x));
   CKC(upload(h, cfg->tile_data_start, (size_t)cfg->n_tiles + 1, &T.tile_data_start));
 

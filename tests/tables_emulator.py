@@ -99,14 +99,14 @@ def lnprob(t, theta, tile=1024):
     cw = _dense(t.contrast, t.n_reg, tile); pw = _dense(t.phot, t.n_reg, tile)
     hi = t.rebin_hi; lo = hi - 1
     ylo = comp[lo] * np.exp2(av_eff * t.ext_lo); yhi = comp[hi] * np.exp2(av_eff * t.ext_hi)
-    m = ylo + (yhi - ylo) * t.rebin_t
-    m = m * (t.data_median / np.median(m))
+    m = ylo + (yhi - ylo) * t.rebin_t                      # unscaled model on the observed pixels
     B = t.poly_basis
     x = t.data_x
     q = np.stack([np.full_like(x, B[0, 0]), B[1, 0] + B[1, 1] * x, B[2, 0] + x * (B[2, 1] + B[2, 2] * x)])
-    a = q @ (t.data_flux / m)
-    dn = t.data_flux / (a @ q)
-    iic = np.sum((m - dn) ** 2 / t.data_err ** 2) / len(m)
+    a = q @ (t.data_flux / m)                               # fit to data/model, unscaled
+    chi_un = np.sum((m - t.data_flux / (a @ q)) ** 2 * (1.0 / (t.data_err * t.data_err)))
+    s = t.data_median / np.median(m)                        # the median scaling factors out: chi2 = s^2 * chi_un
+    iic = s * s * chi_un / len(m)
     icon = 0.0
     for f in range(t.contrast.n):
         con = -2.5 * np.log10(cw[f] @ comps[1]) - (-2.5 * np.log10(cw[f] @ comps[0]))
