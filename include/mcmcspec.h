@@ -93,7 +93,6 @@ typedef struct ms_config {
   const double* data_flux;      /* [n_data] */
   const double* data_err;       /* [n_data] */
   const double* data_x;         /* [n_data] wavelengths mapped onto [-1, 1] */
-  const int32_t* tile_data_start; /* [n_tiles+1] observed pixels whose rebin_hi lies in each tile */
   double poly_basis[9];         /* orthonormal quadratic basis, q_k(x) = sum_j B[3k+j] x^j */
   double data_median;           /* np.median(data_flux) */
 

@@ -44,7 +44,11 @@ constexpr double PC_CM = 3.086e18;      // mft6.py:691
 constexpr double SIGMA_SB = 5.670374e-5;  // mft6.py:79
 constexpr double LSUN = 3.839e33;       // mft6.py:80
 
+constexpr int CHUNK = TILE / NWARP;      // model pixels one warp owns per tile (128)
+constexpr int SEG = CHUNK + 4;           // shared-memory doubles per warp: [pad, prev pixel, CHUNK composites, pad]
+
 static_assert(TILE == 4 * NT, "each thread owns two pixel pairs per tile");
+static_assert(CHUNK == 128, "a warp covers its chunk with two 64-pixel (32 x double2) sub-chunks");
 
 // ------------------------------------------------------------------------------------------
 // Device-side view of the tables (passed by value as a kernel parameter).
@@ -59,9 +63,13 @@ struct DevTables {
   double feh;
   // observed spectrum
   int n_data;
-  const int* rebin_hi; const double* rebin_t; const double* ext_lo; const double* ext_hi;
+  const int* rebin_hi;          // [N] upper bracketing model pixel
+  const double2* rebin_tab;     // [2N] {t, ext_lo}, {(ext_hi - ext_lo) ln 2, ext_hi} per observed pixel
+  const double2* data_fx;       // [N] {flux, x}
   const double* data_flux; const double* data_inv_e2; const double* data_x;
-  const int* tile_data_start;
+  const int* chunk_data_start;  // [n_tiles*NWARP + 1] first observed pixel owned by each 128-pixel chunk;
+                                // bit 31 set when that pixel's lower bracket is the last pixel of the previous chunk
+  double dext_max;              // max |(ext_hi - ext_lo) ln 2|
   const unsigned* tile_cmask; const unsigned* tile_pmask;
   double basis[9];
   double data_median;
@@ -103,6 +111,17 @@ __device__ __forceinline__ double2 ldg_stream(const double* p) {
   double2 v;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
+}
+
+// 1/x to ~1 ulp for finite non-zero x (two Newton steps on the hardware seed); 0 -> inf, NaN -> NaN.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -324,7 +343,7 @@ __device__ __forceinline__ double key_value(unsigned long long k) {
 }
 
 constexpr int LIST_CAP = 256;            // finish by counting once the bin holds at most this many keys
-static_assert(LIST_CAP <= TILE, "the candidate list lives in the (idle) composite tile buffer");
+static_assert(LIST_CAP <= NWARP * SEG, "the candidate list lives in the (idle) composite tile buffer");
 
 struct SelectScratch {
   unsigned hist[256];
@@ -404,7 +423,7 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
       const double q1 = fma(T.basis[4], x, T.basis[3]);
       const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
       const double pfit = a[0] * T.basis[0] + a[1] * q1 + a[2] * q2;
-      const double res = m - T.data_flux[i] / pfit;                     // mft6.py:196, :120 (unscaled)
+      const double res = m - T.data_flux[i] * fast_rcp(pfit);           // mft6.py:196, :120 (unscaled)
       chi = fma(res * res, T.data_inv_e2[i], chi);
       if (!flat) d = (unsigned)((ordered_key(m) >> shift0) & ((1u << width0) - 1u));
     }
@@ -505,11 +524,10 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
                      double* __restrict__ lnprob, const PartsOut parts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int KRED = 2 * NC + NP;
-  double* sF = reinterpret_cast<double*>(smem_raw);                  // [TILE] composite of the current tile
-  double* sRed = sF + TILE;                                          // [NWARP*KRED]
+  double* sF = reinterpret_cast<double*>(smem_raw);                  // [NWARP*SEG] per-warp composite chunks
+  double* sRed = sF + NWARP * SEG;                                          // [NWARP*KRED]
   SelectScratch* sSel = reinterpret_cast<SelectScratch*>(sRed + NWARP * (KRED > 4 ? KRED : 4));
   double* sM = reinterpret_cast<double*>(sSel + 1);                  // [n_data] model on observed pixels
-  __shared__ double sCarry;                                          // composite of the last pixel of the previous tile
   __shared__ WalkerPlan sPlan;
 
   const int tid = threadIdx.x;
@@ -536,16 +554,19 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     return;
   }
 
+  const int lane = tid & 31, warp = tid >> 5;
   double c0[NR], c1[NR];
-  const double* r0[NR];
-  const double* r1[NR];
+  const double* p0[NR];                                              // this lane's pixel pair in each bracketing row,
+  const double* p1[NR];                                              // advanced by one tile per iteration
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     c0[r] = sPlan.coef[0][r]; c1[r] = sPlan.coef[1][r];
-    r0[r] = T.grid + (long long)sPlan.row[0][r] * T.stride;
-    r1[r] = T.grid + (long long)sPlan.row[1][r] * T.stride;
+    p0[r] = T.grid + (long long)sPlan.row[0][r] * T.stride + warp * CHUNK + 2 * lane;
+    p1[r] = T.grid + (long long)sPlan.row[1][r] * T.stride + warp * CHUNK + 2 * lane;
   }
   const double av = sPlan.av;
+  const bool small_dext = av * T.dext_max < 4e-3;                     // exp(x) by a 5th-order polynomial: x^6/720 < 6e-18
+  double* seg = sF + warp * SEG;                                      // seg[1] = pixel before the chunk, seg[2+j] = chunk pixel j
 
   double accC[NC > 0 ? NC : 1][2];
   double accP[NP > 0 ? NP : 1];
@@ -559,30 +580,61 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   int has_nan = 0;
 
   // ------------------------------------------------------------------ phase A: stream the rows
+  // Each warp owns a contiguous 128-pixel chunk of every 1024-pixel tile and the observed pixels
+  // whose upper bracket falls into it, so the rebinning needs no block-wide barrier and the warps
+  // drift apart: while some wait on their row loads others compute.
   const int n_tiles = T.n_tiles;
   for (int tile = 0; tile < n_tiles; ++tile) {
-    const int base = tile * TILE;
+    const int cbase = tile * TILE + warp * CHUNK;                     // first pixel of this warp's chunk
     const unsigned cmask = T.tile_cmask[tile];
     const unsigned pmask = T.tile_pmask[tile];
-    const int d0 = T.tile_data_start[tile], d1 = T.tile_data_start[tile + 1];
-    double last = 0.0;
+    const int ds_raw = T.chunk_data_start[tile * NWARP + warp];
+    const int d0 = ds_raw & 0x7fffffff;
+    const int d1 = T.chunk_data_start[tile * NWARP + warp + 1] & 0x7fffffff;
+    const bool stage = d1 > d0;
+    const bool need_prev = ds_raw < 0;                                // warp-uniform
+    if (need_prev && lane == 0) {
+      // composite of the pixel just before the chunk (owned by another warp / the previous tile)
+      double f = 0.0;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int px = base + half * (2 * NT) + 2 * tid;              // first of this thread's pixel pair
-      double2 a[NR], b[NR];
+      for (int r = 0; r < NR; ++r) f = fma(c0[r], __ldg(p0[r] - 1), f);
+      double g = 0.0;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) a[r] = ldg_stream(r0[r] + px);
+      for (int r = 0; r < NR; ++r) g = fma(c1[r], __ldg(p1[r] - 1), g);
+      seg[1] = f + g;
+    }
 #pragma unroll
-      for (int r = 0; r < NR; ++r) b[r] = ldg_stream(r1[r] + px);
+    for (int h = 0; h < 2; ++h) {
+      const int px = cbase + h * 64 + 2 * lane;
       double2 f1, f2;
-      f1.x = c0[0] * a[0].x; f1.y = c0[0] * a[0].y;
-      f2.x = c1[0] * b[0].x; f2.y = c1[0] * b[0].y;
+      if constexpr (NR <= 4) {
+        double2 a[NR], b[NR];
 #pragma unroll
-      for (int r = 1; r < NR; ++r) {
-        f1.x = fma(c0[r], a[r].x, f1.x); f1.y = fma(c0[r], a[r].y, f1.y);
-        f2.x = fma(c1[r], b[r].x, f2.x); f2.y = fma(c1[r], b[r].y, f2.y);
+        for (int r = 0; r < NR; ++r) a[r] = ldg_stream(p0[r] + h * 64);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) b[r] = ldg_stream(p1[r] + h * 64);
+        f1.x = c0[0] * a[0].x; f1.y = c0[0] * a[0].y;
+        f2.x = c1[0] * b[0].x; f2.y = c1[0] * b[0].y;
+#pragma unroll
+        for (int r = 1; r < NR; ++r) {
+          f1.x = fma(c0[r], a[r].x, f1.x); f1.y = fma(c0[r], a[r].y, f1.y);
+          f2.x = fma(c1[r], b[r].x, f2.x); f2.y = fma(c1[r], b[r].y, f2.y);
+        }
+      } else {
+        // 8 corners per star: one star at a time keeps 8 (not 16) 16-byte loads live
+        double2 a[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) a[r] = ldg_stream(p0[r] + h * 64);
+        f1.x = c0[0] * a[0].x; f1.y = c0[0] * a[0].y;
+#pragma unroll
+        for (int r = 1; r < NR; ++r) { f1.x = fma(c0[r], a[r].x, f1.x); f1.y = fma(c0[r], a[r].y, f1.y); }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) a[r] = ldg_stream(p1[r] + h * 64);
+        f2.x = c1[0] * a[0].x; f2.y = c1[0] * a[0].y;
+#pragma unroll
+        for (int r = 1; r < NR; ++r) { f2.x = fma(c1[r], a[r].x, f2.x); f2.y = fma(c1[r], a[r].y, f2.y); }
       }
-      double2 comp; comp.x = f1.x + f2.x; comp.y = f1.y + f2.y;    // mft6.py:744
+      double2 comp; comp.x = f1.x + f2.x; comp.y = f1.y + f2.y;      // mft6.py:744
 #pragma unroll
       for (int f = 0; f < NC; ++f) {
         if ((cmask >> f) & 1u) {                                      // CTA-uniform
@@ -598,22 +650,36 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
           accP[f] = fma(wv.x, comp.x, accP[f]); accP[f] = fma(wv.y, comp.y, accP[f]);
         }
       }
-      if (d1 > d0) *reinterpret_cast<double2*>(sF + half * (2 * NT) + 2 * tid) = comp;
-      last = comp.y;
+      if (stage) *reinterpret_cast<double2*>(seg + 2 + h * 64 + 2 * lane) = comp;
     }
-    if (d1 > d0) {
-      __syncthreads();
-      for (int i = d0 + tid; i < d1; i += NT) {
-        const int h = T.rebin_hi[i] - base;                          // 0 .. TILE-1
-        const double flo = (h == 0) ? sCarry : sF[h - 1];
-        const double fhi = sF[h];
-        const double ylo = flo * exp2(av * T.ext_lo[i]);             // extinct() then interp1d: mft6.py:1162, :1169
-        const double yhi = fhi * exp2(av * T.ext_hi[i]);
-        const double m = ylo + (yhi - ylo) * T.rebin_t[i];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { p0[r] += TILE; p1[r] += TILE; }
+    if (stage) {
+      __syncwarp();
+      for (int i = d0 + lane; i < d1; i += 32) {
+        const int hl = T.rebin_hi[i] - cbase;                         // 0 .. CHUNK-1
+        const double2 tab0 = __ldg(T.rebin_tab + 2 * i);
+        const double2 tab1 = __ldg(T.rebin_tab + 2 * i + 1);
+        const double2 fx = __ldg(T.data_fx + i);
+        const double flo = seg[1 + hl];
+        const double fhi = seg[2 + hl];
+        // extinct() on the model grid, then interp1d onto the observed pixel (mft6.py:1162, :1169)
+        const double elo = exp2(av * tab0.y);
+        double ehi;
+        if (small_dext) {
+          const double xx = av * tab1.x;                               // E_hi = E_lo * exp(xx), |xx| < 4e-3
+          double pz = fma(xx, 1.0 / 120.0, 1.0 / 24.0);
+          pz = fma(pz, xx, 1.0 / 6.0); pz = fma(pz, xx, 0.5); pz = fma(pz, xx, 1.0); pz = fma(pz, xx, 1.0);
+          ehi = elo * pz;
+        } else {
+          ehi = exp2(av * tab1.y);
+        }
+        const double ylo = flo * elo, yhi = fhi * ehi;
+        const double m = ylo + (yhi - ylo) * tab0.x;
         sM[i] = m;
         // norm_spec's normal equations in the orthonormal basis, on the unscaled model (mft6.py:194-195)
-        const double frac = T.data_flux[i] / m;
-        const double x = T.data_x[i];
+        const double frac = fx.x * fast_rcp(m);
+        const double x = fx.y;
         const double q1 = fma(T.basis[4], x, T.basis[3]);
         const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
         mom[0] = fma(T.basis[0], frac, mom[0]); mom[1] = fma(q1, frac, mom[1]); mom[2] = fma(q2, frac, mom[2]);
@@ -621,10 +687,10 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         const unsigned long long k = ordered_key(m);
         kmin = min(kmin, k); kmax = max(kmax, k);
       }
-      __syncthreads();
+      __syncwarp();
     }
-    if (tid == NT - 1) sCarry = last;
   }
+  __syncthreads();
 
   // ------------------------------------------------------------------ band integrals
   double red[KRED > 0 ? KRED : 1];
@@ -638,7 +704,6 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   const int n = T.n_data;
   block_sum<3>(mom, sRed);
   {
-    const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
@@ -873,7 +938,7 @@ int launch_stream_variant(ms_handle* h, long long nw, double* d_lnp, const Parts
 
 size_t stream_smem_bytes(int n_data, int nc, int np) {
   const int kred = 2 * nc + np;
-  size_t b = (size_t)TILE * 8 + (size_t)NWARP * (kred > 4 ? kred : 4) * 8 + sizeof(SelectScratch);
+  size_t b = (size_t)NWARP * SEG * 8 + (size_t)NWARP * (kred > 4 ? kred : 4) * 8 + sizeof(SelectScratch);
   b += (size_t)n_data * 8;
   return (b + 15) & ~(size_t)15;
 }
@@ -1023,21 +1088,39 @@ int ms_create(const ms_config* cfg, ms_handle** out) {
       h->err = "ms_create: rebin_hi must be ascending and inside the region"; return fail(MS_ERR_INVALID);
     }
   }
-  if (cfg->tile_data_start[0] != 0 || cfg->tile_data_start[cfg->n_tiles] != cfg->n_data) {
-    h->err = "ms_create: tile_data_start does not cover the observed pixels"; return fail(MS_ERR_INVALID);
-  }
   CKC(upload(h, cfg->rebin_hi, cfg->n_data, &T.rebin_hi));
-  CKC(upload(h, cfg->rebin_t, cfg->n_data, &T.rebin_t));
-  CKC(upload(h, cfg->ext_lo, cfg->n_data, &T.ext_lo));
-  CKC(upload(h, cfg->ext_hi, cfg->n_data, &T.ext_hi));
   CKC(upload(h, cfg->data_flux, cfg->n_data, &T.data_flux));
-  {
-    std::vector<double> inv_e2(cfg->n_data);
-    for (int i = 0; i < cfg->n_data; ++i) inv_e2[i] = 1.0 / (cfg->data_err[i] * cfg->data_err[i]);   // mft6.py:120
-    CKC(upload(h, inv_e2.data(), inv_e2.size(), &T.data_inv_e2));
-  }
   CKC(upload(h, cfg->data_x, cfg->n_data, &T.data_x));
-  CKC(upload(h, cfg->tile_data_start, (size_t)cfg->n_tiles + 1, &T.tile_data_start));
+  {
+    const int n = cfg->n_data;
+    const double LN2 = 0.69314718055994530942;
+    std::vector<double> inv_e2(n);
+    std::vector<double2> tab(2 * (size_t)n);
+    std::vector<double2> fx(n);
+    double dmax = 0.0;
+    for (int i = 0; i < n; ++i) {
+      inv_e2[i] = 1.0 / (cfg->data_err[i] * cfg->data_err[i]);                                       // mft6.py:120
+      const double dext = (cfg->ext_hi[i] - cfg->ext_lo[i]) * LN2;
+      dmax = std::max(dmax, std::fabs(dext));
+      tab[2 * i] = make_double2(cfg->rebin_t[i], cfg->ext_lo[i]);
+      tab[2 * i + 1] = make_double2(dext, cfg->ext_hi[i]);
+      fx[i] = make_double2(cfg->data_flux[i], cfg->data_x[i]);
+    }
+    T.dext_max = dmax;
+    CKC(upload(h, inv_e2.data(), inv_e2.size(), &T.data_inv_e2));
+    CKC(upload(h, tab.data(), tab.size(), &T.rebin_tab));
+    CKC(upload(h, fx.data(), fx.size(), &T.data_fx));
+    // observed pixels owned by each 128-pixel chunk (rebin_hi is ascending)
+    const int n_chunks = cfg->n_tiles * NWARP;
+    std::vector<int> cds((size_t)n_chunks + 1);
+    int i = 0;
+    for (int c = 0; c <= n_chunks; ++c) {
+      while (i < n && cfg->rebin_hi[i] < c * CHUNK) ++i;
+      cds[c] = i;
+      if (c < n_chunks && i < n && cfg->rebin_hi[i] == c * CHUNK) cds[c] |= (int)0x80000000;
+    }
+    CKC(upload(h, cds.data(), cds.size(), &T.chunk_data_start));
+  }
 
   // ---- filters
   std::vector<unsigned> cmask(cfg->n_tiles, 0u), pmask(cfg->n_tiles, 0u);

@@ -38,7 +38,7 @@ class MsConfig(C.Structure):
         ('teff_nodes', _dp), ('logg_nodes', _dp), ('feh_nodes', _dp), ('grid', _dp), ('feh', C.c_double),
         ('n_data', C.c_int32), ('n_tiles', C.c_int32),
         ('rebin_hi', _ip), ('rebin_t', _dp), ('ext_lo', _dp), ('ext_hi', _dp),
-        ('data_flux', _dp), ('data_err', _dp), ('data_x', _dp), ('tile_data_start', _ip),
+        ('data_flux', _dp), ('data_err', _dp), ('data_x', _dp),
         ('poly_basis', C.c_double * 9), ('data_median', C.c_double),
         ('n_contrast', C.c_int32), ('n_phot', C.c_int32),
         ('c_tile_lo', _ip), ('c_tile_hi', _ip), ('c_offset', _lp), ('c_weights', _dp),
@@ -138,7 +138,6 @@ def make_config(t: DeviceTables, device=0):
     cfg.rebin_hi, cfg.rebin_t = i32(t.rebin_hi), dbl(t.rebin_t)
     cfg.ext_lo, cfg.ext_hi = dbl(t.ext_lo), dbl(t.ext_hi)
     cfg.data_flux, cfg.data_err, cfg.data_x = dbl(t.data_flux), dbl(t.data_err), dbl(t.data_x)
-    cfg.tile_data_start = i32(t.tile_data_start)
     cfg.poly_basis = (C.c_double * 9)(*np.asarray(t.poly_basis, dtype=np.float64).ravel())
     cfg.data_median = t.data_median
     cfg.n_contrast, cfg.n_phot = t.contrast.n, t.phot.n

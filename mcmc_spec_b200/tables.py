@@ -131,7 +131,6 @@ class DeviceTables:
     data_x: np.ndarray           # abscissae mapped to [-1, 1]
     poly_basis: np.ndarray       # [3,3] q_k(x) = sum_j B[k,j] x^j, orthonormal over data_x
     data_median: float
-    tile_data_start: np.ndarray  # int32 [n_tiles+1] observed pixels owned by each tile
     # filters
     contrast: PackedFilters
     c_mag: np.ndarray
@@ -256,9 +255,6 @@ def build_tables(prob) -> DeviceTables:
     order_ok = np.all(np.diff(hi) >= 0)
     if not order_ok:
         raise ValueError("observed wavelengths must be ascending")
-    n_tiles = (n_reg + TILE - 1) // TILE
-    tile_of = hi // TILE
-    tile_data_start = np.searchsorted(tile_of, np.arange(n_tiles + 1), side='left').astype(np.int32)
 
     # ---- norm_spec abscissae (numpy Polynomial.fit domain mapping, polyutils.mapparms)
     xmin, xmax = data_wl.min(), data_wl.max()
@@ -297,7 +293,7 @@ def build_tables(prob) -> DeviceTables:
         feh_nodes=fehs, feh=float(prob.feh), grid=grid, row_len=int(wl.size), reg_lo=reg_lo, n_reg=n_reg,
         wl_reg=wl_reg, n_data=int(data_wl.size), rebin_hi=hi, rebin_t=rebin_t,
         ext_lo=ext_coef[lo], ext_hi=ext_coef[hi], data_flux=data_flux, data_err=err, data_x=data_x,
-        poly_basis=basis, data_median=float(np.median(data_flux)), tile_data_start=tile_data_start,
+        poly_basis=basis, data_median=float(np.median(data_flux)),
         contrast=contrast, c_mag=np.array(prob.fr[0], dtype=np.float64), c_err=np.array(prob.fr[1], dtype=np.float64),
         phot=phot, p_norm=np.array(p_norm), p_ext=np.array(p_ext),
         p_mag=np.array(prob.fr[3], dtype=np.float64), p_err=np.array(prob.fr[4], dtype=np.float64),

@@ -31,7 +31,6 @@ def test_table_shapes_and_region(small_problem):
     t = build_tables(small_problem)
     assert t.n_tiles == -(-t.n_reg // TILE)
     assert t.rebin_hi.min() >= 1 and t.rebin_hi.max() < t.n_reg and np.all(np.diff(t.rebin_hi) >= 0)
-    assert t.tile_data_start[0] == 0 and t.tile_data_start[-1] == t.n_data
     assert np.all((t.rebin_t >= 0) & (t.rebin_t <= 1))
     # region covers data and every filter, like make_composite's get_spec cut (mft6.py:687)
     lo, hi = t.wl_reg[0], t.wl_reg[-1]
