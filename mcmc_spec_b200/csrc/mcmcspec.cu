@@ -45,7 +45,12 @@ constexpr double SIGMA_SB = 5.670374e-5;  // mft6.py:79
 constexpr double LSUN = 3.839e33;       // mft6.py:80
 
 constexpr int CHUNK = TILE / NWARP;      // model pixels one warp owns per tile (128)
-constexpr int SEG = CHUNK + 4;           // shared-memory doubles per warp: [pad, prev pixel, CHUNK composites, pad]
+constexpr int SEG = CHUNK + CHUNK / 16 + 4;   // shared-memory doubles per warp: previous pixel + CHUNK composites, skewed
+
+// Slot of local pixel q (q = 0: the pixel before the chunk, q = j + 1: chunk pixel j).  One slot is
+// skipped every 16 so that the stride-4 reads of the rebinning (observed pixels are ~4 model pixels
+// apart) fall into distinct banks.
+__device__ __forceinline__ int seg_slot(int q) { return q + (q >> 4); }
 
 static_assert(TILE == 4 * NT, "each thread owns two pixel pairs per tile");
 static_assert(CHUNK == 128, "a warp covers its chunk with two 64-pixel (32 x double2) sub-chunks");
@@ -64,7 +69,8 @@ struct DevTables {
   // observed spectrum
   int n_data;
   const int* rebin_hi;          // [N] upper bracketing model pixel
-  const double2* rebin_tab;     // [2N] {t, ext_lo}, {(ext_hi - ext_lo) ln 2, ext_hi} per observed pixel
+  const double2* rebin_tab0;    // [N] {t, ext_lo}                      (two arrays: each load is fully coalesced)
+  const double2* rebin_tab1;    // [N] {(ext_hi - ext_lo) ln 2, ext_hi}
   const double2* data_fx;       // [N] {flux, x}
   const double* data_flux; const double* data_inv_e2; const double* data_x;
   const int* chunk_data_start;  // [n_tiles*NWARP + 1] first observed pixel owned by each 128-pixel chunk;
@@ -414,22 +420,33 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
   if (tid == 0) S->count = 0;
   __syncthreads();
   double chi = 0.0;
-  for (int r = 0; r < rounds; ++r) {
-    const int i = r * NT + tid;
-    unsigned d = 0xffffffffu;
-    if (i < n) {
-      const double m = sM[i];
-      const double x = T.data_x[i];
-      const double q1 = fma(T.basis[4], x, T.basis[3]);
-      const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
-      const double pfit = a[0] * T.basis[0] + a[1] * q1 + a[2] * q2;
-      const double res = m - T.data_flux[i] * fast_rcp(pfit);           // mft6.py:196, :120 (unscaled)
-      chi = fma(res * res, T.data_inv_e2[i], chi);
-      if (!flat) d = (unsigned)((ordered_key(m) >> shift0) & ((1u << width0) - 1u));
+  const double b0 = T.basis[0], b3 = T.basis[3], b4 = T.basis[4], b6 = T.basis[6], b7 = T.basis[7], b8 = T.basis[8];
+  const double a0b0 = a[0] * b0;
+  for (int r = 0; r < rounds; r += 2) {
+    // two elements per iteration: all table loads are issued before either is consumed
+    const int i0 = r * NT + tid, i1 = i0 + NT;
+    const bool v0 = i0 < n, v1 = (r + 1 < rounds) && (i1 < n);
+    double m0 = 0.0, m1 = 0.0, x0 = 0.0, x1 = 0.0, d0 = 0.0, d1 = 0.0, w0 = 0.0, w1 = 0.0;
+    if (v0) { m0 = sM[i0]; x0 = T.data_x[i0]; d0 = T.data_flux[i0]; w0 = T.data_inv_e2[i0]; }
+    if (v1) { m1 = sM[i1]; x1 = T.data_x[i1]; d1 = T.data_flux[i1]; w1 = T.data_inv_e2[i1]; }
+    unsigned dg0 = 0xffffffffu, dg1 = 0xffffffffu;
+    if (v0) {
+      const double pfit = a0b0 + a[1] * fma(b4, x0, b3) + a[2] * fma(fma(b8, x0, b7), x0, b6);
+      const double res = m0 - d0 * fast_rcp(pfit);                    // mft6.py:196, :120 (unscaled)
+      chi = fma(res * res, w0, chi);
+      if (!flat) dg0 = (unsigned)((ordered_key(m0) >> shift0) & ((1u << width0) - 1u));
+    }
+    if (v1) {
+      const double pfit = a0b0 + a[1] * fma(b4, x1, b3) + a[2] * fma(fma(b8, x1, b7), x1, b6);
+      const double res = m1 - d1 * fast_rcp(pfit);
+      chi = fma(res * res, w1, chi);
+      if (!flat) dg1 = (unsigned)((ordered_key(m1) >> shift0) & ((1u << width0) - 1u));
     }
     if (!flat) {
-      const unsigned peers = __match_any_sync(0xffffffffu, d);
-      if (d != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&S->hist[d], (unsigned)__popc(peers));
+      const unsigned peers0 = __match_any_sync(0xffffffffu, dg0);
+      const unsigned peers1 = __match_any_sync(0xffffffffu, dg1);
+      if (dg0 != 0xffffffffu && lane == __ffs(peers0) - 1) atomicAdd(&S->hist[dg0], (unsigned)__popc(peers0));
+      if (dg1 != 0xffffffffu && lane == __ffs(peers1) - 1) atomicAdd(&S->hist[dg1], (unsigned)__popc(peers1));
     }
   }
   {
@@ -566,7 +583,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   }
   const double av = sPlan.av;
   const bool small_dext = av * T.dext_max < 4e-3;                     // exp(x) by a 5th-order polynomial: x^6/720 < 6e-18
-  double* seg = sF + warp * SEG;                                      // seg[1] = pixel before the chunk, seg[2+j] = chunk pixel j
+  double* seg = sF + warp * SEG;                                      // see seg_slot()
 
   double accC[NC > 0 ? NC : 1][2];
   double accP[NP > 0 ? NP : 1];
@@ -601,7 +618,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
       double g = 0.0;
 #pragma unroll
       for (int r = 0; r < NR; ++r) g = fma(c1[r], __ldg(p1[r] - 1), g);
-      seg[1] = f + g;
+      seg[seg_slot(0)] = f + g;
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -650,7 +667,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
           accP[f] = fma(wv.x, comp.x, accP[f]); accP[f] = fma(wv.y, comp.y, accP[f]);
         }
       }
-      if (stage) *reinterpret_cast<double2*>(seg + 2 + h * 64 + 2 * lane) = comp;
+      if (stage) { seg[seg_slot(h * 64 + 2 * lane + 1)] = comp.x; seg[seg_slot(h * 64 + 2 * lane + 2)] = comp.y; }
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r) { p0[r] += TILE; p1[r] += TILE; }
@@ -658,11 +675,11 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
       __syncwarp();
       for (int i = d0 + lane; i < d1; i += 32) {
         const int hl = T.rebin_hi[i] - cbase;                         // 0 .. CHUNK-1
-        const double2 tab0 = __ldg(T.rebin_tab + 2 * i);
-        const double2 tab1 = __ldg(T.rebin_tab + 2 * i + 1);
+        const double2 tab0 = __ldg(T.rebin_tab0 + i);
+        const double2 tab1 = __ldg(T.rebin_tab1 + i);
         const double2 fx = __ldg(T.data_fx + i);
-        const double flo = seg[1 + hl];
-        const double fhi = seg[2 + hl];
+        const double flo = seg[seg_slot(hl)];
+        const double fhi = seg[seg_slot(hl + 1)];
         // extinct() on the model grid, then interp1d onto the observed pixel (mft6.py:1162, :1169)
         const double elo = exp2(av * tab0.y);
         double ehi;
@@ -1095,20 +1112,21 @@ int ms_create(const ms_config* cfg, ms_handle** out) {
     const int n = cfg->n_data;
     const double LN2 = 0.69314718055994530942;
     std::vector<double> inv_e2(n);
-    std::vector<double2> tab(2 * (size_t)n);
+    std::vector<double2> tab0(n), tab1(n);
     std::vector<double2> fx(n);
     double dmax = 0.0;
     for (int i = 0; i < n; ++i) {
       inv_e2[i] = 1.0 / (cfg->data_err[i] * cfg->data_err[i]);                                       // mft6.py:120
       const double dext = (cfg->ext_hi[i] - cfg->ext_lo[i]) * LN2;
       dmax = std::max(dmax, std::fabs(dext));
-      tab[2 * i] = make_double2(cfg->rebin_t[i], cfg->ext_lo[i]);
-      tab[2 * i + 1] = make_double2(dext, cfg->ext_hi[i]);
+      tab0[i] = make_double2(cfg->rebin_t[i], cfg->ext_lo[i]);
+      tab1[i] = make_double2(dext, cfg->ext_hi[i]);
       fx[i] = make_double2(cfg->data_flux[i], cfg->data_x[i]);
     }
     T.dext_max = dmax;
     CKC(upload(h, inv_e2.data(), inv_e2.size(), &T.data_inv_e2));
-    CKC(upload(h, tab.data(), tab.size(), &T.rebin_tab));
+    CKC(upload(h, tab0.data(), tab0.size(), &T.rebin_tab0));
+    CKC(upload(h, tab1.data(), tab1.size(), &T.rebin_tab1));
     CKC(upload(h, fx.data(), fx.size(), &T.data_fx));
     // observed pixels owned by each 128-pixel chunk (rebin_hi is ascending)
     const int n_chunks = cfg->n_tiles * NWARP;

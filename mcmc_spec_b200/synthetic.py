@@ -370,6 +370,49 @@ def make_problem_c4(seed=2298, **kw):
     return make_problem(**args)
 
 
+def _many_bands(wl, n_contrast, n_phot):
+    span = wl[-1] - wl[0]
+    cc = [synthetic_passband(wl[0] + (0.12 + 0.76 * k / max(n_contrast - 1, 1)) * span, 0.14 * span, 300 + 200 * k,
+                             ripple_seed=30 + k) for k in range(n_contrast)]
+    pc = [synthetic_passband(wl[0] + (0.06 + 0.88 * k / max(n_phot - 1, 1)) * span, (0.05 + 0.004 * k) * span,
+                             200 + 60 * k, ripple_seed=50 + k) for k in range(n_phot)]
+    cn = [f'synth_c{k}' for k in range(n_contrast)]
+    pn = [('2MASS_' if k % 2 else 'SDSS_') + f'b{k}' for k in range(n_phot)]
+    return cc, cn, pc, pn
+
+
+def make_problem_3d_small(seed=2298, **kw):
+    """Reduced 3-D (Teff, log g, [Fe/H]) problem for CPU-oracle parity: 5 x 4 x 3 nodes, 5000-pixel rows,
+    4 contrast + 12 photometric bands."""
+    wl = 5400.0 + 0.5 * np.arange(5000)
+    cc, cn, pc, pn = _many_bands(wl, 4, 12)
+    args = dict(temps=range(3500, 3901, 100), lgs=[4.0, 4.5, 5.0, 5.5], fehs=[-0.5, 0.0, 0.5], feh=0.2,
+                specmin=5400.0, dlam=0.5, n_pix=5000, window_um=(0.60, 0.72), n_data=257, res=1700, seed=seed,
+                contrast_curves=cc, contrast_names=cn, phot_curves=pc, phot_names=pn,
+                truth=[3720.0, 3630.0, 0.10, 0.45, 0.7, 2.5e-3], plx=2.5e-3, plx_err=5e-5)
+    args.update(kw)
+    return make_problem(**args)
+
+
+def make_problem_c5(seed=2298, **kw):
+    """BASELINE config C5 (stress): 26 x 4 x 5 (Teff, log g, [Fe/H]) grid, 100 000-pixel rows (416 MB),
+    25 000 observed pixels, 4 contrast + 12 photometric bands; the fit's metallicity is fixed at +0.1."""
+    n_pix, dlam = 100000, 0.187
+    wl = 5300.0 + dlam * np.arange(n_pix)
+    cc, cn, pc, pn = _many_bands(wl, 4, 12)
+    rng = np.random.default_rng(seed + 13)
+    n_data = int(kw.pop('n_data', 25000))
+    lo, hi = (wl[0] + 0.3) * 1e-4, (wl[-1] - 0.3) * 1e-4
+    step = (hi - lo) / (n_data - 1)
+    data_wl = lo + step * np.arange(n_data)
+    data_wl[1:-1] += rng.uniform(-0.2, 0.2, n_data - 2) * step
+    args = dict(fehs=[-1.0, -0.5, 0.0, 0.3, 0.5], feh=0.1, specmin=5300.0, dlam=dlam, n_pix=n_pix,
+                window_um=(0.5300, (wl[-1] + 1) * 1e-4), n_data=n_data, data_wl_um=data_wl, res=1700, seed=seed,
+                contrast_curves=cc, contrast_names=cn, phot_curves=pc, phot_names=pn)
+    args.update(kw)
+    return make_problem(**args)
+
+
 def sample_prior_box(prob: Problem, n, seed=0, edge_cases=True):
     """theta batch uniform in the prior box of SURVEY.md section 8(d), with forced edge cases."""
     rng = np.random.default_rng(seed)

@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Device-resident throughput of lnprob_stream_kernel on every BASELINE configuration shape.
+
+Supplementary to bench.py (which measures C4 through the sampler): for each shape, `nw` walkers
+uniform in the central third of the prior box are evaluated with ms_lnprob(MS_DEVICE); the
+streaming kernel is timed by the library's own CUDA events.  Prints one JSON line per config:
+evals/s, algorithmic GB/s (B_eval = n_star*2^D*P_reg*8 + 8*ndim + 8) and the fraction of the
+measured HBM copy peak.
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+from mcmc_spec_b200 import synthetic                  # noqa: E402
+from mcmc_spec_b200.posterior import LogPosterior      # noqa: E402
+
+
+def central_third(prob, nw, seed=1):
+    rng = np.random.default_rng(seed)
+    lo = np.array([min(prob.temps), min(prob.temps), 0.0, 0.1, 0.1, 1 / 3000.0])
+    hi = np.array([max(prob.temps), max(prob.temps), 1.0, 1.2, 1.0, 1 / 100.0])
+    a, b = lo + (hi - lo) / 3.0, hi - (hi - lo) / 3.0
+    return a + (b - a) * rng.random((nw, 6))
+
+
+def run(name, prob, nw, reps=5):
+    peak = 6455.6
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+    except Exception:
+        pass
+    lp = LogPosterior(prob)
+    th = torch.tensor(central_third(prob, nw), device='cuda')
+    out = torch.empty(nw, dtype=torch.float64, device='cuda')
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device='cuda')
+    lp.engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        lp.engine.lnprob_device(th.data_ptr(), nw, out.data_ptr())
+    torch.cuda.synchronize()
+    lp.engine.set_timing(True); lp.engine.kernel_time()
+    for _ in range(reps):
+        flush.zero_()
+        lp.engine.lnprob_device(th.data_ptr(), nw, out.data_ptr())
+    torch.cuda.synchronize()
+    ms, nl, nwt = lp.engine.kernel_time()
+    bpe = lp.tables.bytes_per_eval()
+    gbs = nwt * bpe / 1e9 / (ms / 1e3)
+    t = lp.tables
+    print(json.dumps({"config": name, "walkers_per_launch": nw, "n_data": t.n_data, "p_reg": t.n_reg,
+                      "grid_mb": round(t.grid.nbytes / 1e6, 1), "bytes_per_eval": bpe,
+                      "kernel_ms_per_launch": ms / nl, "evals_per_s": nwt / (ms / 1e3), "algorithmic_gbs": gbs,
+                      "frac_of_measured_hbm_peak": gbs / peak,
+                      "finite_frac": float(torch.isfinite(out).double().mean().item())}), flush=True)
+    lp.close()
+    del th, out, flush
+    torch.cuda.empty_cache()
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['c1', 'c4', 'c5']
+    if 'c1' in which:
+        run('C1/C2 shape: 26x4 grid, 135000-px rows (P_reg ~117k synthetic bands), N=1945', synthetic.make_problem(), 8192)
+        run('C1/C2 shape, reference walker count (50)', synthetic.make_problem(), 50, reps=20)
+    if 'c4' in which:
+        run('C4: 26x4 grid, P_reg=32768, N=8192', synthetic.make_problem_c4(), 32768)
+    if 'c5' in which:
+        t0 = time.time()
+        p5 = synthetic.make_problem_c5()
+        print(f'# C5 problem built in {time.time() - t0:.1f} s', flush=True)
+        run('C5: 26x4x5 grid (416 MB), P_reg=100000, N=25000, 4+12 bands', p5, 16384, reps=3)

@@ -5,13 +5,31 @@ from oracle import mft6_oracle as mo
 from oracle import thirdparty as tp
 
 
+def _specs_at_feh(prob):
+    """3-D grids (an extension; the reference has only Teff x log g): the reference's 2-D path runs on
+    the grid linearly interpolated to the fit's fixed [Fe/H], with get_spec's own bracket rule
+    (nearest node + partner on the far side, mft6.py:439-453) and interp_2_spec (mft6.py:198-209)."""
+    z1, z2 = mo._bracket(list(prob.fehs), prob.feh)
+    i1, i2 = list(prob.fehs).index(z1), list(prob.fehs).index(z2)
+    specs = {'wl': prob.wl}
+    for ig, g in enumerate(prob.lgs):
+        for it, t in enumerate(prob.temps):
+            key = '{}, {}'.format(t, g)
+            if i1 == i2:
+                specs[key] = prob.grid[i1, ig, it]
+            else:
+                specs[key] = mo.interp_2_spec(prob.grid[i1, ig, it], prob.grid[i2, ig, it], z1, z2, prob.feh)
+    return specs
+
+
 def to_oracle(prob):
-    """Bind a mcmc_spec_b200.Problem to oracle.mft6_oracle.OracleProblem (2-D grids)."""
+    """Bind a mcmc_spec_b200.Problem to oracle.mft6_oracle.OracleProblem."""
     names = [b.name for b in prob.photbands]
     photlib = {b.name: tp.LibraryFilter(b.name, b.wavelength, b.transmit, b.dtype, b.vega_zero_flux)
                for b in prob.photbands}
     ns = SimpleNamespace(
-        fr=prob.fr, nspec=prob.nspec, data=prob.data, err=prob.err, specs=prob.specs, ctm=prob.ctm,
+        fr=prob.fr, nspec=prob.nspec, data=prob.data, err=prob.err,
+        specs=prob.specs if prob.fehs is None else _specs_at_feh(prob), ctm=prob.ctm,
         ptm=prob.ptm, tmi=prob.tmi, tma=prob.tma, matrix=prob.matrix, temps=list(prob.temps),
         lgs=list(prob.lgs), photlib=photlib,
         dustmap=tp.BayestarSightline(prob.dust_dm_edges, prob.dust_samples), prior=prob.prior,

@@ -164,6 +164,21 @@ def test_c4_shape_against_oracle_and_properties(native_lib):
     lp.close()
 
 
+def test_3d_grid_trilinear_16_passbands(native_lib):
+    """Shape of BASELINE config C5 (Teff x log g x [Fe/H] grid, 4 contrast + 12 photometric bands) at a size
+    the oracle finishes quickly; the oracle runs the reference's 2-D path on the grid interpolated to the fit's
+    fixed [Fe/H] (tests/oracle_adapter.py)."""
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    for feh in (0.2, 0.0, -0.5, 0.25):                      # off-node, on-node, on the edge node, midpoint tie
+        p = synthetic.make_problem_3d_small(feh=feh)
+        lp = LogPosterior(p)
+        theta = synthetic.sample_prior_box(p, 96, seed=int(10 * (feh + 1)))
+        _compare(lp(theta), to_oracle(p).lnprob_batch(theta))
+        lp.close()
+
+
 def test_broaden_rows_matches_oracle_splice(native_lib):
     from mcmc_spec_b200 import native, synthetic
     from oracle import mft6_oracle as mo
