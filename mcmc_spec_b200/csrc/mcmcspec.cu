@@ -33,8 +33,7 @@
 
 namespace {
 
-constexpr int NT = 256;                 // threads per CTA of the streaming kernel
-constexpr int NWARP = NT / 32;
+constexpr int MAXWARP = 16;              // the streaming kernel runs with 256 or 512 threads per CTA
 constexpr int TILE = MS_TILE;           // model pixels per tile (4 per thread)
 constexpr int MAX_STAR = 2;
 constexpr int MAX_CORNER = 8;
@@ -44,7 +43,8 @@ constexpr double PC_CM = 3.086e18;      // mft6.py:691
 constexpr double SIGMA_SB = 5.670374e-5;  // mft6.py:79
 constexpr double LSUN = 3.839e33;       // mft6.py:80
 
-constexpr int CHUNK = TILE / NWARP;      // model pixels one warp owns per tile (128)
+constexpr int CHUNK = 128;               // model pixels a warp owns per step: two 64-pixel (32 x double2) sub-chunks
+constexpr int CHUNKS_PER_TILE = TILE / CHUNK;
 constexpr int SEG = CHUNK + CHUNK / 16 + 4;   // shared-memory doubles per warp: previous pixel + CHUNK composites, skewed
 
 // Slot of local pixel q (q = 0: the pixel before the chunk, q = j + 1: chunk pixel j).  One slot is
@@ -52,8 +52,7 @@ constexpr int SEG = CHUNK + CHUNK / 16 + 4;   // shared-memory doubles per warp:
 // apart) fall into distinct banks.
 __device__ __forceinline__ int seg_slot(int q) { return q + (q >> 4); }
 
-static_assert(TILE == 4 * NT, "each thread owns two pixel pairs per tile");
-static_assert(CHUNK == 128, "a warp covers its chunk with two 64-pixel (32 x double2) sub-chunks");
+static_assert(TILE % CHUNK == 0, "filter masks are per tile, work is per chunk");
 
 // ------------------------------------------------------------------------------------------
 // Device-side view of the tables (passed by value as a kernel parameter).
@@ -73,7 +72,7 @@ struct DevTables {
   const double2* rebin_tab1;    // [N] {(ext_hi - ext_lo) ln 2, ext_hi}
   const double2* data_fx;       // [N] {flux, x}
   const double* data_flux; const double* data_inv_e2; const double* data_x;
-  const int* chunk_data_start;  // [n_tiles*NWARP + 1] first observed pixel owned by each 128-pixel chunk;
+  const int* chunk_data_start;  // [n_tiles*CHUNKS_PER_TILE + 1] first observed pixel owned by each 128-pixel chunk;
                                 // bit 31 set when that pixel's lower bracket is the last pixel of the previous chunk
   double dext_max;              // max |(ext_hi - ext_lo) ln 2|
   const unsigned* tile_cmask; const unsigned* tile_pmask;
@@ -91,6 +90,7 @@ struct DevTables {
   double tmin, tmax;
   double prior_mu[MS_MAX_NDIM], prior_sig[MS_MAX_NDIM];
   int nspec, ndim, ext_flag, dist_fit, rad_prior;
+  int n_cells;                 // number of cell keys (bins of the launch-order counting sort)
 };
 
 // What walker_prep_kernel hands to the streaming kernel.
@@ -101,7 +101,7 @@ struct __align__(16) WalkerPlan {
   double lp;                           // log prior (finite when status == 0)
   double logg[MAX_STAR];
   int status;                          // MS_W_* bits
-  int pad;
+  int cell;                            // grid-cell key of the two stars (walkers of one cell read the same rows)
 };
 
 struct PartsOut {
@@ -137,7 +137,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Sum of K per-thread values over the CTA, in a fixed order; result valid in every thread.
-template <int K>
+template <int K, int NWARP>
 __device__ __forceinline__ void block_sum(double (&v)[K], double* scratch /* [NWARP*K] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -226,9 +226,14 @@ __device__ void dust_prior_moments(const DevTables& T, double plx, double* mu, d
 // walker_prep_kernel
 // ------------------------------------------------------------------------------------------
 __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__ theta, long long nw,
-                                   WalkerPlan* __restrict__ plans) {
+                                   WalkerPlan* __restrict__ plans_out, unsigned* __restrict__ cell_hist) {
   const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (w >= nw) return;
+  // every exit stores the plan and counts the walker in its cell bin
+  auto store = [&](const WalkerPlan& p) {
+    plans_out[w] = p;
+    if (cell_hist) atomicAdd(cell_hist + p.cell, 1u);
+  };
   const int ndim = T.ndim, ns = T.nspec;
   double p[MS_MAX_NDIM];
   bool finite = true;
@@ -239,8 +244,8 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
     plan.logg[s] = CUDART_NAN;
     for (int c = 0; c < MAX_CORNER; ++c) { plan.coef[s][c] = 0.0; plan.row[s][c] = 0; }
   }
-  plan.av = 0.0; plan.lp = -CUDART_INF; plan.status = 0; plan.pad = 0;
-  if (!finite) { plan.status = MS_W_NONFINITE; plans[w] = plan; return; }
+  plan.av = 0.0; plan.lp = -CUDART_INF; plan.status = 0; plan.cell = T.n_cells - 1;
+  if (!finite) { plan.status = MS_W_NONFINITE; store(plan); return; }
 
   // layout mft6.py:1146: T[0..ns), Av, R1, ratios[1..ns), parallax
   const double* temps = p;
@@ -258,7 +263,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
     out = out || (rad[1] < 0.05) || (rad[0] < 0.05);
   }
   if (T.ext_flag && av < 0.0) out = true;
-  if (out) { plan.status = MS_W_PRIOR_BOUNDS; plans[w] = plan; return; }
+  if (out) { plan.status = MS_W_PRIOR_BOUNDS; store(plan); return; }
 
   // ---- isochrone: log g and luminosity per star (mft6.py:66-98)
   double lum[MAX_STAR];
@@ -266,7 +271,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
     double g, l;
     if (!interp_table(T.iso_teff, T.iso_logg, T.n_iso, temps[s], &g) ||
         !interp_table(T.iso_teff, T.iso_lum, T.n_iso, temps[s], &l)) {
-      plan.status = MS_W_OFF_ISOCHRONE; plans[w] = plan; return;
+      plan.status = MS_W_OFF_ISOCHRONE; store(plan); return;
     }
     plan.logg[s] = g; lum[s] = l;
   }
@@ -296,19 +301,19 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
     lp += -0.5 * (z0 * z0);
     lp += -0.5 * (z1 * z1);
   }
-  if (!isfinite(lp)) { plan.status = MS_W_NONFINITE; plans[w] = plan; return; }   // mft6.py:1465
+  if (!isfinite(lp)) { plan.status = MS_W_NONFINITE; store(plan); return; }   // mft6.py:1465
 
   // ---- grid brackets and coefficients
   int z1 = 0, z2 = 0; double wz = 0.0;
   if (T.n_feh > 1 && !bracket_nodes(T.feh_nodes, T.n_feh, T.feh, &z1, &z2, &wz)) {
-    plan.status = MS_W_OFF_GRID; plans[w] = plan; return;
+    plan.status = MS_W_OFF_GRID; store(plan); return;
   }
   const double di = 1.0 / plx;                            // mft6.py:690
   for (int s = 0; s < ns; ++s) {
     int t1, t2, g1, g2; double wt, wg;
     if (!bracket_nodes(T.teff_nodes, T.n_teff, temps[s], &t1, &t2, &wt) ||
         !bracket_nodes(T.logg_nodes, T.n_logg, plan.logg[s], &g1, &g2, &wg)) {
-      plan.status = MS_W_OFF_GRID; plans[w] = plan; return;
+      plan.status = MS_W_OFF_GRID; store(plan); return;
     }
     const double base = (s == 0) ? rad[0] * RSUN_CM / (di * PC_CM) : rad[0] * rad[s] * RSUN_CM / (di * PC_CM);
     const double scale = base * base;                     // mft6.py:691, :700
@@ -325,9 +330,61 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
           ++c;
         }
   }
+  {
+    // cell key: lower Teff / log g node of each star's bracket
+    int key = 0;
+    const int per_star = T.n_teff * T.n_logg;
+    for (int s = 0; s < ns; ++s) {
+      const int r_a = plan.row[s][0] % per_star, r_b = plan.row[s][3] % per_star;   // (t1,g1) and (t2,g2)
+      const int tl = min(r_a % T.n_teff, r_b % T.n_teff), gl = min(r_a / T.n_teff, r_b / T.n_teff);
+      key = key * per_star + gl * T.n_teff + tl;
+    }
+    plan.cell = (T.n_cells > 1) ? min(key, T.n_cells - 2) : 0;
+  }
   plan.av = (T.ext_flag && av > 0.0) ? av : 0.0;          // mft6.py:1161
   plan.lp = lp;
-  plans[w] = plan;
+  store(plan);
+}
+
+// ------------------------------------------------------------------------------------------
+// Launch order: counting sort of the walkers by grid cell, so that CTAs resident at the same time
+// stream the same rows and find them in L2 (matters once the grid exceeds L2: config C5).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) cell_scan_kernel(unsigned* __restrict__ hist, int n_cells) {
+  // exclusive prefix sum in place, single CTA
+  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_cells; base += 1024) {
+    const int i = base + tid;
+    const unsigned v = (i < n_cells) ? hist[i] : 0u;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const unsigned before = carry + (warp ? warp_tot[warp - 1] : 0u) + incl - v;
+    if (i < n_cells) hist[i] = before;
+    __syncthreads();
+    if (tid == 1023) carry = before + v;
+    __syncthreads();
+  }
+}
+
+__global__ void cell_scatter_kernel(const WalkerPlan* __restrict__ plans, long long nw, unsigned* __restrict__ offsets,
+                                    int* __restrict__ order) {
+  const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  order[atomicAdd(offsets + plans[w].cell, 1u)] = (int)w;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -349,11 +406,11 @@ __device__ __forceinline__ double key_value(unsigned long long k) {
 }
 
 constexpr int LIST_CAP = 256;            // finish by counting once the bin holds at most this many keys
-static_assert(LIST_CAP <= NWARP * SEG, "the candidate list lives in the (idle) composite tile buffer");
+static_assert(LIST_CAP <= 8 * SEG, "the candidate list lives in the (idle) composite tile buffer");
 
 struct SelectScratch {
   unsigned hist[256];
-  unsigned long long kmin[NWARP], kmax[NWARP];
+  unsigned long long kmin[MAXWARP], kmax[MAXWARP];
   unsigned long long bcast[4];
   unsigned count;
   int nanflag;
@@ -383,6 +440,7 @@ __device__ __forceinline__ void locate_rank_bin(SelectScratch* S, unsigned rank,
 
 // One histogram pass over the elements whose key matches `prefix` on its top `bits_done` bits.
 // Warp-aggregated shared-memory atomics (neighbouring pixels of a smooth spectrum share a bin).
+template <int NT>
 __device__ __forceinline__ void histogram_pass(const double* sM, int n, SelectScratch* S, unsigned long long prefix,
                                                int bits_done, int shift, int width) {
   const int tid = threadIdx.x, lane = tid & 31;
@@ -403,9 +461,11 @@ __device__ __forceinline__ void histogram_pass(const double* sM, int n, SelectSc
 // Median of sM[0..n) given the block-wide key range [kmin, kmax]; also returns, through *chi_out,
 // sum_i (m_i - d_i/p0(x_i))^2 * inv_e2_i with p0 = a[0] q0 + a[1] q1 + a[2] q2.
 // `list` is scratch for LIST_CAP keys.
+template <int NT>
 __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, unsigned long long* list,
                                    unsigned long long kmin, unsigned long long kmax, const DevTables& T,
                                    const double (&a)[3], double* chi_out, double* red_scratch) {
+  constexpr int NWARP = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rounds = (n + NT - 1) / NT;
   unsigned rank = (unsigned)((n - 1) >> 1);
@@ -416,7 +476,7 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
   const int shift0 = 64 - bits_done - width0;
 
   // ---- pass 1: chi-square terms + histogram of the first 8 differing key bits
-  S->hist[tid] = 0;                                      // NT == 256 bins
+  if (tid < 256) S->hist[tid] = 0;
   if (tid == 0) S->count = 0;
   __syncthreads();
   double chi = 0.0;
@@ -451,7 +511,7 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
   }
   {
     double c1[1] = {chi};
-    block_sum<1>(c1, red_scratch);                        // includes the barriers that publish hist
+    block_sum<1, NWARP>(c1, red_scratch);                 // includes the barriers that publish hist
     *chi_out = c1[0];
   }
   if (flat) return key_value(kmin);
@@ -471,9 +531,9 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
     if (in_bin <= (unsigned)LIST_CAP || bits_done >= 64) break;
     width = min(8, 64 - bits_done);
     shift = 64 - bits_done - width;
-    S->hist[tid] = 0;
+    if (tid < 256) S->hist[tid] = 0;
     __syncthreads();
-    histogram_pass(sM, n, S, prefix, bits_done, shift, width);
+    histogram_pass<NT>(sM, n, S, prefix, bits_done, shift, width);
     __syncthreads();
   }
 
@@ -533,13 +593,16 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
 
 // ------------------------------------------------------------------------------------------
 // lnprob_stream_kernel: one CTA per walker.
-//   NR  grid rows per star (4: Teff x log g, 8: with [Fe/H]);  NC / NP compile-time filter caps.
+//   NR  grid rows per star (4: Teff x log g, 8: with [Fe/H]);  NC / NP compile-time filter caps;
+//   NT  threads per CTA: 256 (two or three CTAs per SM) or 512 when the observed spectrum is so long
+//       that only one CTA fits an SM.
 // ------------------------------------------------------------------------------------------
-template <int NR, int NC, int NP>
-__global__ void __launch_bounds__(NT, 2)
+template <int NR, int NC, int NP, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __restrict__ plans,
-                     double* __restrict__ lnprob, const PartsOut parts) {
+                     const int* __restrict__ order, double* __restrict__ lnprob, const PartsOut parts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NWARP = NT / 32;
   constexpr int KRED = 2 * NC + NP;
   double* sF = reinterpret_cast<double*>(smem_raw);                  // [NWARP*SEG] per-warp composite chunks
   double* sRed = sF + NWARP * SEG;                                          // [NWARP*KRED]
@@ -548,7 +611,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   __shared__ WalkerPlan sPlan;
 
   const int tid = threadIdx.x;
-  const long long w = blockIdx.x;
+  const long long w = order ? order[blockIdx.x] : blockIdx.x;       // launch order: grouped by grid cell
   {
     // cooperative copy of the plan (16-byte chunks)
     const int4* src = reinterpret_cast<const int4*>(plans + w);
@@ -597,17 +660,18 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   int has_nan = 0;
 
   // ------------------------------------------------------------------ phase A: stream the rows
-  // Each warp owns a contiguous 128-pixel chunk of every 1024-pixel tile and the observed pixels
+  // Each warp owns every NWARP-th contiguous 128-pixel chunk of the region and the observed pixels
   // whose upper bracket falls into it, so the rebinning needs no block-wide barrier and the warps
   // drift apart: while some wait on their row loads others compute.
-  const int n_tiles = T.n_tiles;
-  for (int tile = 0; tile < n_tiles; ++tile) {
-    const int cbase = tile * TILE + warp * CHUNK;                     // first pixel of this warp's chunk
+  const int n_chunks = T.n_tiles * CHUNKS_PER_TILE;
+  for (int c = warp; c < n_chunks; c += NWARP) {
+    const int tile = c / CHUNKS_PER_TILE;
+    const int cbase = c * CHUNK;                                      // first pixel of this warp's chunk
     const unsigned cmask = T.tile_cmask[tile];
     const unsigned pmask = T.tile_pmask[tile];
-    const int ds_raw = T.chunk_data_start[tile * NWARP + warp];
+    const int ds_raw = T.chunk_data_start[c];
     const int d0 = ds_raw & 0x7fffffff;
-    const int d1 = T.chunk_data_start[tile * NWARP + warp + 1] & 0x7fffffff;
+    const int d1 = T.chunk_data_start[c + 1] & 0x7fffffff;
     const bool stage = d1 > d0;
     const bool need_prev = ds_raw < 0;                                // warp-uniform
     if (need_prev && lane == 0) {
@@ -670,7 +734,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
       if (stage) { seg[seg_slot(h * 64 + 2 * lane + 1)] = comp.x; seg[seg_slot(h * 64 + 2 * lane + 2)] = comp.y; }
     }
 #pragma unroll
-    for (int r = 0; r < NR; ++r) { p0[r] += TILE; p1[r] += TILE; }
+    for (int r = 0; r < NR; ++r) { p0[r] += NWARP * CHUNK; p1[r] += NWARP * CHUNK; }
     if (stage) {
       __syncwarp();
       for (int i = d0 + lane; i < d1; i += 32) {
@@ -715,11 +779,11 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   for (int f = 0; f < NC; ++f) { red[2 * f] = accC[f][0]; red[2 * f + 1] = accC[f][1]; }
 #pragma unroll
   for (int f = 0; f < NP; ++f) red[2 * NC + f] = accP[f];
-  block_sum<KRED>(red, sRed);
+  block_sum<KRED, NWARP>(red, sRed);
 
   // ------------------------------------------------------------------ phase B: spectral chi-square
   const int n = T.n_data;
-  block_sum<3>(mom, sRed);
+  block_sum<3, NWARP>(mom, sRed);
   {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -738,7 +802,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     __syncthreads();
   }
   double chi_un = CUDART_NAN, med = CUDART_NAN;
-  if (!has_nan) med = block_median_chi(sM, n, sSel, reinterpret_cast<unsigned long long*>(sF), kmin, kmax, T, mom, &chi_un, sRed);  // mft6.py:1173
+  if (!has_nan) med = block_median_chi<NT>(sM, n, sSel, reinterpret_cast<unsigned long long*>(sF), kmin, kmax, T, mom, &chi_un, sRed);  // mft6.py:1173
   const double scale = T.data_median / med;
   if (parts.model) for (int i = tid; i < n; i += NT) parts.model[w * n + i] = sM[i] * scale;
 
@@ -890,9 +954,12 @@ struct ms_handle {
   std::vector<void*> allocs;
   int corners = 4;               // rows per star
   int variant = 0;               // 0: (NC,NP)=(2,6), 1: (4,12)
+  int threads = 256;             // CTA width of the streaming kernel
   size_t smem_bytes = 0;
   // per-call buffers
   WalkerPlan* plans = nullptr; long long plans_cap = 0;
+  int* order = nullptr; unsigned* cell_hist = nullptr; bool use_order = false;
+  size_t grid_bytes = 0, l2_bytes = 0;
   double* d_theta = nullptr; double* d_lnp = nullptr; long long io_cap = 0;
   double* h_theta = nullptr; double* h_lnp = nullptr; long long pin_cap = 0;
   long long launches = 0;
@@ -933,9 +1000,9 @@ int upload(ms_handle* h, const Tp* host, size_t n, const Tp** dev) {
   return MS_OK;
 }
 
-template <int NR, int NC, int NP>
-int launch_stream_variant(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts) {
-  auto kern = lnprob_stream_kernel<NR, NC, NP>;
+template <int NR, int NC, int NP, int NT>
+int launch_stream_threads(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts) {
+  auto kern = lnprob_stream_kernel<NR, NC, NP, NT>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing) {
@@ -946,16 +1013,22 @@ int launch_stream_variant(ms_handle* h, long long nw, double* d_lnp, const Parts
     h->ev_used += 2; h->timed_walkers += nw;
     CK(cudaEventRecord(e0, h->stream));
   }
-  kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, d_lnp, parts);
+  kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, h->use_order ? h->order : nullptr, d_lnp, parts);
   CK(cudaGetLastError());
   if (h->timing) CK(cudaEventRecord(e1, h->stream));
   h->launches += 1;
   return MS_OK;
 }
 
-size_t stream_smem_bytes(int n_data, int nc, int np) {
+template <int NR, int NC, int NP>
+int launch_stream_variant(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts) {
+  if (h->threads == 512) return launch_stream_threads<NR, NC, NP, 512>(h, nw, d_lnp, parts);
+  return launch_stream_threads<NR, NC, NP, 256>(h, nw, d_lnp, parts);
+}
+
+size_t stream_smem_bytes(int n_data, int nc, int np, int nwarp) {
   const int kred = 2 * nc + np;
-  size_t b = (size_t)NWARP * SEG * 8 + (size_t)NWARP * (kred > 4 ? kred : 4) * 8 + sizeof(SelectScratch);
+  size_t b = (size_t)nwarp * SEG * 8 + (size_t)nwarp * (kred > 4 ? kred : 4) * 8 + sizeof(SelectScratch);
   b += (size_t)n_data * 8;
   return (b + 15) & ~(size_t)15;
 }
@@ -963,9 +1036,11 @@ size_t stream_smem_bytes(int n_data, int nc, int np) {
 int ensure_plans(ms_handle* h, long long nw) {
   if (nw <= h->plans_cap) return MS_OK;
   if (h->plans) cudaFree(h->plans);
-  h->plans = nullptr; h->plans_cap = 0;
+  if (h->order) cudaFree(h->order);
+  h->plans = nullptr; h->order = nullptr; h->plans_cap = 0;
   long long cap = nw + nw / 4 + 64;
   CK(cudaMalloc((void**)&h->plans, (size_t)cap * sizeof(WalkerPlan)));
+  CK(cudaMalloc((void**)&h->order, (size_t)cap * sizeof(int)));
   h->plans_cap = cap;
   return MS_OK;
 }
@@ -975,9 +1050,21 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   int rc = ensure_plans(h, nw);
   if (rc) return rc;
   const int pb = 128;
-  walker_prep_kernel<<<(unsigned)((nw + pb - 1) / pb), pb, 0, h->stream>>>(h->T, d_theta, nw, h->plans);
+  const unsigned pg = (unsigned)((nw + pb - 1) / pb);
+  // Grouping walkers by grid cell pays when the grid does not fit L2 (rows are then fetched from HBM once
+  // per group instead of once per walker).  With an L2-resident grid it only concentrates the concurrent
+  // CTAs on the same L2 slices (measured: C4 -4 %, C1 -8 %), so the natural order is kept there.
+  h->use_order = nw >= 1024 && h->T.n_cells > 1 && h->grid_bytes > h->l2_bytes;
+  if (h->use_order) CK(cudaMemsetAsync(h->cell_hist, 0, (size_t)h->T.n_cells * sizeof(unsigned), h->stream));
+  walker_prep_kernel<<<pg, pb, 0, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr);
   CK(cudaGetLastError());
   h->launches += 1;
+  if (h->use_order) {
+    cell_scan_kernel<<<1, 1024, 0, h->stream>>>(h->cell_hist, h->T.n_cells);
+    cell_scatter_kernel<<<pg, pb, 0, h->stream>>>(h->plans, nw, h->cell_hist, h->order);
+    CK(cudaGetLastError());
+    h->launches += 2;
+  }
   if (h->corners == 4) {
     if (h->variant == 0) return launch_stream_variant<4, 2, 6>(h, nw, d_lnp, parts);
     return launch_stream_variant<4, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts);
@@ -1032,6 +1119,8 @@ int ms_destroy(ms_handle* h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   if (h->plans) cudaFree(h->plans);
+  if (h->order) cudaFree(h->order);
+  if (h->cell_hist) cudaFree(h->cell_hist);
   if (h->d_theta) cudaFree(h->d_theta);
   if (h->d_lnp) cudaFree(h->d_lnp);
   if (h->h_theta) cudaFreeHost(h->h_theta);
@@ -1080,6 +1169,12 @@ int ms_create(const ms_config* cfg, ms_handle** out) {
   for (int k = 0; k < 9; ++k) T.basis[k] = cfg->poly_basis[k];
   for (int k = 0; k < MS_MAX_NDIM; ++k) { T.prior_mu[k] = cfg->prior_mu[k]; T.prior_sig[k] = cfg->prior_sig[k]; }
   T.n_iso = cfg->n_iso; T.n_dm = cfg->n_dm; T.n_dust_samples = cfg->n_dust_samples;
+  {
+    const long long per_star = (long long)cfg->n_teff * cfg->n_logg;
+    const long long cells = per_star * per_star + 1;           // + 1: walkers that never reach the grid
+    T.n_cells = (cells <= (1 << 20)) ? (int)cells : 1;
+    CKH(cudaMalloc((void**)&h->cell_hist, (size_t)T.n_cells * sizeof(unsigned)));
+  }
   h->corners = (cfg->n_feh > 1) ? 8 : 4;
   h->variant = (cfg->n_contrast <= 2 && cfg->n_phot <= 6) ? 0 : 1;
 
@@ -1094,6 +1189,10 @@ int ms_create(const ms_config* cfg, ms_handle** out) {
     CKH(cudaMemcpy2D(p, (size_t)T.stride * 8, cfg->grid + cfg->reg_lo, (size_t)cfg->row_len * 8,
                      (size_t)cfg->n_reg * 8, (size_t)n_rows, cudaMemcpyHostToDevice));
     T.grid = static_cast<const double*>(p);
+    h->grid_bytes = (size_t)n_rows * T.stride * 8;
+    int l2 = 0;
+    CKH(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
+    h->l2_bytes = (size_t)l2;
   }
   CKC(upload(h, cfg->teff_nodes, cfg->n_teff, &T.teff_nodes));
   CKC(upload(h, cfg->logg_nodes, cfg->n_logg, &T.logg_nodes));
@@ -1129,7 +1228,7 @@ int ms_create(const ms_config* cfg, ms_handle** out) {
     CKC(upload(h, tab1.data(), tab1.size(), &T.rebin_tab1));
     CKC(upload(h, fx.data(), fx.size(), &T.data_fx));
     // observed pixels owned by each 128-pixel chunk (rebin_hi is ascending)
-    const int n_chunks = cfg->n_tiles * NWARP;
+    const int n_chunks = cfg->n_tiles * CHUNKS_PER_TILE;
     std::vector<int> cds((size_t)n_chunks + 1);
     int i = 0;
     for (int c = 0; c <= n_chunks; ++c) {
@@ -1178,9 +1277,15 @@ int ms_create(const ms_config* cfg, ms_handle** out) {
 
   // ---- shared memory budget of the streaming kernel
   const int nc = h->variant == 0 ? 2 : MS_MAX_CONTRAST, np = h->variant == 0 ? 6 : MS_MAX_PHOT;
-  h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np);
   int max_optin = 0;
   CKH(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  h->threads = 256;
+  h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, 8);
+  if (2 * (h->smem_bytes + 1024) > (size_t)max_optin + 1024) {
+    // two 256-thread CTAs no longer fit an SM: run one 512-thread CTA instead (same warps in flight)
+    h->threads = 512;
+    h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, 16);
+  }
   if (h->smem_bytes + 2048 > (size_t)max_optin) {
     h->err = "ms_create: n_data too large for the shared-memory resident model spectrum"; return fail(MS_ERR_UNSUPPORTED);
   }
