@@ -223,6 +223,8 @@ def run_product_arm(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'            # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():

@@ -180,21 +180,28 @@ int ms_broaden_rows(int device, double* rows, int64_t n_rows, int64_t row_len, i
                     int64_t win_len, const double* taps, int32_t n_taps);
 
 /*
- * Stretch-move half step on device-resident ensembles (emcee RedBlueMove/StretchMove, a = 2;
- * the sampler the reference drives at mft6.py:1491-1510).
- *   ms_stretch_propose: for s < n_s:  z = ((a-1)u+1)^2/a, j = partner in [0,n_c),
- *       q[s] = c[j] - (c[j] - x[s])*z, logfac[s] = (ndim-1) ln z.
- *   ms_stretch_accept:  accept where ln u' < logfac + lnp_q - lnp_x; x, lnp_x updated in place,
- *       accepted[s] incremented.
- * Random numbers are counter based: stream (seed, iteration, split, gid0 + s), so a sharded
- * ensemble draws the same numbers as an unsharded one.  All pointers are device pointers.
+ * Stretch-move half step on a device-resident ensemble (emcee RedBlueMove/StretchMove, a = 2; the
+ * sampler the reference drives at mft6.py:1491-1510).  `state` [nw][ndim+1] holds positions and
+ * log-probabilities; s_idx [n_s] are the state rows this caller updates (its shard of the active
+ * half), c_idx [n_c] the complementary half.  All pointers are device pointers.
+ *   ms_split_keys:      keys[i] (63-bit) whose argsort is the iteration's random red/blue split.
+ *   ms_stretch_propose: z = ((a-1)u+1)^2/a, j ~ randint(n_c),
+ *                       q[s] = c_j - (c_j - x_s) z, logfac[s] = (ndim-1) ln z.
+ *   ms_stretch_accept:  accept where ln u' < logfac + lnp_q - lnp_x; packed[s] = new position |
+ *                       new log-prob | accepted (0/1)   [n_s][ndim+2] -- the all-gather payload.
+ *   ms_stretch_scatter: state[idx[k]] = packed[k][0..ndim]; naccepted[idx[k]] += packed[k][ndim+1].
+ * Random numbers are counter based: stream (seed, iteration, split, gid0 + s), so a sharded ensemble
+ * draws the same numbers as an unsharded one.
  */
-int ms_stretch_propose(ms_handle* h, const double* x, int64_t n_s, const double* c, int64_t n_c,
-                       int32_t ndim, double a, uint64_t seed, uint64_t iteration, int32_t split,
+int ms_split_keys(ms_handle* h, uint64_t seed, uint64_t iteration, int64_t n, int64_t* keys);
+int ms_stretch_propose(ms_handle* h, const double* state, const int64_t* s_idx, int64_t n_s, const int64_t* c_idx,
+                       int64_t n_c, int32_t ndim, double a, uint64_t seed, uint64_t iteration, int32_t split,
                        int64_t gid0, double* q, double* logfac);
-int ms_stretch_accept(ms_handle* h, double* x, double* lnp_x, const double* q, const double* lnp_q,
-                      const double* logfac, int64_t n_s, int32_t ndim, uint64_t seed,
-                      uint64_t iteration, int32_t split, int64_t gid0, int32_t* accepted);
+int ms_stretch_accept(ms_handle* h, const double* state, const int64_t* s_idx, const double* q, const double* lnp_q,
+                      const double* logfac, int64_t n_s, int32_t ndim, uint64_t seed, uint64_t iteration,
+                      int32_t split, int64_t gid0, double* packed);
+int ms_stretch_scatter(ms_handle* h, double* state, int32_t* naccepted, const int64_t* idx, const double* packed,
+                       int64_t n, int32_t ndim);
 
 /*
  * Enqueue on the caller's stream (a cudaStream_t, taken literally: 0 is the CUDA legacy default

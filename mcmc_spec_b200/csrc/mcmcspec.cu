@@ -15,7 +15,8 @@
 //
 // Setup-time operator: broaden_rows_kernel = spec_interpolator's window broadening
 // (mft6.py:124-130, :366-383) as a shared-memory banded stencil.
-// Sampler support: stretch_propose_kernel / stretch_accept_kernel (emcee stretch move, a = 2).
+// Sampler support: split_keys / stretch_propose / stretch_accept / stretch_scatter kernels (emcee
+// stretch move, a = 2) working in place on the replicated ensemble state.
 
 #include "mcmcspec.h"
 
@@ -908,10 +909,23 @@ __host__ __device__ __forceinline__ double counter_uniform(unsigned long long se
   return ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-__global__ void stretch_propose_kernel(const double* __restrict__ x, long long n_s, const double* __restrict__ c,
-                                       long long n_c, int ndim, double a, unsigned long long seed,
-                                       unsigned long long iteration, int split, long long gid0,
-                                       double* __restrict__ q, double* __restrict__ logfac) {
+// 63-bit keys whose argsort is the iteration's random split of the ensemble (emcee shuffles the
+// red/blue assignment every iteration); identical on every rank and in the numpy mirror.
+__global__ void split_keys_kernel(unsigned long long seed, unsigned long long iteration, long long n,
+                                  long long* __restrict__ keys) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long k = mix64(seed ^ 0x5851F42D4C957F2Dull);
+  k = mix64(k ^ iteration);
+  keys[i] = (long long)(mix64(k ^ mix64((unsigned long long)i)) >> 1);
+}
+
+// state [nw][ndim+1] = positions | log-prob (replicated on every rank).  s_idx [n_s] are the state
+// rows this rank updates (its shard of the active half), c_idx [n_c] the complementary half.
+__global__ void stretch_propose_kernel(const double* __restrict__ state, const long long* __restrict__ s_idx,
+                                       long long n_s, const long long* __restrict__ c_idx, long long n_c, int ndim,
+                                       double a, unsigned long long seed, unsigned long long iteration, int split,
+                                       long long gid0, double* __restrict__ q, double* __restrict__ logfac) {
   const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (s >= n_s) return;
   const unsigned long long gid = (unsigned long long)(gid0 + s);
@@ -920,26 +934,40 @@ __global__ void stretch_propose_kernel(const double* __restrict__ x, long long n
   const double z = root * root / a;
   long long j = (long long)(counter_uniform(seed, iteration, split, 1, gid) * (double)n_c);
   if (j >= n_c) j = n_c - 1;
-  for (int k = 0; k < ndim; ++k) {
-    const double cj = c[j * ndim + k];
-    q[s * ndim + k] = cj - (cj - x[s * ndim + k]) * z;
-  }
+  const double* x = state + s_idx[s] * (ndim + 1);
+  const double* c = state + c_idx[j] * (ndim + 1);
+  for (int k = 0; k < ndim; ++k) q[s * ndim + k] = c[k] - (c[k] - x[k]) * z;
   logfac[s] = (double)(ndim - 1) * log(z);
 }
 
-__global__ void stretch_accept_kernel(double* __restrict__ x, double* __restrict__ lnp_x, const double* __restrict__ q,
-                                      const double* __restrict__ lnp_q, const double* __restrict__ logfac,
-                                      long long n_s, int ndim, unsigned long long seed, unsigned long long iteration,
-                                      int split, long long gid0, int* __restrict__ accepted) {
+// packed [n_s][ndim+2] = new position | new log-prob | accepted (0/1): what the all-gather carries.
+__global__ void stretch_accept_kernel(const double* __restrict__ state, const long long* __restrict__ s_idx,
+                                      const double* __restrict__ q, const double* __restrict__ lnp_q,
+                                      const double* __restrict__ logfac, long long n_s, int ndim,
+                                      unsigned long long seed, unsigned long long iteration, int split, long long gid0,
+                                      double* __restrict__ packed) {
   const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (s >= n_s) return;
+  const double* x = state + s_idx[s] * (ndim + 1);
   const double u = counter_uniform(seed, iteration, split, 2, (unsigned long long)(gid0 + s));
-  const double lnpdiff = logfac[s] + lnp_q[s] - lnp_x[s];
-  if (log(u) < lnpdiff) {                                            // -inf proposals never pass; NaN never passes
-    for (int k = 0; k < ndim; ++k) x[s * ndim + k] = q[s * ndim + k];
-    lnp_x[s] = lnp_q[s];
-    if (accepted) accepted[s] += 1;
-  }
+  const double lnpdiff = logfac[s] + lnp_q[s] - x[ndim];
+  const bool acc = log(u) < lnpdiff;                                 // -inf proposals never pass; NaN never passes
+  double* out = packed + s * (ndim + 2);
+  for (int k = 0; k < ndim; ++k) out[k] = acc ? q[s * ndim + k] : x[k];
+  out[ndim] = acc ? lnp_q[s] : x[ndim];
+  out[ndim + 1] = acc ? 1.0 : 0.0;
+}
+
+// state[idx[k]] = packed[k][0..ndim], naccepted[idx[k]] += packed[k][ndim+1]  (idx: the whole active half)
+__global__ void stretch_scatter_kernel(double* __restrict__ state, int* __restrict__ naccepted,
+                                       const long long* __restrict__ idx, const double* __restrict__ packed,
+                                       long long n, int ndim) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double* dst = state + idx[k] * (ndim + 1);
+  const double* src = packed + k * (ndim + 2);
+  for (int d = 0; d <= ndim; ++d) dst[d] = src[d];
+  if (naccepted && src[ndim + 1] != 0.0) naccepted[idx[k]] += 1;
 }
 
 }  // namespace
@@ -1435,29 +1463,57 @@ int ms_broaden_rows(int device, double* rows, int64_t n_rows, int64_t row_len, i
   return rc;
 }
 
-int ms_stretch_propose(ms_handle* h, const double* x, int64_t n_s, const double* c, int64_t n_c, int32_t ndim,
-                       double a, uint64_t seed, uint64_t iteration, int32_t split, int64_t gid0, double* q,
-                       double* logfac) {
+int ms_split_keys(ms_handle* h, uint64_t seed, uint64_t iteration, int64_t n, int64_t* keys) {
   if (!h) return MS_ERR_INVALID;
-  if (n_s < 0 || n_c < 1 || ndim < 1 || !x || !c || !q || !logfac) { set_err(h, "ms_stretch_propose: invalid argument"); return MS_ERR_INVALID; }
-  if (n_s == 0) return MS_OK;
+  if (n < 0 || (n > 0 && !keys)) { set_err(h, "ms_split_keys: invalid argument"); return MS_ERR_INVALID; }
+  if (n == 0) return MS_OK;
   CK(cudaSetDevice(h->device));
-  stretch_propose_kernel<<<(unsigned)((n_s + 127) / 128), 128, 0, h->stream>>>(x, n_s, c, n_c, ndim, a, seed, iteration,
-                                                                             split, gid0, q, logfac);
+  split_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(seed, iteration, n, (long long*)keys);
   CK(cudaGetLastError());
   h->launches += 1;
   return MS_OK;
 }
 
-int ms_stretch_accept(ms_handle* h, double* x, double* lnp_x, const double* q, const double* lnp_q,
-                      const double* logfac, int64_t n_s, int32_t ndim, uint64_t seed, uint64_t iteration,
-                      int32_t split, int64_t gid0, int32_t* accepted) {
+int ms_stretch_propose(ms_handle* h, const double* state, const int64_t* s_idx, int64_t n_s, const int64_t* c_idx,
+                       int64_t n_c, int32_t ndim, double a, uint64_t seed, uint64_t iteration, int32_t split,
+                       int64_t gid0, double* q, double* logfac) {
   if (!h) return MS_ERR_INVALID;
-  if (n_s < 0 || ndim < 1 || !x || !lnp_x || !q || !lnp_q || !logfac) { set_err(h, "ms_stretch_accept: invalid argument"); return MS_ERR_INVALID; }
+  if (n_s < 0 || n_c < 1 || ndim < 1 || !state || !s_idx || !c_idx || !q || !logfac) {
+    set_err(h, "ms_stretch_propose: invalid argument"); return MS_ERR_INVALID;
+  }
   if (n_s == 0) return MS_OK;
   CK(cudaSetDevice(h->device));
-  stretch_accept_kernel<<<(unsigned)((n_s + 127) / 128), 128, 0, h->stream>>>(x, lnp_x, q, lnp_q, logfac, n_s, ndim, seed,
-                                                                            iteration, split, gid0, accepted);
+  stretch_propose_kernel<<<(unsigned)((n_s + 127) / 128), 128, 0, h->stream>>>(
+      state, (const long long*)s_idx, n_s, (const long long*)c_idx, n_c, ndim, a, seed, iteration, split, gid0, q, logfac);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MS_OK;
+}
+
+int ms_stretch_accept(ms_handle* h, const double* state, const int64_t* s_idx, const double* q, const double* lnp_q,
+                      const double* logfac, int64_t n_s, int32_t ndim, uint64_t seed, uint64_t iteration,
+                      int32_t split, int64_t gid0, double* packed) {
+  if (!h) return MS_ERR_INVALID;
+  if (n_s < 0 || ndim < 1 || !state || !s_idx || !q || !lnp_q || !logfac || !packed) {
+    set_err(h, "ms_stretch_accept: invalid argument"); return MS_ERR_INVALID;
+  }
+  if (n_s == 0) return MS_OK;
+  CK(cudaSetDevice(h->device));
+  stretch_accept_kernel<<<(unsigned)((n_s + 127) / 128), 128, 0, h->stream>>>(
+      state, (const long long*)s_idx, q, lnp_q, logfac, n_s, ndim, seed, iteration, split, gid0, packed);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MS_OK;
+}
+
+int ms_stretch_scatter(ms_handle* h, double* state, int32_t* naccepted, const int64_t* idx, const double* packed,
+                       int64_t n, int32_t ndim) {
+  if (!h) return MS_ERR_INVALID;
+  if (n < 0 || ndim < 1 || !state || !idx || !packed) { set_err(h, "ms_stretch_scatter: invalid argument"); return MS_ERR_INVALID; }
+  if (n == 0) return MS_OK;
+  CK(cudaSetDevice(h->device));
+  stretch_scatter_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(state, naccepted, (const long long*)idx,
+                                                                            packed, n, ndim);
   CK(cudaGetLastError());
   h->launches += 1;
   return MS_OK;

@@ -12,13 +12,14 @@ installed here, so its published algorithm is restated:
 
 B200 layout: the full ensemble state (positions + log-probs, nw x (ndim+1) doubles, 3.7 MB at
 65 536 walkers) is replicated on every rank; each rank proposes / evaluates / accepts its
-contiguous shard of the active half and the shards are exchanged by ONE all-gather per half step
-(NCCL over NVLink; the only collective of the path).  Random numbers come from a counter-based
-generator keyed by (seed, iteration, split, slot in the half), so the chain does not depend on the
-number of ranks.  Positions never leave the device.
+contiguous shard of the active half, in place, and the shards are exchanged by ONE all-gather per
+half step (NCCL over NVLink; the only collective of the path).  Random numbers -- the split
+permutation, z, the partner and the acceptance draw -- come from a counter-based generator keyed
+by (seed, iteration, split, slot in the half), so the chain does not depend on the number of
+ranks.  Positions never leave the device; a half step is five kernel launches plus the collective.
 
-``backend`` supplies propose / lnprob / accept on torch tensors.  The product backend is
-``CudaBackend`` (the C ABI kernels); tests plug in a numpy backend to exercise the sharding logic
+``backend`` supplies the five primitives on torch tensors.  The product backend is
+``CudaBackend`` (the C ABI kernels); tests plug in a numpy mirror to exercise the sharding logic
 under gloo on CPUs.
 """
 from __future__ import annotations
@@ -29,8 +30,8 @@ import torch.distributed as dist
 
 
 class CudaBackend:
-    """propose / lnprob / accept through libmcmcspec.so, enqueued on torch's current CUDA stream
-    (so they order with the index/gather plumbing and the NCCL all-gather around them)."""
+    """The sampler primitives through libmcmcspec.so, enqueued on torch's current CUDA stream (so
+    they order with the NCCL all-gather around them)."""
 
     def __init__(self, engine):
         self.engine = engine
@@ -40,33 +41,41 @@ class CudaBackend:
     def _bind(self):
         self.engine.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def lnprob(self, theta):
+    def lnprob(self, theta, out=None):
         self._bind()
         theta = theta.contiguous()
-        out = torch.empty(theta.shape[0], dtype=torch.float64, device=theta.device)
+        if out is None:
+            out = torch.empty(theta.shape[0], dtype=torch.float64, device=theta.device)
         self.engine.lnprob_device(theta.data_ptr(), theta.shape[0], out.data_ptr())
         return out
 
-    def propose(self, x, c, a, seed, iteration, split, gid0):
+    def split_keys(self, seed, iteration, n):
         self._bind()
-        x = x.contiguous(); c = c.contiguous()
-        q = torch.empty_like(x)
-        logfac = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
-        self.engine.stretch_propose(x.data_ptr(), x.shape[0], c.data_ptr(), c.shape[0], a, seed, iteration, split,
-                                    gid0, q.data_ptr(), logfac.data_ptr())
-        return q, logfac
+        keys = torch.empty(n, dtype=torch.int64, device=self.device)
+        self.engine.split_keys(seed, iteration, n, keys.data_ptr())
+        return keys
 
-    def accept(self, x, lnp_x, q, lnp_q, logfac, seed, iteration, split, gid0, accepted):
+    def propose(self, state, s_idx, c_idx, a, seed, iteration, split, gid0, q, logfac):
         self._bind()
-        self.engine.stretch_accept(x.data_ptr(), lnp_x.data_ptr(), q.data_ptr(), lnp_q.data_ptr(), logfac.data_ptr(),
-                                   x.shape[0], seed, iteration, split, gid0, accepted.data_ptr())
+        self.engine.stretch_propose(state.data_ptr(), s_idx.data_ptr(), s_idx.shape[0], c_idx.data_ptr(), c_idx.shape[0],
+                                    a, seed, iteration, split, gid0, q.data_ptr(), logfac.data_ptr())
+
+    def accept(self, state, s_idx, q, lnp_q, logfac, seed, iteration, split, gid0, packed):
+        self._bind()
+        self.engine.stretch_accept(state.data_ptr(), s_idx.data_ptr(), q.data_ptr(), lnp_q.data_ptr(), logfac.data_ptr(),
+                                   s_idx.shape[0], seed, iteration, split, gid0, packed.data_ptr())
+
+    def scatter(self, state, naccepted, idx, packed):
+        self._bind()
+        self.engine.stretch_scatter(state.data_ptr(), naccepted.data_ptr(), idx.data_ptr(), packed.data_ptr(),
+                                    idx.shape[0])
 
 
 class EnsembleSampler:
     """Stretch-move ensemble sampler; attribute names follow emcee where they exist.
 
     nwalkers must be even and nwalkers/2 divisible by the world size.  ``group`` is the
-    torch.distributed process group (None = single process, no collective).
+    torch.distributed process group (None = default group; single process = no collective).
     """
 
     def __init__(self, nwalkers, ndim, backend, a=2.0, seed=0, group=None, rank=0, world_size=1,
@@ -83,8 +92,14 @@ class EnsembleSampler:
         self.iteration = 0
         self.state = None                       # [nw, ndim+1]: positions | log-prob (replicated)
         self.naccepted = torch.zeros(nwalkers, dtype=torch.int32, device=self.device)
-        self._perm_gen = torch.Generator(device='cpu')
-        self.chain = []                         # optional thinned copies of (coords, log_prob)
+        self.chain = []                         # optional thinned copies of the state
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self._q = torch.empty((self.shard, ndim), **f64)
+        self._logfac = torch.empty(self.shard, **f64)
+        self._lnp_q = torch.empty(self.shard, **f64)
+        self._packed = torch.empty((self.shard, ndim + 2), **f64)
+        self._full = self._packed if world_size == 1 else torch.empty((self.half, ndim + 2), **f64)
+        self._fixed = [torch.arange(0, nwalkers, 2, device=self.device), torch.arange(1, nwalkers, 2, device=self.device)]
 
     # ------------------------------------------------------------------ state
     def initialize(self, p0):
@@ -96,7 +111,11 @@ class EnsembleSampler:
         mine = p0[self.rank * per:(self.rank + 1) * per].contiguous()
         lnp = self.backend.lnprob(mine)
         packed = torch.cat([mine, lnp[:, None]], dim=1).contiguous()
-        self.state = self._all_gather(packed)
+        if self.world_size == 1:
+            self.state = packed
+        else:
+            self.state = torch.empty((self.nwalkers, self.ndim + 1), dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(self.state, packed, group=self.group)
         self.iteration = 0
         self.naccepted.zero_()
 
@@ -112,46 +131,29 @@ class EnsembleSampler:
     def acceptance_fraction(self):
         return (self.naccepted.to(torch.float64) / max(self.iteration, 1)).cpu().numpy()
 
-    # ------------------------------------------------------------------ plumbing
-    def _all_gather(self, packed):
-        if self.world_size == 1:
-            return packed
-        out = torch.empty((self.world_size * packed.shape[0], packed.shape[1]), dtype=packed.dtype, device=packed.device)
-        dist.all_gather_into_tensor(out, packed, group=self.group)
-        return out
-
-    def _split_indices(self):
-        nw = self.nwalkers
-        if self.randomize_split:
-            self._perm_gen.manual_seed((self.seed * 1000003 + self.iteration) & 0x7fffffffffffffff)
-            perm = torch.randperm(nw, generator=self._perm_gen)
-        else:
-            perm = torch.arange(nw)
-        inds = torch.arange(nw) % 2
-        halves = [perm[inds == 0], perm[inds == 1]]
-        return [h.to(self.device, non_blocking=True) for h in halves]
-
     # ------------------------------------------------------------------ one iteration
+    def _halves(self):
+        if not self.randomize_split:
+            return self._fixed
+        keys = self.backend.split_keys(self.seed, self.iteration, self.nwalkers)
+        perm = torch.argsort(keys, stable=True)
+        return [perm[0::2].contiguous(), perm[1::2].contiguous()]       # inds = arange(nw) % 2, shuffled
+
     def step(self):
         """One ensemble iteration = two half steps; every walker gets one proposal."""
-        halves = self._split_indices()
-        nd = self.ndim
+        halves = self._halves()
+        be = self.backend
         for split in (0, 1):
             s_idx, c_idx = halves[split], halves[1 - split]
             lo = self.rank * self.shard
             mine = s_idx[lo:lo + self.shard]
-            cur = self.state.index_select(0, mine)                      # [shard, ndim+1]
-            x = cur[:, :nd].contiguous()
-            lnp_x = cur[:, nd].contiguous()
-            comp = self.state.index_select(0, c_idx)[:, :nd].contiguous()
-            q, logfac = self.backend.propose(x, comp, self.a, self.seed, self.iteration, split, lo)
-            lnp_q = self.backend.lnprob(q)
-            acc = torch.zeros(self.shard, dtype=torch.int32, device=self.device)
-            self.backend.accept(x, lnp_x, q, lnp_q, logfac, self.seed, self.iteration, split, lo, acc)
-            packed = torch.cat([x, lnp_x[:, None], acc.to(torch.float64)[:, None]], dim=1).contiguous()
-            full = self._all_gather(packed)                              # [half, ndim+2] in slot order
-            self.state.index_copy_(0, s_idx, full[:, :nd + 1])
-            self.naccepted.index_add_(0, s_idx, full[:, nd + 1].to(torch.int32))
+            be.propose(self.state, mine, c_idx, self.a, self.seed, self.iteration, split, lo, self._q, self._logfac)
+            be.lnprob(self._q, out=self._lnp_q)
+            be.accept(self.state, mine, self._q, self._lnp_q, self._logfac, self.seed, self.iteration, split, lo,
+                      self._packed)
+            if self.world_size > 1:
+                dist.all_gather_into_tensor(self._full, self._packed, group=self.group)   # slot order
+            be.scatter(self.state, self.naccepted, s_idx, self._full)
         self.iteration += 1
 
     def run_mcmc(self, nsteps, thin=0):

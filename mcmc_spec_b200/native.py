@@ -22,7 +22,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmcmcspe
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_destroy', 'ms_last_error', 'ms_stream',
            'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_broaden_rows',
-           'ms_stretch_propose', 'ms_stretch_accept', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_timing',
+           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_timing',
            'ms_kernel_time']
 
 _dp = C.POINTER(C.c_double)
@@ -84,10 +84,12 @@ def load_library(path=None):
     lib.ms_lnprob_parts.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
     lib.ms_model_spectrum.argtypes = [vp, vp, C.c_int64, vp, C.c_int]
     lib.ms_broaden_rows.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32]
-    lib.ms_stretch_propose.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_double, C.c_uint64,
+    lib.ms_split_keys.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int64, vp]
+    lib.ms_stretch_propose.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_double, C.c_uint64,
                                        C.c_uint64, C.c_int32, C.c_int64, vp, vp]
     lib.ms_stretch_accept.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64,
                                       C.c_int32, C.c_int64, vp]
+    lib.ms_stretch_scatter.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_int32]
     lib.ms_launch_count.argtypes = [vp]
     lib.ms_launch_count.restype = C.c_int64
     lib.ms_set_stream.argtypes = [vp, vp]
@@ -254,15 +256,22 @@ class Engine:
     def lnprob_device(self, theta_ptr, nw, lnprob_ptr):
         self._check(self.lib.ms_lnprob(self._h, theta_ptr, nw, lnprob_ptr, MS_DEVICE), 'ms_lnprob')
 
-    def stretch_propose(self, x_ptr, n_s, c_ptr, n_c, a, seed, iteration, split, gid0, q_ptr, logfac_ptr):
-        self._check(self.lib.ms_stretch_propose(self._h, x_ptr, n_s, c_ptr, n_c, self.ndim, a, seed, iteration,
-                                                split, gid0, q_ptr, logfac_ptr), 'ms_stretch_propose')
+    def split_keys(self, seed, iteration, n, keys_ptr):
+        self._check(self.lib.ms_split_keys(self._h, seed, iteration, n, keys_ptr), 'ms_split_keys')
 
-    def stretch_accept(self, x_ptr, lnp_x_ptr, q_ptr, lnp_q_ptr, logfac_ptr, n_s, seed, iteration, split, gid0,
-                       accepted_ptr):
-        self._check(self.lib.ms_stretch_accept(self._h, x_ptr, lnp_x_ptr, q_ptr, lnp_q_ptr, logfac_ptr, n_s,
-                                               self.ndim, seed, iteration, split, gid0, accepted_ptr),
-                    'ms_stretch_accept')
+    def stretch_propose(self, state_ptr, s_idx_ptr, n_s, c_idx_ptr, n_c, a, seed, iteration, split, gid0, q_ptr,
+                        logfac_ptr):
+        self._check(self.lib.ms_stretch_propose(self._h, state_ptr, s_idx_ptr, n_s, c_idx_ptr, n_c, self.ndim, a, seed,
+                                                iteration, split, gid0, q_ptr, logfac_ptr), 'ms_stretch_propose')
+
+    def stretch_accept(self, state_ptr, s_idx_ptr, q_ptr, lnp_q_ptr, logfac_ptr, n_s, seed, iteration, split, gid0,
+                       packed_ptr):
+        self._check(self.lib.ms_stretch_accept(self._h, state_ptr, s_idx_ptr, q_ptr, lnp_q_ptr, logfac_ptr, n_s,
+                                               self.ndim, seed, iteration, split, gid0, packed_ptr), 'ms_stretch_accept')
+
+    def stretch_scatter(self, state_ptr, naccepted_ptr, idx_ptr, packed_ptr, n):
+        self._check(self.lib.ms_stretch_scatter(self._h, state_ptr, naccepted_ptr, idx_ptr, packed_ptr, n, self.ndim),
+                    'ms_stretch_scatter')
 
 
 def broaden_rows(rows, win_lo, win_len, taps, device=0, lib=None):

@@ -27,6 +27,12 @@ def counter_uniform(seed, iteration, split, purpose, gid):
     return ((r >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
 
 
+def split_keys(seed, iteration, n):
+    k = mix64(np.uint64(seed) ^ np.uint64(0x5851F42D4C957F2D))
+    k = mix64(k ^ np.uint64(iteration))
+    return (mix64(k ^ mix64(np.arange(n, dtype=np.uint64))) >> np.uint64(1)).astype(np.int64)
+
+
 def propose(x, c, a, seed, iteration, split, gid0):
     n_s, ndim = x.shape
     gid = gid0 + np.arange(n_s)
@@ -53,16 +59,31 @@ class NumpyBackend:
         self.fn, self.ndim = lnprob_fn, ndim
         self.device = torch.device('cpu')
 
-    def lnprob(self, theta):
-        return torch.from_numpy(np.asarray(self.fn(theta.numpy()), dtype=np.float64))
+    def lnprob(self, theta, out=None):
+        res = torch.from_numpy(np.asarray(self.fn(theta.numpy().copy()), dtype=np.float64))
+        if out is None:
+            return res
+        out.copy_(res)
+        return out
 
-    def propose(self, x, c, a, seed, iteration, split, gid0):
-        q, lf = propose(x.numpy(), c.numpy(), a, seed, iteration, split, gid0)
-        return torch.from_numpy(q), torch.from_numpy(lf)
+    def split_keys(self, seed, iteration, n):
+        return torch.from_numpy(split_keys(seed, iteration, n))
 
-    def accept(self, x, lnp_x, q, lnp_q, logfac, seed, iteration, split, gid0, accepted):
-        m = accept_mask(lnp_x.numpy(), lnp_q.numpy(), logfac.numpy(), seed, iteration, split, gid0)
-        mt = torch.from_numpy(m)
-        x[mt] = q[mt]
-        lnp_x[mt] = lnp_q[mt]
-        accepted += mt.to(torch.int32)
+    def propose(self, state, s_idx, c_idx, a, seed, iteration, split, gid0, q, logfac):
+        nd = self.ndim
+        st = state.numpy()
+        qq, lf = propose(st[s_idx.numpy(), :nd], st[c_idx.numpy(), :nd], a, seed, iteration, split, gid0)
+        q.copy_(torch.from_numpy(qq)); logfac.copy_(torch.from_numpy(lf))
+
+    def accept(self, state, s_idx, q, lnp_q, logfac, seed, iteration, split, gid0, packed):
+        nd = self.ndim
+        cur = state.numpy()[s_idx.numpy()]
+        m = accept_mask(cur[:, nd], lnp_q.numpy(), logfac.numpy(), seed, iteration, split, gid0)
+        out = np.concatenate([cur, np.zeros((cur.shape[0], 1))], axis=1)
+        out[m, :nd] = q.numpy()[m]; out[m, nd] = lnp_q.numpy()[m]; out[m, nd + 1] = 1.0
+        packed.copy_(torch.from_numpy(out))
+
+    def scatter(self, state, naccepted, idx, packed):
+        nd = self.ndim
+        state[idx] = packed[:, :nd + 1]
+        naccepted[idx] += packed[:, nd + 1].to(torch.int32)

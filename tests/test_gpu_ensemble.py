@@ -13,32 +13,45 @@ def small_lp(small_problem, native_lib):
     lp.close()
 
 
-def test_propose_and_accept_kernels_match_numpy(small_lp):
+def test_sampler_kernels_match_numpy(small_lp):
     import torch
     import stretch_reference as sr
     from mcmc_spec_b200.ensemble import CudaBackend
     be = CudaBackend(small_lp.engine)
     rng = np.random.default_rng(0)
-    x = rng.normal(size=(777, 6)); c = rng.normal(size=(500, 6))
-    q, lf = be.propose(torch.tensor(x, device='cuda'), torch.tensor(c, device='cuda'), 2.0, 42, 17, 1, 1000)
-    q_ref, lf_ref = sr.propose(x, c, 2.0, 42, 17, 1, 1000)
+    nw, nd = 1400, 6
+    state = rng.normal(size=(nw, nd + 1))
+    keys = be.split_keys(42, 17, nw).cpu().numpy()
+    assert np.array_equal(keys, sr.split_keys(42, 17, nw)) and keys.min() >= 0 and len(set(keys)) == nw
+    perm = np.argsort(keys, kind='stable')
+    s_idx, c_idx = perm[0::2][100:600].copy(), perm[1::2].copy()
+    dev = lambda a: torch.tensor(a, device='cuda')                         # noqa: E731
+    st = dev(state)
+    q = torch.empty((500, nd), dtype=torch.float64, device='cuda'); lf = torch.empty(500, dtype=torch.float64, device='cuda')
+    be.propose(st, dev(s_idx), dev(c_idx), 2.0, 42, 17, 1, 100, q, lf)
+    q_ref, lf_ref = sr.propose(state[s_idx, :nd], state[c_idx, :nd], 2.0, 42, 17, 1, 100)
     assert np.allclose(q.cpu().numpy(), q_ref, rtol=1e-15, atol=1e-15)       # same partner, same z
     assert np.allclose(lf.cpu().numpy(), lf_ref, rtol=1e-13, atol=1e-15)
-    lnx = rng.normal(size=777); lnq = rng.normal(size=777); lnq[::9] = -np.inf
-    xt, lt = torch.tensor(x, device='cuda'), torch.tensor(lnx, device='cuda')
-    acc = torch.zeros(777, dtype=torch.int32, device='cuda')
-    be.accept(xt, lt, q, torch.tensor(lnq, device='cuda'), lf, 42, 17, 1, 1000, acc)
-    mask = sr.accept_mask(lnx, lnq, lf_ref, 42, 17, 1, 1000)
-    assert np.array_equal(acc.cpu().numpy().astype(bool), mask) and not mask[::9].any()
-    assert np.array_equal(xt.cpu().numpy()[mask], q.cpu().numpy()[mask]) and np.array_equal(xt.cpu().numpy()[~mask], x[~mask])
-    assert np.array_equal(lt.cpu().numpy(), np.where(mask, lnq, lnx))
+    lnq = rng.normal(size=500); lnq[::9] = -np.inf
+    packed = torch.empty((500, nd + 2), dtype=torch.float64, device='cuda')
+    be.accept(st, dev(s_idx), q, dev(lnq), lf, 42, 17, 1, 100, packed)
+    mask = sr.accept_mask(state[s_idx, nd], lnq, lf_ref, 42, 17, 1, 100)
+    pk = packed.cpu().numpy()
+    assert np.array_equal(pk[:, nd + 1].astype(bool), mask) and not mask[::9].any() and mask.any()
+    assert np.array_equal(pk[mask, :nd], q.cpu().numpy()[mask]) and np.array_equal(pk[~mask, :nd + 1], state[s_idx][~mask])
+    assert np.array_equal(pk[:, nd], np.where(mask, lnq, state[s_idx, nd]))
+    nacc = torch.zeros(nw, dtype=torch.int32, device='cuda')
+    be.scatter(st, nacc, dev(s_idx), packed)
+    want = state.copy(); want[s_idx] = pk[:, :nd + 1]
+    assert np.array_equal(st.cpu().numpy(), want)
+    assert np.array_equal(nacc.cpu().numpy()[s_idx], mask.astype(np.int32)) and nacc.sum().item() == mask.sum()
 
 
 def test_fixed_seed_chain_matches_oracle_chain(small_problem, small_oracle, small_lp):
     """Same z / partner / u streams fed to the CUDA path and to the oracle: the chains coincide."""
     import stretch_reference as sr
     from mcmc_spec_b200.ensemble import CudaBackend, EnsembleSampler
-    nw, nsteps = 32, 25
+    nw, nsteps = 32, 120
     t = small_problem.truth
     p0 = t * (1 + 0.01 * np.random.default_rng(1).standard_normal((nw, 6)))
     p0[:, 2] = np.abs(p0[:, 2])
@@ -51,3 +64,11 @@ def test_fixed_seed_chain_matches_oracle_chain(small_problem, small_oracle, smal
     assert np.allclose(g[:, :6], c[:, :6], rtol=1e-12)
     assert np.allclose(g[:, 6], c[:, 6], rtol=1e-9)
     assert gpu.naccepted.sum().item() > 0
+    # ... and so do the posterior summaries the reference reports (median, 16th/84th percentiles)
+    gs, cs = [], []
+    for _ in range(30):
+        gpu.step(); cpu.step()
+        gs.append(gpu.coords.cpu().numpy().copy()); cs.append(cpu.coords.numpy().copy())
+    gq = np.percentile(np.concatenate(gs), [16, 50, 84], axis=0)
+    cq = np.percentile(np.concatenate(cs), [16, 50, 84], axis=0)
+    assert np.allclose(gq, cq, rtol=1e-10)
