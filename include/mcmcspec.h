@@ -143,6 +143,13 @@ int32_t ms_abi_version(void);
 
 /* Upload all tables; replaces the per-call hand-over of `args` (mft6.py:1491). */
 int ms_create(const ms_config* cfg, ms_handle** out);
+/*
+ * Same, but the model grid is not uploaded again: the new handle reads the device rows of
+ * `grid_owner` (same device, same grid shape and consumed region; cfg->grid is ignored).  For
+ * several fits of one grid to different observed spectra (independent ensembles).  The owner must
+ * be destroyed after every handle that shares its grid.
+ */
+int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handle** out);
 int ms_destroy(ms_handle* h);
 /* Message of the last failing call on this handle (or of the last failing ms_create if h==NULL). */
 const char* ms_last_error(const ms_handle* h);

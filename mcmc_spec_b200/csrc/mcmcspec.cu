@@ -988,6 +988,7 @@ struct ms_handle {
   WalkerPlan* plans = nullptr; long long plans_cap = 0;
   int* order = nullptr; unsigned* cell_hist = nullptr; bool use_order = false;
   size_t grid_bytes = 0, l2_bytes = 0;
+  long long grid_sig[4] = {0, 0, 0, 0};   // rows, row length, region start, region length
   double* d_theta = nullptr; double* d_lnp = nullptr; long long io_cap = 0;
   double* h_theta = nullptr; double* h_lnp = nullptr; long long pin_cap = 0;
   long long launches = 0;
@@ -1158,7 +1159,9 @@ int ms_destroy(ms_handle* h) {
   return MS_OK;
 }
 
-int ms_create(const ms_config* cfg, ms_handle** out) {
+int ms_create(const ms_config* cfg, ms_handle** out) { return ms_create_shared(cfg, nullptr, out); }
+
+int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handle** out) {
   if (!cfg || !out) { set_err(nullptr, "ms_create: null argument"); return MS_ERR_INVALID; }
   *out = nullptr;
   if (cfg->abi_version != MS_ABI_VERSION) { set_err(nullptr, "ms_create: ABI version mismatch"); return MS_ERR_INVALID; }
@@ -1209,7 +1212,16 @@ int ms_create(const ms_config* cfg, ms_handle** out) {
   // ---- grid: region cut of every row, padded with zeros to whole tiles
   const long long n_rows = (long long)cfg->n_feh * cfg->n_logg * cfg->n_teff;
   T.stride = (long long)cfg->n_tiles * TILE;
-  {
+  h->grid_sig[0] = n_rows; h->grid_sig[1] = cfg->row_len; h->grid_sig[2] = cfg->reg_lo; h->grid_sig[3] = cfg->n_reg;
+  if (grid_owner) {
+    // several fits of the same model grid (config C3: independent ensembles on different observed
+    // spectra): reuse the owner's device copy of the rows.  The owner must outlive this handle.
+    if (grid_owner->device != h->device || std::memcmp(grid_owner->grid_sig, h->grid_sig, sizeof(h->grid_sig)) != 0) {
+      h->err = "ms_create_shared: grid shape / consumed region / device differ from the owner's"; return fail(MS_ERR_INVALID);
+    }
+    T.grid = grid_owner->T.grid;
+    h->grid_bytes = grid_owner->grid_bytes; h->l2_bytes = grid_owner->l2_bytes;
+  } else {
     void* p = nullptr;
     CKH(cudaMalloc(&p, (size_t)n_rows * T.stride * 8));
     h->allocs.push_back(p);

@@ -20,7 +20,7 @@ MS_W_PRIOR_BOUNDS, MS_W_OFF_ISOCHRONE, MS_W_OFF_GRID, MS_W_NONFINITE = 1, 2, 4, 
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmcmcspec.so')
 
-EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_destroy', 'ms_last_error', 'ms_stream',
+EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
            'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_broaden_rows',
            'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_timing',
            'ms_kernel_time']
@@ -74,6 +74,7 @@ def load_library(path=None):
     lib.ms_config_size.restype = C.c_int64
     lib.ms_abi_version.restype = C.c_int32
     lib.ms_create.argtypes = [C.POINTER(MsConfig), C.POINTER(vp)]
+    lib.ms_create_shared.argtypes = [C.POINTER(MsConfig), vp, C.POINTER(vp)]
     lib.ms_destroy.argtypes = [vp]
     lib.ms_last_error.argtypes = [vp]
     lib.ms_last_error.restype = C.c_char_p
@@ -167,14 +168,20 @@ def make_config(t: DeviceTables, device=0):
 class Engine:
     """Owns one ``ms_handle`` (one GPU, one stream).  Thin, typed wrapper over the C ABI."""
 
-    def __init__(self, tables: DeviceTables, device=0, lib=None):
+    def __init__(self, tables: DeviceTables, device=0, lib=None, grid_owner=None):
+        """``grid_owner``: another Engine on the same device whose device copy of the model grid is
+        reused (ms_create_shared); it is kept alive for as long as this engine lives."""
         self.lib = lib or load_library()
+        self._grid_owner = grid_owner
         self.tables = tables
         self.ndim = 2 * tables.nspec + 2
         self.n_data, self.n_contrast, self.n_phot, self.nspec = tables.n_data, tables.contrast.n, tables.phot.n, tables.nspec
         cfg, keep = make_config(tables, device)
         h = C.c_void_p()
-        rc = self.lib.ms_create(C.byref(cfg), C.byref(h))
+        if grid_owner is None:
+            rc = self.lib.ms_create(C.byref(cfg), C.byref(h))
+        else:
+            rc = self.lib.ms_create_shared(C.byref(cfg), grid_owner._h, C.byref(h))
         del keep
         if rc != 0:
             raise NativeError(f"ms_create failed ({rc}): {self.lib.ms_last_error(None).decode()}")

@@ -27,10 +27,14 @@ from .tables import build_tables
 
 
 class LogPosterior:
-    def __init__(self, problem: Problem, device=0):
+    def __init__(self, problem: Problem, device=0, share_grid_with=None):
+        """``share_grid_with``: another LogPosterior on the same device, built on the same model grid
+        and consumed region, whose device copy of the grid is reused (independent ensembles fitting
+        different observed spectra, BASELINE config C3)."""
         self.problem = problem
         self.tables = build_tables(problem)
-        self.engine = native.Engine(self.tables, device=device)
+        owner = None if share_grid_with is None else share_grid_with.engine
+        self.engine = native.Engine(self.tables, device=device, grid_owner=owner)
         self.ndim = self.engine.ndim
 
     def __call__(self, p0):

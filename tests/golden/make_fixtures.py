@@ -90,5 +90,37 @@ def main():
               'size', os.path.getsize(tmp) // 1024, 'KiB')
 
 
+def make_c3():
+    """Config C3: the 12 Data/synth_spec_* spectra as independent fits of one grid.  Stores only what
+    differs between the fits (the prepared spectra) + oracle values; passbands etc. come from the C1 fixture."""
+    import dataclasses
+    import glob
+    fp = paramfile.parse_param_file(os.path.join(REF, 'param_koi2298.txt'))
+    files = sorted(glob.glob(os.path.join(REF, 'Data', 'synth_spec_*.txt')))
+    assert len(files) == 12
+    base = problem_from_fixture(os.path.join(HERE, 'c1_synth_3850_3425.npz'))
+    rng = np.random.default_rng(17)
+    names, lens, wl, fl, er, thetas, lnps = [], [], [], [], [], [], []
+    for f in files:
+        w, d, e = paramfile.load_observed_spectrum(f, fp.spmin, fp.spmax, fp.mask)
+        prob = dataclasses.replace(base, data=[w, d], err=e)
+        t1, t2 = [float(x) for x in os.path.basename(f)[:-4].split('_')[2:4]]
+        centre = np.array([t1, min(t2, 5400.0), 0.1, 0.5, 0.6, fp.plx])
+        theta = centre * (1 + 0.015 * rng.standard_normal((6, 6)))
+        theta[:, 2] = np.abs(theta[:, 2])
+        lnp = to_oracle(prob).lnprob_batch(theta)
+        names.append(os.path.basename(f)); lens.append(w.size); wl.append(w); fl.append(d); er.append(e)
+        thetas.append(theta); lnps.append(lnp)
+        print(names[-1], 'N =', w.size, 'finite', int(np.isfinite(lnp).sum()))
+    out = os.path.join(HERE, 'c3_synth_all.npz')
+    np.savez_compressed(out, names=np.array(names), lens=np.array(lens), wl=np.concatenate(wl), flux=np.concatenate(fl),
+                        err=np.concatenate(er), theta=np.array(thetas), oracle_lnprob=np.array(lnps))
+    print('c3 size', os.path.getsize(out) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'c3':
+        make_c3()
+    else:
+        main()
+        make_c3()

@@ -24,3 +24,19 @@ def test_oracle_matches_golden(name, n_data):
     assert np.array_equal(np.isfinite(got), np.isfinite(want))
     f = np.isfinite(want)
     assert np.allclose(got[f], want[f], rtol=1e-12, atol=0)
+
+
+def test_oracle_matches_c3_golden():
+    """Config C3 fixture (12 synth spectra, one grid): spot-check two of the fits on the CPU."""
+    import dataclasses
+    fx = np.load(os.path.join(GOLD, 'c3_synth_all.npz'))
+    assert len(fx['names']) == 12 and set(fx['lens']) == {2183}
+    base = golden_io.problem_from_fixture(os.path.join(GOLD, 'c1_synth_3850_3425.npz'))
+    off = np.concatenate([[0], np.cumsum(fx['lens'])])
+    for k in (0, 7):
+        sl = slice(off[k], off[k + 1])
+        prob = dataclasses.replace(base, data=[fx['wl'][sl], fx['flux'][sl]], err=fx['err'][sl])
+        got = to_oracle(prob).lnprob_batch(fx['theta'][k][:3])
+        want = fx['oracle_lnprob'][k][:3]
+        f = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), f) and np.allclose(got[f], want[f], rtol=1e-12, atol=0)

@@ -137,6 +137,35 @@ def test_golden_fixtures_full_size(name, native_lib):
     lp.close()
 
 
+def test_c3_twelve_independent_fits_share_one_grid(native_lib):
+    """BASELINE config C3: the 12 Data/synth_spec_* spectra fitted as independent problems on one GPU with
+    one device copy of the grid; each must equal both the committed oracle values and the stand-alone
+    (own-grid) engine bit for bit."""
+    import dataclasses
+    import golden_io
+    from mcmc_spec_b200.posterior import LogPosterior
+    fx = np.load(os.path.join(GOLD, 'c3_synth_all.npz'))
+    base = golden_io.problem_from_fixture(os.path.join(GOLD, 'c1_synth_3850_3425.npz'))
+    off = np.concatenate([[0], np.cumsum(fx['lens'])])
+    owner, engines = None, []
+    for k in range(12):
+        sl = slice(off[k], off[k + 1])
+        prob = dataclasses.replace(base, data=[fx['wl'][sl], fx['flux'][sl]], err=fx['err'][sl])
+        lp = LogPosterior(prob, share_grid_with=owner)
+        owner = owner or lp
+        engines.append(lp)
+    for k, lp in enumerate(engines):
+        got = lp(fx['theta'][k])
+        _compare(got, fx['oracle_lnprob'][k])
+        if k in (3, 11):                                  # stand-alone engine with its own grid upload
+            sl = slice(off[k], off[k + 1])
+            solo = LogPosterior(dataclasses.replace(base, data=[fx['wl'][sl], fx['flux'][sl]], err=fx['err'][sl]))
+            assert np.array_equal(solo(fx['theta'][k]), got)
+            solo.close()
+    for lp in reversed(engines):                          # the grid owner goes last
+        lp.close()
+
+
 def test_c4_shape_against_oracle_and_properties(native_lib):
     """BASELINE config C4 (8192 observed pixels, 32 768-pixel rows): oracle on a sample + size-independent
     properties on the full batch."""
