@@ -134,7 +134,7 @@ typedef struct ms_config {
   int32_t ext_flag;             /* `a` / `ext` keyword */
   int32_t dist_fit;
   int32_t rad_prior;
-  int32_t reserved;
+  int32_t flavour;              /* 0: mft6.py; 1: mft6_nospec.py (no spectral term, parallax <= 1/100) */
 } ms_config;
 
 /* sizeof(ms_config) as compiled, so a binding can verify its mirror of the struct. */
@@ -173,6 +173,24 @@ int ms_lnprob(ms_handle* h, const double* theta, int64_t nw, double* lnprob, int
 int ms_lnprob_parts(ms_handle* h, const double* theta, int64_t nw, double* lnprob, double* chi2_spec,
                     double* contrast, double* phot, double* lnprior, double* logg, int32_t* status,
                     int where);
+
+/*
+ * Optimiser stage (optimize_fit / fit_spec, mft6.py:856-1137, :1686-1765).
+ * ms_set_optimizer_data: the observed spectra after fit_spec's one-off norm_spec against each
+ *   starting guess (mft6.py:889), flux_sets [n_sets][n_data], host pointer.
+ * ms_optimizer_chisq: fit_spec's `test_cs` for nw proposals (mft6.py:995-1046) -- 3 x the mean spectral
+ *   chi-square of the median-scaled model against flux_sets[set_index[w]], times (n_contrast + n_phot),
+ *   plus the contrast and photometric chi-squares, plus opt_prior terms in chi-square units: Av against
+ *   the Bayestar moments at the proposal's distance (av_prior[w] replaces theta's Av in that term when
+ *   av_prior != NULL, as the initial evaluation at mft6.py:927 needs), the parallax prior when
+ *   dist_fit, and the radius prior with sigmas rad_sigma [nw][nspec] (mft6.py:1038).  The model is
+ *   scaled to the median of its flux set (mft6.py:1011) unless ref_median [nw] is given (the initial
+ *   evaluation scales to the median of the *un-renormalised* spectrum, mft6.py:888).  The box of
+ *   mft6.py:984 is the caller's business.  +inf where the forward model is undefined.  Host pointers.
+ */
+int ms_set_optimizer_data(ms_handle* h, const double* flux_sets, int32_t n_sets);
+int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_index, const double* rad_sigma,
+                       const double* av_prior, const double* ref_median, int64_t nw, double* chisq);
 
 /* Median-scaled model on the observed pixels, out [nw][n_data] (init_cspec after mft6.py:1173). */
 int ms_model_spectrum(ms_handle* h, const double* theta, int64_t nw, double* out, int where);

@@ -76,6 +76,7 @@ struct DevTables {
   const int* chunk_data_start;  // [n_tiles*CHUNKS_PER_TILE + 1] first observed pixel owned by each 128-pixel chunk;
                                 // bit 31 set when that pixel's lower bracket is the last pixel of the previous chunk
   double dext_max;              // max |(ext_hi - ext_lo) ln 2|
+  const double* opt_median;     // [n_sets] np.median of each renormalised optimiser flux set
   const unsigned* tile_cmask; const unsigned* tile_pmask;
   double basis[9];
   double data_median;
@@ -103,6 +104,22 @@ struct __align__(16) WalkerPlan {
   double logg[MAX_STAR];
   int status;                          // MS_W_* bits
   int cell;                            // grid-cell key of the two stars (walkers of one cell read the same rows)
+};
+
+// What is evaluated for a walker.
+//   MODE_POSTERIOR : logposterior of mft6.py (:1459-1470)
+//   MODE_NOSPEC    : logposterior of mft6_nospec.py -- the spectral term is dropped (its :1163-1196) and
+//                    the parallax box is [1/3000, 1/100]
+//   MODE_OPTIMIZER : fit_spec's test chi-square (mft6.py:995-1046): 3 x mean spectral chi-square against
+//                    a fixed, once-renormalised observed spectrum, chi-square priors, no prior box
+enum { MODE_POSTERIOR = 0, MODE_NOSPEC = 1, MODE_OPTIMIZER = 2 };
+
+struct OptIn {
+  const double* flux_sets;      // [n_sets][n_data] observed flux after fit_spec's one-off norm_spec (mft6.py:889)
+  const int* set_index;         // [nw] which set a walker is compared with
+  const double* rad_sigma;      // [nw][nspec] sigma of the radius prior (mft6.py:1038: si[2])
+  const double* av_prior;       // [nw] Av entering the prior term, or NULL (= theta's Av)
+  const double* ref_median;     // [nw] median the model is scaled to, or NULL (= median of the walker's set)
 };
 
 struct PartsOut {
@@ -227,7 +244,8 @@ __device__ void dust_prior_moments(const DevTables& T, double plx, double* mu, d
 // walker_prep_kernel
 // ------------------------------------------------------------------------------------------
 __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__ theta, long long nw,
-                                   WalkerPlan* __restrict__ plans_out, unsigned* __restrict__ cell_hist) {
+                                   WalkerPlan* __restrict__ plans_out, unsigned* __restrict__ cell_hist,
+                                   const int mode, const OptIn opt) {
   const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (w >= nw) return;
   // every exit stores the plan and counts the walker in its cell bin
@@ -254,17 +272,23 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   const double* rad = p + ns + 1;          // rad[0] = R1, rad[1] = R2/R1
   const double plx = p[2 * ns + 1];
 
-  // ---- logprior bounds (mft6.py:1227-1230 / :1287-1290)
-  bool out = false;
-  for (int s = 0; s < ns; ++s) out = out || (temps[s] > T.tmax) || (temps[s] < T.tmin);
-  if (T.dist_fit) {
-    for (int s = 0; s < ns; ++s) out = out || (rad[s] < 0.05);
-    out = out || (rad[0] > 1.5) || (plx < 1.0 / 3000.0) || (plx > 1.0 / 4.0);
-  } else {
-    out = out || (rad[1] < 0.05) || (rad[0] < 0.05);
+  // ---- logprior bounds (mft6.py:1227-1230 / :1287-1290).  fit_spec keeps its proposals inside its own
+  // box on the host (mft6.py:984-985, :1069-1103), so the optimiser mode has none here.
+  if (mode != MODE_OPTIMIZER) {
+    bool out = false;
+    for (int s = 0; s < ns; ++s) out = out || (temps[s] > T.tmax) || (temps[s] < T.tmin);
+    if (T.dist_fit) {
+      const double plx_hi = (mode == MODE_NOSPEC) ? 1.0 / 100.0 : 1.0 / 4.0;     // mft6_nospec.py:1228
+      for (int s = 0; s < ns; ++s) out = out || (rad[s] < 0.05);
+      out = out || (rad[0] > 1.5) || (plx < 1.0 / 3000.0) || (plx > plx_hi);
+    } else {
+      out = out || (rad[1] < 0.05) || (rad[0] < 0.05);
+    }
+    if (T.ext_flag && av < 0.0) out = true;
+    if (out) { plan.status = MS_W_PRIOR_BOUNDS; store(plan); return; }
+  } else if (!(plx > 0.0)) {
+    plan.status = MS_W_PRIOR_BOUNDS; store(plan); return;
   }
-  if (T.ext_flag && av < 0.0) out = true;
-  if (out) { plan.status = MS_W_PRIOR_BOUNDS; store(plan); return; }
 
   // ---- isochrone: log g and luminosity per star (mft6.py:66-98)
   double lum[MAX_STAR];
@@ -279,28 +303,45 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
 
   // ---- prior terms, summed in the reference's order
   double lp = 0.0;
-  if (T.ext_flag) {
+  if (mode == MODE_OPTIMIZER) {
+    // opt_prior terms in chi-square units (mft6.py:833-854, :1030-1046)
     double mu, sig;
     dust_prior_moments(T, plx, &mu, &sig);
     if (sig == 0.0) sig = 0.05;
-    const double z = (av - mu) / sig;
-    lp += -0.5 * (z * z);
-  }
-  const int nprior = T.dist_fit ? ndim : ndim - 2;       // ps has 2*ns+2 or 2*ns entries
-  for (int k = 0; k < nprior; ++k) {
-    if (T.prior_mu[k] != 0.0) {
-      const double z = (p[k] - T.prior_mu[k]) / T.prior_sig[k];
+    const double avp = opt.av_prior ? opt.av_prior[w] : av;
+    { const double z = (avp - mu) / sig; lp += z * z; }
+    if (T.dist_fit) { const double z = (plx - T.prior_mu[ndim - 1]) / T.prior_sig[ndim - 1]; lp += z * z; }
+    if (T.rad_prior) {
+      const double r1m = stefan_boltzmann_radius(lum[0], temps[0]);
+      const double r2m = stefan_boltzmann_radius(lum[1], temps[1]);
+      const double z0 = (rad[0] - r1m) / opt.rad_sigma[w * ns];
+      const double z1 = (rad[1] - r2m / r1m) / opt.rad_sigma[w * ns + 1];
+      lp += z0 * z0 + z1 * z1;
+    }
+  } else {
+    if (T.ext_flag) {
+      double mu, sig;
+      dust_prior_moments(T, plx, &mu, &sig);
+      if (sig == 0.0) sig = 0.05;
+      const double z = (av - mu) / sig;
       lp += -0.5 * (z * z);
     }
-  }
-  if (T.rad_prior) {
-    const double r1m = stefan_boltzmann_radius(lum[0], temps[0]);
-    const double r2m = stefan_boltzmann_radius(lum[1], temps[1]);
-    const double m0 = r1m, m1 = r2m / r1m;
-    const double z0 = (rad[0] - m0) / (0.02 * m0);
-    const double z1 = (rad[1] - m1) / (0.02 * m1);
-    lp += -0.5 * (z0 * z0);
-    lp += -0.5 * (z1 * z1);
+    const int nprior = T.dist_fit ? ndim : ndim - 2;       // ps has 2*ns+2 or 2*ns entries
+    for (int k = 0; k < nprior; ++k) {
+      if (T.prior_mu[k] != 0.0) {
+        const double z = (p[k] - T.prior_mu[k]) / T.prior_sig[k];
+        lp += -0.5 * (z * z);
+      }
+    }
+    if (T.rad_prior) {
+      const double r1m = stefan_boltzmann_radius(lum[0], temps[0]);
+      const double r2m = stefan_boltzmann_radius(lum[1], temps[1]);
+      const double m0 = r1m, m1 = r2m / r1m;
+      const double z0 = (rad[0] - m0) / (0.02 * m0);
+      const double z1 = (rad[1] - m1) / (0.02 * m1);
+      lp += -0.5 * (z0 * z0);
+      lp += -0.5 * (z1 * z1);
+    }
   }
   if (!isfinite(lp)) { plan.status = MS_W_NONFINITE; store(plan); return; }   // mft6.py:1465
 
@@ -342,7 +383,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
     }
     plan.cell = (T.n_cells > 1) ? min(key, T.n_cells - 2) : 0;
   }
-  plan.av = (T.ext_flag && av > 0.0) ? av : 0.0;          // mft6.py:1161
+  plan.av = ((T.ext_flag || mode == MODE_OPTIMIZER) && av > 0.0) ? av : 0.0;   // mft6.py:1161, :1001
   plan.lp = lp;
   store(plan);
 }
@@ -462,7 +503,7 @@ __device__ __forceinline__ void histogram_pass(const double* sM, int n, SelectSc
 // Median of sM[0..n) given the block-wide key range [kmin, kmax]; also returns, through *chi_out,
 // sum_i (m_i - d_i/p0(x_i))^2 * inv_e2_i with p0 = a[0] q0 + a[1] q1 + a[2] q2.
 // `list` is scratch for LIST_CAP keys.
-template <int NT>
+template <int NT, bool DO_CHI>
 __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, unsigned long long* list,
                                    unsigned long long kmin, unsigned long long kmax, const DevTables& T,
                                    const double (&a)[3], double* chi_out, double* red_scratch) {
@@ -488,19 +529,23 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
     const int i0 = r * NT + tid, i1 = i0 + NT;
     const bool v0 = i0 < n, v1 = (r + 1 < rounds) && (i1 < n);
     double m0 = 0.0, m1 = 0.0, x0 = 0.0, x1 = 0.0, d0 = 0.0, d1 = 0.0, w0 = 0.0, w1 = 0.0;
-    if (v0) { m0 = sM[i0]; x0 = T.data_x[i0]; d0 = T.data_flux[i0]; w0 = T.data_inv_e2[i0]; }
-    if (v1) { m1 = sM[i1]; x1 = T.data_x[i1]; d1 = T.data_flux[i1]; w1 = T.data_inv_e2[i1]; }
+    if (v0) { m0 = sM[i0]; if constexpr (DO_CHI) { x0 = T.data_x[i0]; d0 = T.data_flux[i0]; w0 = T.data_inv_e2[i0]; } }
+    if (v1) { m1 = sM[i1]; if constexpr (DO_CHI) { x1 = T.data_x[i1]; d1 = T.data_flux[i1]; w1 = T.data_inv_e2[i1]; } }
     unsigned dg0 = 0xffffffffu, dg1 = 0xffffffffu;
     if (v0) {
-      const double pfit = a0b0 + a[1] * fma(b4, x0, b3) + a[2] * fma(fma(b8, x0, b7), x0, b6);
-      const double res = m0 - d0 * fast_rcp(pfit);                    // mft6.py:196, :120 (unscaled)
-      chi = fma(res * res, w0, chi);
+      if constexpr (DO_CHI) {
+        const double pfit = a0b0 + a[1] * fma(b4, x0, b3) + a[2] * fma(fma(b8, x0, b7), x0, b6);
+        const double res = m0 - d0 * fast_rcp(pfit);                  // mft6.py:196, :120 (unscaled)
+        chi = fma(res * res, w0, chi);
+      }
       if (!flat) dg0 = (unsigned)((ordered_key(m0) >> shift0) & ((1u << width0) - 1u));
     }
     if (v1) {
-      const double pfit = a0b0 + a[1] * fma(b4, x1, b3) + a[2] * fma(fma(b8, x1, b7), x1, b6);
-      const double res = m1 - d1 * fast_rcp(pfit);
-      chi = fma(res * res, w1, chi);
+      if constexpr (DO_CHI) {
+        const double pfit = a0b0 + a[1] * fma(b4, x1, b3) + a[2] * fma(fma(b8, x1, b7), x1, b6);
+        const double res = m1 - d1 * fast_rcp(pfit);
+        chi = fma(res * res, w1, chi);
+      }
       if (!flat) dg1 = (unsigned)((ordered_key(m1) >> shift0) & ((1u << width0) - 1u));
     }
     if (!flat) {
@@ -595,13 +640,15 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
 // ------------------------------------------------------------------------------------------
 // lnprob_stream_kernel: one CTA per walker.
 //   NR  grid rows per star (4: Teff x log g, 8: with [Fe/H]);  NC / NP compile-time filter caps;
+//   MODE what is evaluated (MODE_POSTERIOR / MODE_NOSPEC / MODE_OPTIMIZER);
 //   NT  threads per CTA: 256 (two or three CTAs per SM) or 512 when the observed spectrum is so long
 //       that only one CTA fits an SM.
 // ------------------------------------------------------------------------------------------
-template <int NR, int NC, int NP, int NT>
+template <int NR, int NC, int NP, int NT, int MODE>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __restrict__ plans,
-                     const int* __restrict__ order, double* __restrict__ lnprob, const PartsOut parts) {
+                     const int* __restrict__ order, double* __restrict__ lnprob, const PartsOut parts,
+                     const OptIn opt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NWARP = NT / 32;
   constexpr int KRED = 2 * NC + NP;
@@ -623,7 +670,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   const int status = sPlan.status;
   if (status != 0) {                                                  // mft6.py:1465-1466
     if (tid == 0) {
-      lnprob[w] = -CUDART_INF;
+      lnprob[w] = (MODE == MODE_OPTIMIZER) ? CUDART_INF : -CUDART_INF;
       if (parts.status) parts.status[w] = status;
       if (parts.lnprior) parts.lnprior[w] = -CUDART_INF;
       if (parts.chi2_spec) parts.chi2_spec[w] = CUDART_NAN;
@@ -673,8 +720,8 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     const int ds_raw = T.chunk_data_start[c];
     const int d0 = ds_raw & 0x7fffffff;
     const int d1 = T.chunk_data_start[c + 1] & 0x7fffffff;
-    const bool stage = d1 > d0;
-    const bool need_prev = ds_raw < 0;                                // warp-uniform
+    const bool stage = (MODE != MODE_NOSPEC) && d1 > d0;
+    const bool need_prev = stage && ds_raw < 0;                        // warp-uniform
     if (need_prev && lane == 0) {
       // composite of the pixel just before the chunk (owned by another warp / the previous tile)
       double f = 0.0;
@@ -742,7 +789,6 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         const int hl = T.rebin_hi[i] - cbase;                         // 0 .. CHUNK-1
         const double2 tab0 = __ldg(T.rebin_tab0 + i);
         const double2 tab1 = __ldg(T.rebin_tab1 + i);
-        const double2 fx = __ldg(T.data_fx + i);
         const double flo = seg[seg_slot(hl)];
         const double fhi = seg[seg_slot(hl + 1)];
         // extinct() on the model grid, then interp1d onto the observed pixel (mft6.py:1162, :1169)
@@ -759,12 +805,15 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         const double ylo = flo * elo, yhi = fhi * ehi;
         const double m = ylo + (yhi - ylo) * tab0.x;
         sM[i] = m;
-        // norm_spec's normal equations in the orthonormal basis, on the unscaled model (mft6.py:194-195)
-        const double frac = fx.x * fast_rcp(m);
-        const double x = fx.y;
-        const double q1 = fma(T.basis[4], x, T.basis[3]);
-        const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
-        mom[0] = fma(T.basis[0], frac, mom[0]); mom[1] = fma(q1, frac, mom[1]); mom[2] = fma(q2, frac, mom[2]);
+        if constexpr (MODE == MODE_POSTERIOR) {
+          // norm_spec's normal equations in the orthonormal basis, on the unscaled model (mft6.py:194-195)
+          const double2 fx = __ldg(T.data_fx + i);
+          const double frac = fx.x * fast_rcp(m);
+          const double x = fx.y;
+          const double q1 = fma(T.basis[4], x, T.basis[3]);
+          const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
+          mom[0] = fma(T.basis[0], frac, mom[0]); mom[1] = fma(q1, frac, mom[1]); mom[2] = fma(q2, frac, mom[2]);
+        }
         has_nan |= (m != m);
         const unsigned long long k = ordered_key(m);
         kmin = min(kmin, k); kmax = max(kmax, k);
@@ -784,8 +833,9 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
 
   // ------------------------------------------------------------------ phase B: spectral chi-square
   const int n = T.n_data;
-  block_sum<3, NWARP>(mom, sRed);
-  {
+  double chi_un = CUDART_NAN, med = CUDART_NAN, scale = 1.0;
+  if constexpr (MODE != MODE_NOSPEC) {
+    block_sum<3, NWARP>(mom, sRed);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
@@ -798,18 +848,34 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     __syncthreads();
     kmin = sSel->kmin[0]; kmax = sSel->kmax[0];
 #pragma unroll
-    for (int w = 1; w < NWARP; ++w) { kmin = min(kmin, sSel->kmin[w]); kmax = max(kmax, sSel->kmax[w]); }
+    for (int w2 = 1; w2 < NWARP; ++w2) { kmin = min(kmin, sSel->kmin[w2]); kmax = max(kmax, sSel->kmax[w2]); }
     has_nan = sSel->nanflag;
     __syncthreads();
+    unsigned long long* list = reinterpret_cast<unsigned long long*>(sF);
+    if constexpr (MODE == MODE_POSTERIOR) {
+      if (!has_nan) med = block_median_chi<NT, true>(sM, n, sSel, list, kmin, kmax, T, mom, &chi_un, sRed);  // mft6.py:1173
+      scale = T.data_median / med;
+    } else {
+      // fit_spec: the observed spectrum was renormalised once (mft6.py:889); every proposal is only
+      // median-scaled against it (mft6.py:1010-1014), so the scale does not factor out of the sum
+      double dummy;
+      if (!has_nan) med = block_median_chi<NT, false>(sM, n, sSel, list, kmin, kmax, T, mom, &dummy, sRed);
+      const double* dset = opt.flux_sets + (long long)opt.set_index[w] * n;
+      scale = (opt.ref_median ? opt.ref_median[w] : T.opt_median[opt.set_index[w]]) / med;   // np.median(flux), mft6.py:1011 (:888 at the start)
+      double chi[1] = {0.0};
+      for (int i = tid; i < n; i += NT) {
+        const double r = scale * sM[i] - dset[i];
+        chi[0] = fma(r * r, T.data_inv_e2[i], chi[0]);
+      }
+      block_sum<1, NWARP>(chi, sRed);
+      chi_un = chi[0] / (scale * scale);                              // so that iic below is uniform
+    }
+    if (parts.model) for (int i = tid; i < n; i += NT) parts.model[w * n + i] = sM[i] * scale;
   }
-  double chi_un = CUDART_NAN, med = CUDART_NAN;
-  if (!has_nan) med = block_median_chi<NT>(sM, n, sSel, reinterpret_cast<unsigned long long*>(sF), kmin, kmax, T, mom, &chi_un, sRed);  // mft6.py:1173
-  const double scale = T.data_median / med;
-  if (parts.model) for (int i = tid; i < n; i += NT) parts.model[w * n + i] = sM[i] * scale;
 
   // ------------------------------------------------------------------ final sum (mft6.py:1178-1205)
   if (tid == 0) {
-    const double iic = (scale * scale) * chi_un / (double)n;             // mft6.py:1173-1179
+    const double iic = (MODE == MODE_NOSPEC) ? 0.0 : (scale * scale) * chi_un / (double)n;   // mft6.py:1173-1179
     double icontrast = 0.0, iphot = 0.0;
     for (int f = 0; f < NC; ++f) {
       if (f < T.n_contrast) {
@@ -830,12 +896,20 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         if (parts.phot) parts.phot[w * T.n_phot + f] = mag;
       }
     }
-    const double init_cs = iic * (double)(T.n_contrast + T.n_phot) + icontrast + iphot;   // mft6.py:1191
-    const double lnl = (init_cs != init_cs) ? -CUDART_INF : -0.5 * init_cs;               // mft6.py:1202-1205
-    double out = sPlan.lp + lnl;
+    double out;
     int st = 0;
-    if (out != out) { out = -CUDART_INF; }
-    if (init_cs != init_cs) st |= MS_W_NONFINITE;
+    if constexpr (MODE == MODE_OPTIMIZER) {
+      // test_cs of fit_spec (mft6.py:1016, :1030-1046): x3 spectral weight, priors in chi-square units
+      out = (iic * 3.0) * (double)(T.n_contrast + T.n_phot) + icontrast + iphot + sPlan.lp;
+      if (out != out) { out = CUDART_INF; st |= MS_W_NONFINITE; }     // a NaN never wins `test_cs < chi`
+    } else {
+      const double init_cs = (MODE == MODE_NOSPEC) ? icontrast + iphot                             // mft6_nospec.py:1192
+                                                   : iic * (double)(T.n_contrast + T.n_phot) + icontrast + iphot;   // mft6.py:1191
+      const double lnl = (init_cs != init_cs) ? -CUDART_INF : -0.5 * init_cs;                     // mft6.py:1202-1205
+      out = sPlan.lp + lnl;
+      if (out != out) { out = -CUDART_INF; }
+      if (init_cs != init_cs) st |= MS_W_NONFINITE;
+    }
     lnprob[w] = out;
     if (parts.status) parts.status[w] = st;
     if (parts.lnprior) parts.lnprior[w] = sPlan.lp;
@@ -987,6 +1061,8 @@ struct ms_handle {
   // per-call buffers
   WalkerPlan* plans = nullptr; long long plans_cap = 0;
   int* order = nullptr; unsigned* cell_hist = nullptr; bool use_order = false;
+  bool nospec = false;           // mft6_nospec.py flavour of the posterior
+  double* d_opt_flux = nullptr; double* d_opt_median = nullptr; int opt_sets = 0;   // fit_spec's renormalised spectra
   size_t grid_bytes = 0, l2_bytes = 0;
   long long grid_sig[4] = {0, 0, 0, 0};   // rows, row length, region start, region length
   double* d_theta = nullptr; double* d_lnp = nullptr; long long io_cap = 0;
@@ -1029,9 +1105,9 @@ int upload(ms_handle* h, const Tp* host, size_t n, const Tp** dev) {
   return MS_OK;
 }
 
-template <int NR, int NC, int NP, int NT>
-int launch_stream_threads(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts) {
-  auto kern = lnprob_stream_kernel<NR, NC, NP, NT>;
+template <int NR, int NC, int NP, int NT, int MODE>
+int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts, const OptIn& opt) {
+  auto kern = lnprob_stream_kernel<NR, NC, NP, NT, MODE>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing) {
@@ -1042,17 +1118,24 @@ int launch_stream_threads(ms_handle* h, long long nw, double* d_lnp, const Parts
     h->ev_used += 2; h->timed_walkers += nw;
     CK(cudaEventRecord(e0, h->stream));
   }
-  kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, h->use_order ? h->order : nullptr, d_lnp, parts);
+  kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, h->use_order ? h->order : nullptr, d_lnp, parts, opt);
   CK(cudaGetLastError());
   if (h->timing) CK(cudaEventRecord(e1, h->stream));
   h->launches += 1;
   return MS_OK;
 }
 
+template <int NR, int NC, int NP, int NT>
+int launch_stream_threads(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts, int mode, const OptIn& opt) {
+  if (mode == MODE_OPTIMIZER) return launch_stream_mode<NR, NC, NP, NT, MODE_OPTIMIZER>(h, nw, d_lnp, parts, opt);
+  if (mode == MODE_NOSPEC) return launch_stream_mode<NR, NC, NP, NT, MODE_NOSPEC>(h, nw, d_lnp, parts, opt);
+  return launch_stream_mode<NR, NC, NP, NT, MODE_POSTERIOR>(h, nw, d_lnp, parts, opt);
+}
+
 template <int NR, int NC, int NP>
-int launch_stream_variant(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts) {
-  if (h->threads == 512) return launch_stream_threads<NR, NC, NP, 512>(h, nw, d_lnp, parts);
-  return launch_stream_threads<NR, NC, NP, 256>(h, nw, d_lnp, parts);
+int launch_stream_variant(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts, int mode, const OptIn& opt) {
+  if (h->threads == 512) return launch_stream_threads<NR, NC, NP, 512>(h, nw, d_lnp, parts, mode, opt);
+  return launch_stream_threads<NR, NC, NP, 256>(h, nw, d_lnp, parts, mode, opt);
 }
 
 size_t stream_smem_bytes(int n_data, int nc, int np, int nwarp) {
@@ -1074,7 +1157,9 @@ int ensure_plans(ms_handle* h, long long nw) {
   return MS_OK;
 }
 
-int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d_lnp, const PartsOut& parts) {
+int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d_lnp, const PartsOut& parts,
+                    int mode = -1, const OptIn& opt = OptIn{nullptr, nullptr, nullptr, nullptr, nullptr}) {
+  if (mode < 0) mode = h->nospec ? MODE_NOSPEC : MODE_POSTERIOR;
   if (nw == 0) return MS_OK;
   int rc = ensure_plans(h, nw);
   if (rc) return rc;
@@ -1085,7 +1170,7 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   // CTAs on the same L2 slices (measured: C4 -4 %, C1 -8 %), so the natural order is kept there.
   h->use_order = nw >= 1024 && h->T.n_cells > 1 && h->grid_bytes > h->l2_bytes;
   if (h->use_order) CK(cudaMemsetAsync(h->cell_hist, 0, (size_t)h->T.n_cells * sizeof(unsigned), h->stream));
-  walker_prep_kernel<<<pg, pb, 0, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr);
+  walker_prep_kernel<<<pg, pb, 0, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr, mode, opt);
   CK(cudaGetLastError());
   h->launches += 1;
   if (h->use_order) {
@@ -1095,11 +1180,11 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
     h->launches += 2;
   }
   if (h->corners == 4) {
-    if (h->variant == 0) return launch_stream_variant<4, 2, 6>(h, nw, d_lnp, parts);
-    return launch_stream_variant<4, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts);
+    if (h->variant == 0) return launch_stream_variant<4, 2, 6>(h, nw, d_lnp, parts, mode, opt);
+    return launch_stream_variant<4, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts, mode, opt);
   }
-  if (h->variant == 0) return launch_stream_variant<8, 2, 6>(h, nw, d_lnp, parts);
-  return launch_stream_variant<8, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts);
+  if (h->variant == 0) return launch_stream_variant<8, 2, 6>(h, nw, d_lnp, parts, mode, opt);
+  return launch_stream_variant<8, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts, mode, opt);
 }
 
 int ensure_io(ms_handle* h, long long nw) {
@@ -1150,6 +1235,8 @@ int ms_destroy(ms_handle* h) {
   if (h->plans) cudaFree(h->plans);
   if (h->order) cudaFree(h->order);
   if (h->cell_hist) cudaFree(h->cell_hist);
+  if (h->d_opt_flux) cudaFree(h->d_opt_flux);
+  if (h->d_opt_median) cudaFree(h->d_opt_median);
   if (h->d_theta) cudaFree(h->d_theta);
   if (h->d_lnp) cudaFree(h->d_lnp);
   if (h->h_theta) cudaFreeHost(h->h_theta);
@@ -1195,6 +1282,8 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
   T.n_contrast = cfg->n_contrast; T.n_phot = cfg->n_phot;
   T.nspec = cfg->nspec; T.ndim = 2 * cfg->nspec + 2;
   T.ext_flag = cfg->ext_flag; T.dist_fit = cfg->dist_fit; T.rad_prior = cfg->rad_prior;
+  T.opt_median = nullptr;
+  h->nospec = (cfg->flavour == 1);
   T.tmin = cfg->tmin; T.tmax = cfg->tmax;
   T.data_median = cfg->data_median;
   for (int k = 0; k < 9; ++k) T.basis[k] = cfg->poly_basis[k];
@@ -1369,6 +1458,69 @@ int ms_kernel_time(ms_handle* h, double* total_ms, int64_t* n_launches, int64_t*
   if (n_walkers) *n_walkers = h->timed_walkers;
   h->ev_used = 0; h->timed_walkers = 0;
   return MS_OK;
+}
+
+int ms_set_optimizer_data(ms_handle* h, const double* flux_sets, int32_t n_sets) {
+  if (!h) return MS_ERR_INVALID;
+  if (!flux_sets || n_sets < 1) { set_err(h, "ms_set_optimizer_data: invalid argument"); return MS_ERR_INVALID; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->d_opt_flux) cudaFree(h->d_opt_flux);
+  if (h->d_opt_median) cudaFree(h->d_opt_median);
+  h->d_opt_flux = h->d_opt_median = nullptr; h->opt_sets = 0; h->T.opt_median = nullptr;
+  const int n = h->T.n_data;
+  std::vector<double> med(n_sets), tmp(n);
+  for (int k = 0; k < n_sets; ++k) {                      // np.median of each set (mft6.py:1011)
+    std::copy(flux_sets + (size_t)k * n, flux_sets + (size_t)(k + 1) * n, tmp.begin());
+    std::sort(tmp.begin(), tmp.end());
+    med[k] = (n & 1) ? tmp[n / 2] : (tmp[n / 2 - 1] + tmp[n / 2]) / 2.0;
+  }
+  CK(cudaMalloc((void**)&h->d_opt_flux, (size_t)n_sets * n * 8));
+  CK(cudaMalloc((void**)&h->d_opt_median, (size_t)n_sets * 8));
+  CK(cudaMemcpy(h->d_opt_flux, flux_sets, (size_t)n_sets * n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_opt_median, med.data(), (size_t)n_sets * 8, cudaMemcpyHostToDevice));
+  h->opt_sets = n_sets; h->T.opt_median = h->d_opt_median;
+  return MS_OK;
+}
+
+int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_index, const double* rad_sigma,
+                       const double* av_prior, const double* ref_median, int64_t nw, double* chisq) {
+  if (!h) return MS_ERR_INVALID;
+  if (nw < 0 || (nw > 0 && (!theta || !set_index || !rad_sigma || !chisq))) { set_err(h, "ms_optimizer_chisq: null argument"); return MS_ERR_INVALID; }
+  if (h->opt_sets < 1) { set_err(h, "ms_optimizer_chisq: call ms_set_optimizer_data first"); return MS_ERR_INVALID; }
+  if (nw == 0) return MS_OK;
+  for (int64_t w = 0; w < nw; ++w)
+    if (set_index[w] < 0 || set_index[w] >= h->opt_sets) { set_err(h, "ms_optimizer_chisq: set_index out of range"); return MS_ERR_INVALID; }
+  CK(cudaSetDevice(h->device));
+  const int ndim = h->T.ndim, ns = h->T.nspec;
+  int rc = ensure_io(h, nw);
+  if (rc) return rc;
+  // host buffers in, host buffer out (the optimiser's random walk runs on the host)
+  double* d_rs = nullptr; double* d_avp = nullptr; double* d_med = nullptr; int* d_idx = nullptr;
+  CK(cudaMalloc((void**)&d_rs, (size_t)nw * ns * 8));
+  CK(cudaMalloc((void**)&d_idx, (size_t)nw * 4));
+  if (av_prior) CK(cudaMalloc((void**)&d_avp, (size_t)nw * 8));
+  if (ref_median) CK(cudaMalloc((void**)&d_med, (size_t)nw * 8));
+  cudaError_t e = cudaMemcpyAsync(h->d_theta, theta, (size_t)nw * ndim * 8, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rs, rad_sigma, (size_t)nw * ns * 8, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, set_index, (size_t)nw * 4, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess && av_prior) e = cudaMemcpyAsync(d_avp, av_prior, (size_t)nw * 8, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess && ref_median) e = cudaMemcpyAsync(d_med, ref_median, (size_t)nw * 8, cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) { set_err(h, std::string("ms_optimizer_chisq: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
+  if (rc == MS_OK) {
+    PartsOut parts{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    OptIn opt{h->d_opt_flux, d_idx, d_rs, d_avp, d_med};
+    rc = evaluate_device(h, h->d_theta, nw, h->d_lnp, parts, MODE_OPTIMIZER, opt);
+  }
+  if (rc == MS_OK) {
+    e = cudaMemcpyAsync(chisq, h->d_lnp, (size_t)nw * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { set_err(h, std::string("ms_optimizer_chisq: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
+  } else {
+    cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(d_rs); cudaFree(d_idx); if (d_avp) cudaFree(d_avp); if (d_med) cudaFree(d_med);
+  return rc;
 }
 
 int ms_lnprob_parts(ms_handle* h, const double* theta, int64_t nw, double* lnprob, double* chi2_spec,

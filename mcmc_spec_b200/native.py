@@ -21,7 +21,7 @@ MS_W_PRIOR_BOUNDS, MS_W_OFF_ISOCHRONE, MS_W_OFF_GRID, MS_W_NONFINITE = 1, 2, 4, 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmcmcspec.so')
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
-           'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_broaden_rows',
+           'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows',
            'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_timing',
            'ms_kernel_time']
 
@@ -49,7 +49,7 @@ class MsConfig(C.Structure):
         ('iso_teff', _dp), ('iso_logg', _dp), ('iso_lum', _dp), ('dust_dm_edges', _dp), ('dust_samples', _dp),
         ('tmin', C.c_double), ('tmax', C.c_double),
         ('prior_mu', C.c_double * MS_MAX_NDIM), ('prior_sig', C.c_double * MS_MAX_NDIM),
-        ('ext_flag', C.c_int32), ('dist_fit', C.c_int32), ('rad_prior', C.c_int32), ('reserved', C.c_int32),
+        ('ext_flag', C.c_int32), ('dist_fit', C.c_int32), ('rad_prior', C.c_int32), ('flavour', C.c_int32),
     ]
 
 
@@ -84,6 +84,8 @@ def load_library(path=None):
     lib.ms_lnprob.argtypes = [vp, vp, C.c_int64, vp, C.c_int]
     lib.ms_lnprob_parts.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
     lib.ms_model_spectrum.argtypes = [vp, vp, C.c_int64, vp, C.c_int]
+    lib.ms_set_optimizer_data.argtypes = [vp, vp, C.c_int32]
+    lib.ms_optimizer_chisq.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, vp]
     lib.ms_broaden_rows.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32]
     lib.ms_split_keys.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int64, vp]
     lib.ms_stretch_propose.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_double, C.c_uint64,
@@ -161,6 +163,7 @@ def make_config(t: DeviceTables, device=0):
     cfg.prior_mu = (C.c_double * MS_MAX_NDIM)(*mu)
     cfg.prior_sig = (C.c_double * MS_MAX_NDIM)(*sig)
     cfg.ext_flag, cfg.dist_fit, cfg.rad_prior = t.ext_flag, t.dist_fit, t.rad_prior
+    cfg.flavour = int(getattr(t, 'flavour', 0))
     assert TILE == 1024
     return cfg, keep
 
@@ -257,6 +260,30 @@ class Engine:
         out = np.empty((theta.shape[0], self.n_data), dtype=np.float64)
         self._check(self.lib.ms_model_spectrum(self._h, theta.ctypes.data, theta.shape[0], out.ctypes.data, MS_HOST),
                     'ms_model_spectrum')
+        return out
+
+    # -- optimiser stage
+    def set_optimizer_data(self, flux_sets):
+        flux_sets = np.ascontiguousarray(np.atleast_2d(flux_sets), dtype=np.float64)
+        if flux_sets.shape[1] != self.n_data:
+            raise ValueError("flux_sets must be [n_sets, n_data]")
+        self._check(self.lib.ms_set_optimizer_data(self._h, flux_sets.ctypes.data, flux_sets.shape[0]), 'ms_set_optimizer_data')
+        self._n_opt_sets = flux_sets.shape[0]
+
+    def optimizer_chisq(self, theta, set_index, rad_sigma, av_prior=None, ref_median=None):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        nw = theta.shape[0]
+        set_index = np.ascontiguousarray(set_index, dtype=np.int32)
+        rad_sigma = np.ascontiguousarray(rad_sigma, dtype=np.float64)
+        if theta.shape != (nw, self.ndim) or set_index.shape != (nw,) or rad_sigma.shape != (nw, self.nspec):
+            raise ValueError("optimizer_chisq: shape mismatch")
+        avp = None if av_prior is None else np.ascontiguousarray(av_prior, dtype=np.float64)
+        med = None if ref_median is None else np.ascontiguousarray(np.broadcast_to(ref_median, (nw,)), dtype=np.float64)
+        out = np.empty(nw, dtype=np.float64)
+        self._check(self.lib.ms_optimizer_chisq(self._h, theta.ctypes.data, set_index.ctypes.data, rad_sigma.ctypes.data,
+                                                None if avp is None else avp.ctypes.data,
+                                                None if med is None else med.ctypes.data, nw, out.ctypes.data),
+                    'ms_optimizer_chisq')
         return out
 
     # -- device-pointer calls (asynchronous on the handle's stream)

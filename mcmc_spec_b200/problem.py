@@ -46,6 +46,7 @@ class Problem:
     av: bool = True
     dist_fit: bool = True
     rad_prior: bool = True
+    nospec: bool = False                 # True: the posterior of mft6_nospec.py (no spectral term)
     fehs: Optional[List[float]] = None   # 3-D extension: [Fe/H] nodes
     feh: float = 0.0                     # 3-D extension: the fit's fixed metallicity
     truth: Optional[np.ndarray] = None   # theta the synthetic data were drawn from

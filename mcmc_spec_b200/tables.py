@@ -154,6 +154,7 @@ class DeviceTables:
     ext_flag: int
     dist_fit: int
     rad_prior: int
+    flavour: int = 0             # 1: mft6_nospec.py
 
     @property
     def n_tiles(self):
@@ -301,4 +302,5 @@ def build_tables(prob) -> DeviceTables:
         iso_lum=np.ascontiguousarray(lum5[o]), dust_dm_edges=np.asarray(prob.dust_dm_edges, dtype=np.float64),
         dust_samples=np.ascontiguousarray(prob.dust_samples, dtype=np.float64),
         tmin=float(min(prob.temps)), tmax=float(max(prob.temps)), prior_mu=mu, prior_sig=sig, nspec=ns,
-        ext_flag=int(bool(prob.av)), dist_fit=int(bool(prob.dist_fit)), rad_prior=int(bool(prob.rad_prior)))
+        ext_flag=int(bool(prob.av)), dist_fit=int(bool(prob.dist_fit)), rad_prior=int(bool(prob.rad_prior)),
+        flavour=int(bool(getattr(prob, 'nospec', False))))

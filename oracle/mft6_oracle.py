@@ -245,8 +245,9 @@ def make_composite(teff, logg, rad, distance, contrast_filt, phot_filt, r, specs
 # ---------------------------------------------------------------------------- posterior
 
 def loglikelihood(p0, fr, nspec, data, err, r, specs, ctm, ptm, tmi, tma, matrix, temps, lgs,
-                  photlib, av=True, optimize=False, fs=None, parts=None):
-    """mft6.py:1139-1205 for len(p0) in (6, 8).
+                  photlib, av=True, optimize=False, fs=None, parts=None, nospec=False):
+    """mft6.py:1139-1205 for len(p0) in (6, 8).  ``nospec=True`` gives mft6_nospec.py:1140-1206, where
+    every line of the spectral term is commented out and the total is contrast + photometry only.
 
     ``parts``: optional dict that receives the intermediate quantities (for parity debugging).
     """
@@ -261,22 +262,26 @@ def loglikelihood(p0, fr, nspec, data, err, r, specs, ctm, ptm, tmi, tma, matrix
         temps, lgs, photlib, nspec=nspec, fs=fs)
 
     if av == True and extinct_guess > 0:          # noqa: E712  (as in the reference)
-        init_cspec = extinct(wave1, init_cspec, extinct_guess)
+        if not nospec:
+            init_cspec = extinct(wave1, init_cspec, extinct_guess)
         init_phot = -2.5 * np.log10(extinct(phot_cwl, 10 ** (-0.4 * phot), extinct_guess))
     else:
         init_phot = phot
 
-    init_cspec = interp1d(wave1, init_cspec)(wl * 1e4)
-    init_cspec *= np.median(spec) / np.median(init_cspec)
-    spec = norm_spec(wl, init_cspec, spec)
-
-    ic = chisq(init_cspec, spec, err)
-    iic = np.sum(ic) / len(ic)
     chi_contrast = chisq(contrast, fr[0], fr[1])
     icontrast = np.sum(chi_contrast)
     chi_phot = chisq(init_phot, fr[3], fr[4])
     iphot = np.sum(chi_phot)
-    init_cs = np.sum((iic * (len(chi_contrast) + len(chi_phot)), icontrast, iphot))
+    if nospec:
+        iic = np.nan
+        init_cs = np.sum((icontrast, iphot))                           # mft6_nospec.py:1192
+    else:
+        init_cspec = interp1d(wave1, init_cspec)(wl * 1e4)
+        init_cspec *= np.median(spec) / np.median(init_cspec)
+        spec = norm_spec(wl, init_cspec, spec)
+        ic = chisq(init_cspec, spec, err)
+        iic = np.sum(ic) / len(ic)
+        init_cs = np.sum((iic * (len(chi_contrast) + len(chi_phot)), icontrast, iphot))
 
     if parts is not None:
         parts.update(model=init_cspec, data_renorm=spec, chi2_spec=iic, contrast=np.array(contrast),
@@ -290,10 +295,11 @@ def loglikelihood(p0, fr, nspec, data, err, r, specs, ctm, ptm, tmi, tma, matrix
 
 
 def logprior(p0, nspec, tmin, tmax, matrix, dustmap, prior=0, ext=True, dist_fit=True,
-             rad_prior=False):
+             rad_prior=False, plx_max=1 / 4):
     """mft6.py:1207-1327 -- the two 6-parameter branches (binary; dist_fit True / False).
 
     ``dustmap.query(distance_pc)`` stands for ``bayestar(SkyCoord(ra, dec, distance), 'samples')``.
+    ``plx_max``: 1/4 in mft6.py:1227, 1/100 in mft6_nospec.py:1228.
     """
     temps = p0[:nspec]
     if len(p0) != 6:
@@ -315,7 +321,7 @@ def logprior(p0, nspec, tmin, tmax, matrix, dustmap, prior=0, ext=True, dist_fit
             rad = p0[nspec:2 * nspec]
         dist = p0[2 * nspec + 1]
         if (any(t > tmax for t in temps) or any(t < tmin for t in temps)
-                or any(r < 0.05 for r in rad) or rad[0] > 1.5 or dist < 1 / 3000 or dist > 1 / 4):
+                or any(r < 0.05 for r in rad) or rad[0] > 1.5 or dist < 1 / 3000 or dist > plx_max):
             return -np.inf
         if ext == True and extinct_val < 0:        # noqa: E712
             return -np.inf
@@ -361,17 +367,100 @@ def logprior(p0, nspec, tmin, tmax, matrix, dustmap, prior=0, ext=True, dist_fit
 
 def logposterior(p0, fr, nspec, data, err, r, specs, ctm, ptm, tmi, tma, tmin, tmax, matrix,
                  temps, lgs, photlib, dustmap, prior=0, a=True, dist_fit=True, rad_prior=False,
-                 fs=None, parts=None):
-    """mft6.py:1459-1470 -- prior first; a non-finite prior short-circuits to -inf."""
+                 fs=None, parts=None, nospec=False):
+    """mft6.py:1459-1470 -- prior first; a non-finite prior short-circuits to -inf.
+    ``nospec=True``: the same function of mft6_nospec.py."""
     lp = logprior(p0, nspec, tmin, tmax, matrix, dustmap, prior=prior, ext=a, dist_fit=dist_fit,
-                  rad_prior=rad_prior)
+                  rad_prior=rad_prior, plx_max=(1 / 100 if nospec else 1 / 4))
     if parts is not None:
         parts['lp'] = lp
     if not np.isfinite(lp):
         return -np.inf
     lh = loglikelihood(p0, fr, nspec, data, err, r, specs, ctm, ptm, tmi, tma, matrix, temps,
-                       lgs, photlib, av=a, fs=fs, parts=parts)
+                       lgs, photlib, av=a, fs=fs, parts=parts, nospec=nospec)
     return lp + lh
+
+
+# ---------------------------------------------------------------------------- optimiser stage
+
+def opt_prior(vals, pval, psig):
+    """mft6.py:833-854 -- sum of ((value - prior)/sigma)^2 over the priors that are defined."""
+    pp = []
+    if len(pval) == 1 or type(pval) == float:
+        try:
+            pp.append(((float(vals) - float(pval[0])) / float(psig[0])) ** 2)
+        except TypeError:
+            pp.append(((vals[0] - pval[0]) / psig[0]) ** 2)
+    else:
+        for k, p in enumerate(pval):
+            if p != 0:
+                pp.append(((vals[k] - pval[k]) / (psig[k])) ** 2)
+    return np.sum(pp)
+
+
+def _dust_moments(dustmap, plx):
+    av_guess = dustmap.query(1 / plx) * 3.1 * 0.884
+    mu, sig = np.mean(av_guess), np.std(av_guess)
+    return mu, (0.05 if sig == 0 else sig)
+
+
+def fit_spec_init(wl_aa, flux, err, reg, t_guess, av, rad_guess, fr_guess, specs, distance, ctm, ptm, tmi, tma,
+                  matrix, temps, lgs, photlib, dustmap, nspec=2, dist_fit=True, rad_prior=False, fs=None):
+    """mft6.py:859-930 (distance given): the starting chi-square of one optimiser walker and the observed
+    spectrum after its one-off renormalisation.  ``wl_aa`` is the data wavelength in Angstrom (the
+    reference multiplies its argument by 1e4 in place, :860).  Returns (init_cs, flux_renormalised).
+
+    Quirks kept: the initial model is *not* extincted (:880 commented out) and the initial photometric
+    chi-square uses the unextincted magnitudes (:902 uses ``phot``, not ``init_phot``)."""
+    dist, pprior, psig = distance
+    extinct_guess, eprior, esig = av
+    lg_guess = [get_logg(t, matrix) for t in t_guess]
+    wave1, init_cspec, contrast, phot_cwl, phot = make_composite(
+        t_guess, lg_guess, rad_guess, dist, fr_guess[2], fr_guess[5], reg, specs, ctm, ptm, tmi, tma,
+        temps, lgs, photlib, nspec=nspec, fs=fs)
+    init_cspec = interp1d(wave1, init_cspec)(wl_aa)
+    init_cspec *= np.median(flux) / np.median(init_cspec)
+    flux = norm_spec(wl_aa, init_cspec, flux)
+    iic = np.sum(chisq(init_cspec, flux, err)) / len(flux) * 3
+    chi_contrast = chisq(contrast, fr_guess[0], fr_guess[1])
+    ip = chisq(phot, fr_guess[3], fr_guess[4])
+    init_cs = np.sum((iic * (len(chi_contrast) + len(ip)), np.sum(chi_contrast), np.sum(ip)))
+    if dist_fit == True:                           # noqa: E712
+        init_cs += opt_prior([dist], [pprior], [psig])
+    if rad_prior == True:                          # noqa: E712
+        r1, r2 = get_radius(t_guess[0], matrix), get_radius(t_guess[1], matrix)
+        init_cs += opt_prior(rad_guess, [r1, r2 / r1], [0.05 * r for r in rad_guess])
+    mu, sig = _dust_moments(dustmap, dist)
+    init_cs += opt_prior([extinct_guess], [mu], [sig])
+    return init_cs, flux
+
+
+def fit_spec_test_cs(var_par, wl_aa, flux, err, reg, fr_guess, specs, pprior, psig, rad_sigma, ctm, ptm, tmi, tma,
+                     matrix, temps, lgs, photlib, dustmap, nspec=2, dist_fit=True, rad_prior=False, fs=None):
+    """mft6.py:989-1046 -- chi-square of one in-box proposal ``var_par = [T[2], Av, rad[2], plx]`` against
+    the renormalised ``flux``; ``rad_sigma`` is ``si[2]`` (:1038)."""
+    mu, sig = _dust_moments(dustmap, var_par[3])
+    logg_guess = [get_logg(v, matrix) for v in var_par[0]]
+    test_wave1, test_cspec, test_contrast, test_phot_cwl, test_phot = make_composite(
+        var_par[0], logg_guess, var_par[2], float(var_par[3]), fr_guess[2], fr_guess[5], reg, specs, ctm, ptm,
+        tmi, tma, temps, lgs, photlib, nspec=nspec, fs=fs)
+    if var_par[1] > 0:
+        test_cspec = extinct(test_wave1, test_cspec, var_par[1])
+        test_phot = -2.5 * np.log10(extinct(test_phot_cwl, 10 ** (-0.4 * test_phot), var_par[1]))
+    test_cspec = interp1d(test_wave1, test_cspec)(wl_aa)
+    test_cspec *= np.median(flux) / np.median(test_cspec)
+    tc = chisq(test_cspec, flux, err)
+    ttc = np.sum(tc) / len(tc) * 3
+    chi_contrast = chisq(test_contrast, fr_guess[0], fr_guess[1])
+    chi_phot = chisq(test_phot, fr_guess[3], fr_guess[4])
+    test_cs = np.sum((ttc * (len(chi_contrast) + len(chi_phot)), np.sum(chi_contrast), np.sum(chi_phot)))
+    test_cs += opt_prior(var_par[1], [mu], [sig])
+    if dist_fit == True:                           # noqa: E712
+        test_cs += opt_prior([var_par[3]], [pprior], [psig])
+    if rad_prior == True and nspec == 2:           # noqa: E712
+        r1, r2 = get_radius(var_par[0][0], matrix), get_radius(var_par[0][1], matrix)
+        test_cs += opt_prior(var_par[2], [r1, r2 / r1], np.array(rad_sigma))
+    return test_cs
 
 
 # ---------------------------------------------------------------------------- problem-level glue
@@ -396,7 +485,7 @@ class OracleProblem:
                             p.specs, p.ctm, p.ptm, p.tmi, p.tma, self.tmin, self.tmax, p.matrix,
                             p.temps, p.lgs, p.photlib, p.dustmap, prior=p.prior, a=p.av,
                             dist_fit=p.dist_fit, rad_prior=p.rad_prior,
-                            fs=getattr(p, 'fs', None), parts=parts)
+                            fs=getattr(p, 'fs', None), parts=parts, nospec=getattr(p, 'nospec', False))
 
     def lnprob_batch(self, theta):
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))

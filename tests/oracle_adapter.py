@@ -33,5 +33,6 @@ def to_oracle(prob):
         ptm=prob.ptm, tmi=prob.tmi, tma=prob.tma, matrix=prob.matrix, temps=list(prob.temps),
         lgs=list(prob.lgs), photlib=photlib,
         dustmap=tp.BayestarSightline(prob.dust_dm_edges, prob.dust_samples), prior=prob.prior,
-        av=prob.av, dist_fit=prob.dist_fit, rad_prior=prob.rad_prior, fs=names)
+        av=prob.av, dist_fit=prob.dist_fit, rad_prior=prob.rad_prior, fs=names,
+        nospec=getattr(prob, 'nospec', False))
     return mo.OracleProblem(ns)
