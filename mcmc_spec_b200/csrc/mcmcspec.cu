@@ -36,7 +36,7 @@ namespace {
 
 constexpr int MAXWARP = 16;              // the streaming kernel runs with 256 or 512 threads per CTA
 constexpr int TILE = MS_TILE;           // model pixels per tile (4 per thread)
-constexpr int MAX_STAR = 2;
+constexpr int MAX_STAR = 3;              // binaries and triples (mft6.py nspec = 2 / 3)
 constexpr int MAX_CORNER = 8;
 
 constexpr double RSUN_CM = 6.957e10;    // mft6.py:81, :691
@@ -277,12 +277,23 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   if (mode != MODE_OPTIMIZER) {
     bool out = false;
     for (int s = 0; s < ns; ++s) out = out || (temps[s] > T.tmax) || (temps[s] < T.tmin);
-    if (T.dist_fit) {
-      const double plx_hi = (mode == MODE_NOSPEC) ? 1.0 / 100.0 : 1.0 / 4.0;     // mft6_nospec.py:1228
-      for (int s = 0; s < ns; ++s) out = out || (rad[s] < 0.05);
-      out = out || (rad[0] > 1.5) || (plx < 1.0 / 3000.0) || (plx > plx_hi);
+    if (ns == 2) {
+      if (T.dist_fit) {
+        const double plx_hi = (mode == MODE_NOSPEC) ? 1.0 / 100.0 : 1.0 / 4.0;     // mft6_nospec.py:1228
+        for (int s = 0; s < ns; ++s) out = out || (rad[s] < 0.05);
+        out = out || (rad[0] > 1.5) || (plx < 1.0 / 3000.0) || (plx > plx_hi);
+      } else {
+        out = out || (rad[1] < 0.05) || (rad[0] < 0.05);
+      }
     } else {
-      out = out || (rad[1] < 0.05) || (rad[0] < 0.05);
+      // triples, mft6.py:1346 / :1408: no upper bound on R1, parallax from 1/1000; without a distance
+      // only the two ratios and the sign of the parallax are checked
+      if (T.dist_fit) {
+        for (int s = 0; s < ns; ++s) out = out || (rad[s] < 0.05);
+        out = out || (plx < 1.0 / 1000.0) || (plx > 1.0 / 4.0);
+      } else {
+        out = out || (rad[1] < 0.05) || (rad[2] < 0.05) || (plx < 0.0);
+      }
     }
     if (T.ext_flag && av < 0.0) out = true;
     if (out) { plan.status = MS_W_PRIOR_BOUNDS; store(plan); return; }
@@ -334,13 +345,13 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
       }
     }
     if (T.rad_prior) {
+      // mft6.py:1262-1269 (binaries), :1381-1389 (triples): 2 % Gaussians on R1 and on the ratios
       const double r1m = stefan_boltzmann_radius(lum[0], temps[0]);
-      const double r2m = stefan_boltzmann_radius(lum[1], temps[1]);
-      const double m0 = r1m, m1 = r2m / r1m;
-      const double z0 = (rad[0] - m0) / (0.02 * m0);
-      const double z1 = (rad[1] - m1) / (0.02 * m1);
-      lp += -0.5 * (z0 * z0);
-      lp += -0.5 * (z1 * z1);
+      for (int s = 0; s < ns; ++s) {
+        const double m = (s == 0) ? r1m : stefan_boltzmann_radius(lum[s], temps[s]) / r1m;
+        const double z = (rad[s] - m) / (0.02 * m);
+        lp += -0.5 * (z * z);
+      }
     }
   }
   if (!isfinite(lp)) { plan.status = MS_W_NONFINITE; store(plan); return; }   // mft6.py:1465
@@ -376,7 +387,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
     // cell key: lower Teff / log g node of each star's bracket
     int key = 0;
     const int per_star = T.n_teff * T.n_logg;
-    for (int s = 0; s < ns; ++s) {
+    for (int s = 0; s < 2; ++s) {                                       // the first two stars name the cell
       const int r_a = plan.row[s][0] % per_star, r_b = plan.row[s][3] % per_star;   // (t1,g1) and (t2,g2)
       const int tl = min(r_a % T.n_teff, r_b % T.n_teff), gl = min(r_a / T.n_teff, r_b / T.n_teff);
       key = key * per_star + gl * T.n_teff + tl;
@@ -640,18 +651,19 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
 // ------------------------------------------------------------------------------------------
 // lnprob_stream_kernel: one CTA per walker.
 //   NR  grid rows per star (4: Teff x log g, 8: with [Fe/H]);  NC / NP compile-time filter caps;
+//   NS   number of stars (2, or 3 for triples: mft6.py nspec);
 //   MODE what is evaluated (MODE_POSTERIOR / MODE_NOSPEC / MODE_OPTIMIZER);
 //   NT  threads per CTA: 256 (two or three CTAs per SM) or 512 when the observed spectrum is so long
 //       that only one CTA fits an SM.
 // ------------------------------------------------------------------------------------------
-template <int NR, int NC, int NP, int NT, int MODE>
+template <int NR, int NC, int NP, int NT, int MODE, int NS>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __restrict__ plans,
                      const int* __restrict__ order, double* __restrict__ lnprob, const PartsOut parts,
                      const OptIn opt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NWARP = NT / 32;
-  constexpr int KRED = 2 * NC + NP;
+  constexpr int KRED = NS * NC + NP;
   double* sF = reinterpret_cast<double*>(smem_raw);                  // [NWARP*SEG] per-warp composite chunks
   double* sRed = sF + NWARP * SEG;                                          // [NWARP*KRED]
   SelectScratch* sSel = reinterpret_cast<SelectScratch*>(sRed + NWARP * (KRED > 4 ? KRED : 4));
@@ -683,23 +695,27 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   }
 
   const int lane = tid & 31, warp = tid >> 5;
-  double c0[NR], c1[NR];
-  const double* p0[NR];                                              // this lane's pixel pair in each bracketing row,
-  const double* p1[NR];                                              // advanced by one tile per iteration
+  double cf[NS][NR];
+  const double* pr[NS][NR];                                          // this lane's pixel pair in each bracketing row,
+#pragma unroll                                                       // advanced past the other warps' chunks per step
+  for (int s = 0; s < NS; ++s) {
 #pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    c0[r] = sPlan.coef[0][r]; c1[r] = sPlan.coef[1][r];
-    p0[r] = T.grid + (long long)sPlan.row[0][r] * T.stride + warp * CHUNK + 2 * lane;
-    p1[r] = T.grid + (long long)sPlan.row[1][r] * T.stride + warp * CHUNK + 2 * lane;
+    for (int r = 0; r < NR; ++r) {
+      cf[s][r] = sPlan.coef[s][r];
+      pr[s][r] = T.grid + (long long)sPlan.row[s][r] * T.stride + warp * CHUNK + 2 * lane;
+    }
   }
   const double av = sPlan.av;
   const bool small_dext = av * T.dext_max < 4e-3;                     // exp(x) by a 5th-order polynomial: x^6/720 < 6e-18
   double* seg = sF + warp * SEG;                                      // see seg_slot()
 
-  double accC[NC > 0 ? NC : 1][2];
+  double accC[NC > 0 ? NC : 1][NS];
   double accP[NP > 0 ? NP : 1];
 #pragma unroll
-  for (int f = 0; f < NC; ++f) { accC[f][0] = 0.0; accC[f][1] = 0.0; }
+  for (int f = 0; f < NC; ++f) {
+#pragma unroll
+    for (int st = 0; st < NS; ++st) accC[f][st] = 0.0;
+  }
 #pragma unroll
   for (int f = 0; f < NP; ++f) accP[f] = 0.0;
 
@@ -724,52 +740,57 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     const bool need_prev = stage && ds_raw < 0;                        // warp-uniform
     if (need_prev && lane == 0) {
       // composite of the pixel just before the chunk (owned by another warp / the previous tile)
-      double f = 0.0;
+      double tot = 0.0;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) f = fma(c0[r], __ldg(p0[r] - 1), f);
-      double g = 0.0;
+      for (int st = 0; st < NS; ++st) {
+        double f = 0.0;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) g = fma(c1[r], __ldg(p1[r] - 1), g);
-      seg[seg_slot(0)] = f + g;
+        for (int r = 0; r < NR; ++r) f = fma(cf[st][r], __ldg(pr[st][r] - 1), f);
+        tot += f;
+      }
+      seg[seg_slot(0)] = tot;
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int px = cbase + h * 64 + 2 * lane;
-      double2 f1, f2;
-      if constexpr (NR <= 4) {
-        double2 a[NR], b[NR];
+      double2 fs[NS];                                                 // this pixel pair's flux of each star
+      if constexpr (NS * NR <= 8) {
+        // all rows of all stars in flight at once (binaries on a Teff x log g grid)
+        double2 a[NS][NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) a[r] = ldg_stream(p0[r] + h * 64);
+        for (int st = 0; st < NS; ++st) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) b[r] = ldg_stream(p1[r] + h * 64);
-        f1.x = c0[0] * a[0].x; f1.y = c0[0] * a[0].y;
-        f2.x = c1[0] * b[0].x; f2.y = c1[0] * b[0].y;
+          for (int r = 0; r < NR; ++r) a[st][r] = ldg_stream(pr[st][r] + h * 64);
+        }
 #pragma unroll
-        for (int r = 1; r < NR; ++r) {
-          f1.x = fma(c0[r], a[r].x, f1.x); f1.y = fma(c0[r], a[r].y, f1.y);
-          f2.x = fma(c1[r], b[r].x, f2.x); f2.y = fma(c1[r], b[r].y, f2.y);
+        for (int st = 0; st < NS; ++st) {
+          fs[st].x = cf[st][0] * a[st][0].x; fs[st].y = cf[st][0] * a[st][0].y;
+#pragma unroll
+          for (int r = 1; r < NR; ++r) { fs[st].x = fma(cf[st][r], a[st][r].x, fs[st].x); fs[st].y = fma(cf[st][r], a[st][r].y, fs[st].y); }
         }
       } else {
-        // 8 corners per star: one star at a time keeps 8 (not 16) 16-byte loads live
-        double2 a[NR];
+        // 8 corners per star or three stars: one star at a time keeps at most 8 16-byte loads live
 #pragma unroll
-        for (int r = 0; r < NR; ++r) a[r] = ldg_stream(p0[r] + h * 64);
-        f1.x = c0[0] * a[0].x; f1.y = c0[0] * a[0].y;
+        for (int st = 0; st < NS; ++st) {
+          double2 a[NR];
 #pragma unroll
-        for (int r = 1; r < NR; ++r) { f1.x = fma(c0[r], a[r].x, f1.x); f1.y = fma(c0[r], a[r].y, f1.y); }
+          for (int r = 0; r < NR; ++r) a[r] = ldg_stream(pr[st][r] + h * 64);
+          fs[st].x = cf[st][0] * a[0].x; fs[st].y = cf[st][0] * a[0].y;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) a[r] = ldg_stream(p1[r] + h * 64);
-        f2.x = c1[0] * a[0].x; f2.y = c1[0] * a[0].y;
-#pragma unroll
-        for (int r = 1; r < NR; ++r) { f2.x = fma(c1[r], a[r].x, f2.x); f2.y = fma(c1[r], a[r].y, f2.y); }
+          for (int r = 1; r < NR; ++r) { fs[st].x = fma(cf[st][r], a[r].x, fs[st].x); fs[st].y = fma(cf[st][r], a[r].y, fs[st].y); }
+        }
       }
-      double2 comp; comp.x = f1.x + f2.x; comp.y = f1.y + f2.y;      // mft6.py:744
+      double2 comp = fs[0];                                           // mft6.py:744 / :753
+#pragma unroll
+      for (int st = 1; st < NS; ++st) { comp.x += fs[st].x; comp.y += fs[st].y; }
 #pragma unroll
       for (int f = 0; f < NC; ++f) {
         if ((cmask >> f) & 1u) {                                      // CTA-uniform
           const double2 wv = __ldg(reinterpret_cast<const double2*>(T.c_wbase[f] + px));
-          accC[f][0] = fma(wv.x, f1.x, accC[f][0]); accC[f][0] = fma(wv.y, f1.y, accC[f][0]);
-          accC[f][1] = fma(wv.x, f2.x, accC[f][1]); accC[f][1] = fma(wv.y, f2.y, accC[f][1]);
+#pragma unroll
+          for (int st = 0; st < NS; ++st) {
+            accC[f][st] = fma(wv.x, fs[st].x, accC[f][st]); accC[f][st] = fma(wv.y, fs[st].y, accC[f][st]);
+          }
         }
       }
 #pragma unroll
@@ -782,13 +803,18 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
       if (stage) { seg[seg_slot(h * 64 + 2 * lane + 1)] = comp.x; seg[seg_slot(h * 64 + 2 * lane + 2)] = comp.y; }
     }
 #pragma unroll
-    for (int r = 0; r < NR; ++r) { p0[r] += NWARP * CHUNK; p1[r] += NWARP * CHUNK; }
+    for (int st = 0; st < NS; ++st) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) pr[st][r] += NWARP * CHUNK;
+    }
     if (stage) {
       __syncwarp();
       for (int i = d0 + lane; i < d1; i += 32) {
         const int hl = T.rebin_hi[i] - cbase;                         // 0 .. CHUNK-1
         const double2 tab0 = __ldg(T.rebin_tab0 + i);
         const double2 tab1 = __ldg(T.rebin_tab1 + i);
+        double2 fx = make_double2(0.0, 0.0);                            // issued with the other table loads
+        if constexpr (MODE == MODE_POSTERIOR) fx = __ldg(T.data_fx + i);
         const double flo = seg[seg_slot(hl)];
         const double fhi = seg[seg_slot(hl + 1)];
         // extinct() on the model grid, then interp1d onto the observed pixel (mft6.py:1162, :1169)
@@ -807,7 +833,6 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         sM[i] = m;
         if constexpr (MODE == MODE_POSTERIOR) {
           // norm_spec's normal equations in the orthonormal basis, on the unscaled model (mft6.py:194-195)
-          const double2 fx = __ldg(T.data_fx + i);
           const double frac = fx.x * fast_rcp(m);
           const double x = fx.y;
           const double q1 = fma(T.basis[4], x, T.basis[3]);
@@ -826,9 +851,12 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   // ------------------------------------------------------------------ band integrals
   double red[KRED > 0 ? KRED : 1];
 #pragma unroll
-  for (int f = 0; f < NC; ++f) { red[2 * f] = accC[f][0]; red[2 * f + 1] = accC[f][1]; }
+  for (int f = 0; f < NC; ++f) {
 #pragma unroll
-  for (int f = 0; f < NP; ++f) red[2 * NC + f] = accP[f];
+    for (int st = 0; st < NS; ++st) red[NS * f + st] = accC[f][st];
+  }
+#pragma unroll
+  for (int f = 0; f < NP; ++f) red[NS * NC + f] = accP[f];
   block_sum<KRED, NWARP>(red, sRed);
 
   // ------------------------------------------------------------------ phase B: spectral chi-square
@@ -879,9 +907,12 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     double icontrast = 0.0, iphot = 0.0;
     for (int f = 0; f < NC; ++f) {
       if (f < T.n_contrast) {
-        const double m0 = -2.5 * log10(red[2 * f]);
-        const double m1 = -2.5 * log10(red[2 * f + 1]);
-        const double con = m1 - m0;                                   // mft6.py:741
+        // binaries: secondary - primary (mft6.py:741); triples: the first half of the filters measures the
+        // secondary, the second half the tertiary, both against the primary (mft6.py:747-749)
+        const int other = (NS == 2 || f < T.n_contrast / 2) ? 1 : 2;
+        const double m0 = -2.5 * log10(red[NS * f]);
+        const double m1 = -2.5 * log10(red[NS * f + other]);
+        const double con = m1 - m0;
         const double d = con - T.c_mag[f];
         icontrast += (d * d) / (T.c_err[f] * T.c_err[f]);
         if (parts.contrast) parts.contrast[w * T.n_contrast + f] = con;
@@ -889,7 +920,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     }
     for (int f = 0; f < NP; ++f) {
       if (f < T.n_phot) {
-        double mag = -2.5 * log10(red[2 * NC + f] * T.p_norm[f]);     // mft6.py:780-782
+        double mag = -2.5 * log10(red[NS * NC + f] * T.p_norm[f]);    // mft6.py:780-782
         mag += av * T.p_ext[f];                                       // mft6.py:1163 (av == 0 when skipped)
         const double d = mag - T.p_mag[f];
         iphot += (d * d) / (T.p_err[f] * T.p_err[f]);
@@ -1105,9 +1136,9 @@ int upload(ms_handle* h, const Tp* host, size_t n, const Tp** dev) {
   return MS_OK;
 }
 
-template <int NR, int NC, int NP, int NT, int MODE>
+template <int NR, int NC, int NP, int NT, int MODE, int NS>
 int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts, const OptIn& opt) {
-  auto kern = lnprob_stream_kernel<NR, NC, NP, NT, MODE>;
+  auto kern = lnprob_stream_kernel<NR, NC, NP, NT, MODE, NS>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing) {
@@ -1127,9 +1158,18 @@ int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut
 
 template <int NR, int NC, int NP, int NT>
 int launch_stream_threads(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts, int mode, const OptIn& opt) {
-  if (mode == MODE_OPTIMIZER) return launch_stream_mode<NR, NC, NP, NT, MODE_OPTIMIZER>(h, nw, d_lnp, parts, opt);
-  if (mode == MODE_NOSPEC) return launch_stream_mode<NR, NC, NP, NT, MODE_NOSPEC>(h, nw, d_lnp, parts, opt);
-  return launch_stream_mode<NR, NC, NP, NT, MODE_POSTERIOR>(h, nw, d_lnp, parts, opt);
+  if (h->T.nspec == 3) {
+    // triples: Teff x log g grids, posterior flavours only
+    if constexpr (NR == 4) {
+      if (mode == MODE_NOSPEC) return launch_stream_mode<NR, NC, NP, NT, MODE_NOSPEC, 3>(h, nw, d_lnp, parts, opt);
+      if (mode == MODE_POSTERIOR) return launch_stream_mode<NR, NC, NP, NT, MODE_POSTERIOR, 3>(h, nw, d_lnp, parts, opt);
+    }
+    set_err(h, "triples are built for (Teff, log g) grids and the posterior modes only");
+    return MS_ERR_UNSUPPORTED;
+  }
+  if (mode == MODE_OPTIMIZER) return launch_stream_mode<NR, NC, NP, NT, MODE_OPTIMIZER, 2>(h, nw, d_lnp, parts, opt);
+  if (mode == MODE_NOSPEC) return launch_stream_mode<NR, NC, NP, NT, MODE_NOSPEC, 2>(h, nw, d_lnp, parts, opt);
+  return launch_stream_mode<NR, NC, NP, NT, MODE_POSTERIOR, 2>(h, nw, d_lnp, parts, opt);
 }
 
 template <int NR, int NC, int NP>
@@ -1138,8 +1178,8 @@ int launch_stream_variant(ms_handle* h, long long nw, double* d_lnp, const Parts
   return launch_stream_threads<NR, NC, NP, 256>(h, nw, d_lnp, parts, mode, opt);
 }
 
-size_t stream_smem_bytes(int n_data, int nc, int np, int nwarp) {
-  const int kred = 2 * nc + np;
+size_t stream_smem_bytes(int n_data, int nc, int np, int nwarp, int nstar) {
+  const int kred = nstar * nc + np;
   size_t b = (size_t)nwarp * SEG * 8 + (size_t)nwarp * (kred > 4 ? kred : 4) * 8 + sizeof(SelectScratch);
   b += (size_t)n_data * 8;
   return (b + 15) & ~(size_t)15;
@@ -1252,7 +1292,8 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
   if (!cfg || !out) { set_err(nullptr, "ms_create: null argument"); return MS_ERR_INVALID; }
   *out = nullptr;
   if (cfg->abi_version != MS_ABI_VERSION) { set_err(nullptr, "ms_create: ABI version mismatch"); return MS_ERR_INVALID; }
-  if (cfg->nspec != 2) { set_err(nullptr, "ms_create: only nspec == 2 (binaries) is built"); return MS_ERR_UNSUPPORTED; }
+  if (cfg->nspec != 2 && cfg->nspec != 3) { set_err(nullptr, "ms_create: nspec must be 2 (binary) or 3 (triple)"); return MS_ERR_UNSUPPORTED; }
+  if (cfg->nspec == 3 && cfg->n_feh > 1) { set_err(nullptr, "ms_create: triples are built for (Teff, log g) grids only"); return MS_ERR_UNSUPPORTED; }
   if (cfg->n_contrast < 0 || cfg->n_contrast > MS_MAX_CONTRAST || cfg->n_phot < 0 || cfg->n_phot > MS_MAX_PHOT) {
     set_err(nullptr, "ms_create: too many filters"); return MS_ERR_UNSUPPORTED;
   }
@@ -1409,11 +1450,11 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
   int max_optin = 0;
   CKH(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   h->threads = 256;
-  h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, 8);
+  h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, 8, cfg->nspec);
   if (2 * (h->smem_bytes + 1024) > (size_t)max_optin + 1024) {
     // two 256-thread CTAs no longer fit an SM: run one 512-thread CTA instead (same warps in flight)
     h->threads = 512;
-    h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, 16);
+    h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, 16, cfg->nspec);
   }
   if (h->smem_bytes + 2048 > (size_t)max_optin) {
     h->err = "ms_create: n_data too large for the shared-memory resident model spectrum"; return fail(MS_ERR_UNSUPPORTED);
@@ -1488,6 +1529,7 @@ int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_ind
   if (!h) return MS_ERR_INVALID;
   if (nw < 0 || (nw > 0 && (!theta || !set_index || !rad_sigma || !chisq))) { set_err(h, "ms_optimizer_chisq: null argument"); return MS_ERR_INVALID; }
   if (h->opt_sets < 1) { set_err(h, "ms_optimizer_chisq: call ms_set_optimizer_data first"); return MS_ERR_INVALID; }
+  if (h->T.nspec != 2) { set_err(h, "ms_optimizer_chisq: the optimiser stage is built for binaries"); return MS_ERR_UNSUPPORTED; }
   if (nw == 0) return MS_OK;
   for (int64_t w = 0; w < nw; ++w)
     if (set_index[w] < 0 || set_index[w] >= h->opt_sets) { set_err(h, "ms_optimizer_chisq: set_index out of range"); return MS_ERR_INVALID; }

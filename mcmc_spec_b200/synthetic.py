@@ -198,10 +198,12 @@ def _interp_node_axis(nodes, v):
 def _draw_model(prob_like, theta):
     grid, wl, temps, lgs, matrix = (prob_like['grid'], prob_like['wl'], prob_like['temps'],
                                     prob_like['lgs'], prob_like['matrix'])
-    t1, t2, av, r1, ratio, plx = theta
+    ns = (len(theta) - 2) // 2
+    av, r1, plx = theta[ns], theta[ns + 1], theta[-1]
+    stars = [(theta[0], r1)] + [(theta[k], r1 * theta[ns + 1 + k]) for k in range(1, ns)]
     track = matrix[matrix[:, 1] == 9.0][:220]
     comps = []
-    for t, rad in ((t1, r1), (t2, r1 * ratio)):
+    for t, rad in stars:
         g = np.interp(t, track[:, 4], track[:, 5])
         jt, ut = _interp_node_axis(temps, t)
         jg, ug = _interp_node_axis(lgs, g)
@@ -226,7 +228,7 @@ def make_problem(*, temps=None, lgs=None, specmin=3000.0, specmax=30000.0, dlam=
                  phot_names=None, truth=None, plx=2.0732e-3, plx_err=0.0277e-3, snr=150.0,
                  seed=2298, fehs=None, feh=0.0, rad_prior=True, dist_fit=True,
                  data_flux=None, data_err=None, cmag=None, cerr=None, pmag=None, perr=None,
-                 ctm=None, ptm=None, pfilt_names=None):
+                 ctm=None, ptm=None, pfilt_names=None, nspec=2, nospec=False):
     """Assemble a synthetic ``Problem``.
 
     Defaults give the reference's koi2298 shapes (26 x 4 nodes, 135 000-pixel rows at 0.2 A,
@@ -289,13 +291,15 @@ def make_problem(*, temps=None, lgs=None, specmin=3000.0, specmax=30000.0, dlam=
 
     # ---- truth and observed data
     if truth is None:
-        truth = np.array([3850.0, 3425.0, 0.12, 0.4994, 0.61, plx])
+        truth = (np.array([3850.0, 3425.0, 0.12, 0.4994, 0.61, plx]) if nspec == 2 else
+                 np.array([3850.0, 3600.0, 3300.0, 0.12, 0.4994, 0.78, 0.5, plx]))
     truth = np.asarray(truth, dtype=np.float64)
     like = dict(grid=grid if fehs is None else None, wl=wl, temps=temps, lgs=lgs, matrix=matrix)
     if fehs is not None:
         like['grid'] = slice_feh(grid, fehs, feh)
-    pri, sec = _draw_model(like, truth)
-    comp = pri + sec
+    comps = _draw_model(like, truth)
+    pri, sec = comps[0], comps[1]
+    comp = sum(comps)
     if data_wl_um is None:
         lo, hi = window_um
         step = (hi - lo) / (n_data + 1)
@@ -303,8 +307,9 @@ def make_problem(*, temps=None, lgs=None, specmin=3000.0, specmax=30000.0, dlam=
         data_wl_um = np.sort(data_wl_um)
     data_wl_um = np.asarray(data_wl_um, dtype=np.float64)
     if data_flux is None:
-        ext = comp * 10.0 ** (-0.4 * truth[2] * _ccm89_k(wl))
+        ext = comp * 10.0 ** (-0.4 * truth[nspec] * _ccm89_k(wl))
         clean = np.interp(data_wl_um * 1e4, wl, ext)
+        av_true = truth[nspec]
         cont = 1.0 + 0.03 * (data_wl_um - data_wl_um.mean()) / np.ptp(data_wl_um)
         sigma = clean / snr
         flux = clean * cont + rng.normal(0.0, sigma)
@@ -322,23 +327,24 @@ def make_problem(*, temps=None, lgs=None, specmin=3000.0, specmax=30000.0, dlam=
             o = np.argsort(w, kind='mergesort')
             inb = (wl >= w.min()) & (wl <= w.max())
             tr = np.interp(wl[inb], w[o], t[o])
-            m = [-2.5 * np.log10(np.trapezoid(s[inb] * tr, wl[inb])) for s in (pri, sec)]
+            m = [-2.5 * np.log10(np.trapezoid(s[inb] * tr, wl[inb])) for s in comps]
+            other = 1 if (nspec == 2 or len(cmag) < len(contrast_curves) // 2) else 2          # mft6.py:747-749
             cerr.append(0.05)
-            cmag.append(float(m[1] - m[0] + rng.normal(0, 0.03)))
+            cmag.append(float(m[other] - m[0] + rng.normal(0, 0.03)))
     if pmag is None:
         pmag, perr = [], []
         for b in phot_bands:
-            m = -2.5 * np.log10(band_flux(b, wl, comp) / b.zero_flux) + truth[2] * float(_ccm89_k(np.mean(b.wavelength)))
+            m = -2.5 * np.log10(band_flux(b, wl, comp) / b.zero_flux) + truth[nspec] * float(_ccm89_k(np.mean(b.wavelength)))
             perr.append(0.03)
             pmag.append(float(m + rng.normal(0, 0.02)))
     phot_names_fr = list(pfilt_names) if pfilt_names is not None else [b.name for b in phot_bands]
     fr = [list(cmag), list(cerr), np.array(contrast_names), np.array(pmag, dtype=float), list(perr),
           np.array(phot_names_fr)]
-    ndim = 6
+    ndim = 2 * nspec + 2
     prior = [*np.zeros(2 * ndim - 2), plx, plx_err]              # mft6.py:3689
     return Problem(grid=grid, wl=wl, temps=temps, lgs=lgs, data=[data_wl_um, data_flux], err=data_err,
                    fr=fr, ctm=ctm, ptm=ptm, tmi=tmi, tma=tma, matrix=matrix, dust_dm_edges=dm_edges,
-                   dust_samples=dust_samples, photbands=phot_bands, prior=prior, nspec=2, av=True,
+                   dust_samples=dust_samples, photbands=phot_bands, prior=prior, nspec=nspec, nospec=nospec, av=True,
                    dist_fit=dist_fit, rad_prior=rad_prior, fehs=None if fehs is None else list(fehs),
                    feh=feh, truth=truth, meta=dict(seed=seed, res=res, window_um=tuple(window_um)))
 
@@ -411,6 +417,32 @@ def make_problem_c5(seed=2298, **kw):
                 contrast_curves=cc, contrast_names=cn, phot_curves=pc, phot_names=pn)
     args.update(kw)
     return make_problem(**args)
+
+
+def make_problem_triple_small(seed=2298, **kw):
+    """Reduced triple-star problem (nspec = 3, 8 parameters): 6 x 4 nodes, 6000-pixel rows, 4 contrast
+    filters (the first two constrain the secondary, the last two the tertiary: mft6.py:747-749)."""
+    wl = 5400.0 + 0.5 * np.arange(6000)
+    cc, cn, _, _ = _many_bands(wl, 4, 6)
+    args = dict(nspec=3, contrast_curves=cc, contrast_names=cn, truth=[3800.0, 3650.0, 3480.0, 0.10, 0.45, 0.8, 0.6, 2.5e-3])
+    args.update(kw)
+    return make_problem_small(seed=seed, **args)
+
+
+def sample_prior_box_triple(prob: Problem, n, seed=0):
+    """theta batch for triples: [T1, T2, T3, Av, R1, R2/R1, R3/R1, plx] with a few forced edge cases."""
+    rng = np.random.default_rng(seed)
+    tmin, tmax = float(min(prob.temps)), float(max(prob.temps))
+    th = np.empty((n, 8), dtype=np.float64)
+    th[:, 0:3] = rng.uniform(tmin, tmax, (n, 3))
+    th[:, 3] = rng.uniform(0.0, 1.0, n)
+    th[:, 4] = rng.uniform(0.1, 1.8, n)                                   # no upper bound on R1 for triples
+    th[:, 5:7] = rng.uniform(0.1, 1.0, (n, 2))
+    th[:, 7] = rng.uniform(1 / 1000.0, 1 / 100.0, n)
+    if n >= 8:
+        th[0, 0] = tmin; th[1, 2] = tmax; th[2, 1] = float(prob.temps[1])
+        th[3, 3] = 0.0; th[4, 3] = -0.01; th[5, 6] = 0.04; th[6, 7] = 1 / 1500.0; th[7, 1] = tmax + 1
+    return th
 
 
 def sample_prior_box(prob: Problem, n, seed=0, edge_cases=True):

@@ -302,8 +302,10 @@ def logprior(p0, nspec, tmin, tmax, matrix, dustmap, prior=0, ext=True, dist_fit
     ``plx_max``: 1/4 in mft6.py:1227, 1/100 in mft6_nospec.py:1228.
     """
     temps = p0[:nspec]
+    if len(p0) == 8:
+        return _logprior_triple(p0, nspec, tmin, tmax, matrix, dustmap, prior, ext, dist_fit, rad_prior)
     if len(p0) != 6:
-        raise NotImplementedError("only the binary (6-parameter) branches are restated")
+        raise ValueError("P0 doesn't match what I was expecting")          # mft6.py:1456-1457 prints this
     pp = []
 
     def av_term(extinct_val, plx):
@@ -362,6 +364,49 @@ def logprior(p0, nspec, tmin, tmax, matrix, dustmap, prior=0, ext=True, dist_fit
         model_radius2 = get_radius(temps[1], matrix)
         for k, p in enumerate([model_radius1, model_radius2 / model_radius1]):
             pp.append(-0.5 * ((rad_for_prior[k] - p) / (0.02 * p)) ** 2)
+    return np.sum(pp)
+
+
+def _logprior_triple(p0, nspec, tmin, tmax, matrix, dustmap, prior, ext, dist_fit, rad_prior):
+    """mft6.py:1329-1454 -- the two 8-parameter (triple) branches.  Quirks kept: no upper bound on R1 and a
+    parallax floor of 1/1000 with a distance (:1346); without one only the two ratios and the sign of the
+    parallax are checked (:1408).  With ``dist_fit`` the reference returns its sum only inside
+    ``if rad_prior`` (:1381-1393); ``rad_prior=False`` there falls off the end of the function (None ->
+    TypeError in logposterior), which is reported here as a ValueError."""
+    temps = p0[:nspec]
+    rad1, rad2, rad, dist = p0[-3], p0[-2], p0[-4], p0[-1]
+    extinct_val = p0[nspec] if dist_fit else p0[-5]
+    pp = []
+    if dist_fit == True:                           # noqa: E712
+        if (any(t > tmax for t in temps) or any(t < tmin for t in temps)
+                or any(r < 0.05 for r in [rad, rad1, rad2]) or dist < 1 / 1000 or dist > 1 / 4):
+            return -np.inf
+    else:
+        if any(t > tmax for t in temps) or any(t < tmin for t in temps) or rad1 < 0.05 or rad2 < 0.05 or dist < 0:
+            return -np.inf
+    if ext == True and extinct_val < 0:            # noqa: E712
+        return -np.inf
+    elif ext == True:                              # noqa: E712
+        mu, sig = _dust_moments(dustmap, dist)
+        pp.append(-0.5 * ((extinct_val - mu) / sig) ** 2)
+    if not (np.isscalar(prior) and prior == 0):
+        prior = list(prior)
+        if dist_fit == True:                       # noqa: E712
+            ps = prior[:nspec] + [prior[2 * nspec]] + prior[2 * nspec + 2:3 * nspec + 2] + [prior[-2]]
+            ss = (prior[nspec:2 * nspec] + [prior[2 * nspec + 1]] + prior[3 * nspec + 2:4 * nspec + 2]
+                  + [prior[-1]])
+        else:
+            ps = prior[:nspec] + [prior[2 * nspec]] + prior[2 * nspec + 2:3 * nspec + 1]
+            ss = prior[nspec:2 * nspec] + [prior[2 * nspec + 1]] + prior[3 * nspec + 2:4 * nspec + 1]
+        for k, p in enumerate(ps):
+            if p != 0:
+                pp.append(-0.5 * ((p0[k] - p) / ss[k]) ** 2)
+    if rad_prior == True:                          # noqa: E712
+        m1, m2, m3 = (get_radius(temps[k], matrix) for k in range(3))
+        for val, p in zip([rad, rad1, rad2], [m1, m2 / m1, m3 / m1]):
+            pp.append(-0.5 * ((val - p) / (0.02 * p)) ** 2)
+    elif dist_fit == True:                         # noqa: E712
+        raise ValueError("mft6.py:1329-1393 returns None for a triple with dist_fit and without rad_prior")
     return np.sum(pp)
 
 

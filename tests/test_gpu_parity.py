@@ -208,6 +208,36 @@ def test_3d_grid_trilinear_16_passbands(native_lib):
         lp.close()
 
 
+def test_triple_star_mode(native_lib):
+    """nspec = 3: 8-parameter vectors, third gather, split contrast list
+    (mft6.py:746-751), the 8-parameter prior branches (mft6.py:1329-1454)."""
+    import dataclasses
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    p = synthetic.make_problem_triple_small()
+    lp = LogPosterior(p)
+    assert lp.ndim == 8
+    theta = synthetic.sample_prior_box_triple(p, 256, seed=8)
+    theta[100:] = p.truth * (1 + 0.004 * np.random.default_rng(1).standard_normal((156, 8)))
+    theta[100:, 3] = np.abs(theta[100:, 3])
+    orc = to_oracle(p)
+    _compare(lp(theta), orc.lnprob_batch(theta))
+    parts = lp.parts(theta[100:108])
+    assert np.all(parts['status'] == 0)
+    for k in range(8):
+        ref = {}
+        orc.lnprob(theta[100 + k], ref)
+        assert np.allclose(parts['contrast'][k], ref['contrast'], rtol=1e-11)      # 2 x secondary, 2 x tertiary
+        assert np.allclose(parts['logg'][k], ref['logg'], rtol=1e-14) and parts['logg'].shape == (8, 3)
+    lp.close()
+    # without a distance prior only the ratios and the sign of the parallax are boxed (mft6.py:1408)
+    p2 = dataclasses.replace(p, dist_fit=False)
+    lp2 = LogPosterior(p2)
+    _compare(lp2(theta), to_oracle(p2).lnprob_batch(theta))
+    lp2.close()
+
+
 def test_broaden_rows_matches_oracle_splice(native_lib):
     from mcmc_spec_b200 import native, synthetic
     from oracle import mft6_oracle as mo
