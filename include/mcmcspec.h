@@ -196,6 +196,15 @@ int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_ind
 int ms_model_spectrum(ms_handle* h, const double* theta, int64_t nw, double* out, int where);
 
 /*
+ * Band magnitudes of each component, out [nw][n_contrast][nspec] = -2.5 log10(trapz(F_k * T, lambda))
+ * (mft6.py:729-733): what the posterior-predictive sweep of plot_results derives per sample through
+ * make_composite(plot=True) (mft6.py:785-828, :2486-2509) -- e.g. the Kepler magnitudes of primary
+ * and secondary, hence Delta Kp and the planet-radius correction factors -- when the band of interest
+ * is passed as one of the contrast filters.  NaN for walkers outside the prior box.
+ */
+int ms_component_mags(ms_handle* h, const double* theta, int64_t nw, double* out, int where);
+
+/*
  * Instrumental broadening of grid rows in place (host rows [n_rows][row_len]): the operator of
  * spec_interpolator/broaden, mft6.py:366-383 and :124-130 -- pixels [win_lo, win_lo+win_len) of
  * every row are convolved with the sum-normalised `taps` (odd n_taps, zero padded 'same'), then
@@ -235,6 +244,15 @@ int ms_stretch_scatter(ms_handle* h, double* state, int32_t* naccepted, const in
  */
 int ms_set_stream(ms_handle* h, void* stream);
 int ms_use_own_stream(ms_handle* h);
+
+/*
+ * CTAs per walker in the streaming kernel.  One CTA per walker cannot fill the GPU for ensembles of a
+ * few dozen walkers (the reference runs 50): a thread-block cluster of 2/4/8 CTAs then shares a walker
+ * (partial sums and the rebinned model meet in the leader CTA through distributed shared memory).
+ * 0 = automatic (clusters only while nw * ctas <= the number of SMs), 1 = never, 2/4/8 = forced.  Values
+ * agree with the one-CTA path to rounding (the partial sums are combined in a different order).
+ */
+int ms_set_cluster(ms_handle* h, int ctas_per_walker);
 
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 int64_t ms_launch_count(const ms_handle* h);

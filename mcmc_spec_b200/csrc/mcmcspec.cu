@@ -20,6 +20,7 @@
 
 #include "mcmcspec.h"
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -31,6 +32,8 @@
 #include <new>
 #include <string>
 #include <vector>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -125,6 +128,7 @@ struct OptIn {
 struct PartsOut {
   double* chi2_spec; double* contrast; double* phot; double* lnprior; double* logg; int* status;
   double* model;                        // [nw][n_data] median-scaled model
+  double* comp_mag;                     // [nw][n_contrast][nspec] -2.5 log10 of each component's band flux (mft6.py:733)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -660,7 +664,7 @@ template <int NR, int NC, int NP, int NT, int MODE, int NS>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __restrict__ plans,
                      const int* __restrict__ order, double* __restrict__ lnprob, const PartsOut parts,
-                     const OptIn opt) {
+                     const OptIn opt, const int csize) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NWARP = NT / 32;
   constexpr int KRED = NS * NC + NP;
@@ -670,8 +674,18 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   double* sM = reinterpret_cast<double*>(sSel + 1);                  // [n_data] model on observed pixels
   __shared__ WalkerPlan sPlan;
 
+  // Small ensembles (the reference runs 50 walkers) cannot fill 148 SMs with one CTA per walker: a
+  // thread-block cluster of `csize` CTAs then shares a walker.  Each CTA streams every csize-th group of
+  // chunks, rebinned pixels are stored straight into the leader CTA's model vector through distributed
+  // shared memory, the band sums are combined over the cluster, and the leader alone runs phase B.
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = (csize > 1) ? cluster.block_rank() : 0u;
+  __shared__ double sExport[MAX_STAR * MS_MAX_CONTRAST + MS_MAX_PHOT + 3];
+  __shared__ unsigned long long sExportKey[3];
+
   const int tid = threadIdx.x;
-  const long long w = order ? order[blockIdx.x] : blockIdx.x;       // launch order: grouped by grid cell
+  const long long slot = blockIdx.x / csize;
+  const long long w = order ? order[slot] : slot;                    // launch order: grouped by grid cell
   {
     // cooperative copy of the plan (16-byte chunks)
     const int4* src = reinterpret_cast<const int4*>(plans + w);
@@ -681,6 +695,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   __syncthreads();
   const int status = sPlan.status;
   if (status != 0) {                                                  // mft6.py:1465-1466
+    if (crank != 0) return;
     if (tid == 0) {
       lnprob[w] = (MODE == MODE_OPTIMIZER) ? CUDART_INF : -CUDART_INF;
       if (parts.status) parts.status[w] = status;
@@ -689,6 +704,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
       if (parts.logg) for (int s = 0; s < T.nspec; ++s) parts.logg[w * T.nspec + s] = sPlan.logg[s];
       if (parts.contrast) for (int c = 0; c < T.n_contrast; ++c) parts.contrast[w * T.n_contrast + c] = CUDART_NAN;
       if (parts.phot) for (int f = 0; f < T.n_phot; ++f) parts.phot[w * T.n_phot + f] = CUDART_NAN;
+      if (parts.comp_mag) for (int f = 0; f < T.n_contrast * NS; ++f) parts.comp_mag[w * T.n_contrast * NS + f] = CUDART_NAN;
     }
     if (parts.model) for (int i = tid; i < T.n_data; i += NT) parts.model[w * T.n_data + i] = CUDART_NAN;
     return;
@@ -702,7 +718,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       cf[s][r] = sPlan.coef[s][r];
-      pr[s][r] = T.grid + (long long)sPlan.row[s][r] * T.stride + warp * CHUNK + 2 * lane;
+      pr[s][r] = T.grid + (long long)sPlan.row[s][r] * T.stride + (crank * NWARP + warp) * CHUNK + 2 * lane;
     }
   }
   const double av = sPlan.av;
@@ -728,7 +744,9 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   // whose upper bracket falls into it, so the rebinning needs no block-wide barrier and the warps
   // drift apart: while some wait on their row loads others compute.
   const int n_chunks = T.n_tiles * CHUNKS_PER_TILE;
-  for (int c = warp; c < n_chunks; c += NWARP) {
+  const int cstep = csize * NWARP;
+  double* sM_dst = (csize > 1) ? cluster.map_shared_rank(sM, 0) : sM;   // the leader's model vector
+  for (int c = crank * NWARP + warp; c < n_chunks; c += cstep) {
     const int tile = c / CHUNKS_PER_TILE;
     const int cbase = c * CHUNK;                                      // first pixel of this warp's chunk
     const unsigned cmask = T.tile_cmask[tile];
@@ -805,7 +823,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
 #pragma unroll
     for (int st = 0; st < NS; ++st) {
 #pragma unroll
-      for (int r = 0; r < NR; ++r) pr[st][r] += NWARP * CHUNK;
+      for (int r = 0; r < NR; ++r) pr[st][r] += cstep * CHUNK;
     }
     if (stage) {
       __syncwarp();
@@ -830,7 +848,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         }
         const double ylo = flo * elo, yhi = fhi * ehi;
         const double m = ylo + (yhi - ylo) * tab0.x;
-        sM[i] = m;
+        sM_dst[i] = m;
         if constexpr (MODE == MODE_POSTERIOR) {
           // norm_spec's normal equations in the orthonormal basis, on the unscaled model (mft6.py:194-195)
           const double frac = fx.x * fast_rcp(m);
@@ -879,6 +897,30 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     for (int w2 = 1; w2 < NWARP; ++w2) { kmin = min(kmin, sSel->kmin[w2]); kmax = max(kmax, sSel->kmax[w2]); }
     has_nan = sSel->nanflag;
     __syncthreads();
+  }
+  if (csize > 1) {
+    // combine the cluster's partial sums in rank order (deterministic), then let the helpers go
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < KRED; ++k) sExport[k] = red[k];
+      sExport[KRED] = mom[0]; sExport[KRED + 1] = mom[1]; sExport[KRED + 2] = mom[2];
+      sExportKey[0] = kmin; sExportKey[1] = kmax; sExportKey[2] = (unsigned long long)has_nan;
+    }
+    cluster.sync();                                                   // also publishes the remote sM stores
+    if (crank == 0) {
+      for (int r = 1; r < csize; ++r) {
+        const double* e = cluster.map_shared_rank(sExport, r);
+        const unsigned long long* ek = cluster.map_shared_rank(sExportKey, r);
+#pragma unroll
+        for (int k = 0; k < KRED; ++k) red[k] += e[k];
+        mom[0] += e[KRED]; mom[1] += e[KRED + 1]; mom[2] += e[KRED + 2];
+        kmin = min(kmin, ek[0]); kmax = max(kmax, ek[1]); has_nan |= (int)ek[2];
+      }
+    }
+    cluster.sync();                                                   // helpers' shared memory was read
+    if (crank != 0) return;
+  }
+  if constexpr (MODE != MODE_NOSPEC) {
     unsigned long long* list = reinterpret_cast<unsigned long long*>(sF);
     if constexpr (MODE == MODE_POSTERIOR) {
       if (!has_nan) med = block_median_chi<NT, true>(sM, n, sSel, list, kmin, kmax, T, mom, &chi_un, sRed);  // mft6.py:1173
@@ -916,6 +958,8 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         const double d = con - T.c_mag[f];
         icontrast += (d * d) / (T.c_err[f] * T.c_err[f]);
         if (parts.contrast) parts.contrast[w * T.n_contrast + f] = con;
+        if (parts.comp_mag)
+          for (int st = 0; st < NS; ++st) parts.comp_mag[(w * T.n_contrast + f) * NS + st] = -2.5 * log10(red[NS * f + st]);
       }
     }
     for (int f = 0; f < NP; ++f) {
@@ -1088,6 +1132,8 @@ struct ms_handle {
   int corners = 4;               // rows per star
   int variant = 0;               // 0: (NC,NP)=(2,6), 1: (4,12)
   int threads = 256;             // CTA width of the streaming kernel
+  int cluster = 0;               // CTAs per walker: 0 = automatic (small batches), 1 = never, 2/4/8 = forced
+  int num_sms = 148;
   size_t smem_bytes = 0;
   // per-call buffers
   WalkerPlan* plans = nullptr; long long plans_cap = 0;
@@ -1149,7 +1195,25 @@ int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut
     h->ev_used += 2; h->timed_walkers += nw;
     CK(cudaEventRecord(e0, h->stream));
   }
-  kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, h->use_order ? h->order : nullptr, d_lnp, parts, opt);
+  // cluster size: enough CTAs for two per SM, at most 8 per walker (portable limit)
+  int csize = h->cluster;
+  if (csize <= 0) {
+    csize = 1;
+    while (csize < 8 && (long long)nw * csize * 2 <= 2ll * h->num_sms) csize *= 2;
+  }
+  const int* order = h->use_order ? h->order : nullptr;
+  if (csize == 1) {
+    kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, order, d_lnp, parts, opt, 1);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(nw * csize)); cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = h->smem_bytes; cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kern, h->T, (const WalkerPlan*)h->plans, order, d_lnp, parts, opt, csize));
+  }
   CK(cudaGetLastError());
   if (h->timing) CK(cudaEventRecord(e1, h->stream));
   h->launches += 1;
@@ -1364,6 +1428,7 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     CKH(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
     h->l2_bytes = (size_t)l2;
   }
+  CKH(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   CKC(upload(h, cfg->teff_nodes, cfg->n_teff, &T.teff_nodes));
   CKC(upload(h, cfg->logg_nodes, cfg->n_logg, &T.logg_nodes));
   CKC(upload(h, cfg->feh_nodes, cfg->n_feh, &T.feh_nodes));
@@ -1478,6 +1543,15 @@ int ms_use_own_stream(ms_handle* h) {
   return MS_OK;
 }
 
+int ms_set_cluster(ms_handle* h, int ctas_per_walker) {
+  if (!h) return MS_ERR_INVALID;
+  if (ctas_per_walker != 0 && ctas_per_walker != 1 && ctas_per_walker != 2 && ctas_per_walker != 4 && ctas_per_walker != 8) {
+    set_err(h, "ms_set_cluster: 0 (automatic), 1, 2, 4 or 8"); return MS_ERR_INVALID;
+  }
+  h->cluster = ctas_per_walker;
+  return MS_OK;
+}
+
 int ms_set_timing(ms_handle* h, int enabled) {
   if (!h) return MS_ERR_INVALID;
   h->timing = enabled != 0;
@@ -1550,7 +1624,7 @@ int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_ind
   if (e == cudaSuccess && ref_median) e = cudaMemcpyAsync(d_med, ref_median, (size_t)nw * 8, cudaMemcpyHostToDevice, h->stream);
   if (e != cudaSuccess) { set_err(h, std::string("ms_optimizer_chisq: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
   if (rc == MS_OK) {
-    PartsOut parts{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    PartsOut parts{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     OptIn opt{h->d_opt_flux, d_idx, d_rs, d_avp, d_med};
     rc = evaluate_device(h, h->d_theta, nw, h->d_lnp, parts, MODE_OPTIMIZER, opt);
   }
@@ -1573,7 +1647,7 @@ int ms_lnprob_parts(ms_handle* h, const double* theta, int64_t nw, double* lnpro
   CK(cudaSetDevice(h->device));
   const int ndim = h->T.ndim;
   if (where == MS_DEVICE) {
-    PartsOut parts{chi2_spec, contrast, phot, lnprior, logg, status, nullptr};
+    PartsOut parts{chi2_spec, contrast, phot, lnprior, logg, status, nullptr, nullptr};
     return evaluate_device(h, theta, nw, lnprob, parts);
   }
   if (where != MS_HOST) { set_err(h, "ms_lnprob: bad `where`"); return MS_ERR_INVALID; }
@@ -1588,7 +1662,7 @@ int ms_lnprob_parts(ms_handle* h, const double* theta, int64_t nw, double* lnpro
                  {logg, (size_t)nw * h->T.nspec * 8, nullptr}, {status, (size_t)nw * 4, nullptr}};
   for (auto& o : opts) if (o.host && o.bytes) CK(cudaMalloc(&o.dev, o.bytes));
   PartsOut parts{(double*)opts[0].dev, (double*)opts[1].dev, (double*)opts[2].dev, (double*)opts[3].dev,
-                 (double*)opts[4].dev, (int*)opts[5].dev, nullptr};
+                 (double*)opts[4].dev, (int*)opts[5].dev, nullptr, nullptr};
   rc = evaluate_device(h, h->d_theta, nw, h->d_lnp, parts);
   if (rc == MS_OK) {
     cudaError_t e = cudaMemcpyAsync(h->h_lnp, h->d_lnp, (size_t)nw * 8, cudaMemcpyDeviceToHost, h->stream);
@@ -1621,13 +1695,43 @@ int ms_model_spectrum(ms_handle* h, const double* theta, int64_t nw, double* out
     d_theta = h->d_theta;
     CK(cudaMalloc((void**)&d_out, (size_t)nw * n * 8));
   }
-  PartsOut parts{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_out};
+  PartsOut parts{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_out, nullptr};
   rc = evaluate_device(h, d_theta, nw, h->d_lnp, parts);
   if (where == MS_HOST) {
     if (rc == MS_OK) {
       cudaError_t e = cudaMemcpyAsync(out, d_out, (size_t)nw * n * 8, cudaMemcpyDeviceToHost, h->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
       if (e != cudaSuccess) { set_err(h, std::string("ms_model_spectrum: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
+    }
+    cudaFree(d_out);
+  }
+  return rc;
+}
+
+int ms_component_mags(ms_handle* h, const double* theta, int64_t nw, double* out, int where) {
+  if (!h) return MS_ERR_INVALID;
+  if (nw < 0 || (nw > 0 && (!theta || !out))) { set_err(h, "ms_component_mags: null argument"); return MS_ERR_INVALID; }
+  if (nw == 0 || h->T.n_contrast == 0) return MS_OK;
+  CK(cudaSetDevice(h->device));
+  const int ndim = h->T.ndim;
+  const size_t per = (size_t)h->T.n_contrast * h->T.nspec;
+  int rc = ensure_io(h, nw);
+  if (rc) return rc;
+  const double* d_theta = theta;
+  double* d_out = out;
+  if (where == MS_HOST) {
+    std::memcpy(h->h_theta, theta, (size_t)nw * ndim * 8);
+    CK(cudaMemcpyAsync(h->d_theta, h->h_theta, (size_t)nw * ndim * 8, cudaMemcpyHostToDevice, h->stream));
+    d_theta = h->d_theta;
+    CK(cudaMalloc((void**)&d_out, (size_t)nw * per * 8));
+  }
+  PartsOut parts{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_out};
+  rc = evaluate_device(h, d_theta, nw, h->d_lnp, parts);
+  if (where == MS_HOST) {
+    if (rc == MS_OK) {
+      cudaError_t e = cudaMemcpyAsync(out, d_out, (size_t)nw * per * 8, cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { set_err(h, std::string("ms_component_mags: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
     }
     cudaFree(d_out);
   }

@@ -21,8 +21,8 @@ MS_W_PRIOR_BOUNDS, MS_W_OFF_ISOCHRONE, MS_W_OFF_GRID, MS_W_NONFINITE = 1, 2, 4, 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmcmcspec.so')
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
-           'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows',
-           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_timing',
+           'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_component_mags', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows',
+           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_timing',
            'ms_kernel_time']
 
 _dp = C.POINTER(C.c_double)
@@ -84,6 +84,7 @@ def load_library(path=None):
     lib.ms_lnprob.argtypes = [vp, vp, C.c_int64, vp, C.c_int]
     lib.ms_lnprob_parts.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
     lib.ms_model_spectrum.argtypes = [vp, vp, C.c_int64, vp, C.c_int]
+    lib.ms_component_mags.argtypes = [vp, vp, C.c_int64, vp, C.c_int]
     lib.ms_set_optimizer_data.argtypes = [vp, vp, C.c_int32]
     lib.ms_optimizer_chisq.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, vp]
     lib.ms_broaden_rows.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32]
@@ -97,6 +98,7 @@ def load_library(path=None):
     lib.ms_launch_count.restype = C.c_int64
     lib.ms_set_stream.argtypes = [vp, vp]
     lib.ms_use_own_stream.argtypes = [vp]
+    lib.ms_set_cluster.argtypes = [vp, C.c_int]
     lib.ms_set_timing.argtypes = [vp, C.c_int]
     lib.ms_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     for name in EXPORTS:
@@ -225,6 +227,10 @@ class Engine:
     def use_own_stream(self):
         self._check(self.lib.ms_use_own_stream(self._h), 'ms_use_own_stream')
 
+    def set_cluster(self, ctas_per_walker):
+        """CTAs per walker: 0 automatic, 1 never, 2/4/8 forced (thread-block clusters for small ensembles)."""
+        self._check(self.lib.ms_set_cluster(self._h, int(ctas_per_walker)), 'ms_set_cluster')
+
     def set_timing(self, enabled):
         self._check(self.lib.ms_set_timing(self._h, int(bool(enabled))), 'ms_set_timing')
 
@@ -260,6 +266,14 @@ class Engine:
         out = np.empty((theta.shape[0], self.n_data), dtype=np.float64)
         self._check(self.lib.ms_model_spectrum(self._h, theta.ctypes.data, theta.shape[0], out.ctypes.data, MS_HOST),
                     'ms_model_spectrum')
+        return out
+
+    def component_mags_host(self, theta):
+        """[nw, n_contrast, nspec] band magnitudes of the individual stars (make_composite's ``mag``)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        out = np.empty((theta.shape[0], self.n_contrast, self.nspec), dtype=np.float64)
+        self._check(self.lib.ms_component_mags(self._h, theta.ctypes.data, theta.shape[0], out.ctypes.data, MS_HOST),
+                    'ms_component_mags')
         return out
 
     # -- optimiser stage

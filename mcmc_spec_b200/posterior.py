@@ -54,5 +54,12 @@ class LogPosterior:
         """Median-scaled model on the observed pixels (``init_cspec`` after mft6.py:1173)."""
         return self.engine.model_spectrum_host(np.atleast_2d(np.asarray(theta, dtype=np.float64)))
 
+    def component_mags(self, theta):
+        """Band magnitude of every component through every contrast filter, [nw, n_contrast, nspec]
+        (``mag`` of make_composite, mft6.py:729-733): pass the Kepler / Gaia curves as contrast filters to
+        get the per-sample component magnitudes of the reference's posterior-predictive sweep
+        (mft6.py:2486-2509)."""
+        return self.engine.component_mags_host(np.atleast_2d(np.asarray(theta, dtype=np.float64)))
+
     def close(self):
         self.engine.close()

@@ -68,6 +68,25 @@ def test_parts_match_oracle(small_problem, small_oracle, small_gpu):
             assert np.allclose(model[k], ref['model'], rtol=1e-13)
 
 
+def test_component_magnitudes(small_problem, small_oracle, small_gpu):
+    """Per-component band magnitudes (make_composite's ``mag``): their difference is the contrast."""
+    from mcmc_spec_b200 import synthetic
+    theta = synthetic.sample_prior_box(small_problem, 40, seed=19, edge_cases=False)
+    mags = small_gpu.component_mags(theta)
+    parts = small_gpu.parts(theta)
+    assert mags.shape == (40, 2, 2)
+    assert np.allclose(mags[:, :, 1] - mags[:, :, 0], parts['contrast'], rtol=1e-13, atol=1e-13)
+    from oracle import mft6_oracle as mo
+    o = small_oracle.p
+    k = 3
+    lg = [mo.get_logg(t, o.matrix) for t in theta[k, :2]]
+    w, spec, con, cwl, ph = mo.make_composite(theta[k, :2], lg, theta[k, 3:5], theta[k, 5], o.fr[2], o.fr[5], small_oracle.r,
+                                              o.specs, o.ctm, o.ptm, o.tmi, o.tma, o.temps, o.lgs, o.photlib, fs=o.fs)
+    assert np.allclose(mags[k, :, 1] - mags[k, :, 0], con, rtol=1e-12)
+    bad = theta[:2].copy(); bad[0, 2] = -1.0
+    assert np.all(np.isnan(small_gpu.component_mags(bad)[0])) and np.all(np.isfinite(small_gpu.component_mags(bad)[1]))
+
+
 def test_status_bits_and_domain_failures(small_problem, small_gpu):
     from mcmc_spec_b200 import native
     t = small_problem.truth
@@ -85,12 +104,36 @@ def test_status_bits_and_domain_failures(small_problem, small_gpu):
 def test_batch_split_and_permutation_are_bit_identical(small_problem, small_gpu):
     from mcmc_spec_b200 import synthetic
     theta = synthetic.sample_prior_box(small_problem, 600, seed=33)
+    small_gpu.engine.set_cluster(1)                         # one CTA per walker whatever the batch size
     full = small_gpu(theta)
     parts = np.concatenate([small_gpu(theta[:77]), small_gpu(theta[77:301]), small_gpu(theta[301:])])
     assert np.array_equal(full, parts)
     perm = np.random.default_rng(0).permutation(600)
     assert np.array_equal(small_gpu(theta[perm]), full[perm])
     assert small_gpu(theta[:0]).shape == (0,)               # empty batch
+    small_gpu.engine.set_cluster(0)
+
+
+def test_cluster_split_of_a_walker(small_problem, small_oracle, small_gpu):
+    """Thread-block clusters of 2/4/8 CTAs per walker (small ensembles): same values to rounding, and the
+    automatic choice kicks in for a 50-walker ensemble like the reference's."""
+    from mcmc_spec_b200 import synthetic
+    theta = synthetic.sample_prior_box(small_problem, 50, seed=71)
+    want = small_oracle.lnprob_batch(theta)
+    small_gpu.engine.set_cluster(1)
+    one = small_gpu(theta)
+    for c in (2, 4, 8, 0):
+        small_gpu.engine.set_cluster(c)
+        got = small_gpu(theta)
+        _compare(got, want)
+        f = np.isfinite(one)
+        assert np.array_equal(np.isfinite(got), f) and np.allclose(got[f], one[f], rtol=1e-13, atol=0)
+        assert np.array_equal(got, small_gpu(theta))        # deterministic within a mode
+        parts = small_gpu.parts(theta)
+        model = small_gpu.model_spectrum(theta[16:20])
+        assert np.allclose(np.median(model, axis=1), np.median(small_problem.data[1]), rtol=1e-14)
+        assert np.array_equal(parts['lnprob'], got)
+    small_gpu.engine.set_cluster(0)
 
 
 @pytest.mark.parametrize('n_data', [7, 255, 256, 300, 301, 1025])
