@@ -47,7 +47,7 @@ constexpr double PC_CM = 3.086e18;      // mft6.py:691
 constexpr double SIGMA_SB = 5.670374e-5;  // mft6.py:79
 constexpr double LSUN = 3.839e33;       // mft6.py:80
 
-constexpr int CHUNK = 128;               // model pixels a warp owns per step: two 64-pixel (32 x double2) sub-chunks
+constexpr int CHUNK = 128;               // model pixels a warp owns per step: 32 lanes x 4 pixels (one 256-bit load per row)
 constexpr int CHUNKS_PER_TILE = TILE / CHUNK;
 constexpr int SEG = CHUNK + CHUNK / 16 + 4;   // shared-memory doubles per warp: previous pixel + CHUNK composites, skewed
 
@@ -71,11 +71,10 @@ struct DevTables {
   double feh;
   // observed spectrum
   int n_data;
-  const int* rebin_hi;          // [N] upper bracketing model pixel
-  const double2* rebin_tab0;    // [N] {t, ext_lo}                      (two arrays: each load is fully coalesced)
-  const double2* rebin_tab1;    // [N] {(ext_hi - ext_lo) ln 2, ext_hi}
-  const double2* data_fx;       // [N] {flux, x}
-  const double* data_flux; const double* data_inv_e2; const double* data_x;
+  // 32-byte records, one 256-bit load per observed pixel and lane (fully coalesced):
+  const double* rebin_rec;      // [N][4] {t, ext_lo, (ext_hi - ext_lo) ln 2, upper bracketing pixel (as a double)}
+  const double* data_rec;       // [N][4] {x, flux, 1/err^2, 0}
+  const double* data_inv_e2;    // [N]
   const int* chunk_data_start;  // [n_tiles*CHUNKS_PER_TILE + 1] first observed pixel owned by each 128-pixel chunk;
                                 // bit 31 set when that pixel's lower bracket is the last pixel of the previous chunk
   double dext_max;              // max |(ext_hi - ext_lo) ln 2|
@@ -134,12 +133,6 @@ struct PartsOut {
 // ------------------------------------------------------------------------------------------
 // Small device helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double2 ldg_stream(const double* p) {
-  // grid rows are streamed once per CTA: keep them out of L1
-  double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
-}
 
 // 1/x to ~1 ulp for finite non-zero x (two Newton steps on the hardware seed); 0 -> inf, NaN -> NaN.
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -150,6 +143,20 @@ __device__ __forceinline__ double fast_rcp(double x) {
   e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   return r;
+}
+
+// Blackwell 256-bit global loads (LDG.E.256): four consecutive pixels per lane and instruction.
+struct __align__(32) dbl4 { double x, y, z, w; };
+__device__ __forceinline__ dbl4 ldg_stream4(const double* p) {
+  dbl4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ dbl4 ldg_cached4(const double* p) {
+  dbl4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -544,8 +551,8 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
     const int i0 = r * NT + tid, i1 = i0 + NT;
     const bool v0 = i0 < n, v1 = (r + 1 < rounds) && (i1 < n);
     double m0 = 0.0, m1 = 0.0, x0 = 0.0, x1 = 0.0, d0 = 0.0, d1 = 0.0, w0 = 0.0, w1 = 0.0;
-    if (v0) { m0 = sM[i0]; if constexpr (DO_CHI) { x0 = T.data_x[i0]; d0 = T.data_flux[i0]; w0 = T.data_inv_e2[i0]; } }
-    if (v1) { m1 = sM[i1]; if constexpr (DO_CHI) { x1 = T.data_x[i1]; d1 = T.data_flux[i1]; w1 = T.data_inv_e2[i1]; } }
+    if (v0) { m0 = sM[i0]; if constexpr (DO_CHI) { const dbl4 r0 = ldg_cached4(T.data_rec + 4 * (long long)i0); x0 = r0.x; d0 = r0.y; w0 = r0.z; } }
+    if (v1) { m1 = sM[i1]; if constexpr (DO_CHI) { const dbl4 r1 = ldg_cached4(T.data_rec + 4 * (long long)i1); x1 = r1.x; d1 = r1.y; w1 = r1.z; } }
     unsigned dg0 = 0xffffffffu, dg1 = 0xffffffffu;
     if (v0) {
       if constexpr (DO_CHI) {
@@ -718,7 +725,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       cf[s][r] = sPlan.coef[s][r];
-      pr[s][r] = T.grid + (long long)sPlan.row[s][r] * T.stride + (crank * NWARP + warp) * CHUNK + 2 * lane;
+      pr[s][r] = T.grid + (long long)sPlan.row[s][r] * T.stride + (crank * NWARP + warp) * CHUNK + 4 * lane;
     }
   }
   const double av = sPlan.av;
@@ -768,57 +775,74 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
       }
       seg[seg_slot(0)] = tot;
     }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int px = cbase + h * 64 + 2 * lane;
-      double2 fs[NS];                                                 // this pixel pair's flux of each star
+    {
+      const int px = cbase + 4 * lane;                                // this lane's four pixels of the chunk
+      dbl4 fs[NS];                                                    // their flux, per star
       if constexpr (NS * NR <= 8) {
-        // all rows of all stars in flight at once (binaries on a Teff x log g grid)
-        double2 a[NS][NR];
+        // all rows of all stars in flight at once (binaries on a Teff x log g grid): 8 x 32 bytes per lane
+        dbl4 a[NS][NR];
 #pragma unroll
         for (int st = 0; st < NS; ++st) {
 #pragma unroll
-          for (int r = 0; r < NR; ++r) a[st][r] = ldg_stream(pr[st][r] + h * 64);
+          for (int r = 0; r < NR; ++r) a[st][r] = ldg_stream4(pr[st][r]);
         }
 #pragma unroll
         for (int st = 0; st < NS; ++st) {
-          fs[st].x = cf[st][0] * a[st][0].x; fs[st].y = cf[st][0] * a[st][0].y;
+          const double c = cf[st][0];
+          fs[st].x = c * a[st][0].x; fs[st].y = c * a[st][0].y; fs[st].z = c * a[st][0].z; fs[st].w = c * a[st][0].w;
 #pragma unroll
-          for (int r = 1; r < NR; ++r) { fs[st].x = fma(cf[st][r], a[st][r].x, fs[st].x); fs[st].y = fma(cf[st][r], a[st][r].y, fs[st].y); }
+          for (int r = 1; r < NR; ++r) {
+            const double cr = cf[st][r];
+            fs[st].x = fma(cr, a[st][r].x, fs[st].x); fs[st].y = fma(cr, a[st][r].y, fs[st].y);
+            fs[st].z = fma(cr, a[st][r].z, fs[st].z); fs[st].w = fma(cr, a[st][r].w, fs[st].w);
+          }
         }
       } else {
-        // 8 corners per star or three stars: one star at a time keeps at most 8 16-byte loads live
+        // 8 corners per star or three stars: one star at a time
 #pragma unroll
         for (int st = 0; st < NS; ++st) {
-          double2 a[NR];
+          dbl4 a[NR];
 #pragma unroll
-          for (int r = 0; r < NR; ++r) a[r] = ldg_stream(pr[st][r] + h * 64);
-          fs[st].x = cf[st][0] * a[0].x; fs[st].y = cf[st][0] * a[0].y;
+          for (int r = 0; r < NR; ++r) a[r] = ldg_stream4(pr[st][r]);
+          const double c = cf[st][0];
+          fs[st].x = c * a[0].x; fs[st].y = c * a[0].y; fs[st].z = c * a[0].z; fs[st].w = c * a[0].w;
 #pragma unroll
-          for (int r = 1; r < NR; ++r) { fs[st].x = fma(cf[st][r], a[r].x, fs[st].x); fs[st].y = fma(cf[st][r], a[r].y, fs[st].y); }
+          for (int r = 1; r < NR; ++r) {
+            const double cr = cf[st][r];
+            fs[st].x = fma(cr, a[r].x, fs[st].x); fs[st].y = fma(cr, a[r].y, fs[st].y);
+            fs[st].z = fma(cr, a[r].z, fs[st].z); fs[st].w = fma(cr, a[r].w, fs[st].w);
+          }
         }
       }
-      double2 comp = fs[0];                                           // mft6.py:744 / :753
+      dbl4 comp = fs[0];                                              // mft6.py:744 / :753
 #pragma unroll
-      for (int st = 1; st < NS; ++st) { comp.x += fs[st].x; comp.y += fs[st].y; }
+      for (int st = 1; st < NS; ++st) { comp.x += fs[st].x; comp.y += fs[st].y; comp.z += fs[st].z; comp.w += fs[st].w; }
 #pragma unroll
       for (int f = 0; f < NC; ++f) {
-        if ((cmask >> f) & 1u) {                                      // CTA-uniform
-          const double2 wv = __ldg(reinterpret_cast<const double2*>(T.c_wbase[f] + px));
+        if ((cmask >> f) & 1u) {                                      // warp-uniform
+          const dbl4 wv = ldg_cached4(T.c_wbase[f] + px);
 #pragma unroll
           for (int st = 0; st < NS; ++st) {
-            accC[f][st] = fma(wv.x, fs[st].x, accC[f][st]); accC[f][st] = fma(wv.y, fs[st].y, accC[f][st]);
+            double acc = accC[f][st];
+            acc = fma(wv.x, fs[st].x, acc); acc = fma(wv.y, fs[st].y, acc);
+            acc = fma(wv.z, fs[st].z, acc); acc = fma(wv.w, fs[st].w, acc);
+            accC[f][st] = acc;
           }
         }
       }
 #pragma unroll
       for (int f = 0; f < NP; ++f) {
         if ((pmask >> f) & 1u) {
-          const double2 wv = __ldg(reinterpret_cast<const double2*>(T.p_wbase[f] + px));
-          accP[f] = fma(wv.x, comp.x, accP[f]); accP[f] = fma(wv.y, comp.y, accP[f]);
+          const dbl4 wv = ldg_cached4(T.p_wbase[f] + px);
+          double acc = accP[f];
+          acc = fma(wv.x, comp.x, acc); acc = fma(wv.y, comp.y, acc); acc = fma(wv.z, comp.z, acc); acc = fma(wv.w, comp.w, acc);
+          accP[f] = acc;
         }
       }
-      if (stage) { seg[seg_slot(h * 64 + 2 * lane + 1)] = comp.x; seg[seg_slot(h * 64 + 2 * lane + 2)] = comp.y; }
+      if (stage) {
+        seg[seg_slot(4 * lane + 1)] = comp.x; seg[seg_slot(4 * lane + 2)] = comp.y;
+        seg[seg_slot(4 * lane + 3)] = comp.z; seg[seg_slot(4 * lane + 4)] = comp.w;
+      }
     }
 #pragma unroll
     for (int st = 0; st < NS; ++st) {
@@ -828,31 +852,30 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     if (stage) {
       __syncwarp();
       for (int i = d0 + lane; i < d1; i += 32) {
-        const int hl = T.rebin_hi[i] - cbase;                         // 0 .. CHUNK-1
-        const double2 tab0 = __ldg(T.rebin_tab0 + i);
-        const double2 tab1 = __ldg(T.rebin_tab1 + i);
-        double2 fx = make_double2(0.0, 0.0);                            // issued with the other table loads
-        if constexpr (MODE == MODE_POSTERIOR) fx = __ldg(T.data_fx + i);
+        const dbl4 rec = ldg_cached4(T.rebin_rec + 4 * (long long)i);
+        dbl4 drec; drec.x = drec.y = drec.z = drec.w = 0.0;            // issued with the other table load
+        if constexpr (MODE == MODE_POSTERIOR) drec = ldg_cached4(T.data_rec + 4 * (long long)i);
+        const int hl = (int)rec.w - cbase;                            // 0 .. CHUNK-1
         const double flo = seg[seg_slot(hl)];
         const double fhi = seg[seg_slot(hl + 1)];
         // extinct() on the model grid, then interp1d onto the observed pixel (mft6.py:1162, :1169)
-        const double elo = exp2(av * tab0.y);
+        const double elo = exp2(av * rec.y);
         double ehi;
         if (small_dext) {
-          const double xx = av * tab1.x;                               // E_hi = E_lo * exp(xx), |xx| < 4e-3
+          const double xx = av * rec.z;                                // E_hi = E_lo * exp(xx), |xx| < 4e-3
           double pz = fma(xx, 1.0 / 120.0, 1.0 / 24.0);
           pz = fma(pz, xx, 1.0 / 6.0); pz = fma(pz, xx, 0.5); pz = fma(pz, xx, 1.0); pz = fma(pz, xx, 1.0);
           ehi = elo * pz;
         } else {
-          ehi = exp2(av * tab1.y);
+          ehi = exp2(av * fma(rec.z, 1.4426950408889634, rec.y));   // ext_hi = ext_lo + dext / ln 2
         }
         const double ylo = flo * elo, yhi = fhi * ehi;
-        const double m = ylo + (yhi - ylo) * tab0.x;
+        const double m = ylo + (yhi - ylo) * rec.x;
         sM_dst[i] = m;
         if constexpr (MODE == MODE_POSTERIOR) {
           // norm_spec's normal equations in the orthonormal basis, on the unscaled model (mft6.py:194-195)
-          const double frac = fx.x * fast_rcp(m);
-          const double x = fx.y;
+          const double frac = drec.y * fast_rcp(m);
+          const double x = drec.x;
           const double q1 = fma(T.basis[4], x, T.basis[3]);
           const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
           mom[0] = fma(T.basis[0], frac, mom[0]); mom[1] = fma(q1, frac, mom[1]); mom[2] = fma(q2, frac, mom[2]);
@@ -1439,29 +1462,22 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
       h->err = "ms_create: rebin_hi must be ascending and inside the region"; return fail(MS_ERR_INVALID);
     }
   }
-  CKC(upload(h, cfg->rebin_hi, cfg->n_data, &T.rebin_hi));
-  CKC(upload(h, cfg->data_flux, cfg->n_data, &T.data_flux));
-  CKC(upload(h, cfg->data_x, cfg->n_data, &T.data_x));
   {
     const int n = cfg->n_data;
     const double LN2 = 0.69314718055994530942;
-    std::vector<double> inv_e2(n);
-    std::vector<double2> tab0(n), tab1(n);
-    std::vector<double2> fx(n);
+    std::vector<double> inv_e2(n), rrec(4 * (size_t)n), drec(4 * (size_t)n);
     double dmax = 0.0;
     for (int i = 0; i < n; ++i) {
       inv_e2[i] = 1.0 / (cfg->data_err[i] * cfg->data_err[i]);                                       // mft6.py:120
       const double dext = (cfg->ext_hi[i] - cfg->ext_lo[i]) * LN2;
       dmax = std::max(dmax, std::fabs(dext));
-      tab0[i] = make_double2(cfg->rebin_t[i], cfg->ext_lo[i]);
-      tab1[i] = make_double2(dext, cfg->ext_hi[i]);
-      fx[i] = make_double2(cfg->data_flux[i], cfg->data_x[i]);
+      rrec[4 * i] = cfg->rebin_t[i]; rrec[4 * i + 1] = cfg->ext_lo[i]; rrec[4 * i + 2] = dext; rrec[4 * i + 3] = (double)cfg->rebin_hi[i];
+      drec[4 * i] = cfg->data_x[i]; drec[4 * i + 1] = cfg->data_flux[i]; drec[4 * i + 2] = inv_e2[i]; drec[4 * i + 3] = 0.0;
     }
     T.dext_max = dmax;
     CKC(upload(h, inv_e2.data(), inv_e2.size(), &T.data_inv_e2));
-    CKC(upload(h, tab0.data(), tab0.size(), &T.rebin_tab0));
-    CKC(upload(h, tab1.data(), tab1.size(), &T.rebin_tab1));
-    CKC(upload(h, fx.data(), fx.size(), &T.data_fx));
+    CKC(upload(h, rrec.data(), rrec.size(), &T.rebin_rec));
+    CKC(upload(h, drec.data(), drec.size(), &T.data_rec));
     // observed pixels owned by each 128-pixel chunk (rebin_hi is ascending)
     const int n_chunks = cfg->n_tiles * CHUNKS_PER_TILE;
     std::vector<int> cds((size_t)n_chunks + 1);
