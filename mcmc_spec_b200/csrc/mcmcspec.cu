@@ -75,11 +75,11 @@ struct DevTables {
   const double* rebin_rec;      // [N][4] {t, ext_lo, (ext_hi - ext_lo) ln 2, upper bracketing pixel (as a double)}
   const double* data_rec;       // [N][4] {x, flux, 1/err^2, 0}
   const double* data_inv_e2;    // [N]
-  const int* chunk_data_start;  // [n_tiles*CHUNKS_PER_TILE + 1] first observed pixel owned by each 128-pixel chunk;
-                                // bit 31 set when that pixel's lower bracket is the last pixel of the previous chunk
+  const int4* chunk_meta;       // [n_tiles*CHUNKS_PER_TILE] {contrast filter mask, photometric filter mask, first observed
+                                // pixel owned by the chunk (bit 31: its lower bracket is the last pixel of the previous
+                                // chunk), one past the last observed pixel}: one 16-byte load per chunk
   double dext_max;              // max |(ext_hi - ext_lo) ln 2|
   const double* opt_median;     // [n_sets] np.median of each renormalised optimiser flux set
-  const unsigned* tile_cmask; const unsigned* tile_pmask;
   double basis[9];
   double data_median;
   // filters: pointer such that weight of region pixel p is wbase[p]
@@ -754,13 +754,12 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   const int cstep = csize * NWARP;
   double* sM_dst = (csize > 1) ? cluster.map_shared_rank(sM, 0) : sM;   // the leader's model vector
   for (int c = crank * NWARP + warp; c < n_chunks; c += cstep) {
-    const int tile = c / CHUNKS_PER_TILE;
     const int cbase = c * CHUNK;                                      // first pixel of this warp's chunk
-    const unsigned cmask = T.tile_cmask[tile];
-    const unsigned pmask = T.tile_pmask[tile];
-    const int ds_raw = T.chunk_data_start[c];
+    const int4 meta = __ldg(T.chunk_meta + c);
+    const unsigned cmask = (unsigned)meta.x, pmask = (unsigned)meta.y;
+    const int ds_raw = meta.z;
     const int d0 = ds_raw & 0x7fffffff;
-    const int d1 = T.chunk_data_start[c + 1] & 0x7fffffff;
+    const int d1 = meta.w;
     const bool stage = (MODE != MODE_NOSPEC) && d1 > d0;
     const bool need_prev = stage && ds_raw < 0;                        // warp-uniform
     if (need_prev && lane == 0) {
@@ -1457,6 +1456,7 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
   CKC(upload(h, cfg->feh_nodes, cfg->n_feh, &T.feh_nodes));
 
   // ---- observed spectrum tables
+  std::vector<int> chunk_start;
   for (int i = 0; i < cfg->n_data; ++i) {
     if (cfg->rebin_hi[i] < 1 || cfg->rebin_hi[i] >= cfg->n_reg || (i && cfg->rebin_hi[i] < cfg->rebin_hi[i - 1])) {
       h->err = "ms_create: rebin_hi must be ascending and inside the region"; return fail(MS_ERR_INVALID);
@@ -1487,7 +1487,7 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
       cds[c] = i;
       if (c < n_chunks && i < n && cfg->rebin_hi[i] == c * CHUNK) cds[c] |= (int)0x80000000;
     }
-    CKC(upload(h, cds.data(), cds.size(), &T.chunk_data_start));
+    chunk_start = cds;
   }
 
   // ---- filters
@@ -1516,8 +1516,14 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     T.p_norm[f] = cfg->p_norm[f]; T.p_ext[f] = cfg->p_ext[f];
     T.p_mag[f] = cfg->p_mag[f]; T.p_err[f] = cfg->p_err[f];
   }
-  CKC(upload(h, cmask.data(), cmask.size(), &T.tile_cmask));
-  CKC(upload(h, pmask.data(), pmask.size(), &T.tile_pmask));
+  {
+    const int n_chunks = cfg->n_tiles * CHUNKS_PER_TILE;
+    std::vector<int4> meta(n_chunks);
+    for (int c = 0; c < n_chunks; ++c)
+      meta[c] = make_int4((int)cmask[c / CHUNKS_PER_TILE], (int)pmask[c / CHUNKS_PER_TILE], chunk_start[c],
+                          chunk_start[c + 1] & 0x7fffffff);
+    CKC(upload(h, meta.data(), meta.size(), &T.chunk_meta));
+  }
 
   // ---- isochrone, dust
   CKC(upload(h, cfg->iso_teff, cfg->n_iso, &T.iso_teff));
