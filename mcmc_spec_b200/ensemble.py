@@ -100,6 +100,7 @@ class EnsembleSampler:
         self._packed = torch.empty((self.shard, ndim + 2), **f64)
         self._full = self._packed if world_size == 1 else torch.empty((self.half, ndim + 2), **f64)
         self._fixed = [torch.arange(0, nwalkers, 2, device=self.device), torch.arange(1, nwalkers, 2, device=self.device)]
+        self._side, self._next = None, None
 
     # ------------------------------------------------------------------ state
     def initialize(self, p0):
@@ -132,12 +133,35 @@ class EnsembleSampler:
         return (self.naccepted.to(torch.float64) / max(self.iteration, 1)).cpu().numpy()
 
     # ------------------------------------------------------------------ one iteration
-    def _halves(self):
-        if not self.randomize_split:
-            return self._fixed
-        keys = self.backend.split_keys(self.seed, self.iteration, self.nwalkers)
+    def _compute_halves(self, iteration):
+        keys = self.backend.split_keys(self.seed, iteration, self.nwalkers)
         perm = torch.argsort(keys, stable=True)
         return [perm[0::2].contiguous(), perm[1::2].contiguous()]       # inds = arange(nw) % 2, shuffled
+
+    def _halves(self):
+        """Red/blue split of this iteration.  The permutation depends only on (seed, iteration), so on a
+        GPU the one for the *next* iteration is computed on a side stream while this iteration's kernels
+        run, which takes the 65 536-key sort off the critical path."""
+        if not self.randomize_split:
+            return self._fixed
+        if self.device.type != 'cuda':
+            return self._compute_halves(self.iteration)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        if self._next is None or self._next[0] != self.iteration:
+            self._next = (self.iteration, self._compute_halves(self.iteration), None)
+        it, halves, ev = self._next
+        if ev is not None:
+            main.wait_event(ev)
+        for h in halves:
+            h.record_stream(main)
+        with torch.cuda.stream(self._side):
+            nxt = self._compute_halves(self.iteration + 1)
+            ev2 = torch.cuda.Event()
+            ev2.record(self._side)
+        self._next = (self.iteration + 1, nxt, ev2)
+        return halves
 
     def step(self):
         """One ensemble iteration = two half steps; every walker gets one proposal."""
