@@ -193,7 +193,11 @@ def orthonormal_quadratic_basis(x):
     return np.asarray(B, dtype=np.float64)
 
 
-def build_tables(prob) -> DeviceTables:
+def build_tables(prob, component_bands=None) -> DeviceTables:
+    """``component_bands``: optional list replacing the contrast filters by bands whose per-component
+    flux is wanted (the posterior-predictive sweep, mft6.py:785-816): ``('energy', wl, tm)`` -- the
+    contrast-type integral ``trapz(F_k * tran, wl)`` of mft6.py:798 -- or ``('library', PhotBand)`` --
+    pyphot ``get_flux(F_k)`` (:813).  The consumed region stays the one of the fit's own filters."""
     wl = np.asarray(prob.wl, dtype=np.float64)
     data_wl, data_flux = (np.asarray(a, dtype=np.float64) for a in prob.data)
     err = np.asarray(prob.err, dtype=np.float64)
@@ -222,6 +226,30 @@ def build_tables(prob) -> DeviceTables:
         if inb.size:
             row[inb] = np.interp(wl_reg[inb], ws, ts) * trapz_weights(wl_reg[inb])
         crows.append(row)
+    c_mag, c_err = np.array(prob.fr[0], dtype=np.float64), np.array(prob.fr[1], dtype=np.float64)
+    if component_bands is not None:
+        crows = []
+        for spec in component_bands:
+            row = np.zeros(n_reg)
+            if spec[0] == 'energy':
+                ws, ts = _sorted_curve(spec[1], spec[2])
+                inb = np.where((wl_reg <= ws[-1]) & (wl_reg >= ws[0]))[0]
+                if inb.size:
+                    row[inb] = np.interp(wl_reg[inb], ws, ts) * trapz_weights(wl_reg[inb])
+            elif spec[0] == 'library':
+                band = spec[1]
+                T = np.interp(wl_reg, band.wavelength, band.transmit, left=0.0, right=0.0)
+                nz = np.nonzero(T > 0)[0]
+                if nz.size:
+                    lo, hi = max(0, nz.min() - 5), min(n_reg, nz.max() + 5)
+                    lam = wl_reg[lo:hi]
+                    kern = lam * T[lo:hi] if 'photon' in band.dtype else T[lo:hi]
+                    row[lo:hi] = kern * trapz_weights(lam) / np.trapezoid(kern, lam)
+            else:
+                raise ValueError("component band kind must be 'energy' or 'library'")
+            crows.append(row)
+        # no observed contrast belongs to these bands: infinite errors keep them out of the chi-square
+        c_mag, c_err = np.zeros(len(crows)), np.full(len(crows), np.inf)
     contrast = _pack(crows, n_reg)
 
     # ---- photometric library filters (pyphot get_flux; mft6.py:771-783)
@@ -295,7 +323,7 @@ def build_tables(prob) -> DeviceTables:
         wl_reg=wl_reg, n_data=int(data_wl.size), rebin_hi=hi, rebin_t=rebin_t,
         ext_lo=ext_coef[lo], ext_hi=ext_coef[hi], data_flux=data_flux, data_err=err, data_x=data_x,
         poly_basis=basis, data_median=float(np.median(data_flux)),
-        contrast=contrast, c_mag=np.array(prob.fr[0], dtype=np.float64), c_err=np.array(prob.fr[1], dtype=np.float64),
+        contrast=contrast, c_mag=c_mag, c_err=c_err,
         phot=phot, p_norm=np.array(p_norm), p_ext=np.array(p_ext),
         p_mag=np.array(prob.fr[3], dtype=np.float64), p_err=np.array(prob.fr[4], dtype=np.float64),
         iso_teff=np.ascontiguousarray(teff5[o]), iso_logg=np.ascontiguousarray(logg5[o]),

@@ -242,6 +242,51 @@ def make_composite(teff, logg, rad, distance, contrast_filt, phot_filt, r, specs
             np.array([float(p) for p in phot_cwl]), np.array([p for p in phot_phot]))
 
 
+def make_composite_plot(teff, logg, rad, distance, r, specs, ctm, ptm, tmi, tma, temps, lgs,
+                        kepler_curve, gaia_lib):
+    """mft6.py:651-716 + :785-816 -- ``make_composite(..., plot=True)`` for binaries: the component
+    spectra on the consumed region, each component's energy-weighted Kepler band magnitude
+    (``np.trapz(F_k * tran, wl)``, no zero point) and its pyphot ``Gaia_G`` Vega magnitude
+    ``-2.5 log10(get_flux(F_k)) - Vega_zero_mag``; plus the composite's Gaia magnitude.
+
+    ``kepler_curve``: (ran, tm) of ``get_transmission('kepler', res)``; ``gaia_lib``: the
+    ``lib['Gaia_G']`` stand-in (thirdparty.LibraryFilter with ``Vega_zero_flux``).  The reference
+    also interpolates the ``'gaia,g'`` bps curve (:789, :794) but never uses the result.  The
+    ``nspec == 3`` branch divides by an undefined-at-that-point list ``zp`` (:820) and is not restated.
+
+    Returns (wl, spec1, pri_spec, sec_spec, pri_mag, sec_mag, gaia_pri, gaia_sec, gaiamag).
+    """
+    wls, _, _, _ = ctm
+    phot_wls, _, _, _ = ptm
+    wlmin, wlmax = np.inf, 0
+    for w in list(wls) + list(phot_wls):
+        wlmin = min(wlmin, min(w)); wlmax = max(wlmax, max(w))
+    region = [min(min(r), tmi / 1e4, wlmin / 1e4) - 1e-4, max(max(r), tma / 1e4, wlmax / 1e4) + 1e-4]
+
+    pri_wl, pri_spec = get_spec(teff[0], logg[0], region, specs, temps, lgs)
+    sec_wl, sec_spec = get_spec(teff[1], logg[1], region, specs, temps, lgs)
+    if not type(distance) == bool:
+        di = 1 / distance
+        pri_spec = pri_spec * (rad[0] * RSUN / (di * PC_CM)) ** 2
+        sec_spec = sec_spec * (rad[0] * rad[1] * RSUN / (di * PC_CM)) ** 2
+    else:
+        sec_spec = sec_spec * rad[0] ** 2                                   # mft6.py:703
+    spec1 = pri_spec + sec_spec
+
+    ran, tm = kepler_curve
+    inband = np.where((pri_wl >= min(ran)) & (pri_wl <= max(ran)))
+    data_tm = interp1d(ran, tm)(pri_wl[inband])
+    pri_phot = np.trapezoid(pri_spec[inband] * data_tm, pri_wl[inband])    # :798
+    sec_phot = np.trapezoid(sec_spec[inband] * data_tm, pri_wl[inband])    # :799
+    pri_mag, sec_mag = -2.5 * np.log10(pri_phot), -2.5 * np.log10(sec_phot)
+
+    vega_zero_mag = -2.5 * np.log10(gaia_lib.Vega_zero_flux)                # pyphot Vega_zero_mag
+    gaiamag = -2.5 * np.log10(gaia_lib.get_flux(pri_wl, spec1) / gaia_lib.Vega_zero_flux)   # :812
+    gaia_pri = -2.5 * np.log10(gaia_lib.get_flux(pri_wl, pri_spec)) - vega_zero_mag         # :813
+    gaia_sec = -2.5 * np.log10(gaia_lib.get_flux(pri_wl, sec_spec)) - vega_zero_mag         # :814
+    return pri_wl, spec1, pri_spec, sec_spec, pri_mag, sec_mag, gaia_pri, gaia_sec, gaiamag
+
+
 # ---------------------------------------------------------------------------- posterior
 
 def loglikelihood(p0, fr, nspec, data, err, r, specs, ctm, ptm, tmi, tma, matrix, temps, lgs,

@@ -221,3 +221,37 @@ def test_splice_broadened_grid_layout():
 def test_median_even_odd_is_numpy():
     # the CUDA path's median is compared against np.median through the oracle; record the convention
     assert np.median([3.0, 1.0, 2.0, 10.0]) == 2.5 and np.median([3.0, 1.0, 2.0]) == 2.0
+
+
+def test_plot_branch_is_consistent_with_the_contrast_integral(small_problem, small_oracle):
+    """make_composite(plot=True) integrates each component through the Kepler curve exactly as the
+    contrast loop does (mft6.py:798 vs :729-731): feeding a contrast filter's curve must return that
+    filter's contrast; the composite Gaia flux is the sum of the component fluxes."""
+    from oracle import mft6_oracle as mo
+    from oracle import thirdparty as tp
+    o = small_oracle.p
+    t = small_problem.truth
+    lg = [mo.get_logg(v, o.matrix) for v in t[:2]]
+    w, spec, con, cwl, ph = mo.make_composite(t[:2], lg, t[3:5], t[5], o.fr[2], o.fr[5], small_oracle.r, o.specs,
+                                              o.ctm, o.ptm, o.tmi, o.tma, o.temps, o.lgs, o.photlib, fs=o.fs)
+    kep = (o.ctm[0][0], o.ctm[1][0])
+    b = small_problem.photbands[0]
+    glib = tp.LibraryFilter('Gaia_G', b.wavelength, b.transmit, 'photon', 3.0e-9)
+    out = mo.make_composite_plot(t[:2], lg, t[3:5], t[5], small_oracle.r, o.specs, o.ctm, o.ptm, o.tmi, o.tma,
+                                 o.temps, o.lgs, kep, glib)
+    wl, spec1, pri, sec, pm, sm, gp, gs, gm = out
+    assert np.array_equal(wl, w) and np.allclose(spec1, spec, rtol=1e-15)
+    assert abs((sm - pm) - con[0]) < 1e-12
+    fl = 10 ** (-0.4 * gp) + 10 ** (-0.4 * gs)
+    assert abs(-2.5 * np.log10(fl) - gm) < 1e-12
+
+
+def test_correction_factors_closed_form(tmp_path):
+    """mft6.py:2531-2532: equal-brightness components -> sqrt(2) and ratio*sqrt(2); files are np.savetxt columns."""
+    from mcmc_spec_b200 import predictive
+    pc, sc = predictive.correction_factors(np.array([0.0, 2.5]), np.array([1.0, 0.5]))
+    assert np.allclose(pc, [np.sqrt(2.0), np.sqrt(1.1)]) and np.allclose(sc, [np.sqrt(2.0), 0.5 * np.sqrt(11.0)])
+    res = dict(kep_contrast=[0.0, 2.5], gaia_sec=[1.0, 2.0], gaia_pri=[3.0, 4.0], pri_corr=pc, sec_corr=sc)
+    predictive.write_sweep(str(tmp_path), res)
+    assert np.allclose(np.loadtxt(tmp_path / 'sec_corr.txt'), sc)
+    assert predictive.percentile_summary([-1.0, -2.0, -3.0])[0] == 2.0
