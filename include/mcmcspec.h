@@ -254,6 +254,16 @@ int ms_use_own_stream(ms_handle* h);
  */
 int ms_set_cluster(ms_handle* h, int ctas_per_walker);
 
+/*
+ * Walkers per CTA for large batches.  enabled = 1: batches of at least 8 walkers per SM are launched in
+ * grid-cell order with two cell-mates per CTA; the two thread groups request the same bracketing rows,
+ * filter weights and per-pixel records back to back, so every second request is served by the SM's L1
+ * instead of L2 (L2->SM traffic halves).  enabled = 0: always one walker per CTA.  enabled = -1
+ * (default): on for stream-dominated shapes (model pixels >= 16 x observed pixels), where it pays.
+ * A walker's value does not depend on the setting or on its partner (bit-identical).
+ */
+int ms_set_pairing(ms_handle* h, int enabled);
+
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 int64_t ms_launch_count(const ms_handle* h);
 

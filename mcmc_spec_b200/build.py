@@ -19,15 +19,17 @@ def nvcc_path():
     raise RuntimeError('nvcc not found')
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/mcmcspec.cu -> libmcmcspec.so for sm_100a; returns the library path."""
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile csrc/mcmcspec.cu -> libmcmcspec.so for sm_100a; returns the library path.
+    ``defines`` / ``out``: tuning builds with extra -D macros into another file (scripts/tune_variants.py)."""
+    lib = out or LIB
     deps = [SRC, os.path.join(ROOT, 'include', 'mcmcspec.h')]
-    if (not force and os.path.exists(LIB)
-            and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps)):
-        return LIB
+    if (not force and os.path.exists(lib)
+            and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps)):
+        return lib
     cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
            '-shared', '-Xcompiler', '-fPIC', '-cudart', 'static', '-I', os.path.join(ROOT, 'include'),
-           '-o', LIB, SRC]
+           '-o', lib, SRC] + ['-D' + d for d in defines]
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')
@@ -36,7 +38,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed building libmcmcspec.so')
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':

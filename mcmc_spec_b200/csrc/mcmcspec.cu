@@ -159,6 +159,27 @@ __device__ __forceinline__ dbl4 ldg_cached4(const double* p) {
   return v;
 }
 
+#ifndef MS_NT_SMALL
+#define MS_NT_SMALL 256                  // CTA width when two CTAs share an SM
+#endif
+#ifndef MS_NT_LARGE
+#define MS_NT_LARGE 512                  // CTA width when one CTA owns an SM
+#endif
+#ifndef MS_PAIRING_DEFAULT
+#define MS_PAIRING_DEFAULT -1
+#endif
+#ifndef MS_FORCE_LARGE
+#define MS_FORCE_LARGE 0
+#endif
+#ifndef MS_CHI_UNROLL
+#define MS_CHI_UNROLL 4
+#endif
+
+// Barrier over the NT threads of one walker's thread group.  A CTA holds one group (bar 0 == __syncthreads)
+// or two groups working on two walkers (bars 1 and 2), see lnprob_stream_kernel.
+template <int NT>
+__device__ __forceinline__ void gsync(int bar) { asm volatile("bar.sync %0, %1;" :: "r"(bar), "n"(NT) : "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -167,14 +188,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Sum of K per-thread values over the CTA, in a fixed order; result valid in every thread.
 template <int K, int NWARP>
-__device__ __forceinline__ void block_sum(double (&v)[K], double* scratch /* [NWARP*K] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void block_sum(double (&v)[K], double* scratch /* [NWARP*K] */, int bar) {
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x % (NWARP * 32)) >> 5;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const double s = warp_sum(v[k]);
     if (lane == 0) scratch[warp * K + k] = s;
   }
-  __syncthreads();
+  gsync<NWARP * 32>(bar);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double s = 0.0;
@@ -182,7 +203,7 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* scratch /* [NW
     for (int w = 0; w < NWARP; ++w) s += scratch[w * K + k];
     v[k] = s;
   }
-  __syncthreads();
+  gsync<NWARP * 32>(bar);
 }
 
 // np.interp / interp1d(kind='linear', bounds_error=True) on an ascending table.
@@ -507,7 +528,7 @@ __device__ __forceinline__ void locate_rank_bin(SelectScratch* S, unsigned rank,
 template <int NT>
 __device__ __forceinline__ void histogram_pass(const double* sM, int n, SelectScratch* S, unsigned long long prefix,
                                                int bits_done, int shift, int width) {
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x % NT, lane = tid & 31;
   const unsigned long long himask = (bits_done == 0) ? 0ull : (~0ull << (64 - bits_done));
   const int rounds = (n + NT - 1) / NT;
   for (int r = 0; r < rounds; ++r) {
@@ -528,9 +549,9 @@ __device__ __forceinline__ void histogram_pass(const double* sM, int n, SelectSc
 template <int NT, bool DO_CHI>
 __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, unsigned long long* list,
                                    unsigned long long kmin, unsigned long long kmax, const DevTables& T,
-                                   const double (&a)[3], double* chi_out, double* red_scratch) {
+                                   const double (&a)[3], double* chi_out, double* red_scratch, int bar) {
   constexpr int NWARP = NT / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x % NT, lane = tid & 31, warp = tid >> 5;
   const int rounds = (n + NT - 1) / NT;
   unsigned rank = (unsigned)((n - 1) >> 1);
   const bool flat = (kmin == kmax);
@@ -540,46 +561,51 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
   const int shift0 = 64 - bits_done - width0;
 
   // ---- pass 1: chi-square terms + histogram of the first 8 differing key bits
-  if (tid < 256) S->hist[tid] = 0;
+  for (int b = tid; b < 256; b += NT) S->hist[b] = 0;
   if (tid == 0) S->count = 0;
-  __syncthreads();
+  gsync<NT>(bar);
   double chi = 0.0;
   const double b0 = T.basis[0], b3 = T.basis[3], b4 = T.basis[4], b6 = T.basis[6], b7 = T.basis[7], b8 = T.basis[8];
   const double a0b0 = a[0] * b0;
-  for (int r = 0; r < rounds; r += 2) {
-    // two elements per iteration: all table loads are issued before either is consumed
-    const int i0 = r * NT + tid, i1 = i0 + NT;
-    const bool v0 = i0 < n, v1 = (r + 1 < rounds) && (i1 < n);
-    double m0 = 0.0, m1 = 0.0, x0 = 0.0, x1 = 0.0, d0 = 0.0, d1 = 0.0, w0 = 0.0, w1 = 0.0;
-    if (v0) { m0 = sM[i0]; if constexpr (DO_CHI) { const dbl4 r0 = ldg_cached4(T.data_rec + 4 * (long long)i0); x0 = r0.x; d0 = r0.y; w0 = r0.z; } }
-    if (v1) { m1 = sM[i1]; if constexpr (DO_CHI) { const dbl4 r1 = ldg_cached4(T.data_rec + 4 * (long long)i1); x1 = r1.x; d1 = r1.y; w1 = r1.z; } }
-    unsigned dg0 = 0xffffffffu, dg1 = 0xffffffffu;
-    if (v0) {
-      if constexpr (DO_CHI) {
-        const double pfit = a0b0 + a[1] * fma(b4, x0, b3) + a[2] * fma(fma(b8, x0, b7), x0, b6);
-        const double res = m0 - d0 * fast_rcp(pfit);                  // mft6.py:196, :120 (unscaled)
-        chi = fma(res * res, w0, chi);
+  constexpr int U = MS_CHI_UNROLL;                           // elements per thread and iteration
+  for (int r = 0; r < rounds; r += U) {
+    // all table loads of the iteration are issued before any is consumed
+    double m[U], x[U], d[U], wgt[U];
+    bool v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = (r + u) * NT + tid;
+      v[u] = (r + u < rounds) && (i < n);
+      m[u] = 0.0; x[u] = 0.0; d[u] = 0.0; wgt[u] = 0.0;
+      if (v[u]) {
+        m[u] = sM[i];
+        if constexpr (DO_CHI) { const dbl4 rec = ldg_cached4(T.data_rec + 4 * (long long)i); x[u] = rec.x; d[u] = rec.y; wgt[u] = rec.z; }
       }
-      if (!flat) dg0 = (unsigned)((ordered_key(m0) >> shift0) & ((1u << width0) - 1u));
     }
-    if (v1) {
-      if constexpr (DO_CHI) {
-        const double pfit = a0b0 + a[1] * fma(b4, x1, b3) + a[2] * fma(fma(b8, x1, b7), x1, b6);
-        const double res = m1 - d1 * fast_rcp(pfit);
-        chi = fma(res * res, w1, chi);
+    unsigned dg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      dg[u] = 0xffffffffu;
+      if (v[u]) {
+        if constexpr (DO_CHI) {
+          const double pfit = a0b0 + a[1] * fma(b4, x[u], b3) + a[2] * fma(fma(b8, x[u], b7), x[u], b6);
+          const double res = m[u] - d[u] * fast_rcp(pfit);                // mft6.py:196, :120 (unscaled)
+          chi = fma(res * res, wgt[u], chi);
+        }
+        if (!flat) dg[u] = (unsigned)((ordered_key(m[u]) >> shift0) & ((1u << width0) - 1u));
       }
-      if (!flat) dg1 = (unsigned)((ordered_key(m1) >> shift0) & ((1u << width0) - 1u));
     }
     if (!flat) {
-      const unsigned peers0 = __match_any_sync(0xffffffffu, dg0);
-      const unsigned peers1 = __match_any_sync(0xffffffffu, dg1);
-      if (dg0 != 0xffffffffu && lane == __ffs(peers0) - 1) atomicAdd(&S->hist[dg0], (unsigned)__popc(peers0));
-      if (dg1 != 0xffffffffu && lane == __ffs(peers1) - 1) atomicAdd(&S->hist[dg1], (unsigned)__popc(peers1));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned peers = __match_any_sync(0xffffffffu, dg[u]);
+        if (dg[u] != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&S->hist[dg[u]], (unsigned)__popc(peers));
+      }
     }
   }
   {
     double c1[1] = {chi};
-    block_sum<1, NWARP>(c1, red_scratch);                 // includes the barriers that publish hist
+    block_sum<1, NWARP>(c1, red_scratch, bar);                 // includes the barriers that publish hist
     *chi_out = c1[0];
   }
   if (flat) return key_value(kmin);
@@ -589,20 +615,20 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
   unsigned in_bin = 0;
   while (true) {
     if (warp == 0) locate_rank_bin(S, rank, lane);
-    __syncthreads();
+    gsync<NT>(bar);
     const unsigned digit = (unsigned)S->bcast[0];
     rank -= (unsigned)S->bcast[1];
     in_bin = (unsigned)S->bcast[2];
     prefix |= ((unsigned long long)digit) << shift;
     bits_done += width;
-    __syncthreads();
+    gsync<NT>(bar);
     if (in_bin <= (unsigned)LIST_CAP || bits_done >= 64) break;
     width = min(8, 64 - bits_done);
     shift = 64 - bits_done - width;
-    if (tid < 256) S->hist[tid] = 0;
-    __syncthreads();
+    for (int b = tid; b < 256; b += NT) S->hist[b] = 0;
+    gsync<NT>(bar);
     histogram_pass<NT>(sM, n, S, prefix, bits_done, shift, width);
-    __syncthreads();
+    gsync<NT>(bar);
   }
 
   double v1, v2;
@@ -619,7 +645,7 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
       const unsigned long long k = ordered_key(sM[i]);
       if ((k & himask) == prefix) list[atomicAdd(&S->count, 1u)] = k;
     }
-    __syncthreads();
+    gsync<NT>(bar);
     const unsigned cnt = S->count;                         // == in_bin
     for (unsigned t = tid; t < cnt; t += NT) {
       const unsigned long long mine = list[t];
@@ -631,11 +657,11 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
       if (below == rank) S->bcast[0] = mine;
       if (below == rank + 1) S->bcast[1] = mine;
     }
-    __syncthreads();
+    gsync<NT>(bar);
     v1 = key_value(S->bcast[0]);
     v2 = key_value(S->bcast[1]);
     need_next = (rank + 1 >= cnt);
-    __syncthreads();
+    gsync<NT>(bar);
   }
   if (n & 1) return v1;
   if (need_next) {
@@ -649,37 +675,49 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kgt = min(kgt, __shfl_xor_sync(0xffffffffu, kgt, o));
     if (lane == 0) S->kmin[warp] = kgt;
-    __syncthreads();
+    gsync<NT>(bar);
     kgt = S->kmin[0];
 #pragma unroll
     for (int w = 1; w < NWARP; ++w) kgt = min(kgt, S->kmin[w]);
-    __syncthreads();
+    gsync<NT>(bar);
     v2 = key_value(kgt);
   }
   return (v1 + v2) / 2.0;
 }
 
 // ------------------------------------------------------------------------------------------
-// lnprob_stream_kernel: one CTA per walker.
+// lnprob_stream_kernel: one thread group of NT threads per walker, G groups per CTA.
 //   NR  grid rows per star (4: Teff x log g, 8: with [Fe/H]);  NC / NP compile-time filter caps;
 //   NS   number of stars (2, or 3 for triples: mft6.py nspec);
 //   MODE what is evaluated (MODE_POSTERIOR / MODE_NOSPEC / MODE_OPTIMIZER);
-//   NT  threads per CTA: 256 (two or three CTAs per SM) or 512 when the observed spectrum is so long
-//       that only one CTA fits an SM.
+//   NT  threads per walker: 256, or 512 when the observed spectrum is so long that only one walker
+//       fits an SM;
+//   G   walkers per CTA.  G = 1: one CTA per walker, two CTAs per SM.  G = 2: the CTA evaluates two
+//       walkers that the host made neighbours in the launch order because they sit in the same grid
+//       cell (same bracketing rows).  Warp k of either group owns the same chunks, the two warps meet
+//       at a two-warp named barrier before every chunk and then request the same row sectors, filter
+//       weights and per-pixel records back to back, so the second request is served by the SM's L1
+//       (hit or pending-miss merge) instead of L2.  Each walker's arithmetic is exactly that of G = 1;
+//       the pairing only changes where its operands come from, never its value.
 // ------------------------------------------------------------------------------------------
-template <int NR, int NC, int NP, int NT, int MODE, int NS>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
+template <int NR, int NC, int NP, int NT, int MODE, int NS, int G>
+__global__ void __launch_bounds__(NT * G, (NT * G <= 256) ? 2 : 1)
 lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __restrict__ plans,
                      const int* __restrict__ order, double* __restrict__ lnprob, const PartsOut parts,
-                     const OptIn opt, const int csize) {
+                     const OptIn opt, const int csize, const long long nw, const long long pair_stride,
+                     const unsigned group_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NWARP = NT / 32;
   constexpr int KRED = NS * NC + NP;
-  double* sF = reinterpret_cast<double*>(smem_raw);                  // [NWARP*SEG] per-warp composite chunks
+  const int grp = (G > 1) ? (int)(threadIdx.x / NT) : 0;             // which of the CTA's walkers this thread serves
+  const int bar = (G > 1) ? 1 + grp : 0;                             // the group's named barrier (0 == __syncthreads)
+  unsigned char* smem_grp = smem_raw + (size_t)grp * group_bytes;
+  double* sF = reinterpret_cast<double*>(smem_grp);                  // [NWARP*SEG] per-warp composite chunks
   double* sRed = sF + NWARP * SEG;                                          // [NWARP*KRED]
   SelectScratch* sSel = reinterpret_cast<SelectScratch*>(sRed + NWARP * (KRED > 4 ? KRED : 4));
   double* sM = reinterpret_cast<double*>(sSel + 1);                  // [n_data] model on observed pixels
-  __shared__ WalkerPlan sPlan;
+  __shared__ WalkerPlan sPlanG[G];
+  WalkerPlan& sPlan = sPlanG[grp];
 
   // Small ensembles (the reference runs 50 walkers) cannot fill 148 SMs with one CTA per walker: a
   // thread-block cluster of `csize` CTAs then shares a walker.  Each CTA streams every csize-th group of
@@ -690,16 +728,31 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   __shared__ double sExport[MAX_STAR * MS_MAX_CONTRAST + MS_MAX_PHOT + 3];
   __shared__ unsigned long long sExportKey[3];
 
-  const int tid = threadIdx.x;
-  const long long slot = blockIdx.x / csize;
-  const long long w = order ? order[slot] : slot;                    // launch order: grouped by grid cell
-  {
+  const int tid = (G > 1) ? (int)(threadIdx.x % NT) : (int)threadIdx.x;
+  long long slot;
+  if constexpr (G > 1) {
+    // CTA b takes pair (b * pair_stride) mod n_pairs of the cell-sorted order: neighbours in time come from
+    // different cells (spreads the L2 slices in use), the two walkers of a CTA from the same one
+    const long long n_pairs = (nw + G - 1) / G;
+    slot = (((long long)blockIdx.x * pair_stride) % n_pairs) * G + grp;
+  } else {
+    slot = blockIdx.x / csize;
+  }
+  const bool present = slot < nw;
+  const long long w = present ? (order ? order[slot] : slot) : 0;   // launch order: grouped by grid cell
+  if (present) {
     // cooperative copy of the plan (16-byte chunks)
     const int4* src = reinterpret_cast<const int4*>(plans + w);
     int4* dst = reinterpret_cast<int4*>(&sPlan);
     if (tid < (int)(sizeof(WalkerPlan) / sizeof(int4))) dst[tid] = src[tid];
+  } else if (tid == 0) {
+    sPlan.status = MS_W_NONFINITE;
   }
   __syncthreads();
+  // the two warps of a pair synchronise only while both walkers stream (uniform over the CTA)
+  bool paired = false;
+  if constexpr (G > 1) paired = (sPlanG[0].status == 0) && (sPlanG[G - 1].status == 0);
+  if (!present) return;
   const int status = sPlan.status;
   if (status != 0) {                                                  // mft6.py:1465-1466
     if (crank != 0) return;
@@ -762,6 +815,9 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     const int d1 = meta.w;
     const bool stage = (MODE != MODE_NOSPEC) && d1 > d0;
     const bool need_prev = stage && ds_raw < 0;                        // warp-uniform
+    if constexpr (G > 1) {
+      if (paired) asm volatile("bar.sync %0, 64;" :: "r"(1 + G + warp) : "memory");   // meet the partner's warp
+    }
     if (need_prev && lane == 0) {
       // composite of the pixel just before the chunk (owned by another warp / the previous tile)
       double tot = 0.0;
@@ -783,7 +839,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
 #pragma unroll
         for (int st = 0; st < NS; ++st) {
 #pragma unroll
-          for (int r = 0; r < NR; ++r) a[st][r] = ldg_stream4(pr[st][r]);
+          for (int r = 0; r < NR; ++r) a[st][r] = (G > 1) ? ldg_cached4(pr[st][r]) : ldg_stream4(pr[st][r]);
         }
 #pragma unroll
         for (int st = 0; st < NS; ++st) {
@@ -802,7 +858,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         for (int st = 0; st < NS; ++st) {
           dbl4 a[NR];
 #pragma unroll
-          for (int r = 0; r < NR; ++r) a[r] = ldg_stream4(pr[st][r]);
+          for (int r = 0; r < NR; ++r) a[r] = (G > 1) ? ldg_cached4(pr[st][r]) : ldg_stream4(pr[st][r]);
           const double c = cf[st][0];
           fs[st].x = c * a[0].x; fs[st].y = c * a[0].y; fs[st].z = c * a[0].z; fs[st].w = c * a[0].w;
 #pragma unroll
@@ -886,7 +942,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
       __syncwarp();
     }
   }
-  __syncthreads();
+  gsync<NT>(bar);
 
   // ------------------------------------------------------------------ band integrals
   double red[KRED > 0 ? KRED : 1];
@@ -897,13 +953,13 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   }
 #pragma unroll
   for (int f = 0; f < NP; ++f) red[NS * NC + f] = accP[f];
-  block_sum<KRED, NWARP>(red, sRed);
+  block_sum<KRED, NWARP>(red, sRed, bar);
 
   // ------------------------------------------------------------------ phase B: spectral chi-square
   const int n = T.n_data;
   double chi_un = CUDART_NAN, med = CUDART_NAN, scale = 1.0;
   if constexpr (MODE != MODE_NOSPEC) {
-    block_sum<3, NWARP>(mom, sRed);
+    block_sum<3, NWARP>(mom, sRed, bar);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
@@ -911,14 +967,14 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
       has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, o);
     }
     if (tid == 0) sSel->nanflag = 0;
-    __syncthreads();
+    gsync<NT>(bar);
     if (lane == 0) { sSel->kmin[warp] = kmin; sSel->kmax[warp] = kmax; if (has_nan) sSel->nanflag = 1; }
-    __syncthreads();
+    gsync<NT>(bar);
     kmin = sSel->kmin[0]; kmax = sSel->kmax[0];
 #pragma unroll
     for (int w2 = 1; w2 < NWARP; ++w2) { kmin = min(kmin, sSel->kmin[w2]); kmax = max(kmax, sSel->kmax[w2]); }
     has_nan = sSel->nanflag;
-    __syncthreads();
+    gsync<NT>(bar);
   }
   if (csize > 1) {
     // combine the cluster's partial sums in rank order (deterministic), then let the helpers go
@@ -945,13 +1001,13 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   if constexpr (MODE != MODE_NOSPEC) {
     unsigned long long* list = reinterpret_cast<unsigned long long*>(sF);
     if constexpr (MODE == MODE_POSTERIOR) {
-      if (!has_nan) med = block_median_chi<NT, true>(sM, n, sSel, list, kmin, kmax, T, mom, &chi_un, sRed);  // mft6.py:1173
+      if (!has_nan) med = block_median_chi<NT, true>(sM, n, sSel, list, kmin, kmax, T, mom, &chi_un, sRed, bar);  // mft6.py:1173
       scale = T.data_median / med;
     } else {
       // fit_spec: the observed spectrum was renormalised once (mft6.py:889); every proposal is only
       // median-scaled against it (mft6.py:1010-1014), so the scale does not factor out of the sum
       double dummy;
-      if (!has_nan) med = block_median_chi<NT, false>(sM, n, sSel, list, kmin, kmax, T, mom, &dummy, sRed);
+      if (!has_nan) med = block_median_chi<NT, false>(sM, n, sSel, list, kmin, kmax, T, mom, &dummy, sRed, bar);
       const double* dset = opt.flux_sets + (long long)opt.set_index[w] * n;
       scale = (opt.ref_median ? opt.ref_median[w] : T.opt_median[opt.set_index[w]]) / med;   // np.median(flux), mft6.py:1011 (:888 at the start)
       double chi[1] = {0.0};
@@ -959,7 +1015,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         const double r = scale * sM[i] - dset[i];
         chi[0] = fma(r * r, T.data_inv_e2[i], chi[0]);
       }
-      block_sum<1, NWARP>(chi, sRed);
+      block_sum<1, NWARP>(chi, sRed, bar);
       chi_un = chi[0] / (scale * scale);                              // so that iic below is uniform
     }
     if (parts.model) for (int i = tid; i < n; i += NT) parts.model[w * n + i] = sM[i] * scale;
@@ -1160,6 +1216,9 @@ struct ms_handle {
   // per-call buffers
   WalkerPlan* plans = nullptr; long long plans_cap = 0;
   int* order = nullptr; unsigned* cell_hist = nullptr; bool use_order = false;
+  int pairing = MS_PAIRING_DEFAULT;  // 0: one walker per CTA, 1: two cell-mates per CTA for large batches, -1: automatic
+  bool pair_now = false;         // decided per call (evaluate_device)
+  int max_optin_smem = 0;
   bool nospec = false;           // mft6_nospec.py flavour of the posterior
   double* d_opt_flux = nullptr; double* d_opt_median = nullptr; int opt_sets = 0;   // fit_spec's renormalised spectra
   size_t grid_bytes = 0, l2_bytes = 0;
@@ -1204,10 +1263,10 @@ int upload(ms_handle* h, const Tp* host, size_t n, const Tp** dev) {
   return MS_OK;
 }
 
+long long gcd_ll(long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; }
+
 template <int NR, int NC, int NP, int NT, int MODE, int NS>
 int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts, const OptIn& opt) {
-  auto kern = lnprob_stream_kernel<NR, NC, NP, NT, MODE, NS>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing) {
     if (h->ev_used + 2 > h->ev_pool.size()) {
@@ -1217,24 +1276,45 @@ int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut
     h->ev_used += 2; h->timed_walkers += nw;
     CK(cudaEventRecord(e0, h->stream));
   }
-  // cluster size: enough CTAs for two per SM, at most 8 per walker (portable limit)
-  int csize = h->cluster;
-  if (csize <= 0) {
-    csize = 1;
-    while (csize < 8 && (long long)nw * csize * 2 <= 2ll * h->num_sms) csize *= 2;
-  }
   const int* order = h->use_order ? h->order : nullptr;
-  if (csize == 1) {
-    kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, order, d_lnp, parts, opt, 1);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(nw * csize)); cfg.blockDim = dim3(NT);
-    cfg.dynamicSmemBytes = h->smem_bytes; cfg.stream = h->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, kern, h->T, (const WalkerPlan*)h->plans, order, d_lnp, parts, opt, csize));
+  constexpr bool CAN_PAIR = (NT == MS_NT_SMALL) && (MODE == MODE_POSTERIOR) && (NS == 2);
+  bool launched = false;
+  if constexpr (CAN_PAIR) {
+    if (h->pair_now) {
+      // two cell-mates per CTA (see the kernel's header comment); `order` is the cell-sorted launch order
+      auto kern2 = lnprob_stream_kernel<NR, NC, NP, NT, MODE, NS, 2>;
+      CK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * h->smem_bytes)));
+      const long long n_pairs = (nw + 1) / 2;
+      long long stride = (long long)((double)n_pairs * 0.381966) | 1ll;
+      while (gcd_ll(stride, n_pairs) != 1) stride += 2;
+      kern2<<<(unsigned)n_pairs, 2 * NT, 2 * h->smem_bytes, h->stream>>>(h->T, h->plans, order, d_lnp, parts, opt, 1, nw,
+                                                                          stride % n_pairs, (unsigned)h->smem_bytes);
+      launched = true;
+    }
+  }
+  if (!launched) {
+    auto kern = lnprob_stream_kernel<NR, NC, NP, NT, MODE, NS, 1>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    // cluster size: enough CTAs for two per SM, at most 8 per walker (portable limit)
+    int csize = h->cluster;
+    if (csize <= 0) {
+      csize = 1;
+      while (csize < 8 && (long long)nw * csize * 2 <= 2ll * h->num_sms) csize *= 2;
+    }
+    if (csize == 1) {
+      kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, order, d_lnp, parts, opt, 1, nw, 1ll,
+                                                           (unsigned)h->smem_bytes);
+    } else {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(nw * csize)); cfg.blockDim = dim3(NT);
+      cfg.dynamicSmemBytes = h->smem_bytes; cfg.stream = h->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, kern, h->T, (const WalkerPlan*)h->plans, order, d_lnp, parts, opt, csize, (long long)nw,
+                            1ll, (unsigned)h->smem_bytes));
+    }
   }
   CK(cudaGetLastError());
   if (h->timing) CK(cudaEventRecord(e1, h->stream));
@@ -1260,8 +1340,8 @@ int launch_stream_threads(ms_handle* h, long long nw, double* d_lnp, const Parts
 
 template <int NR, int NC, int NP>
 int launch_stream_variant(ms_handle* h, long long nw, double* d_lnp, const PartsOut& parts, int mode, const OptIn& opt) {
-  if (h->threads == 512) return launch_stream_threads<NR, NC, NP, 512>(h, nw, d_lnp, parts, mode, opt);
-  return launch_stream_threads<NR, NC, NP, 256>(h, nw, d_lnp, parts, mode, opt);
+  if (h->threads == MS_NT_LARGE) return launch_stream_threads<NR, NC, NP, MS_NT_LARGE>(h, nw, d_lnp, parts, mode, opt);
+  return launch_stream_threads<NR, NC, NP, MS_NT_SMALL>(h, nw, d_lnp, parts, mode, opt);
 }
 
 size_t stream_smem_bytes(int n_data, int nc, int np, int nwarp, int nstar) {
@@ -1295,6 +1375,16 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   // per group instead of once per walker).  With an L2-resident grid it only concentrates the concurrent
   // CTAs on the same L2 slices (measured: C4 -4 %, C1 -8 %), so the natural order is kept there.
   h->use_order = nw >= 1024 && h->T.n_cells > 1 && h->grid_bytes > h->l2_bytes;
+  // Two walkers per CTA pay when (a) the batch still fills the machine with half as many CTAs, (b) both
+  // walkers' shared memory fits one SM and (c) cell-mates exist to be paired: the launch order is then
+  // always the cell-sorted one.
+  // Measured (profiles/): pairing halves the L2->SM traffic (L1 hit rate 53 %), which pays on stream-dominated
+  // shapes (C1/C2: +5 %) and costs the pair barriers where the observed-pixel work dominates (C4: -5 %).
+  const bool want_pair = h->pairing > 0 || (h->pairing < 0 && (long long)h->T.n_reg >= 16ll * h->T.n_data);
+  h->pair_now = want_pair && h->cluster <= 1 && mode == MODE_POSTERIOR && h->T.nspec == 2 &&
+                h->threads == MS_NT_SMALL && h->T.n_cells > 1 && nw >= 8ll * h->num_sms &&
+                2 * h->smem_bytes + 2048 <= (size_t)h->max_optin_smem;
+  if (h->pair_now) h->use_order = true;
   if (h->use_order) CK(cudaMemsetAsync(h->cell_hist, 0, (size_t)h->T.n_cells * sizeof(unsigned), h->stream));
   walker_prep_kernel<<<pg, pb, 0, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr, mode, opt);
   CK(cudaGetLastError());
@@ -1536,12 +1626,13 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
   const int nc = h->variant == 0 ? 2 : MS_MAX_CONTRAST, np = h->variant == 0 ? 6 : MS_MAX_PHOT;
   int max_optin = 0;
   CKH(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-  h->threads = 256;
-  h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, 8, cfg->nspec);
-  if (2 * (h->smem_bytes + 1024) > (size_t)max_optin + 1024) {
-    // two 256-thread CTAs no longer fit an SM: run one 512-thread CTA instead (same warps in flight)
-    h->threads = 512;
-    h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, 16, cfg->nspec);
+  h->max_optin_smem = max_optin;
+  h->threads = MS_NT_SMALL;
+  h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, MS_NT_SMALL / 32, cfg->nspec);
+  if (MS_FORCE_LARGE || 2 * (h->smem_bytes + 1024) > (size_t)max_optin + 1024) {
+    // two CTAs no longer fit an SM: run one wide CTA instead (same warps in flight)
+    h->threads = MS_NT_LARGE;
+    h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, MS_NT_LARGE / 32, cfg->nspec);
   }
   if (h->smem_bytes + 2048 > (size_t)max_optin) {
     h->err = "ms_create: n_data too large for the shared-memory resident model spectrum"; return fail(MS_ERR_UNSUPPORTED);
@@ -1571,6 +1662,12 @@ int ms_set_cluster(ms_handle* h, int ctas_per_walker) {
     set_err(h, "ms_set_cluster: 0 (automatic), 1, 2, 4 or 8"); return MS_ERR_INVALID;
   }
   h->cluster = ctas_per_walker;
+  return MS_OK;
+}
+
+int ms_set_pairing(ms_handle* h, int enabled) {
+  if (!h) return MS_ERR_INVALID;
+  h->pairing = enabled < 0 ? -1 : (enabled != 0);
   return MS_OK;
 }
 

@@ -18,11 +18,12 @@ MS_MAX_CONTRAST, MS_MAX_PHOT, MS_MAX_NDIM = 4, 12, 8
 MS_HOST, MS_DEVICE = 0, 1
 MS_W_PRIOR_BOUNDS, MS_W_OFF_ISOCHRONE, MS_W_OFF_GRID, MS_W_NONFINITE = 1, 2, 4, 8
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmcmcspec.so')
+# MCMCSPEC_LIB: another build of the same library (kernel tuning variants, scripts/tune_variants.py)
+_LIB_PATH = os.environ.get('MCMCSPEC_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmcmcspec.so')
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
            'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_component_mags', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows',
-           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_timing',
+           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_timing',
            'ms_kernel_time']
 
 _dp = C.POINTER(C.c_double)
@@ -99,6 +100,7 @@ def load_library(path=None):
     lib.ms_set_stream.argtypes = [vp, vp]
     lib.ms_use_own_stream.argtypes = [vp]
     lib.ms_set_cluster.argtypes = [vp, C.c_int]
+    lib.ms_set_pairing.argtypes = [vp, C.c_int]
     lib.ms_set_timing.argtypes = [vp, C.c_int]
     lib.ms_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     for name in EXPORTS:
@@ -230,6 +232,11 @@ class Engine:
     def set_cluster(self, ctas_per_walker):
         """CTAs per walker: 0 automatic, 1 never, 2/4/8 forced (thread-block clusters for small ensembles)."""
         self._check(self.lib.ms_set_cluster(self._h, int(ctas_per_walker)), 'ms_set_cluster')
+
+    def set_pairing(self, enabled):
+        """Two cell-mates per CTA for large batches: True / False / None (automatic, the default); values are
+        bit-identical either way."""
+        self._check(self.lib.ms_set_pairing(self._h, -1 if enabled is None else int(bool(enabled))), 'ms_set_pairing')
 
     def set_timing(self, enabled):
         self._check(self.lib.ms_set_timing(self._h, int(bool(enabled))), 'ms_set_timing')

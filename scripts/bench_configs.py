@@ -36,6 +36,8 @@ def run(name, prob, nw, reps=5):
     except Exception:
         pass
     lp = LogPosterior(prob)
+    if os.environ.get('MS_PAIRING') == '0':
+        lp.engine.set_pairing(False)
     th = torch.tensor(central_third(prob, nw), device='cuda')
     out = torch.empty(nw, dtype=torch.float64, device='cuda')
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device='cuda')

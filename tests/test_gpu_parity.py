@@ -114,6 +114,30 @@ def test_batch_split_and_permutation_are_bit_identical(small_problem, small_gpu)
     small_gpu.engine.set_cluster(0)
 
 
+def test_paired_walkers_are_bit_identical(small_problem, small_oracle, small_gpu):
+    """Large batches run two cell-mates per CTA (ms_set_pairing): a walker's value must not depend on that,
+    nor on who its partner is (odd batch size, prior-rejected partners, shuffled order)."""
+    from mcmc_spec_b200 import synthetic
+    theta = synthetic.sample_prior_box(small_problem, 2 * 1184 + 1, seed=77)
+    eng = small_gpu.engine
+    eng.set_pairing(False)
+    single = small_gpu(theta)
+    eng.set_pairing(True)
+    paired = small_gpu(theta)
+    assert np.array_equal(single, paired)
+    assert np.isneginf(paired).any() and np.isfinite(paired).any()
+    perm = np.random.default_rng(3).permutation(len(theta))
+    assert np.array_equal(small_gpu(theta[perm]), paired[perm])
+    # all walkers in one grid cell: every CTA holds a true pair
+    t = np.tile(small_problem.truth, (2400, 1))
+    t[:, 0] += np.linspace(-20.0, 20.0, 2400); t[:, 3] *= np.linspace(0.9, 1.1, 2400)
+    eng.set_pairing(False); a = small_gpu(t)
+    eng.set_pairing(True); b = small_gpu(t)
+    assert np.array_equal(a, b) and np.isfinite(b).all()
+    want = small_oracle.lnprob_batch(t[::300])
+    assert np.max(np.abs(b[::300] - want) / np.abs(want)) <= 1e-9
+
+
 def test_cluster_split_of_a_walker(small_problem, small_oracle, small_gpu):
     """Thread-block clusters of 2/4/8 CTAs per walker (small ensembles): same values to rounding, and the
     automatic choice kicks in for a 50-walker ensemble like the reference's."""
