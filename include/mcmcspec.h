@@ -214,6 +214,18 @@ int ms_broaden_rows(int device, double* rows, int64_t n_rows, int64_t row_len, i
                     int64_t win_len, const double* taps, int32_t n_taps);
 
 /*
+ * Model-grid assembly on the GPU: the numeric part of spec_interpolator (btsettl branch), mft6.py:343-383.
+ * Node r's native spectrum is (src_x, src_y)[src_off[r] .. src_off[r+1]) with ascending src_x; every node
+ * is linearly interpolated onto the common grid x_dst[row_len] (interp1d semantics, bit-for-bit np.interp;
+ * an abscissa outside a node's range is an error, as interp1d's bounds_error raises), then -- when
+ * win_len > 0 -- pixels [win_lo, win_lo+win_len) are broadened as by ms_broaden_rows and spliced between
+ * the untouched blue and red parts.  rows_out: host [n_rows][row_len].
+ */
+int ms_build_grid(int device, const double* src_x, const double* src_y, const int64_t* src_off, int64_t n_rows,
+                  const double* x_dst, int64_t row_len, int64_t win_lo, int64_t win_len, const double* taps,
+                  int32_t n_taps, double* rows_out);
+
+/*
  * Stretch-move half step on a device-resident ensemble (emcee RedBlueMove/StretchMove, a = 2; the
  * sampler the reference drives at mft6.py:1491-1510).  `state` [nw][ndim+1] holds positions and
  * log-probabilities; s_idx [n_s] are the state rows this caller updates (its shard of the active

@@ -1118,6 +1118,50 @@ __global__ void broaden_patch_kernel(double* __restrict__ rows, long long row_le
 }
 
 // ------------------------------------------------------------------------------------------
+// resample_rows_kernel: spec_interpolator's ``interp1d(spold, spec1)(wl)`` (mft6.py:369-371) for all
+// nodes at once: row r of the output is the node's native spectrum (src_x, src_y)[off[r] .. off[r+1])
+// linearly interpolated onto the common wavelength grid x_dst.  Same arithmetic as scipy's linear
+// interp1d on 1-D data (np.interp): bracket dx[j] <= x < dx[j+1], slope * (x - dx[j]) + dy[j] with
+// separately rounded multiply and add (no FMA contraction), exact node hits return the node value.
+// Out-of-range abscissae raise `*oob` (interp1d's bounds_error=True).
+// grid = (ceil(row_len / 256), n_rows)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+resample_rows_kernel(const double* __restrict__ src_x, const double* __restrict__ src_y,
+                     const long long* __restrict__ off, const double* __restrict__ x_dst, long long row_len,
+                     double* __restrict__ out, int* __restrict__ oob) {
+  const long long r = blockIdx.y;
+  const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (j >= row_len) return;
+  const double* x = src_x + off[r];
+  const double* y = src_y + off[r];
+  const long long n = off[r + 1] - off[r];
+  const double v = x_dst[j];
+  if (!(v >= x[0] && v <= x[n - 1])) { atomicOr(oob, (v < x[0]) ? 1 : 2); out[r * row_len + j] = CUDART_NAN; return; }
+  double res;
+  if (v == x[n - 1]) {
+    res = y[n - 1];
+  } else {
+    long long lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) >> 1;
+      if (x[mid] <= v) lo = mid; else hi = mid;
+    }
+    if (x[lo] == v) {
+      res = y[lo];
+    } else {
+      const double slope = __ddiv_rn(__dsub_rn(y[lo + 1], y[lo]), __dsub_rn(x[lo + 1], x[lo]));
+      res = __dadd_rn(__dmul_rn(slope, __dsub_rn(v, x[lo])), y[lo]);
+      if (res != res) {                                   // np.interp: "if we get nan in one direction, try the other"
+        res = __dadd_rn(__dmul_rn(slope, __dsub_rn(v, x[lo + 1])), y[lo + 1]);
+        if (res != res && y[lo] == y[lo + 1]) res = y[lo];
+      }
+    }
+  }
+  out[r * row_len + j] = res;
+}
+
+// ------------------------------------------------------------------------------------------
 // Stretch move (emcee RedBlueMove + StretchMove, a = 2) with a counter-based generator.
 // ------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
@@ -1889,6 +1933,73 @@ int ms_broaden_rows(int device, double* rows, int64_t n_rows, int64_t row_len, i
   }
   if (e != cudaSuccess) { set_err(h, std::string("ms_broaden_rows: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
   cudaFree(d_in); cudaFree(d_out); cudaFree(d_taps);
+  return rc;
+}
+
+int ms_build_grid(int device, const double* src_x, const double* src_y, const int64_t* src_off, int64_t n_rows,
+                  const double* x_dst, int64_t row_len, int64_t win_lo, int64_t win_len, const double* taps,
+                  int32_t n_taps, double* rows_out) {
+  ms_handle* h = nullptr;   // errors land in the create-error slot
+  if (!src_x || !src_y || !src_off || !x_dst || !rows_out || n_rows < 0 || row_len <= 0 || win_lo < 0 || win_len < 0 ||
+      win_lo + win_len > row_len || win_len > 0x7fffffff) {
+    set_err(h, "ms_build_grid: invalid argument"); return MS_ERR_INVALID;
+  }
+  if (win_len > 0 && (!taps || n_taps < 1 || (n_taps % 2) == 0 || n_taps > 4097 || win_len < n_taps)) {
+    set_err(h, "ms_build_grid: n_taps must be odd and not exceed the window"); return MS_ERR_INVALID;
+  }
+  if (n_rows == 0) return MS_OK;
+  for (int64_t r = 0; r < n_rows; ++r)
+    if (src_off[r + 1] - src_off[r] < 2) { set_err(h, "ms_build_grid: a node spectrum needs at least two samples"); return MS_ERR_INVALID; }
+  CK(cudaSetDevice(device));
+  const size_t n_src = (size_t)src_off[n_rows];
+  double *d_sx = nullptr, *d_sy = nullptr, *d_x = nullptr, *d_rows = nullptr, *d_rows2 = nullptr, *d_taps = nullptr;
+  long long* d_off = nullptr; int* d_oob = nullptr;
+  int rc = MS_OK;
+  cudaError_t e = cudaMalloc((void**)&d_sx, n_src * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_sy, n_src * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_off, (size_t)(n_rows + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_x, (size_t)row_len * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_rows, (size_t)n_rows * row_len * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_oob, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(d_oob, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(d_sx, src_x, n_src * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_sy, src_y, n_src * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_off, src_off, (size_t)(n_rows + 1) * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_x, x_dst, (size_t)row_len * 8, cudaMemcpyHostToDevice);
+  int oob = 0;
+  if (e == cudaSuccess) {
+    dim3 grid((unsigned)((row_len + 255) / 256), (unsigned)n_rows);
+    resample_rows_kernel<<<grid, 256>>>(d_sx, d_sy, d_off, d_x, row_len, d_rows, d_oob);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(&oob, d_oob, sizeof(int), cudaMemcpyDeviceToHost);
+  }
+  double* d_final = d_rows;
+  if (e == cudaSuccess && oob == 0 && win_len > 0) {
+    // window broadening + splice (mft6.py:373-376): the stencil reads the resampled rows and writes a copy
+    e = cudaMalloc((void**)&d_rows2, (size_t)n_rows * row_len * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_taps, (size_t)n_taps * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(d_taps, taps, (size_t)n_taps * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_rows2, d_rows, (size_t)n_rows * row_len * 8, cudaMemcpyDeviceToDevice);
+    const size_t smem = ((size_t)BT + 2 * (size_t)n_taps) * 8;
+    if (e == cudaSuccess && smem > 48 * 1024)
+      e = cudaFuncSetAttribute(broaden_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      dim3 grid((unsigned)((win_len + BT - 1) / BT), (unsigned)n_rows);
+      broaden_rows_kernel<<<grid, 256, smem>>>(d_rows, d_rows2, row_len, win_lo, (int)win_len, d_taps, n_taps);
+      broaden_patch_kernel<<<(unsigned)n_rows, 32>>>(d_rows2, row_len, win_lo, (int)win_len);
+      e = cudaGetLastError();
+    }
+    d_final = d_rows2;
+  }
+  if (e == cudaSuccess && oob == 0) e = cudaMemcpy(rows_out, d_final, (size_t)n_rows * row_len * 8, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { set_err(h, std::string("ms_build_grid: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
+  else if (oob) {
+    set_err(h, (oob & 1) ? "A value in x_new is below the interpolation range." : "A value in x_new is above the interpolation range.");
+    rc = MS_ERR_INVALID;
+  }
+  cudaFree(d_sx); cudaFree(d_sy); cudaFree(d_off); cudaFree(d_x); cudaFree(d_rows); cudaFree(d_oob);
+  if (d_rows2) cudaFree(d_rows2);
+  if (d_taps) cudaFree(d_taps);
   return rc;
 }
 

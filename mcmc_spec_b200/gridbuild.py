@@ -9,10 +9,11 @@ broaden **only the data window** to the instrument resolution (``broaden`` :124-
 ``pyasl.instrBroadGaussFast(maxsig=5)`` + the 5/10-sample patch) and splice it between the
 untouched blue and red parts (:373-383).
 
-The text reading and the linear resampling stay on the host (numpy); the 104 x 9750-pixel banded
-stencil runs in ``broaden_rows_kernel`` through ``ms_broaden_rows`` (no CPU fallback: it raises if
-the library or a GPU is missing).  The BT-Settl files themselves are not in the reference
-repository, so tests write small synthetic files of the same format.
+Only the text reading stays on the host; resampling every node onto the common grid
+(``resample_rows_kernel``), the banded broadening stencil of the data window (``broaden_rows_kernel``)
+and the splice run on the GPU in one ``ms_build_grid`` call (no CPU fallback: it raises if the
+library or a GPU is missing).  The BT-Settl files themselves are not in the reference repository,
+so tests write small synthetic files of the same format.
 """
 from __future__ import annotations
 
@@ -20,7 +21,6 @@ import glob
 import os
 
 import numpy as np
-from scipy.interpolate import interp1d
 
 from . import native
 
@@ -51,16 +51,13 @@ def node_file(model_dir, temp, logg):
 
 
 def read_node(path, specrange):
-    """``wavelength flux`` rows within +-100 A of the requested range (mft6.py:353-357)."""
+    """``wavelength flux`` rows within +-100 A of the requested range (mft6.py:353-357).  The reference
+    splits every line on single blanks in a Python loop; here the two leading columns are parsed in bulk
+    (same values: both go through the C ``strtod``)."""
     lo, hi = min(specrange) - 100, max(specrange) + 100
-    wl, fl = [], []
-    with open(path) as fh:
-        for line in fh:
-            li = line.split(' ')
-            w = float(li[0])
-            if lo <= w <= hi:
-                wl.append(w); fl.append(float(li[1]))
-    return np.array(wl), np.array(fl)
+    tab = np.loadtxt(path, usecols=(0, 1), dtype=np.float64, ndmin=2)
+    keep = (tab[:, 0] >= lo) & (tab[:, 0] <= hi)
+    return tab[keep, 0], tab[keep, 1]
 
 
 def gaussian_taps(window_wl, resolution, maxsig=5):
@@ -98,11 +95,17 @@ def spec_interpolator(model_dir, w, trange, lgrange, specrange, resolution=10000
     """
     t, l = discover_nodes(model_dir, trange, lgrange)
     temps, lgs = sorted(t), sorted(l)
-    wl = np.arange(min(specrange), max(specrange), 0.2)
-    grid = np.empty((len(lgs), len(temps), wl.size), dtype=np.float64)
-    for ig, g in enumerate(lgs):
-        for it, temp in enumerate(temps):
+    wl = np.arange(min(specrange), max(specrange), 0.2)               # mft6.py:343
+    node_wl, node_fl = [], []
+    for g in lgs:
+        for temp in temps:
             spold, spec1 = read_node(node_file(model_dir, temp, g), specrange)
-            grid[ig, it] = interp1d(spold, spec1)(wl)                 # mft6.py:369-371
-    broaden_and_splice(grid.reshape(-1, wl.size), wl, w, resolution, device=device)
-    return grid, wl, temps, lgs
+            o = np.argsort(spold, kind='mergesort')                    # interp1d(assume_sorted=False)
+            node_wl.append(spold[o]); node_fl.append(spec1[o])
+    inwin = np.where((wl >= min(w)) & (wl <= max(w)))[0]
+    if inwin.size:
+        taps = gaussian_taps(wl[inwin], resolution)
+        rows = native.build_grid(node_wl, node_fl, wl, int(inwin[0]), int(inwin.size), taps, device=device)
+    else:
+        rows = native.build_grid(node_wl, node_fl, wl, device=device)
+    return rows.reshape(len(lgs), len(temps), wl.size), wl, temps, lgs

@@ -22,7 +22,7 @@ MS_W_PRIOR_BOUNDS, MS_W_OFF_ISOCHRONE, MS_W_OFF_GRID, MS_W_NONFINITE = 1, 2, 4, 
 _LIB_PATH = os.environ.get('MCMCSPEC_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmcmcspec.so')
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
-           'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_component_mags', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows',
+           'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_component_mags', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows', 'ms_build_grid',
            'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_timing',
            'ms_kernel_time']
 
@@ -89,6 +89,7 @@ def load_library(path=None):
     lib.ms_set_optimizer_data.argtypes = [vp, vp, C.c_int32]
     lib.ms_optimizer_chisq.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, vp]
     lib.ms_broaden_rows.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32]
+    lib.ms_build_grid.argtypes = [C.c_int, vp, vp, vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32, vp]
     lib.ms_split_keys.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int64, vp]
     lib.ms_stretch_propose.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_double, C.c_uint64,
                                        C.c_uint64, C.c_int32, C.c_int64, vp, vp]
@@ -340,3 +341,27 @@ def broaden_rows(rows, win_lo, win_len, taps, device=0, lib=None):
     if rc != 0:
         raise NativeError(f"ms_broaden_rows failed ({rc}): {lib.ms_last_error(None).decode()}")
     return rows
+
+
+def build_grid(node_wl, node_flux, wl, win_lo=0, win_len=0, taps=None, device=0, lib=None):
+    """Resample ragged node spectra onto ``wl`` and broaden the window, on the GPU (ms_build_grid).
+    ``node_wl`` / ``node_flux``: lists of ascending wavelength / flux arrays, one pair per grid row.
+    Returns rows [n_rows, len(wl)].  Raises ValueError for an out-of-range abscissa (interp1d)."""
+    lib = lib or load_library()
+    lens = np.array([len(w) for w in node_wl], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    sx = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=np.float64) for w in node_wl]))
+    sy = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.float64) for f in node_flux]))
+    if sx.shape != sy.shape:
+        raise ValueError("node wavelength and flux arrays differ in length")
+    wl = np.ascontiguousarray(wl, dtype=np.float64)
+    out = np.empty((len(lens), wl.size), dtype=np.float64)
+    tp = np.ascontiguousarray(taps if taps is not None else [1.0], dtype=np.float64)
+    rc = lib.ms_build_grid(int(device), sx.ctypes.data, sy.ctypes.data, off.ctypes.data, len(lens), wl.ctypes.data,
+                           wl.size, int(win_lo), int(win_len), tp.ctypes.data, int(tp.size), out.ctypes.data)
+    if rc != 0:
+        msg = lib.ms_last_error(None).decode()
+        if 'interpolation range' in msg:
+            raise ValueError(msg)
+        raise NativeError(f"ms_build_grid failed ({rc}): {msg}")
+    return out
