@@ -214,6 +214,22 @@ def _draw_model(prob_like, theta):
     return comps
 
 
+def isochrone_radius(matrix, teff):
+    """Radius [Rsun] the isochrone assigns to ``teff`` (data generation; the relation of mft6.py:66-85)."""
+    track = matrix[matrix[:, 1] == 9.0][:220]
+    o = np.argsort(track[:, 4], kind='mergesort')
+    lum = np.interp(teff, track[o, 4], track[o, 6])
+    return np.sqrt(lum * LSUN / (4 * np.pi * SIGMA_SB * teff ** 4)) / RSUN
+
+
+def consistent_truth(t1, t2, av, plx, matrix=None, seed=2298):
+    """A binary whose radii sit on the isochrone, so that the 2 % radius prior (mft6.py:1262-1269) and the
+    likelihood agree and a fit can recover the truth: [T1, T2, Av, R(T1), R(T2)/R(T1), plx]."""
+    matrix = make_isochrone_matrix(seed) if matrix is None else matrix
+    r1, r2 = isochrone_radius(matrix, float(t1)), isochrone_radius(matrix, float(t2))
+    return np.array([t1, t2, av, r1, r2 / r1, plx], dtype=np.float64)
+
+
 def slice_feh(grid4, fehs, feh):
     """Linear [Fe/H] interpolation of a 4-D grid to the fit's fixed metallicity (data generation)."""
     j, u = _interp_node_axis(fehs, feh)

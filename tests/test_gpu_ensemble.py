@@ -72,3 +72,40 @@ def test_fixed_seed_chain_matches_oracle_chain(small_problem, small_oracle, smal
     gq = np.percentile(np.concatenate(gs), [16, 50, 84], axis=0)
     cq = np.percentile(np.concatenate(cs), [16, 50, 84], axis=0)
     assert np.allclose(gq, cq, rtol=1e-10)
+
+
+def test_independent_chains_agree_within_monte_carlo_error(small_problem, small_oracle, small_lp):
+    """Independently seeded chains -- CUDA posterior + device sampler vs numpy oracle + numpy sampler -- give
+    the same posterior medians and 16/84 percentiles within the stated Monte-Carlo tolerance:
+    |delta| <= 4 sigma_MC, sigma_MC = 1.25 * std * sqrt(tau / n_samples) per chain, added in quadrature
+    (1.25: a percentile's standard error relative to the mean's, normal approximation)."""
+    import stretch_reference as sr
+    from mcmc_spec_b200 import fit
+    from mcmc_spec_b200.ensemble import CudaBackend, EnsembleSampler
+    nw = 24
+    t = small_problem.truth
+    p0 = t * (1 + 0.005 * np.random.default_rng(8).standard_normal((nw, 6)))
+    p0[:, 2] = np.abs(p0[:, 2])
+
+    def run(sampler, start, burn, steps):
+        sampler.initialize(start)
+        sampler.run_mcmc(burn)
+        out = []
+        for _ in range(steps):
+            sampler.step()
+            c = sampler.coords
+            out.append((c.cpu().numpy() if c.is_cuda else c.numpy()).copy())
+        return np.array(out)                                            # [steps, nw, ndim]
+
+    g = run(EnsembleSampler(nw, 6, CudaBackend(small_lp.engine), seed=101), p0, 1000, 6000)
+    # the (slow) oracle chain starts from an equilibrated ensemble -- the device chain's last state -- with its
+    # own random streams; tau is taken from the long chain (same dynamics), a 300-step chain cannot estimate it
+    c = run(EnsembleSampler(nw, 6, sr.NumpyBackend(small_oracle.lnprob_batch, 6), seed=202), g[-1], 20, 300)
+    tau = np.maximum(fit.integrated_autocorr_time(g), 1.0)
+    gq = np.percentile(g.reshape(-1, 6), [16, 50, 84], axis=0)
+    cq = np.percentile(c.reshape(-1, 6), [16, 50, 84], axis=0)
+    std = g.reshape(-1, 6).std(axis=0)
+    sig = 1.25 * std * np.sqrt(tau / (g.shape[0] * nw) + tau / (c.shape[0] * nw))
+    assert np.all(np.abs(gq - cq) <= 4.0 * sig), (np.abs(gq - cq) / sig, tau)
+    # the comparison has teeth: the tolerance is a fraction of the posterior width
+    assert np.all(4.0 * sig < 1.5 * std)
