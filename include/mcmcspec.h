@@ -250,6 +250,17 @@ int ms_stretch_scatter(ms_handle* h, double* state, int32_t* naccepted, const in
                        int64_t n, int32_t ndim);
 
 /*
+ * One whole ensemble iteration (both half steps) for a single-rank ensemble of at most 2048 walkers, enqueued
+ * from one call: the iteration's red/blue split (hashed keys sorted in one CTA; randomize_split = 0 gives
+ * evens/odds), then per half: propose, evaluate (prep + streaming kernel), accept, scatter -- in place on
+ * `state` [nw][ndim+1] (device).  Same random streams and arithmetic as the per-kernel entry points above,
+ * i.e. the same chain; what it removes is the host round trip between launches, which dominates ensembles as
+ * small as the reference's 50 walkers (emcee loop at mft6.py:1491-1510).
+ */
+int ms_stretch_iteration(ms_handle* h, double* state, int32_t* naccepted, int64_t nw, double a, uint64_t seed,
+                         uint64_t iteration, int32_t randomize_split);
+
+/*
  * Enqueue on the caller's stream (a cudaStream_t, taken literally: 0 is the CUDA legacy default
  * stream) instead of the handle's own, e.g. the stream a collective library runs on.  The caller
  * keeps ownership.  ms_use_own_stream() goes back to the stream the handle created.

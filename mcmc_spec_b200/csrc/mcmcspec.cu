@@ -1191,6 +1191,42 @@ __global__ void split_keys_kernel(unsigned long long seed, unsigned long long it
   keys[i] = (long long)(mix64(k ^ mix64((unsigned long long)i)) >> 1);
 }
 
+// The iteration's red/blue split for small ensembles, in one CTA: hashed keys (as split_keys_kernel),
+// bitonic sort of (key, index) pairs in shared memory -- the order torch.argsort(keys, stable=True) gives --
+// and the two halves perm[0::2], perm[1::2] written out.  randomize == 0: the fixed split (evens, odds).
+constexpr int SPLIT_SMALL_MAX = 2048;
+__global__ void __launch_bounds__(1024)
+split_perm_small_kernel(unsigned long long seed, unsigned long long iteration, int n, int npow, int randomize,
+                        long long* __restrict__ h0, long long* __restrict__ h1) {
+  __shared__ unsigned long long sk[SPLIT_SMALL_MAX];
+  __shared__ int si[SPLIT_SMALL_MAX];
+  const int tid = threadIdx.x;
+  unsigned long long kbase = mix64(seed ^ 0x5851F42D4C957F2Dull);
+  kbase = mix64(kbase ^ iteration);
+  for (int i = tid; i < npow; i += 1024) {
+    unsigned long long key = ~0ull;
+    if (i < n) key = randomize ? (mix64(kbase ^ mix64((unsigned long long)i)) >> 1) : (unsigned long long)i;
+    sk[i] = key; si[i] = i;
+  }
+  __syncthreads();
+  for (int k = 2; k <= npow; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < npow; i += 1024) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;
+          const unsigned long long ka = sk[i], kb = sk[ixj];
+          const int ia = si[i], ib = si[ixj];
+          const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
+          if (a_gt_b == up) { sk[i] = kb; sk[ixj] = ka; si[i] = ib; si[ixj] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += 1024) ((i & 1) ? h1 : h0)[i >> 1] = (long long)si[i];
+}
+
 // state [nw][ndim+1] = positions | log-prob (replicated on every rank).  s_idx [n_s] are the state
 // rows this rank updates (its shard of the active half), c_idx [n_c] the complementary half.
 __global__ void stretch_propose_kernel(const double* __restrict__ state, const long long* __restrict__ s_idx,
@@ -1270,6 +1306,9 @@ struct ms_handle {
   double* d_theta = nullptr; double* d_lnp = nullptr; long long io_cap = 0;
   double* h_theta = nullptr; double* h_lnp = nullptr; long long pin_cap = 0;
   long long launches = 0;
+  // ms_stretch_iteration scratch (single-rank fused iteration)
+  long long* it_half[2] = {nullptr, nullptr}; double* it_q = nullptr; double* it_logfac = nullptr; double* it_lnp = nullptr;
+  double* it_packed = nullptr; long long it_cap = 0;
   cudaStream_t own_stream = nullptr;
   // optional device-side timing of the streaming kernel
   bool timing = false;
@@ -1501,6 +1540,12 @@ int ms_destroy(ms_handle* h) {
   if (h->d_lnp) cudaFree(h->d_lnp);
   if (h->h_theta) cudaFreeHost(h->h_theta);
   if (h->h_lnp) cudaFreeHost(h->h_lnp);
+  if (h->it_half[0]) cudaFree(h->it_half[0]);
+  if (h->it_half[1]) cudaFree(h->it_half[1]);
+  if (h->it_q) cudaFree(h->it_q);
+  if (h->it_logfac) cudaFree(h->it_logfac);
+  if (h->it_lnp) cudaFree(h->it_lnp);
+  if (h->it_packed) cudaFree(h->it_packed);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return MS_OK;
@@ -2001,6 +2046,54 @@ int ms_build_grid(int device, const double* src_x, const double* src_y, const in
   if (d_rows2) cudaFree(d_rows2);
   if (d_taps) cudaFree(d_taps);
   return rc;
+}
+
+int ms_stretch_iteration(ms_handle* h, double* state, int32_t* naccepted, int64_t nw, double a, uint64_t seed,
+                         uint64_t iteration, int32_t randomize_split) {
+  if (!h) return MS_ERR_INVALID;
+  if (!state || nw < 2 || (nw % 2) || nw > SPLIT_SMALL_MAX) {
+    set_err(h, "ms_stretch_iteration: nw must be even and at most 2048 (larger ensembles: the per-kernel entry points)");
+    return MS_ERR_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  const int ndim = h->T.ndim;
+  const long long half = nw / 2;
+  if (half > h->it_cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 2; ++k) { if (h->it_half[k]) cudaFree(h->it_half[k]); h->it_half[k] = nullptr; }
+    if (h->it_q) cudaFree(h->it_q); if (h->it_logfac) cudaFree(h->it_logfac);
+    if (h->it_lnp) cudaFree(h->it_lnp); if (h->it_packed) cudaFree(h->it_packed);
+    h->it_q = h->it_logfac = h->it_lnp = h->it_packed = nullptr; h->it_cap = 0;
+    for (int k = 0; k < 2; ++k) CK(cudaMalloc((void**)&h->it_half[k], (size_t)half * 8));
+    CK(cudaMalloc((void**)&h->it_q, (size_t)half * ndim * 8));
+    CK(cudaMalloc((void**)&h->it_logfac, (size_t)half * 8));
+    CK(cudaMalloc((void**)&h->it_lnp, (size_t)half * 8));
+    CK(cudaMalloc((void**)&h->it_packed, (size_t)half * (ndim + 2) * 8));
+    h->it_cap = half;
+  }
+  int npow = 2;
+  while (npow < nw) npow <<= 1;
+  split_perm_small_kernel<<<1, 1024, 0, h->stream>>>(seed, iteration, (int)nw, npow, randomize_split, h->it_half[0], h->it_half[1]);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  const unsigned g = (unsigned)((half + 127) / 128);
+  const PartsOut none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int split = 0; split < 2; ++split) {
+    const long long* s_idx = h->it_half[split];
+    const long long* c_idx = h->it_half[1 - split];
+    stretch_propose_kernel<<<g, 128, 0, h->stream>>>(state, s_idx, half, c_idx, half, ndim, a, seed, iteration, split, 0ll,
+                                                     h->it_q, h->it_logfac);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    const int rc = evaluate_device(h, h->it_q, half, h->it_lnp, none);
+    if (rc) return rc;
+    stretch_accept_kernel<<<g, 128, 0, h->stream>>>(state, s_idx, h->it_q, h->it_lnp, h->it_logfac, half, ndim, seed,
+                                                    iteration, split, 0ll, h->it_packed);
+    stretch_scatter_kernel<<<g, 128, 0, h->stream>>>(state, naccepted, s_idx, h->it_packed, half, ndim);
+    CK(cudaGetLastError());
+    h->launches += 2;
+  }
+  return MS_OK;
 }
 
 int ms_split_keys(ms_handle* h, uint64_t seed, uint64_t iteration, int64_t n, int64_t* keys) {

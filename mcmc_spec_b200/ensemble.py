@@ -70,6 +70,14 @@ class CudaBackend:
         self.engine.stretch_scatter(state.data_ptr(), naccepted.data_ptr(), idx.data_ptr(), packed.data_ptr(),
                                     idx.shape[0])
 
+    FUSED_MAX_WALKERS = 2048
+
+    def iteration(self, state, naccepted, a, seed, iteration, randomize_split):
+        """One whole iteration enqueued by a single C call (single rank, small ensembles)."""
+        self._bind()
+        self.engine.stretch_iteration(state.data_ptr(), naccepted.data_ptr(), state.shape[0], a, seed, iteration,
+                                      randomize_split)
+
 
 class EnsembleSampler:
     """Stretch-move ensemble sampler; attribute names follow emcee where they exist.
@@ -101,6 +109,7 @@ class EnsembleSampler:
         self._full = self._packed if world_size == 1 else torch.empty((self.half, ndim + 2), **f64)
         self._fixed = [torch.arange(0, nwalkers, 2, device=self.device), torch.arange(1, nwalkers, 2, device=self.device)]
         self._side, self._next = None, None
+        self.fused = True                       # allow the one-call iteration where the backend offers it
 
     # ------------------------------------------------------------------ state
     def initialize(self, p0):
@@ -165,8 +174,14 @@ class EnsembleSampler:
 
     def step(self):
         """One ensemble iteration = two half steps; every walker gets one proposal."""
-        halves = self._halves()
         be = self.backend
+        if (self.world_size == 1 and hasattr(be, 'iteration') and self.nwalkers <= be.FUSED_MAX_WALKERS
+                and self.fused and self.state.is_contiguous()):
+            # small single-rank ensembles are launch bound: the whole iteration goes down in one call
+            be.iteration(self.state, self.naccepted, self.a, self.seed, self.iteration, self.randomize_split)
+            self.iteration += 1
+            return
+        halves = self._halves()
         for split in (0, 1):
             s_idx, c_idx = halves[split], halves[1 - split]
             lo = self.rank * self.shard

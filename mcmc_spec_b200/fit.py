@@ -90,13 +90,16 @@ def integrated_autocorr_time(chain, c=5):
     if x.ndim == 2:
         x = x[:, :, None]
     n_t, n_w, n_d = x.shape
+    # function_1d for every (walker, parameter) series at once: one batched FFT along the step axis
+    n = _next_pow_two(n_t)
+    f = np.fft.fft(x - np.mean(x, axis=0), n=2 * n, axis=0)
+    acf = np.fft.ifft(f * np.conjugate(f), axis=0)[:n_t].real
+    with np.errstate(invalid='ignore', divide='ignore'):
+        acf /= acf[0]
     tau = np.empty(n_d)
     for d in range(n_d):
-        f = np.zeros(n_t)
-        for k in range(n_w):
-            f += autocorr_function_1d(x[:, k, d])
-        f /= n_w
-        taus = 2.0 * np.cumsum(f) - 1.0
+        fm = acf[:, :, d].sum(axis=1) / n_w
+        taus = 2.0 * np.cumsum(fm) - 1.0
         tau[d] = taus[_auto_window(taus, c)]
     return tau
 

@@ -23,7 +23,7 @@ _LIB_PATH = os.environ.get('MCMCSPEC_LIB') or os.path.join(os.path.dirname(os.pa
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
            'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_component_mags', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows', 'ms_build_grid',
-           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_timing',
+           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_timing',
            'ms_kernel_time']
 
 _dp = C.POINTER(C.c_double)
@@ -96,6 +96,7 @@ def load_library(path=None):
     lib.ms_stretch_accept.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64,
                                       C.c_int32, C.c_int64, vp]
     lib.ms_stretch_scatter.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_int32]
+    lib.ms_stretch_iteration.argtypes = [vp, vp, vp, C.c_int64, C.c_double, C.c_uint64, C.c_uint64, C.c_int32]
     lib.ms_launch_count.argtypes = [vp]
     lib.ms_launch_count.restype = C.c_int64
     lib.ms_set_stream.argtypes = [vp, vp]
@@ -324,6 +325,10 @@ class Engine:
                        packed_ptr):
         self._check(self.lib.ms_stretch_accept(self._h, state_ptr, s_idx_ptr, q_ptr, lnp_q_ptr, logfac_ptr, n_s,
                                                self.ndim, seed, iteration, split, gid0, packed_ptr), 'ms_stretch_accept')
+
+    def stretch_iteration(self, state_ptr, naccepted_ptr, nw, a, seed, iteration, randomize_split=True):
+        self._check(self.lib.ms_stretch_iteration(self._h, state_ptr, naccepted_ptr, nw, a, seed, iteration,
+                                                  int(bool(randomize_split))), 'ms_stretch_iteration')
 
     def stretch_scatter(self, state_ptr, naccepted_ptr, idx_ptr, packed_ptr, n):
         self._check(self.lib.ms_stretch_scatter(self._h, state_ptr, naccepted_ptr, idx_ptr, packed_ptr, n, self.ndim),

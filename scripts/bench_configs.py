@@ -64,6 +64,34 @@ def run(name, prob, nw, reps=5):
     torch.cuda.empty_cache()
 
 
+def run_c1_sampler(nw=50, steps=2000):
+    """Latency of one stretch-move iteration of the reference-sized ensemble (50 walkers, C1/C2 shape):
+    the one-call fused iteration against the per-kernel path driven from Python."""
+    from mcmc_spec_b200.ensemble import CudaBackend, EnsembleSampler
+    prob = synthetic.make_problem(truth=synthetic.consistent_truth(3850.0, 3425.0, 0.12, 2.0732e-3))
+    lp = LogPosterior(prob)
+    p0 = prob.truth * (1 + 0.01 * np.random.default_rng(0).standard_normal((nw, 6)))
+    p0[:, 2] = np.abs(p0[:, 2])
+    res = {}
+    for name, fused in (('fused_one_call', True), ('per_kernel_calls', False)):
+        s = EnsembleSampler(nw, 6, CudaBackend(lp.engine), seed=1)
+        s.fused = fused
+        s.initialize(p0)
+        s.run_mcmc(50)
+        torch.cuda.synchronize()
+        lp.engine.set_timing(True); lp.engine.kernel_time()
+        t0 = time.perf_counter()
+        s.run_mcmc(steps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ms, nl, nwt = lp.engine.kernel_time()
+        lp.engine.set_timing(False)
+        res[name] = {"ms_per_iteration": 1e3 * dt / steps, "evals_per_s": nw * steps / dt,
+                     "stream_kernel_ms_per_iteration": ms / steps}
+    print(json.dumps({"config": "C1 sampler: 50 walkers (25 proposals per half step), C1/C2 shape", **res}), flush=True)
+    lp.close()
+
+
 def run_c3(n_fits=12, nw=25, reps=50):
     """BASELINE config C3: 12 independent 50-walker ensembles (one half step = 25 proposals each) on one GPU,
     one device copy of the grid, every fit on its own stream so their launches overlap."""
@@ -112,10 +140,12 @@ def run_c3(n_fits=12, nw=25, reps=50):
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['c1', 'c3', 'c4', 'c5']
+    which = sys.argv[1:] or ['c1', 'c1s', 'c3', 'c4', 'c5']
     if 'c1' in which:
         run('C1/C2 shape: 26x4 grid, 135000-px rows (P_reg ~117k synthetic bands), N=1945', synthetic.make_problem(), 8192)
         run('C1/C2 shape, reference walker count (50)', synthetic.make_problem(), 50, reps=20)
+    if 'c1s' in which:
+        run_c1_sampler()
     if 'c3' in which:
         run_c3()
     if 'c4' in which:

@@ -109,3 +109,25 @@ def test_independent_chains_agree_within_monte_carlo_error(small_problem, small_
     assert np.all(np.abs(gq - cq) <= 4.0 * sig), (np.abs(gq - cq) / sig, tau)
     # the comparison has teeth: the tolerance is a fraction of the posterior width
     assert np.all(4.0 * sig < 1.5 * std)
+
+
+@pytest.mark.parametrize('nw,randomize', [(50, True), (32, False), (2048, True), (6, True)])
+def test_fused_iteration_is_the_same_chain(small_problem, small_lp, nw, randomize):
+    """ms_stretch_iteration (one call per iteration: in-kernel split sort + both half steps) walks exactly the
+    chain of the per-kernel path (torch argsort + five launches per half step)."""
+    from mcmc_spec_b200.ensemble import CudaBackend, EnsembleSampler
+    t = small_problem.truth
+    p0 = t * (1 + 0.01 * np.random.default_rng(nw).standard_normal((nw, 6)))
+    p0[:, 2] = np.abs(p0[:, 2])
+    a = EnsembleSampler(nw, 6, CudaBackend(small_lp.engine), seed=5, randomize_split=randomize)
+    b = EnsembleSampler(nw, 6, CudaBackend(small_lp.engine), seed=5, randomize_split=randomize)
+    b.fused = False
+    a.initialize(p0); b.initialize(p0)
+    n0 = small_lp.engine.launch_count
+    a.run_mcmc(12)
+    n1 = small_lp.engine.launch_count
+    b.run_mcmc(12)
+    assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
+    assert np.array_equal(a.naccepted.cpu().numpy(), b.naccepted.cpu().numpy())
+    assert a.naccepted.sum().item() > 0 and a.iteration == b.iteration == 12
+    assert n1 - n0 == 12 * (1 + 2 * 5)                    # split + 2 x (propose, prep, stream, accept, scatter)
