@@ -275,6 +275,29 @@ def test_3d_grid_trilinear_16_passbands(native_lib):
         lp.close()
 
 
+def test_c5_full_size_cell_ordered_launch(native_lib):
+    """BASELINE config C5 at full size: 26x4x5 grid (416 MB > L2, so walkers are launched grouped by grid
+    cell), 100 000-pixel rows, 25 000 observed pixels (one 512-thread CTA per SM), 4 + 12 bands.  Oracle on a
+    sample; the launch order must not change any value (the same walkers in small batches take the natural
+    order); scale invariance of the spectral chi-square."""
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    p = synthetic.make_problem_c5()
+    lp = LogPosterior(p)
+    assert lp.tables.n_data == 25000 and lp.tables.n_reg == 100000 and lp.tables.grid.nbytes > 400e6
+    theta = synthetic.sample_prior_box(p, 2048, seed=5)
+    got = lp(theta)                                              # >= 1024 walkers: cell-ordered launch
+    _compare(got[:12], to_oracle(p).lnprob_batch(theta[:12]))
+    pieces = np.concatenate([lp(theta[k:k + 256]) for k in range(0, 2048, 256)])   # natural order
+    assert np.array_equal(pieces, got)
+    a = lp.parts(theta[300:332]); th2 = theta[300:332].copy(); th2[:, 3] *= 0.8
+    b = lp.parts(th2)
+    ok = (a['status'] == 0) & (b['status'] == 0)
+    assert ok.sum() > 8 and np.allclose(a['chi2_spec'][ok], b['chi2_spec'][ok], rtol=1e-10)
+    lp.close()
+
+
 def test_triple_star_mode(native_lib):
     """nspec = 3: 8-parameter vectors, third gather, split contrast list
     (mft6.py:746-751), the 8-parameter prior branches (mft6.py:1329-1454)."""
