@@ -276,7 +276,9 @@ def run_product_arm(args, rank, local_rank, world):
     # ---- end-to-end through the host-buffer API (pinned staging + H2D + kernels + D2H per call)
     lp.engine.use_own_stream()
     per_rank = nw // world
-    host_theta = initial_ensemble(prob, per_rank, seed=100 + rank)
+    # the inputs are this rank's share of the ensemble as the timed chain left it (host copy): the same kind of
+    # walkers the device-resident measurement evaluates
+    host_theta = np.ascontiguousarray(sampler.coords.detach().cpu().numpy()[rank * per_rank:(rank + 1) * per_rank])
     halves = [np.ascontiguousarray(host_theta[:per_rank // 2]), np.ascontiguousarray(host_theta[per_rank // 2:])]
     for _ in range(2):
         for h in halves:
@@ -307,7 +309,14 @@ def run_product_arm(args, rank, local_rank, world):
                     "algorithmic_bytes_per_launch": bpe * k_walkers / max(k_launches, 1),
                     "kernel_share_of_step": k_ms / float(step_ms.sum()),
                     "note": "algorithmic bytes are grid-row bytes consumed; the 27 MB grid is L2-resident, so DRAM traffic "
-                            "is far below algorithmic bytes (see profiles/)"}
+                            "is far below algorithmic bytes and frac > 1 against the HBM copy peak is expected; ncu shows no "
+                            "saturated unit (issue 44 %, L1TEX 59 %, L2 55 %, fp64 26 %): the kernel is latency bound at "
+                            "16 warps/SM (see profiles/, DESIGN.md section 3.2)"}
+        if traffic and traffic.get("l2_read_bytes_per_launch") and k_launches and \
+                abs(k_walkers / k_launches - 32768) < 1:
+            # L2 -> SM bytes of the same launch shape (ncu lts__t_sectors_srcunit_tex_op_read x 32 B)
+            roofline["l2_traffic"] = traffic["l2_read_bytes_per_launch"]
+            roofline["l2_achieved_gbs"] = traffic["l2_read_bytes_per_launch"] / 1e9 / (k_ms / k_launches / 1e3)
         line = {"metric": METRIC, "value": nw * args.steps / total_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -316,7 +325,7 @@ def run_product_arm(args, rank, local_rank, world):
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nw * 6 * 8),
                         "d2h_bytes_per_step": int(nw * 8), "steps": args.e2e_steps,
-                        "api": "LogPosterior.__call__(theta_host[nw/2/N, 6]) -> ms_lnprob(MS_HOST), two calls per step per rank"},
+                        "api": "LogPosterior.__call__(theta_host[nw/2/N, 6]) -> ms_lnprob(MS_HOST), two calls per step per rank; inputs = the ensemble after the timed chain"},
                 "gpu_launches": int(launches), "clocks": clock_summary}
         if cpu is not None:
             line["cpu_baseline"] = cpu

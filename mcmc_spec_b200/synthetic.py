@@ -302,8 +302,8 @@ def make_problem(*, temps=None, lgs=None, specmin=3000.0, specmax=30000.0, dlam=
     # span and the central wavelengths (mft6.py:3588-3595); here they coincide with the library.
     if ptm is None:
         ptm = _filter_table([(b.wavelength, b.transmit) for b in phot_bands], res)
-    tmi = min(min(min(w) for w in ctm[0]), min(min(w) for w in ptm[0]))
-    tma = max(max(max(w) for w in ctm[0]), max(max(w) for w in ptm[0]))
+    tmi = min([min(w) for w in ctm[0]] + [min(w) for w in ptm[0]])          # mft6.py:3577-3597 (either list may be empty)
+    tma = max([max(w) for w in ctm[0]] + [max(w) for w in ptm[0]])
 
     # ---- truth and observed data
     if truth is None:

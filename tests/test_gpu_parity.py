@@ -275,6 +275,33 @@ def test_3d_grid_trilinear_16_passbands(native_lib):
         lp.close()
 
 
+def test_filter_count_variants(native_lib):
+    """No contrast measurement at all with the three-band (2MASS-only) photometry list of mft6.py:766-767; a
+    single contrast filter; four contrast + twelve photometric bands on a 2-D grid (the wide kernel variant)."""
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    base = synthetic.make_problem_small()
+    wl = base.wl
+    span = wl[-1] - wl[0]
+    mk = lambda c, w, k: synthetic.synthetic_passband(wl[0] + c * span, w * span, 200, ripple_seed=30 + k)   # noqa: E731
+    three = [mk(0.3, 0.2, 0), mk(0.55, 0.2, 1), mk(0.8, 0.25, 2)]
+    cases = [
+        synthetic.make_problem_small(contrast_curves=[], contrast_names=[], phot_curves=three,
+                                     phot_names=['2MASS_J', '2MASS_H', '2MASS_Ks']),
+        synthetic.make_problem_small(contrast_curves=[three[0]], contrast_names=['c0']),
+    ]
+    cc, cn, pc, pn = synthetic._many_bands(wl, 4, 12)
+    cases.append(synthetic.make_problem_small(contrast_curves=cc, contrast_names=cn, phot_curves=pc, phot_names=pn))
+    for prob in cases:
+        lp = LogPosterior(prob)
+        theta = synthetic.sample_prior_box(prob, 128, seed=3)
+        _compare(lp(theta), to_oracle(prob).lnprob_batch(theta))
+        parts = lp.parts(theta[:4])
+        assert parts['contrast'].shape == (4, len(prob.fr[0])) and parts['phot'].shape == (4, len(prob.fr[3]))
+        lp.close()
+
+
 def test_c5_full_size_cell_ordered_launch(native_lib):
     """BASELINE config C5 at full size: 26x4x5 grid (416 MB > L2, so walkers are launched grouped by grid
     cell), 100 000-pixel rows, 25 000 observed pixels (one 512-thread CTA per SM), 4 + 12 bands.  Oracle on a
