@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MS_ABI_VERSION 1
+#define MS_ABI_VERSION 2
 #define MS_TILE 1024            /* model pixels per streaming tile; filter weights are tile padded */
 #define MS_MAX_CONTRAST 4
 #define MS_MAX_PHOT 12
@@ -135,6 +135,9 @@ typedef struct ms_config {
   int32_t dist_fit;
   int32_t rad_prior;
   int32_t flavour;              /* 0: mft6.py; 1: mft6_nospec.py (no spectral term, parallax <= 1/100) */
+  int32_t feh_free;             /* extension for 3-D grids (binaries): [Fe/H] is a walker parameter, the trailing
+                                   column of theta ([nw][ndim + 1]); outside the nodes -> -inf.  0: fixed `feh` */
+  int32_t reserved0;
 } ms_config;
 
 /* sizeof(ms_config) as compiled, so a binding can verify its mirror of the struct. */
@@ -286,6 +289,14 @@ int ms_set_cluster(ms_handle* h, int ctas_per_walker);
  * A walker's value does not depend on the setting or on its partner (bit-identical).
  */
 int ms_set_pairing(ms_handle* h, int enabled);
+
+/*
+ * Launch order of batches of >= 1024 walkers.  1: grouped by grid cell (counting sort on the device), so that
+ * CTAs resident together stream the same rows and a grid larger than L2 is fetched from HBM about once per
+ * cell group instead of once per walker; 0: the caller's order; -1 (default): grouped when the grid exceeds
+ * the device's L2.  Values do not depend on the order.
+ */
+int ms_set_cell_order(ms_handle* h, int mode);
 
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 int64_t ms_launch_count(const ms_handle* h);

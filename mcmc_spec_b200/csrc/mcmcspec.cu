@@ -94,6 +94,7 @@ struct DevTables {
   double tmin, tmax;
   double prior_mu[MS_MAX_NDIM], prior_sig[MS_MAX_NDIM];
   int nspec, ndim, ext_flag, dist_fit, rad_prior;
+  int feh_free, ncol;           // per-walker [Fe/H] as an extra trailing column of theta; ncol = ndim + feh_free
   int n_cells;                 // number of cell keys (bins of the launch-order counting sort)
 };
 
@@ -288,7 +289,10 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   const int ndim = T.ndim, ns = T.nspec;
   double p[MS_MAX_NDIM];
   bool finite = true;
-  for (int k = 0; k < ndim; ++k) { p[k] = theta[w * ndim + k]; finite = finite && isfinite(p[k]); }
+  for (int k = 0; k < ndim; ++k) { p[k] = theta[w * T.ncol + k]; finite = finite && isfinite(p[k]); }
+  // 3-D grids: the metallicity is fixed for the fit, or (an extension, for grids beyond L2) a walker parameter
+  const double fehv = T.feh_free ? theta[w * T.ncol + ndim] : T.feh;
+  finite = finite && isfinite(fehv);
 
   WalkerPlan plan;
   for (int s = 0; s < MAX_STAR; ++s) {
@@ -390,7 +394,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
 
   // ---- grid brackets and coefficients
   int z1 = 0, z2 = 0; double wz = 0.0;
-  if (T.n_feh > 1 && !bracket_nodes(T.feh_nodes, T.n_feh, T.feh, &z1, &z2, &wz)) {
+  if (T.n_feh > 1 && !bracket_nodes(T.feh_nodes, T.n_feh, fehv, &z1, &z2, &wz)) {
     plan.status = MS_W_OFF_GRID; store(plan); return;
   }
   const double di = 1.0 / plx;                            // mft6.py:690
@@ -424,6 +428,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
       const int tl = min(r_a % T.n_teff, r_b % T.n_teff), gl = min(r_a / T.n_teff, r_b / T.n_teff);
       key = key * per_star + gl * T.n_teff + tl;
     }
+    if (T.n_feh > 1) key = key * T.n_feh + min(z1, z2);
     plan.cell = (T.n_cells > 1) ? min(key, T.n_cells - 2) : 0;
   }
   plan.av = ((T.ext_flag || mode == MODE_OPTIMIZER) && av > 0.0) ? av : 0.0;   // mft6.py:1161, :1001
@@ -1126,27 +1131,43 @@ __global__ void broaden_patch_kernel(double* __restrict__ rows, long long row_le
 // Out-of-range abscissae raise `*oob` (interp1d's bounds_error=True).
 // grid = (ceil(row_len / 256), n_rows)
 // ------------------------------------------------------------------------------------------
+// largest j with x[j] <= v, for x[0] <= v (ascending x[lo..hi])
+__device__ __forceinline__ long long bracket_below(const double* __restrict__ x, long long lo, long long hi, double v) {
+  while (hi - lo > 1) {
+    const long long mid = (lo + hi) >> 1;
+    if (x[mid] <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(256)
 resample_rows_kernel(const double* __restrict__ src_x, const double* __restrict__ src_y,
                      const long long* __restrict__ off, const double* __restrict__ x_dst, long long row_len,
                      double* __restrict__ out, int* __restrict__ oob) {
   const long long r = blockIdx.y;
-  const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (j >= row_len) return;
+  const long long j0 = blockIdx.x * (long long)blockDim.x;
+  const long long j = j0 + threadIdx.x;
   const double* x = src_x + off[r];
   const double* y = src_y + off[r];
   const long long n = off[r + 1] - off[r];
+  // two-level search: the CTA's 256 ascending abscissae fall into one short stretch of the node spectrum,
+  // located once per CTA; every thread then searches only that stretch (a few L1-resident steps)
+  __shared__ long long s_lo, s_hi;
+  if (threadIdx.x == 0) {
+    const long long jl = min(j0 + (long long)blockDim.x - 1, row_len - 1);
+    const double v0 = x_dst[j0], v1 = x_dst[jl];
+    s_lo = (v0 >= x[0] && v0 <= x[n - 1]) ? bracket_below(x, 0, n - 1, v0) : 0;
+    s_hi = (v1 >= x[0] && v1 < x[n - 1]) ? bracket_below(x, 0, n - 1, v1) + 1 : n - 1;
+  }
+  __syncthreads();
+  if (j >= row_len) return;
   const double v = x_dst[j];
   if (!(v >= x[0] && v <= x[n - 1])) { atomicOr(oob, (v < x[0]) ? 1 : 2); out[r * row_len + j] = CUDART_NAN; return; }
   double res;
   if (v == x[n - 1]) {
     res = y[n - 1];
   } else {
-    long long lo = 0, hi = n - 1;
-    while (hi - lo > 1) {
-      const long long mid = (lo + hi) >> 1;
-      if (x[mid] <= v) lo = mid; else hi = mid;
-    }
+    const long long lo = bracket_below(x, s_lo, s_hi, v);
     if (x[lo] == v) {
       res = y[lo];
     } else {
@@ -1298,6 +1319,7 @@ struct ms_handle {
   int* order = nullptr; unsigned* cell_hist = nullptr; bool use_order = false;
   int pairing = MS_PAIRING_DEFAULT;  // 0: one walker per CTA, 1: two cell-mates per CTA for large batches, -1: automatic
   bool pair_now = false;         // decided per call (evaluate_device)
+  int cell_order = -1;           // launch order: -1 automatic (cell-sorted when the grid exceeds L2), 0 natural, 1 cell-sorted
   int max_optin_smem = 0;
   bool nospec = false;           // mft6_nospec.py flavour of the posterior
   double* d_opt_flux = nullptr; double* d_opt_median = nullptr; int opt_sets = 0;   // fit_spec's renormalised spectra
@@ -1457,7 +1479,7 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   // Grouping walkers by grid cell pays when the grid does not fit L2 (rows are then fetched from HBM once
   // per group instead of once per walker).  With an L2-resident grid it only concentrates the concurrent
   // CTAs on the same L2 slices (measured: C4 -4 %, C1 -8 %), so the natural order is kept there.
-  h->use_order = nw >= 1024 && h->T.n_cells > 1 && h->grid_bytes > h->l2_bytes;
+  h->use_order = nw >= 1024 && h->T.n_cells > 1 && (h->cell_order < 0 ? h->grid_bytes > h->l2_bytes : h->cell_order > 0);
   // Two walkers per CTA pay when (a) the batch still fills the machine with half as many CTAs, (b) both
   // walkers' shared memory fits one SM and (c) cell-mates exist to be paired: the launch order is then
   // always the cell-sorted one.
@@ -1558,6 +1580,9 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
   *out = nullptr;
   if (cfg->abi_version != MS_ABI_VERSION) { set_err(nullptr, "ms_create: ABI version mismatch"); return MS_ERR_INVALID; }
   if (cfg->nspec != 2 && cfg->nspec != 3) { set_err(nullptr, "ms_create: nspec must be 2 (binary) or 3 (triple)"); return MS_ERR_UNSUPPORTED; }
+  if (cfg->feh_free && (cfg->n_feh < 2 || cfg->nspec != 2)) {
+    set_err(nullptr, "ms_create: a free [Fe/H] needs a 3-D grid and is built for binaries"); return MS_ERR_UNSUPPORTED;
+  }
   if (cfg->nspec == 3 && cfg->n_feh > 1) { set_err(nullptr, "ms_create: triples are built for (Teff, log g) grids only"); return MS_ERR_UNSUPPORTED; }
   if (cfg->n_contrast < 0 || cfg->n_contrast > MS_MAX_CONTRAST || cfg->n_phot < 0 || cfg->n_phot > MS_MAX_PHOT) {
     set_err(nullptr, "ms_create: too many filters"); return MS_ERR_UNSUPPORTED;
@@ -1587,6 +1612,7 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
   T.n_data = cfg->n_data;
   T.n_contrast = cfg->n_contrast; T.n_phot = cfg->n_phot;
   T.nspec = cfg->nspec; T.ndim = 2 * cfg->nspec + 2;
+  T.feh_free = (cfg->feh_free != 0); T.ncol = T.ndim + T.feh_free;
   T.ext_flag = cfg->ext_flag; T.dist_fit = cfg->dist_fit; T.rad_prior = cfg->rad_prior;
   T.opt_median = nullptr;
   h->nospec = (cfg->flavour == 1);
@@ -1597,7 +1623,7 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
   T.n_iso = cfg->n_iso; T.n_dm = cfg->n_dm; T.n_dust_samples = cfg->n_dust_samples;
   {
     const long long per_star = (long long)cfg->n_teff * cfg->n_logg;
-    const long long cells = per_star * per_star + 1;           // + 1: walkers that never reach the grid
+    const long long cells = per_star * per_star * (cfg->n_feh > 1 ? cfg->n_feh : 1) + 1;   // + 1: walkers that never reach the grid
     T.n_cells = (cells <= (1 << 20)) ? (int)cells : 1;
     CKH(cudaMalloc((void**)&h->cell_hist, (size_t)T.n_cells * sizeof(unsigned)));
   }
@@ -1760,6 +1786,12 @@ int ms_set_pairing(ms_handle* h, int enabled) {
   return MS_OK;
 }
 
+int ms_set_cell_order(ms_handle* h, int mode) {
+  if (!h) return MS_ERR_INVALID;
+  h->cell_order = mode < 0 ? -1 : (mode != 0);
+  return MS_OK;
+}
+
 int ms_set_timing(ms_handle* h, int enabled) {
   if (!h) return MS_ERR_INVALID;
   h->timing = enabled != 0;
@@ -1811,7 +1843,7 @@ int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_ind
   if (!h) return MS_ERR_INVALID;
   if (nw < 0 || (nw > 0 && (!theta || !set_index || !rad_sigma || !chisq))) { set_err(h, "ms_optimizer_chisq: null argument"); return MS_ERR_INVALID; }
   if (h->opt_sets < 1) { set_err(h, "ms_optimizer_chisq: call ms_set_optimizer_data first"); return MS_ERR_INVALID; }
-  if (h->T.nspec != 2) { set_err(h, "ms_optimizer_chisq: the optimiser stage is built for binaries"); return MS_ERR_UNSUPPORTED; }
+  if (h->T.nspec != 2 || h->T.feh_free) { set_err(h, "ms_optimizer_chisq: the optimiser stage is built for binaries at a fixed [Fe/H]"); return MS_ERR_UNSUPPORTED; }
   if (nw == 0) return MS_OK;
   for (int64_t w = 0; w < nw; ++w)
     if (set_index[w] < 0 || set_index[w] >= h->opt_sets) { set_err(h, "ms_optimizer_chisq: set_index out of range"); return MS_ERR_INVALID; }
@@ -1853,7 +1885,7 @@ int ms_lnprob_parts(ms_handle* h, const double* theta, int64_t nw, double* lnpro
   if (nw < 0 || (nw > 0 && (!theta || !lnprob))) { set_err(h, "ms_lnprob: null argument"); return MS_ERR_INVALID; }
   if (nw == 0) return MS_OK;
   CK(cudaSetDevice(h->device));
-  const int ndim = h->T.ndim;
+  const int ndim = h->T.ncol;                          // columns of theta
   if (where == MS_DEVICE) {
     PartsOut parts{chi2_spec, contrast, phot, lnprior, logg, status, nullptr, nullptr};
     return evaluate_device(h, theta, nw, lnprob, parts);
@@ -1892,7 +1924,7 @@ int ms_model_spectrum(ms_handle* h, const double* theta, int64_t nw, double* out
   if (nw < 0 || (nw > 0 && (!theta || !out))) { set_err(h, "ms_model_spectrum: null argument"); return MS_ERR_INVALID; }
   if (nw == 0) return MS_OK;
   CK(cudaSetDevice(h->device));
-  const int ndim = h->T.ndim, n = h->T.n_data;
+  const int ndim = h->T.ncol, n = h->T.n_data;
   int rc = ensure_io(h, nw);
   if (rc) return rc;
   const double* d_theta = theta;
@@ -1921,7 +1953,7 @@ int ms_component_mags(ms_handle* h, const double* theta, int64_t nw, double* out
   if (nw < 0 || (nw > 0 && (!theta || !out))) { set_err(h, "ms_component_mags: null argument"); return MS_ERR_INVALID; }
   if (nw == 0 || h->T.n_contrast == 0) return MS_OK;
   CK(cudaSetDevice(h->device));
-  const int ndim = h->T.ndim;
+  const int ndim = h->T.ncol;
   const size_t per = (size_t)h->T.n_contrast * h->T.nspec;
   int rc = ensure_io(h, nw);
   if (rc) return rc;
@@ -2056,7 +2088,7 @@ int ms_stretch_iteration(ms_handle* h, double* state, int32_t* naccepted, int64_
     return MS_ERR_INVALID;
   }
   CK(cudaSetDevice(h->device));
-  const int ndim = h->T.ndim;
+  const int ndim = h->T.ncol;
   const long long half = nw / 2;
   if (half > h->it_cap) {
     CK(cudaStreamSynchronize(h->stream));

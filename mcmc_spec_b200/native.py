@@ -13,7 +13,7 @@ import numpy as np
 
 from .tables import DeviceTables, TILE
 
-MS_ABI_VERSION = 1
+MS_ABI_VERSION = 2
 MS_MAX_CONTRAST, MS_MAX_PHOT, MS_MAX_NDIM = 4, 12, 8
 MS_HOST, MS_DEVICE = 0, 1
 MS_W_PRIOR_BOUNDS, MS_W_OFF_ISOCHRONE, MS_W_OFF_GRID, MS_W_NONFINITE = 1, 2, 4, 8
@@ -23,7 +23,7 @@ _LIB_PATH = os.environ.get('MCMCSPEC_LIB') or os.path.join(os.path.dirname(os.pa
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
            'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_component_mags', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows', 'ms_build_grid',
-           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_timing',
+           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_cell_order', 'ms_set_timing',
            'ms_kernel_time']
 
 _dp = C.POINTER(C.c_double)
@@ -51,6 +51,7 @@ class MsConfig(C.Structure):
         ('tmin', C.c_double), ('tmax', C.c_double),
         ('prior_mu', C.c_double * MS_MAX_NDIM), ('prior_sig', C.c_double * MS_MAX_NDIM),
         ('ext_flag', C.c_int32), ('dist_fit', C.c_int32), ('rad_prior', C.c_int32), ('flavour', C.c_int32),
+        ('feh_free', C.c_int32), ('reserved0', C.c_int32),
     ]
 
 
@@ -103,6 +104,7 @@ def load_library(path=None):
     lib.ms_use_own_stream.argtypes = [vp]
     lib.ms_set_cluster.argtypes = [vp, C.c_int]
     lib.ms_set_pairing.argtypes = [vp, C.c_int]
+    lib.ms_set_cell_order.argtypes = [vp, C.c_int]
     lib.ms_set_timing.argtypes = [vp, C.c_int]
     lib.ms_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     for name in EXPORTS:
@@ -170,6 +172,7 @@ def make_config(t: DeviceTables, device=0):
     cfg.prior_sig = (C.c_double * MS_MAX_NDIM)(*sig)
     cfg.ext_flag, cfg.dist_fit, cfg.rad_prior = t.ext_flag, t.dist_fit, t.rad_prior
     cfg.flavour = int(getattr(t, 'flavour', 0))
+    cfg.feh_free = int(getattr(t, 'feh_free', 0))
     assert TILE == 1024
     return cfg, keep
 
@@ -183,7 +186,7 @@ class Engine:
         self.lib = lib or load_library()
         self._grid_owner = grid_owner
         self.tables = tables
-        self.ndim = 2 * tables.nspec + 2
+        self.ndim = 2 * tables.nspec + 2 + int(getattr(tables, 'feh_free', 0))      # columns of theta
         self.n_data, self.n_contrast, self.n_phot, self.nspec = tables.n_data, tables.contrast.n, tables.phot.n, tables.nspec
         cfg, keep = make_config(tables, device)
         h = C.c_void_p()
@@ -239,6 +242,10 @@ class Engine:
         """Two cell-mates per CTA for large batches: True / False / None (automatic, the default); values are
         bit-identical either way."""
         self._check(self.lib.ms_set_pairing(self._h, -1 if enabled is None else int(bool(enabled))), 'ms_set_pairing')
+
+    def set_cell_order(self, mode):
+        """Launch order of large batches: True grouped by grid cell, False natural, None automatic (default)."""
+        self._check(self.lib.ms_set_cell_order(self._h, -1 if mode is None else int(bool(mode))), 'ms_set_cell_order')
 
     def set_timing(self, enabled):
         self._check(self.lib.ms_set_timing(self._h, int(bool(enabled))), 'ms_set_timing')

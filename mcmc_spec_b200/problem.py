@@ -49,12 +49,13 @@ class Problem:
     nospec: bool = False                 # True: the posterior of mft6_nospec.py (no spectral term)
     fehs: Optional[List[float]] = None   # 3-D extension: [Fe/H] nodes
     feh: float = 0.0                     # 3-D extension: the fit's fixed metallicity
+    feh_free: bool = False               # 3-D extension: [Fe/H] is a walker parameter (trailing column of theta)
     truth: Optional[np.ndarray] = None   # theta the synthetic data were drawn from
     meta: dict = field(default_factory=dict)
 
     @property
     def ndim(self):
-        return 6 if self.nspec == 2 else 8
+        return (6 if self.nspec == 2 else 8) + int(self.feh_free)
 
     @property
     def specs(self):

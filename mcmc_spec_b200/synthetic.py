@@ -244,7 +244,7 @@ def make_problem(*, temps=None, lgs=None, specmin=3000.0, specmax=30000.0, dlam=
                  phot_names=None, truth=None, plx=2.0732e-3, plx_err=0.0277e-3, snr=150.0,
                  seed=2298, fehs=None, feh=0.0, rad_prior=True, dist_fit=True,
                  data_flux=None, data_err=None, cmag=None, cerr=None, pmag=None, perr=None,
-                 ctm=None, ptm=None, pfilt_names=None, nspec=2, nospec=False):
+                 ctm=None, ptm=None, pfilt_names=None, nspec=2, nospec=False, feh_free=False):
     """Assemble a synthetic ``Problem``.
 
     Defaults give the reference's koi2298 shapes (26 x 4 nodes, 135 000-pixel rows at 0.2 A,
@@ -362,7 +362,7 @@ def make_problem(*, temps=None, lgs=None, specmin=3000.0, specmax=30000.0, dlam=
                    fr=fr, ctm=ctm, ptm=ptm, tmi=tmi, tma=tma, matrix=matrix, dust_dm_edges=dm_edges,
                    dust_samples=dust_samples, photbands=phot_bands, prior=prior, nspec=nspec, nospec=nospec, av=True,
                    dist_fit=dist_fit, rad_prior=rad_prior, fehs=None if fehs is None else list(fehs),
-                   feh=feh, truth=truth, meta=dict(seed=seed, res=res, window_um=tuple(window_um)))
+                   feh=feh, feh_free=bool(feh_free), truth=truth, meta=dict(seed=seed, res=res, window_um=tuple(window_um)))
 
 
 def make_problem_small(seed=2298, **kw):
@@ -486,4 +486,11 @@ def sample_prior_box(prob: Problem, n, seed=0, edge_cases=True):
         th[13, 5] = 1 / 3000.0                                            # far edge of parallax box
         th[14, 5] = 1 / 50.0                                              # nearer than first dust slice
         th[15, 3] = 1.5                                                   # R1 at its upper bound
+    if getattr(prob, 'feh_free', False):
+        # free-metallicity extension: trailing [Fe/H] column, uniform over the nodes, with node / edge / outside cases
+        z = rng.uniform(min(prob.fehs), max(prob.fehs), n)
+        if edge_cases and n >= 24:
+            z[16] = prob.fehs[1]; z[17] = min(prob.fehs); z[18] = max(prob.fehs)
+            z[19] = max(prob.fehs) + 0.01; z[20] = min(prob.fehs) - 0.01; z[21] = 0.5 * (prob.fehs[0] + prob.fehs[1])
+        th = np.concatenate([th, z[:, None]], axis=1)
     return th

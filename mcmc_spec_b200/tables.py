@@ -155,6 +155,7 @@ class DeviceTables:
     dist_fit: int
     rad_prior: int
     flavour: int = 0             # 1: mft6_nospec.py
+    feh_free: int = 0            # 1: [Fe/H] is the trailing walker parameter (3-D grids)
 
     @property
     def n_tiles(self):
@@ -163,7 +164,7 @@ class DeviceTables:
     def bytes_per_eval(self):
         """Algorithmic bytes of one evaluation:
         n_star * 2^D * P_reg * 8 + 8*ndim + 8."""
-        ndim = 6 if self.nspec == 2 else 8
+        ndim = (6 if self.nspec == 2 else 8) + int(self.feh_free)
         corners = 4 if self.feh_nodes.size <= 1 else 8
         return self.nspec * corners * self.n_reg * 8 + 8 * ndim + 8
 
@@ -299,8 +300,8 @@ def build_tables(prob, component_bands=None) -> DeviceTables:
     o = np.argsort(teff5, kind='mergesort')
 
     # ---- prior vector (mft6.py:1241-1260 / :1298-1315)
-    ndim = prob.ndim
     ns = prob.nspec
+    ndim = 2 * ns + 2                       # the reference's parameters (a free [Fe/H] column carries no Gaussian prior)
     mu = np.zeros(ndim); sig = np.ones(ndim)
     pr = prob.prior
     if not (np.isscalar(pr) and pr == 0):
@@ -331,4 +332,4 @@ def build_tables(prob, component_bands=None) -> DeviceTables:
         dust_samples=np.ascontiguousarray(prob.dust_samples, dtype=np.float64),
         tmin=float(min(prob.temps)), tmax=float(max(prob.temps)), prior_mu=mu, prior_sig=sig, nspec=ns,
         ext_flag=int(bool(prob.av)), dist_fit=int(bool(prob.dist_fit)), rad_prior=int(bool(prob.rad_prior)),
-        flavour=int(bool(getattr(prob, 'nospec', False))))
+        flavour=int(bool(getattr(prob, 'nospec', False))), feh_free=int(bool(getattr(prob, 'feh_free', False))))

@@ -26,10 +26,16 @@ def central_third(prob, nw, seed=1):
     lo = np.array([min(prob.temps), min(prob.temps), 0.0, 0.1, 0.1, 1 / 3000.0])
     hi = np.array([max(prob.temps), max(prob.temps), 1.0, 1.2, 1.0, 1 / 100.0])
     a, b = lo + (hi - lo) / 3.0, hi - (hi - lo) / 3.0
-    return a + (b - a) * rng.random((nw, 6))
+    th = a + (b - a) * rng.random((nw, 6))
+    if getattr(prob, 'feh_free', False):
+        # free metallicity (HBM-bound stress): the whole Teff and [Fe/H] node ranges, so that the walkers touch
+        # every reachable row of the grid (~26 x 2-3 x 5 rows x 0.8 MB, far beyond the 126 MB L2)
+        th[:, 0:2] = rng.uniform(lo[0], hi[0], (nw, 2))
+        th = np.concatenate([th, rng.uniform(min(prob.fehs), max(prob.fehs), (nw, 1))], axis=1)
+    return th
 
 
-def run(name, prob, nw, reps=5):
+def run(name, prob, nw, reps=5, cell_order=None):
     peak = 6455.6
     try:
         peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
@@ -38,6 +44,7 @@ def run(name, prob, nw, reps=5):
     lp = LogPosterior(prob)
     if os.environ.get('MS_PAIRING') == '0':
         lp.engine.set_pairing(False)
+    lp.engine.set_cell_order(cell_order)
     th = torch.tensor(central_third(prob, nw), device='cuda')
     out = torch.empty(nw, dtype=torch.float64, device='cuda')
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device='cuda')
@@ -154,4 +161,9 @@ if __name__ == '__main__':
         t0 = time.time()
         p5 = synthetic.make_problem_c5()
         print(f'# C5 problem built in {time.time() - t0:.1f} s', flush=True)
-        run('C5: 26x4x5 grid (416 MB), P_reg=100000, N=25000, 4+12 bands', p5, 16384, reps=3)
+        run('C5: 26x4x5 grid (416 MB), P_reg=100000, N=25000, 4+12 bands, fixed [Fe/H] (2 of 5 planes in use)', p5, 16384, reps=3)
+        import dataclasses
+        run('C5 free [Fe/H]: same grid, metallicity per walker (all 5 planes in use: HBM bound)',
+            dataclasses.replace(p5, feh_free=True), 16384, reps=3)
+        run('C5 free [Fe/H], walkers launched in the caller\'s (random) order: rows come from HBM',
+            dataclasses.replace(p5, feh_free=True), 16384, reps=3, cell_order=False)

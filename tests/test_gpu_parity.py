@@ -275,6 +275,46 @@ def test_3d_grid_trilinear_16_passbands(native_lib):
         lp.close()
 
 
+def test_free_metallicity_walkers(native_lib):
+    """Extension for grids beyond L2: [Fe/H] as a per-walker trailing column (7-vector).  Each walker must equal
+    the fixed-[Fe/H] fit at its own metallicity (oracle on the grid interpolated there), walkers outside the
+    nodes are outside the prior box, and the 7-column ensemble samples through the same stretch-move kernels."""
+    import dataclasses
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.ensemble import CudaBackend, EnsembleSampler
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    p = synthetic.make_problem_3d_small(feh_free=True)
+    lp = LogPosterior(p)
+    assert lp.ndim == 7
+    theta = synthetic.sample_prior_box(p, 96, seed=4)
+    assert theta.shape == (96, 7)
+    got = lp(theta)
+    _compare(got, to_oracle(p).lnprob_batch(theta))
+    assert got[19] == -np.inf and got[20] == -np.inf and np.isfinite(got[17]) and np.isfinite(got[18])
+    # the same walker through a fixed-[Fe/H] handle: bit-identical
+    k = int(np.flatnonzero(np.isfinite(got))[5])
+    fixed = LogPosterior(dataclasses.replace(p, feh=float(theta[k, 6]), feh_free=False))
+    assert fixed(theta[k, :6]) == got[k]
+    fixed.close()
+    # large batch: cell-sorted pairs / natural order agree (the cell key carries the [Fe/H] bracket)
+    big = synthetic.sample_prior_box(p, 2600, seed=6, edge_cases=False)
+    lp.engine.set_pairing(True); a = lp(big)
+    lp.engine.set_pairing(False); b = lp(big)
+    assert np.array_equal(a, b)
+    # sampling in 7 dimensions
+    t7 = np.concatenate([p.truth, [p.feh]])
+    p0 = t7 * (1 + 0.005 * np.random.default_rng(2).standard_normal((32, 7)))
+    p0[:, 2] = np.abs(p0[:, 2]); p0[:, 6] = p.feh + 0.05 * np.random.default_rng(3).standard_normal(32)
+    s = EnsembleSampler(32, 7, CudaBackend(lp.engine), seed=1)
+    s.initialize(p0)
+    s.run_mcmc(40)
+    st = s.state.cpu().numpy()
+    assert np.all(np.isfinite(st[:, 7])) and s.naccepted.sum().item() > 0
+    assert np.allclose(lp(st[:, :7]), st[:, 7], rtol=0, atol=0)
+    lp.close()
+
+
 def test_filter_count_variants(native_lib):
     """No contrast measurement at all with the three-band (2MASS-only) photometry list of mft6.py:766-767; a
     single contrast filter; four contrast + twelve photometric bands on a 2-D grid (the wide kernel variant)."""
@@ -323,6 +363,15 @@ def test_c5_full_size_cell_ordered_launch(native_lib):
     ok = (a['status'] == 0) & (b['status'] == 0)
     assert ok.sum() > 8 and np.allclose(a['chi2_spec'][ok], b['chi2_spec'][ok], rtol=1e-10)
     lp.close()
+    # free metallicity: the walkers spread over all five [Fe/H] planes (the HBM-bound form of the stress shape)
+    import dataclasses
+    pf = dataclasses.replace(p, feh_free=True)
+    lpf = LogPosterior(pf)
+    th7 = synthetic.sample_prior_box(pf, 2048, seed=7)
+    gotf = lpf(th7)
+    _compare(gotf[:24], to_oracle(pf).lnprob_batch(th7[:24]))
+    assert np.array_equal(np.concatenate([lpf(th7[k:k + 512]) for k in range(0, 2048, 512)]), gotf)
+    lpf.close()
 
 
 def test_triple_star_mode(native_lib):
