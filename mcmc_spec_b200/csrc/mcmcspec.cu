@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -94,6 +95,7 @@ struct DevTables {
   double tmin, tmax;
   double prior_mu[MS_MAX_NDIM], prior_sig[MS_MAX_NDIM];
   int nspec, ndim, ext_flag, dist_fit, rad_prior;
+  int nospec;                   // mft6_nospec.py flavour (no spectral term), also for the optimiser's chi-square
   int feh_free, ncol;           // per-walker [Fe/H] as an extra trailing column of theta; ncol = ndim + feh_free
   int n_cells;                 // number of cell keys (bins of the launch-order counting sort)
 };
@@ -1058,7 +1060,9 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     int st = 0;
     if constexpr (MODE == MODE_OPTIMIZER) {
       // test_cs of fit_spec (mft6.py:1016, :1030-1046): x3 spectral weight, priors in chi-square units
-      out = (iic * 3.0) * (double)(T.n_contrast + T.n_phot) + icontrast + iphot + sPlan.lp;
+      // mft6_nospec.py's fit_spec comments the spectral term out (its :1016-1030): contrast + photometry + priors
+      out = T.nospec ? (icontrast + iphot + sPlan.lp)
+                     : ((iic * 3.0) * (double)(T.n_contrast + T.n_phot) + icontrast + iphot + sPlan.lp);
       if (out != out) { out = CUDART_INF; st |= MS_W_NONFINITE; }     // a NaN never wins `test_cs < chi`
     } else {
       const double init_cs = (MODE == MODE_NOSPEC) ? icontrast + iphot                             // mft6_nospec.py:1192
@@ -1397,6 +1401,13 @@ namespace {
 
 std::string g_create_error;
 
+// NVTX ranges around the entry points (header-only NVTX3; a no-op unless a profiler is attached), replacing
+// the reference's dead time.time() markers (mft6.py:397, :548, :1148, :1151, :3511-3514).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 #define CK(call)                                                                      \
   do {                                                                                \
     cudaError_t e__ = (call);                                                         \
@@ -1629,6 +1640,7 @@ int ms_destroy(ms_handle* h) {
 int ms_create(const ms_config* cfg, ms_handle** out) { return ms_create_shared(cfg, nullptr, out); }
 
 int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handle** out) {
+  NvtxRange nvtx_range("ms_create_shared");
   if (!cfg || !out) { set_err(nullptr, "ms_create: null argument"); return MS_ERR_INVALID; }
   *out = nullptr;
   if (cfg->abi_version != MS_ABI_VERSION) { set_err(nullptr, "ms_create: ABI version mismatch"); return MS_ERR_INVALID; }
@@ -1669,6 +1681,7 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
   T.ext_flag = cfg->ext_flag; T.dist_fit = cfg->dist_fit; T.rad_prior = cfg->rad_prior;
   T.opt_median = nullptr;
   h->nospec = (cfg->flavour == 1);
+  T.nospec = h->nospec ? 1 : 0;
   T.tmin = cfg->tmin; T.tmax = cfg->tmax;
   T.data_median = cfg->data_median;
   for (int k = 0; k < 9; ++k) T.basis[k] = cfg->poly_basis[k];
@@ -1893,6 +1906,7 @@ int ms_set_optimizer_data(ms_handle* h, const double* flux_sets, int32_t n_sets)
 
 int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_index, const double* rad_sigma,
                        const double* av_prior, const double* ref_median, int64_t nw, double* chisq) {
+  NvtxRange nvtx_range("ms_optimizer_chisq");
   if (!h) return MS_ERR_INVALID;
   if (nw < 0 || (nw > 0 && (!theta || !set_index || !rad_sigma || !chisq))) { set_err(h, "ms_optimizer_chisq: null argument"); return MS_ERR_INVALID; }
   if (h->opt_sets < 1) { set_err(h, "ms_optimizer_chisq: call ms_set_optimizer_data first"); return MS_ERR_INVALID; }
@@ -1934,6 +1948,7 @@ int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_ind
 
 int ms_lnprob_parts(ms_handle* h, const double* theta, int64_t nw, double* lnprob, double* chi2_spec,
                     double* contrast, double* phot, double* lnprior, double* logg, int32_t* status, int where) {
+  NvtxRange nvtx_range("ms_lnprob_parts");
   if (!h) return MS_ERR_INVALID;
   if (nw < 0 || (nw > 0 && (!theta || !lnprob))) { set_err(h, "ms_lnprob: null argument"); return MS_ERR_INVALID; }
   if (nw == 0) return MS_OK;
@@ -1973,6 +1988,7 @@ int ms_lnprob(ms_handle* h, const double* theta, int64_t nw, double* lnprob, int
 }
 
 int ms_model_spectrum(ms_handle* h, const double* theta, int64_t nw, double* out, int where) {
+  NvtxRange nvtx_range("ms_model_spectrum");
   if (!h) return MS_ERR_INVALID;
   if (nw < 0 || (nw > 0 && (!theta || !out))) { set_err(h, "ms_model_spectrum: null argument"); return MS_ERR_INVALID; }
   if (nw == 0) return MS_OK;
@@ -2002,6 +2018,7 @@ int ms_model_spectrum(ms_handle* h, const double* theta, int64_t nw, double* out
 }
 
 int ms_component_mags(ms_handle* h, const double* theta, int64_t nw, double* out, int where) {
+  NvtxRange nvtx_range("ms_component_mags");
   if (!h) return MS_ERR_INVALID;
   if (nw < 0 || (nw > 0 && (!theta || !out))) { set_err(h, "ms_component_mags: null argument"); return MS_ERR_INVALID; }
   if (nw == 0 || h->T.n_contrast == 0) return MS_OK;
@@ -2033,6 +2050,7 @@ int ms_component_mags(ms_handle* h, const double* theta, int64_t nw, double* out
 
 int ms_broaden_rows(int device, double* rows, int64_t n_rows, int64_t row_len, int64_t win_lo, int64_t win_len,
                     const double* taps, int32_t n_taps) {
+  NvtxRange nvtx_range("ms_broaden_rows");
   ms_handle* h = nullptr;   // errors land in the create-error slot
   if (!rows || !taps || n_rows < 0 || row_len <= 0 || win_lo < 0 || win_len < 0 || win_lo + win_len > row_len ||
       n_taps < 1 || (n_taps % 2) == 0 || n_taps > 4097 || (win_len > 0 && win_len < n_taps) || win_len > 0x7fffffff) {
@@ -2069,6 +2087,7 @@ int ms_broaden_rows(int device, double* rows, int64_t n_rows, int64_t row_len, i
 int ms_build_grid(int device, const double* src_x, const double* src_y, const int64_t* src_off, int64_t n_rows,
                   const double* x_dst, int64_t row_len, int64_t win_lo, int64_t win_len, const double* taps,
                   int32_t n_taps, double* rows_out) {
+  NvtxRange nvtx_range("ms_build_grid");
   ms_handle* h = nullptr;   // errors land in the create-error slot
   if (!src_x || !src_y || !src_off || !x_dst || !rows_out || n_rows < 0 || row_len <= 0 || win_lo < 0 || win_len < 0 ||
       win_lo + win_len > row_len || win_len > 0x7fffffff) {
@@ -2135,6 +2154,7 @@ int ms_build_grid(int device, const double* src_x, const double* src_y, const in
 
 int ms_stretch_iteration(ms_handle* h, double* state, int32_t* naccepted, int64_t nw, double a, uint64_t seed,
                          uint64_t iteration, int32_t randomize_split) {
+  NvtxRange nvtx_range("ms_stretch_iteration");
   if (!h) return MS_ERR_INVALID;
   if (!state || nw < 2 || (nw % 2) || nw > SPLIT_SMALL_MAX) {
     set_err(h, "ms_stretch_iteration: nw must be even and at most 2048 (larger ensembles: the per-kernel entry points)");

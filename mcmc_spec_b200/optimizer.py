@@ -37,11 +37,15 @@ class GpuChisq:
         theta0 = np.asarray(theta0, dtype=np.float64)
         bare = theta0.copy()
         bare[:, 2] = 0.0                                   # the initial model is not extincted (mft6.py:880)
-        model = self.engine.model_spectrum_host(bare)      # interp1d + median scaling, mft6.py:884-888
-        sets = np.empty_like(model)
-        for k in range(model.shape[0]):                    # norm_spec, once per walk (mft6.py:889)
-            frac = self.flux / model[k]
-            sets[k] = self.flux / np.polynomial.Polynomial.fit(self.wl_aa, frac, deg=2)(self.wl_aa)
+        if getattr(self.lp.problem, 'nospec', False):
+            # mft6_nospec.py: no spectral term, hence no renormalised spectrum (its fit_spec :885-895 commented out)
+            sets = np.tile(self.flux, (theta0.shape[0], 1))
+        else:
+            model = self.engine.model_spectrum_host(bare)  # interp1d + median scaling, mft6.py:884-888
+            sets = np.empty_like(model)
+            for k in range(model.shape[0]):                # norm_spec, once per walk (mft6.py:889)
+                frac = self.flux / model[k]
+                sets[k] = self.flux / np.polynomial.Polynomial.fit(self.wl_aa, frac, deg=2)(self.wl_aa)
         self.engine.set_optimizer_data(sets)
         idx = np.arange(theta0.shape[0], dtype=np.int32)
         rad_sigma = 0.05 * theta0[:, 3:5]                   # mft6.py:916

@@ -495,7 +495,7 @@ def _dust_moments(dustmap, plx):
 
 
 def fit_spec_init(wl_aa, flux, err, reg, t_guess, av, rad_guess, fr_guess, specs, distance, ctm, ptm, tmi, tma,
-                  matrix, temps, lgs, photlib, dustmap, nspec=2, dist_fit=True, rad_prior=False, fs=None):
+                  matrix, temps, lgs, photlib, dustmap, nspec=2, dist_fit=True, rad_prior=False, fs=None, nospec=False):
     """mft6.py:859-930 (distance given): the starting chi-square of one optimiser walker and the observed
     spectrum after its one-off renormalisation.  ``wl_aa`` is the data wavelength in Angstrom (the
     reference multiplies its argument by 1e4 in place, :860).  Returns (init_cs, flux_renormalised).
@@ -508,13 +508,16 @@ def fit_spec_init(wl_aa, flux, err, reg, t_guess, av, rad_guess, fr_guess, specs
     wave1, init_cspec, contrast, phot_cwl, phot = make_composite(
         t_guess, lg_guess, rad_guess, dist, fr_guess[2], fr_guess[5], reg, specs, ctm, ptm, tmi, tma,
         temps, lgs, photlib, nspec=nspec, fs=fs)
-    init_cspec = interp1d(wave1, init_cspec)(wl_aa)
-    init_cspec *= np.median(flux) / np.median(init_cspec)
-    flux = norm_spec(wl_aa, init_cspec, flux)
-    iic = np.sum(chisq(init_cspec, flux, err)) / len(flux) * 3
     chi_contrast = chisq(contrast, fr_guess[0], fr_guess[1])
     ip = chisq(phot, fr_guess[3], fr_guess[4])
-    init_cs = np.sum((iic * (len(chi_contrast) + len(ip)), np.sum(chi_contrast), np.sum(ip)))
+    if nospec:                                     # mft6_nospec.py:885-905: the spectral lines are commented out
+        init_cs = np.sum((np.sum(chi_contrast), np.sum(ip)))
+    else:
+        init_cspec = interp1d(wave1, init_cspec)(wl_aa)
+        init_cspec *= np.median(flux) / np.median(init_cspec)
+        flux = norm_spec(wl_aa, init_cspec, flux)
+        iic = np.sum(chisq(init_cspec, flux, err)) / len(flux) * 3
+        init_cs = np.sum((iic * (len(chi_contrast) + len(ip)), np.sum(chi_contrast), np.sum(ip)))
     if dist_fit == True:                           # noqa: E712
         init_cs += opt_prior([dist], [pprior], [psig])
     if rad_prior == True:                          # noqa: E712
@@ -526,7 +529,7 @@ def fit_spec_init(wl_aa, flux, err, reg, t_guess, av, rad_guess, fr_guess, specs
 
 
 def fit_spec_test_cs(var_par, wl_aa, flux, err, reg, fr_guess, specs, pprior, psig, rad_sigma, ctm, ptm, tmi, tma,
-                     matrix, temps, lgs, photlib, dustmap, nspec=2, dist_fit=True, rad_prior=False, fs=None):
+                     matrix, temps, lgs, photlib, dustmap, nspec=2, dist_fit=True, rad_prior=False, fs=None, nospec=False):
     """mft6.py:989-1046 -- chi-square of one in-box proposal ``var_par = [T[2], Av, rad[2], plx]`` against
     the renormalised ``flux``; ``rad_sigma`` is ``si[2]`` (:1038)."""
     mu, sig = _dust_moments(dustmap, var_par[3])
@@ -535,15 +538,19 @@ def fit_spec_test_cs(var_par, wl_aa, flux, err, reg, fr_guess, specs, pprior, ps
         var_par[0], logg_guess, var_par[2], float(var_par[3]), fr_guess[2], fr_guess[5], reg, specs, ctm, ptm,
         tmi, tma, temps, lgs, photlib, nspec=nspec, fs=fs)
     if var_par[1] > 0:
-        test_cspec = extinct(test_wave1, test_cspec, var_par[1])
+        if not nospec:
+            test_cspec = extinct(test_wave1, test_cspec, var_par[1])
         test_phot = -2.5 * np.log10(extinct(test_phot_cwl, 10 ** (-0.4 * test_phot), var_par[1]))
-    test_cspec = interp1d(test_wave1, test_cspec)(wl_aa)
-    test_cspec *= np.median(flux) / np.median(test_cspec)
-    tc = chisq(test_cspec, flux, err)
-    ttc = np.sum(tc) / len(tc) * 3
     chi_contrast = chisq(test_contrast, fr_guess[0], fr_guess[1])
     chi_phot = chisq(test_phot, fr_guess[3], fr_guess[4])
-    test_cs = np.sum((ttc * (len(chi_contrast) + len(chi_phot)), np.sum(chi_contrast), np.sum(chi_phot)))
+    if nospec:                                     # mft6_nospec.py:1005-1030
+        test_cs = np.sum((np.sum(chi_contrast), np.sum(chi_phot)))
+    else:
+        test_cspec = interp1d(test_wave1, test_cspec)(wl_aa)
+        test_cspec *= np.median(flux) / np.median(test_cspec)
+        tc = chisq(test_cspec, flux, err)
+        ttc = np.sum(tc) / len(tc) * 3
+        test_cs = np.sum((ttc * (len(chi_contrast) + len(chi_phot)), np.sum(chi_contrast), np.sum(chi_phot)))
     test_cs += opt_prior(var_par[1], [mu], [sig])
     if dist_fit == True:                           # noqa: E712
         test_cs += opt_prior([var_par[3]], [pprior], [psig])

@@ -16,7 +16,8 @@ class OracleChisq:
     def _common(self):
         o = self.o
         return dict(ctm=o.ctm, ptm=o.ptm, tmi=o.tmi, tma=o.tma, matrix=o.matrix, temps=o.temps, lgs=o.lgs,
-                    photlib=o.photlib, dustmap=o.dustmap, nspec=2, dist_fit=o.dist_fit, rad_prior=o.rad_prior, fs=o.fs)
+                    photlib=o.photlib, dustmap=o.dustmap, nspec=2, dist_fit=o.dist_fit, rad_prior=o.rad_prior, fs=o.fs,
+                    nospec=bool(getattr(self.p, 'nospec', False)))
 
     def start(self, theta0):
         o = self.o

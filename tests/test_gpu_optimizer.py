@@ -77,3 +77,31 @@ def test_nospec_flavour_matches_oracle(small_problem, native_lib):
     full = LogPosterior(small_problem)
     assert not np.allclose(full(theta)[f], got[f])                   # the spectral term really is gone
     full.close(); lp.close()
+
+
+def test_nospec_optimizer_chisq_matches_oracle(small_problem, native_lib):
+    """fit_spec of mft6_nospec.py: the optimiser's chi-square without the spectral term (contrast + photometry +
+    the chi-square priors)."""
+    from mcmc_spec_b200.optimizer import GpuChisq
+    from mcmc_spec_b200.posterior import LogPosterior
+    from opt_reference import OracleChisq
+    from oracle_adapter import to_oracle
+    prob = dataclasses.replace(small_problem, nospec=True)
+    lp = LogPosterior(prob)
+    gpu, orc = GpuChisq(lp), OracleChisq(prob, to_oracle(prob))
+    theta0 = _starts(prob, 16, 5)
+    g_cs, _ = gpu.start(theta0)
+    o_cs, _ = orc.start(theta0)
+    assert np.allclose(g_cs, o_cs, rtol=1e-9)
+    rng = np.random.default_rng(6)
+    theta = theta0[rng.integers(0, 16, 64)] * (1 + 0.03 * rng.standard_normal((64, 6)))
+    theta[:, 2] = np.abs(theta[:, 2])
+    theta[:, 0:2] = np.clip(theta[:, 0:2], min(prob.temps) + 1, max(prob.temps) - 1)
+    idx = rng.integers(0, 16, 64).astype(np.int32)
+    rs = 0.1 * theta0[idx, 3:5]
+    got, want = gpu.test(theta, idx, rs), orc.test(theta, idx, rs)
+    assert np.all(np.isfinite(want)) and np.max(np.abs(got - want) / np.abs(want)) < 1e-9
+    full = GpuChisq(LogPosterior(small_problem))
+    full.start(theta0)
+    assert not np.allclose(full.test(theta, idx, rs), got)          # the spectral term really is gone
+    lp.close()
