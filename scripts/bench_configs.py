@@ -99,6 +99,30 @@ def run_c1_sampler(nw=50, steps=2000):
     lp.close()
 
 
+def run_c1_host_calls(nw=25, reps=2000):
+    """The drop-in use of the reference's integration: emcee calls ``lnprob(P[25, 6])`` with host arrays once per
+    half step (vectorize=True).  Latency of that call (pinned staging, H2D, prep + streaming kernel, D2H, sync)."""
+    prob = synthetic.make_problem(truth=synthetic.consistent_truth(3850.0, 3425.0, 0.12, 2.0732e-3))
+    lp = LogPosterior(prob)
+    th = prob.truth * (1 + 0.01 * np.random.default_rng(0).standard_normal((nw, 6)))
+    th[:, 2] = np.abs(th[:, 2])
+    for _ in range(20):
+        lp(th)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        lp(th)
+    dt = (time.perf_counter() - t0) / reps
+    one = th[0].copy()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        lp(one)
+    dt1 = (time.perf_counter() - t0) / reps
+    print(json.dumps({"config": "C1 host calls: LogPosterior(P[25, 6]) as emcee's vectorised log_prob_fn, C1/C2 shape",
+                      "ms_per_call_25_walkers": dt * 1e3, "evals_per_s": nw / dt,
+                      "ms_per_call_scalar_form": dt1 * 1e3}), flush=True)
+    lp.close()
+
+
 def run_c3(n_fits=12, nw=25, reps=50):
     """BASELINE config C3: 12 independent 50-walker ensembles (one half step = 25 proposals each) on one GPU,
     one device copy of the grid, every fit on its own stream so their launches overlap."""
@@ -147,10 +171,12 @@ def run_c3(n_fits=12, nw=25, reps=50):
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['c1', 'c1s', 'c3', 'c4', 'c5']
+    which = sys.argv[1:] or ['c1', 'c1h', 'c1s', 'c3', 'c4', 'c5']
     if 'c1' in which:
         run('C1/C2 shape: 26x4 grid, 135000-px rows (P_reg ~117k synthetic bands), N=1945', synthetic.make_problem(), 8192)
         run('C1/C2 shape, reference walker count (50)', synthetic.make_problem(), 50, reps=20)
+    if 'c1h' in which:
+        run_c1_host_calls()
     if 'c1s' in which:
         run_c1_sampler()
     if 'c3' in which:
