@@ -1388,6 +1388,7 @@ struct ms_handle {
   // ms_stretch_iteration scratch (single-rank fused iteration)
   long long* it_half[2] = {nullptr, nullptr}; double* it_q = nullptr; double* it_logfac = nullptr; double* it_lnp = nullptr;
   double* it_packed = nullptr; long long it_cap = 0;
+  unsigned char* scratch = nullptr; size_t scratch_cap = 0;   // per-call inputs of ms_optimizer_chisq (grown on demand)
   cudaStream_t own_stream = nullptr;
   // optional device-side timing of the streaming kernel
   bool timing = false;
@@ -1400,6 +1401,17 @@ struct ms_handle {
 namespace {
 
 std::string g_create_error;
+
+// Device temporaries of one call: freed on every exit path.
+struct DevMem {
+  void* p = nullptr;
+  DevMem() = default;
+  DevMem(const DevMem&) = delete;
+  DevMem& operator=(const DevMem&) = delete;
+  ~DevMem() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <typename Tp> Tp* as() const { return static_cast<Tp*>(p); }
+};
 
 // NVTX ranges around the entry points (header-only NVTX3; a no-op unless a profiler is attached), replacing
 // the reference's dead time.time() markers (mft6.py:397, :548, :1148, :1151, :3511-3514).
@@ -1626,6 +1638,7 @@ int ms_destroy(ms_handle* h) {
   if (h->d_lnp) cudaFree(h->d_lnp);
   if (h->h_theta) cudaFreeHost(h->h_theta);
   if (h->h_lnp) cudaFreeHost(h->h_lnp);
+  if (h->scratch) cudaFree(h->scratch);
   if (h->it_half[0]) cudaFree(h->it_half[0]);
   if (h->it_half[1]) cudaFree(h->it_half[1]);
   if (h->it_q) cudaFree(h->it_q);
@@ -1918,12 +1931,21 @@ int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_ind
   const int ndim = h->T.ndim, ns = h->T.nspec;
   int rc = ensure_io(h, nw);
   if (rc) return rc;
-  // host buffers in, host buffer out (the optimiser's random walk runs on the host)
-  double* d_rs = nullptr; double* d_avp = nullptr; double* d_med = nullptr; int* d_idx = nullptr;
-  CK(cudaMalloc((void**)&d_rs, (size_t)nw * ns * 8));
-  CK(cudaMalloc((void**)&d_idx, (size_t)nw * 4));
-  if (av_prior) CK(cudaMalloc((void**)&d_avp, (size_t)nw * 8));
-  if (ref_median) CK(cudaMalloc((void**)&d_med, (size_t)nw * 8));
+  // host buffers in, host buffer out (the optimiser's random walk runs on the host); the per-call inputs live in
+  // one handle-owned scratch buffer (this entry point is called thousands of times per fit)
+  const size_t a8 = ((size_t)nw * 8 + 255) & ~(size_t)255;
+  const size_t need = ns * a8 + 3 * a8;
+  if (need > h->scratch_cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr; h->scratch_cap = 0;
+    CK(cudaMalloc((void**)&h->scratch, need + need / 2));
+    h->scratch_cap = need + need / 2;
+  }
+  double* d_rs = reinterpret_cast<double*>(h->scratch);
+  int* d_idx = reinterpret_cast<int*>(h->scratch + ns * a8);
+  double* d_avp = av_prior ? reinterpret_cast<double*>(h->scratch + ns * a8 + a8) : nullptr;
+  double* d_med = ref_median ? reinterpret_cast<double*>(h->scratch + ns * a8 + 2 * a8) : nullptr;
   cudaError_t e = cudaMemcpyAsync(h->d_theta, theta, (size_t)nw * ndim * 8, cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_rs, rad_sigma, (size_t)nw * ns * 8, cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, set_index, (size_t)nw * 4, cudaMemcpyHostToDevice, h->stream);
@@ -1942,7 +1964,6 @@ int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_ind
   } else {
     cudaStreamSynchronize(h->stream);
   }
-  cudaFree(d_rs); cudaFree(d_idx); if (d_avp) cudaFree(d_avp); if (d_med) cudaFree(d_med);
   return rc;
 }
 
@@ -1968,7 +1989,9 @@ int ms_lnprob_parts(ms_handle* h, const double* theta, int64_t nw, double* lnpro
   Opt opts[6] = {{chi2_spec, (size_t)nw * 8, nullptr}, {contrast, (size_t)nw * h->T.n_contrast * 8, nullptr},
                  {phot, (size_t)nw * h->T.n_phot * 8, nullptr}, {lnprior, (size_t)nw * 8, nullptr},
                  {logg, (size_t)nw * h->T.nspec * 8, nullptr}, {status, (size_t)nw * 4, nullptr}};
-  for (auto& o : opts) if (o.host && o.bytes) CK(cudaMalloc(&o.dev, o.bytes));
+  DevMem opt_mem[6];
+  for (int k = 0; k < 6; ++k)
+    if (opts[k].host && opts[k].bytes) { CK(opt_mem[k].alloc(opts[k].bytes)); opts[k].dev = opt_mem[k].p; }
   PartsOut parts{(double*)opts[0].dev, (double*)opts[1].dev, (double*)opts[2].dev, (double*)opts[3].dev,
                  (double*)opts[4].dev, (int*)opts[5].dev, nullptr, nullptr};
   rc = evaluate_device(h, h->d_theta, nw, h->d_lnp, parts);
@@ -1979,7 +2002,6 @@ int ms_lnprob_parts(ms_handle* h, const double* theta, int64_t nw, double* lnpro
     if (e != cudaSuccess) { set_err(h, std::string("ms_lnprob: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
     else std::memcpy(lnprob, h->h_lnp, (size_t)nw * 8);
   }
-  for (auto& o : opts) if (o.dev) cudaFree(o.dev);
   return rc;
 }
 
@@ -1998,11 +2020,13 @@ int ms_model_spectrum(ms_handle* h, const double* theta, int64_t nw, double* out
   if (rc) return rc;
   const double* d_theta = theta;
   double* d_out = out;
+  DevMem tmp_out;
   if (where == MS_HOST) {
     std::memcpy(h->h_theta, theta, (size_t)nw * ndim * 8);
     CK(cudaMemcpyAsync(h->d_theta, h->h_theta, (size_t)nw * ndim * 8, cudaMemcpyHostToDevice, h->stream));
     d_theta = h->d_theta;
-    CK(cudaMalloc((void**)&d_out, (size_t)nw * n * 8));
+    CK(tmp_out.alloc((size_t)nw * n * 8));
+    d_out = tmp_out.as<double>();
   }
   PartsOut parts{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_out, nullptr};
   rc = evaluate_device(h, d_theta, nw, h->d_lnp, parts);
@@ -2011,8 +2035,9 @@ int ms_model_spectrum(ms_handle* h, const double* theta, int64_t nw, double* out
       cudaError_t e = cudaMemcpyAsync(out, d_out, (size_t)nw * n * 8, cudaMemcpyDeviceToHost, h->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
       if (e != cudaSuccess) { set_err(h, std::string("ms_model_spectrum: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
+    } else {
+      cudaStreamSynchronize(h->stream);
     }
-    cudaFree(d_out);
   }
   return rc;
 }
@@ -2029,11 +2054,13 @@ int ms_component_mags(ms_handle* h, const double* theta, int64_t nw, double* out
   if (rc) return rc;
   const double* d_theta = theta;
   double* d_out = out;
+  DevMem tmp_out;
   if (where == MS_HOST) {
     std::memcpy(h->h_theta, theta, (size_t)nw * ndim * 8);
     CK(cudaMemcpyAsync(h->d_theta, h->h_theta, (size_t)nw * ndim * 8, cudaMemcpyHostToDevice, h->stream));
     d_theta = h->d_theta;
-    CK(cudaMalloc((void**)&d_out, (size_t)nw * per * 8));
+    CK(tmp_out.alloc((size_t)nw * per * 8));
+    d_out = tmp_out.as<double>();
   }
   PartsOut parts{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_out};
   rc = evaluate_device(h, d_theta, nw, h->d_lnp, parts);
@@ -2042,8 +2069,9 @@ int ms_component_mags(ms_handle* h, const double* theta, int64_t nw, double* out
       cudaError_t e = cudaMemcpyAsync(out, d_out, (size_t)nw * per * 8, cudaMemcpyDeviceToHost, h->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
       if (e != cudaSuccess) { set_err(h, std::string("ms_component_mags: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
+    } else {
+      cudaStreamSynchronize(h->stream);
     }
-    cudaFree(d_out);
   }
   return rc;
 }
@@ -2058,11 +2086,12 @@ int ms_broaden_rows(int device, double* rows, int64_t n_rows, int64_t row_len, i
   }
   if (n_rows == 0 || win_len == 0) return MS_OK;
   CK(cudaSetDevice(device));
-  double *d_in = nullptr, *d_out = nullptr, *d_taps = nullptr;
   const long long chunk = std::max<long long>(1, std::min<long long>(n_rows, (1ll << 28) / row_len));   // <= 2 GiB per buffer
-  CK(cudaMalloc((void**)&d_in, (size_t)chunk * row_len * 8));
-  CK(cudaMalloc((void**)&d_out, (size_t)chunk * row_len * 8));
-  CK(cudaMalloc((void**)&d_taps, (size_t)n_taps * 8));
+  DevMem m_in, m_out, m_taps;
+  CK(m_in.alloc((size_t)chunk * row_len * 8));
+  CK(m_out.alloc((size_t)chunk * row_len * 8));
+  CK(m_taps.alloc((size_t)n_taps * 8));
+  double *d_in = m_in.as<double>(), *d_out = m_out.as<double>(), *d_taps = m_taps.as<double>();
   int rc = MS_OK;
   cudaError_t e = cudaMemcpy(d_taps, taps, (size_t)n_taps * 8, cudaMemcpyHostToDevice);
   const size_t smem = ((size_t)bpad_host(BT + n_taps - 1) + 1 + (size_t)n_taps) * 8;
@@ -2080,7 +2109,6 @@ int ms_broaden_rows(int device, double* rows, int64_t n_rows, int64_t row_len, i
     if (e == cudaSuccess) e = cudaMemcpy(rows + r0 * row_len, d_out, (size_t)nr * row_len * 8, cudaMemcpyDeviceToHost);
   }
   if (e != cudaSuccess) { set_err(h, std::string("ms_broaden_rows: ") + cudaGetErrorString(e)); rc = MS_ERR_CUDA; }
-  cudaFree(d_in); cudaFree(d_out); cudaFree(d_taps);
   return rc;
 }
 
