@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(NT * G, (NT * G <= 256) ? 2 : 1)
 lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __restrict__ plans,
                      const int* __restrict__ order, double* __restrict__ lnprob, const PartsOut parts,
                      const OptIn opt, const int csize, const long long nw, const long long pair_stride,
-                     const unsigned group_bytes) {
+                     const unsigned group_bytes, double* __restrict__ model_scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NWARP = NT / 32;
   constexpr int KRED = NS * NC + NP;
@@ -722,7 +722,10 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   double* sF = reinterpret_cast<double*>(smem_grp);                  // [NWARP*SEG] per-warp composite chunks
   double* sRed = sF + NWARP * SEG;                                          // [NWARP*KRED]
   SelectScratch* sSel = reinterpret_cast<SelectScratch*>(sRed + NWARP * (KRED > 4 ? KRED : 4));
-  double* sM = reinterpret_cast<double*>(sSel + 1);                  // [n_data] model on observed pixels
+  // [n_data] model on the observed pixels: in shared memory, or -- observed spectra too long for it (more than
+  // ~27 000 pixels) -- in a global scratch row per launch slot, which then lives in L2 between the two phases
+  double* sM = model_scratch ? model_scratch + (size_t)(blockIdx.x / csize) * (size_t)T.n_data
+                             : reinterpret_cast<double*>(sSel + 1);
   __shared__ WalkerPlan sPlanG[G];
   WalkerPlan& sPlan = sPlanG[grp];
 
@@ -1388,6 +1391,7 @@ struct ms_handle {
   // ms_stretch_iteration scratch (single-rank fused iteration)
   long long* it_half[2] = {nullptr, nullptr}; double* it_q = nullptr; double* it_logfac = nullptr; double* it_lnp = nullptr;
   double* it_packed = nullptr; long long it_cap = 0;
+  bool model_global = false; double* model_scratch = nullptr; size_t model_scratch_cap = 0;   // observed spectra beyond shared memory
   unsigned char* scratch = nullptr; size_t scratch_cap = 0;   // per-call inputs of ms_optimizer_chisq (grown on demand)
   cudaStream_t own_stream = nullptr;
   // optional device-side timing of the streaming kernel
@@ -1469,7 +1473,7 @@ int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut
       long long stride = (long long)((double)n_pairs * 0.381966) | 1ll;
       while (gcd_ll(stride, n_pairs) != 1) stride += 2;
       kern2<<<(unsigned)n_pairs, 2 * NT, 2 * h->smem_bytes, h->stream>>>(h->T, h->plans, order, d_lnp, parts, opt, 1, nw,
-                                                                          stride % n_pairs, (unsigned)h->smem_bytes);
+                                                                          stride % n_pairs, (unsigned)h->smem_bytes, nullptr);
       launched = true;
     }
   }
@@ -1482,9 +1486,22 @@ int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut
       csize = 1;
       while (csize < 8 && (long long)nw * csize * 2 <= 2ll * h->num_sms) csize *= 2;
     }
+    if (h->model_global) {
+      // the model vector of every launch slot lives in a global scratch row (grown on demand)
+      csize = 1;
+      const size_t need = (size_t)nw * (size_t)h->T.n_data;
+      if (need > h->model_scratch_cap) {
+        if (need * 8 > (size_t)64 << 30) { set_err(h, "ms_lnprob: batch x observed pixels exceeds the 64 GiB model scratch; evaluate in smaller batches"); return MS_ERR_UNSUPPORTED; }
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->model_scratch) cudaFree(h->model_scratch);
+        h->model_scratch = nullptr; h->model_scratch_cap = 0;
+        CK(cudaMalloc((void**)&h->model_scratch, need * 8));
+        h->model_scratch_cap = need;
+      }
+    }
     if (csize == 1) {
       kern<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, order, d_lnp, parts, opt, 1, nw, 1ll,
-                                                           (unsigned)h->smem_bytes);
+                                                           (unsigned)h->smem_bytes, h->model_global ? h->model_scratch : nullptr);
     } else {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3((unsigned)(nw * csize)); cfg.blockDim = dim3(NT);
@@ -1494,7 +1511,7 @@ int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut
       attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       CK(cudaLaunchKernelEx(&cfg, kern, h->T, (const WalkerPlan*)h->plans, order, d_lnp, parts, opt, csize, (long long)nw,
-                            1ll, (unsigned)h->smem_bytes));
+                            1ll, (unsigned)h->smem_bytes, (double*)nullptr));
     }
   }
   CK(cudaGetLastError());
@@ -1562,7 +1579,7 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   // Measured (profiles/): pairing halves the L2->SM traffic (L1 hit rate 53 %), which pays on stream-dominated
   // shapes (C1/C2: +5 %) and costs the pair barriers where the observed-pixel work dominates (C4: -5 %).
   const bool want_pair = h->pairing > 0 || (h->pairing < 0 && (long long)h->T.n_reg >= 16ll * h->T.n_data);
-  h->pair_now = want_pair && h->cluster <= 1 && mode == MODE_POSTERIOR && h->T.nspec == 2 &&
+  h->pair_now = want_pair && !h->model_global && h->cluster <= 1 && mode == MODE_POSTERIOR && h->T.nspec == 2 &&
                 h->threads == MS_NT_SMALL && h->T.n_cells > 1 && nw >= 8ll * h->num_sms &&
                 2 * h->smem_bytes + 2048 <= (size_t)h->max_optin_smem;
   if (h->pair_now) h->use_order = true;
@@ -1639,6 +1656,7 @@ int ms_destroy(ms_handle* h) {
   if (h->h_theta) cudaFreeHost(h->h_theta);
   if (h->h_lnp) cudaFreeHost(h->h_lnp);
   if (h->scratch) cudaFree(h->scratch);
+  if (h->model_scratch) cudaFree(h->model_scratch);
   if (h->it_half[0]) cudaFree(h->it_half[0]);
   if (h->it_half[1]) cudaFree(h->it_half[1]);
   if (h->it_q) cudaFree(h->it_q);
@@ -1829,7 +1847,11 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     h->smem_bytes = stream_smem_bytes(cfg->n_data, nc, np, MS_NT_LARGE / 32, cfg->nspec);
   }
   if (h->smem_bytes + 2048 > (size_t)max_optin) {
-    h->err = "ms_create: n_data too large for the shared-memory resident model spectrum"; return fail(MS_ERR_UNSUPPORTED);
+    // the observed spectrum does not fit shared memory: keep the per-walker model vector in a global scratch row
+    // (L2 resident between the streaming and the chi-square phase); two 256-thread CTAs per SM again
+    h->model_global = true;
+    h->threads = MS_NT_SMALL;
+    h->smem_bytes = stream_smem_bytes(0, nc, np, MS_NT_SMALL / 32, cfg->nspec);
   }
   CKH(cudaStreamSynchronize(h->stream));
 #undef CKC

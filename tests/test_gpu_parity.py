@@ -275,6 +275,25 @@ def test_3d_grid_trilinear_16_passbands(native_lib):
         lp.close()
 
 
+def test_observed_spectrum_longer_than_shared_memory(native_lib):
+    """More observed pixels than the shared-memory resident model vector can hold (~27 000): the per-walker model
+    vector moves to a global scratch row; same values, same edge behaviour."""
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    p = synthetic.make_problem_small(n_pix=140000, dlam=0.03, n_data=40001, window_um=(0.56, 0.94))
+    lp = LogPosterior(p)
+    assert lp.tables.n_data == 40001
+    theta = synthetic.sample_prior_box(p, 300, seed=9)
+    got = lp(theta)
+    _compare(got[:40], to_oracle(p).lnprob_batch(theta[:40]))
+    assert np.array_equal(np.concatenate([lp(theta[:7]), lp(theta[7:150]), lp(theta[150:])]), got)   # small batches too
+    model = lp.model_spectrum(theta[20:24])
+    ok = np.isfinite(got[20:24])
+    assert np.allclose(np.median(model[ok], axis=1), np.median(p.data[1]), rtol=1e-14)
+    lp.close()
+
+
 def test_free_metallicity_walkers(native_lib):
     """Extension for grids beyond L2: [Fe/H] as a per-walker trailing column (7-vector).  Each walker must equal
     the fixed-[Fe/H] fit at its own metallicity (oracle on the grid interpolated there), walkers outside the
