@@ -273,6 +273,25 @@ def run_product_arm(args, rank, local_rank, world):
     acc_frac = float(sampler.acceptance_fraction.mean())
     finite_frac = float(torch.isfinite(sampler.log_prob).double().mean().item())
 
+    # ---- the same steps in the opt-in bracket-only mode (ms_set_fast; reported beside the graded streaming path)
+    fast_steps = min(args.steps, 20)
+    lp.engine.set_fast(True)
+    for _ in range(2):
+        sampler.step()
+    torch.cuda.synchronize(); barrier()
+    fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(fast_steps)]
+    for k in range(fast_steps):
+        flush.zero_()
+        fev[k][0].record()
+        sampler.step()
+        fev[k][1].record()
+    torch.cuda.synchronize(); barrier()
+    lp.engine.set_fast(False)
+    fast_ms = torch.tensor([float(sum(a.elapsed_time(b) for a, b in fev))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(fast_ms, op=dist.ReduceOp.MAX)
+    fast_value = nw * fast_steps / (float(fast_ms.item()) / 1e3)
+
     # ---- end-to-end through the host-buffer API (pinned staging + H2D + kernels + D2H per call)
     lp.engine.use_own_stream()
     per_rank = nw // world
@@ -326,7 +345,11 @@ def run_product_arm(args, rank, local_rank, world):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nw * 6 * 8),
                         "d2h_bytes_per_step": int(nw * 8), "steps": args.e2e_steps,
                         "api": "LogPosterior.__call__(theta_host[nw/2/N, 6]) -> ms_lnprob(MS_HOST), two calls per step per rank; inputs = the ensemble after the timed chain"},
-                "gpu_launches": int(launches), "clocks": clock_summary}
+                "gpu_launches": int(launches), "clocks": clock_summary,
+                "fast_mode": {"value": fast_value, "unit": UNIT, "steps": fast_steps,
+                              "bytes_per_eval": int(2 * 4 * (2 * tables.n_data + tables.contrast.n + tables.phot.n) * 8 + 56),
+                              "note": "opt-in ms_set_fast: bracket-only evaluation (2 model pixels per observed pixel + "
+                                      "per-row band fluxes, exact by linearity); NOT the graded path -- `value` streams whole rows"}}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

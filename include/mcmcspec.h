@@ -291,6 +291,19 @@ int ms_set_cluster(ms_handle* h, int ctas_per_walker);
 int ms_set_pairing(ms_handle* h, int enabled);
 
 /*
+ * Bracket-only evaluation (default off; the streaming kernels stay the reference path).  Interpolation in the grid,
+ * dilution, np.trapz and the linear rebinning of mft6.py:1169 are linear in the grid rows, and the interpolation
+ * weights do not depend on wavelength.  With enabled = 1 an evaluation therefore reads (i) only the two model
+ * pixels that bracket each observed pixel, from a compact [row][n_data][2] copy of the grid built at ms_create
+ * (extinction is still applied at those model pixels before the rebinning, mft6.py:1162 -> :1169), and (ii) the
+ * band fluxes of its 2^D rows per star from a [row][band] table, instead of streaming n_star * 2^D whole rows:
+ * n_star * 2^D * (2 n_data + n_bands) * 8 bytes per evaluation.  The model on the observed pixels is
+ * bit-identical to the streaming path; chi-square, contrasts and magnitudes agree to rounding (summation order).  Posterior flavours
+ * only (the optimiser stage keeps streaming).
+ */
+int ms_set_fast(ms_handle* h, int enabled);
+
+/*
  * Launch order of batches of >= 1024 walkers.  1: grouped by grid cell (counting sort on the device), so that
  * CTAs resident together stream the same rows and a grid larger than L2 is fetched from HBM about once per
  * cell group instead of once per walker; 0: the caller's order; -1 (default): grouped when the grid exceeds

@@ -42,6 +42,7 @@ constexpr int MAXWARP = 16;              // the streaming kernel runs with 256 o
 constexpr int TILE = MS_TILE;           // model pixels per tile (4 per thread)
 constexpr int MAX_STAR = 3;              // binaries and triples (mft6.py nspec = 2 / 3)
 constexpr int MAX_CORNER = 8;
+constexpr int BAND_COLS = MS_MAX_CONTRAST + MS_MAX_PHOT;
 
 constexpr double RSUN_CM = 6.957e10;    // mft6.py:81, :691
 constexpr double PC_CM = 3.086e18;      // mft6.py:691
@@ -98,6 +99,9 @@ struct DevTables {
   int nospec;                   // mft6_nospec.py flavour (no spectral term), also for the optimiser's chi-square
   int feh_free, ncol;           // per-walker [Fe/H] as an extra trailing column of theta; ncol = ndim + feh_free
   int n_cells;                 // number of cell keys (bins of the launch-order counting sort)
+  // bracket-only mode (ms_set_fast): what an evaluation needs of the grid when linearity is used
+  const double2* bracket;      // [n_rows][n_data] {row[hi-1], row[hi]}: the two model pixels bracketing each observed pixel
+  const double* bandsum;       // [n_rows][BAND_COLS] sum_p w_f[p] row[p]: contrast f -> column f, photometric f -> MS_MAX_CONTRAST + f
 };
 
 // What walker_prep_kernel hands to the streaming kernel.
@@ -692,6 +696,38 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
   return (v1 + v2) / 2.0;
 }
 
+// One observed pixel: extinct() at the two bracketing model pixels, interp1d onto the observed wavelength
+// (mft6.py:1162, :1169), then the bookkeeping of phase B (norm_spec moments in the orthonormal basis on the
+// unscaled model, mft6.py:194-195; key range and NaN flag for the median).  Returns the model value.
+template <int MODE>
+__device__ __forceinline__ double observed_pixel(const DevTables& T, const dbl4& rec, const dbl4& drec, double flo, double fhi,
+                                                 double av, bool small_dext, double (&mom)[3], unsigned long long& kmin,
+                                                 unsigned long long& kmax, int& has_nan) {
+  const double elo = exp2(av * rec.y);
+  double ehi;
+  if (small_dext) {
+    const double xx = av * rec.z;                                // E_hi = E_lo * exp(xx), |xx| < 4e-3
+    double pz = fma(xx, 1.0 / 120.0, 1.0 / 24.0);
+    pz = fma(pz, xx, 1.0 / 6.0); pz = fma(pz, xx, 0.5); pz = fma(pz, xx, 1.0); pz = fma(pz, xx, 1.0);
+    ehi = elo * pz;
+  } else {
+    ehi = exp2(av * fma(rec.z, 1.4426950408889634, rec.y));   // ext_hi = ext_lo + dext / ln 2
+  }
+  const double ylo = flo * elo, yhi = fhi * ehi;
+  const double m = ylo + (yhi - ylo) * rec.x;
+  if constexpr (MODE == MODE_POSTERIOR) {
+    const double frac = drec.y * fast_rcp(m);
+    const double x = drec.x;
+    const double q1 = fma(T.basis[4], x, T.basis[3]);
+    const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
+    mom[0] = fma(T.basis[0], frac, mom[0]); mom[1] = fma(q1, frac, mom[1]); mom[2] = fma(q2, frac, mom[2]);
+  }
+  has_nan |= (m != m);
+  const unsigned long long k = ordered_key(m);
+  kmin = min(kmin, k); kmax = max(kmax, k);
+  return m;
+}
+
 // ------------------------------------------------------------------------------------------
 // lnprob_stream_kernel: one thread group of NT threads per walker, G groups per CTA.
 //   NR  grid rows per star (4: Teff x log g, 8: with [Fe/H]);  NC / NP compile-time filter caps;
@@ -706,8 +742,15 @@ __device__ double block_median_chi(const double* sM, int n, SelectScratch* S, un
 //       weights and per-pixel records back to back, so the second request is served by the SM's L1
 //       (hit or pending-miss merge) instead of L2.  Each walker's arithmetic is exactly that of G = 1;
 //       the pairing only changes where its operands come from, never its value.
+//   FAST 1: bracket-only evaluation (ms_set_fast; SURVEY.md section 8(d), "algebraic note").  Interpolation, dilution,
+//       trapezoid integration and linear rebinning are all linear in the grid rows and the interpolation
+//       weights do not depend on wavelength, so (i) the spectral term needs only the two model pixels that
+//       bracket each observed pixel -- a compact [row][N][2] copy of the grid, read fully coalesced -- and (ii)
+//       every band flux of a component is the same weighted sum of per-row band fluxes tabulated once.  The model
+//       vector is bit-identical to the streaming path, moments and band sums agree to rounding.  The streaming path stays
+//       the default.
 // ------------------------------------------------------------------------------------------
-template <int NR, int NC, int NP, int NT, int MODE, int NS, int G>
+template <int NR, int NC, int NP, int NT, int MODE, int NS, int G, int FAST>
 __global__ void __launch_bounds__(NT * G, (NT * G <= 256) ? 2 : 1)
 lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __restrict__ plans,
                      const int* __restrict__ order, double* __restrict__ lnprob, const PartsOut parts,
@@ -809,6 +852,39 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
   unsigned long long kmin = ~0ull, kmax = 0ull;                      // key range of the model, for the median
   int has_nan = 0;
 
+  if constexpr (FAST) {
+    // ---------------------------------------------------------------- phase A, bracket-only
+    if constexpr (MODE != MODE_NOSPEC) {
+      const int n_obs = T.n_data;
+      const double2* br[NS][NR];
+#pragma unroll
+      for (int st = 0; st < NS; ++st) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) br[st][r] = T.bracket + (long long)sPlan.row[st][r] * n_obs;
+      }
+      for (int i = tid; i < n_obs; i += NT) {
+        const dbl4 rec = ldg_cached4(T.rebin_rec + 4 * (long long)i);
+        dbl4 drec; drec.x = drec.y = drec.z = drec.w = 0.0;
+        if constexpr (MODE == MODE_POSTERIOR) drec = ldg_cached4(T.data_rec + 4 * (long long)i);
+        double2 b[NS][NR];
+#pragma unroll
+        for (int st = 0; st < NS; ++st) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) b[st][r] = __ldg(br[st][r] + i);
+        }
+        // same operation order as the streaming path: per star an FMA chain over its rows, then the sum over stars
+        double flo = 0.0, fhi = 0.0;
+#pragma unroll
+        for (int st = 0; st < NS; ++st) {
+          double l = cf[st][0] * b[st][0].x, u = cf[st][0] * b[st][0].y;
+#pragma unroll
+          for (int r = 1; r < NR; ++r) { l = fma(cf[st][r], b[st][r].x, l); u = fma(cf[st][r], b[st][r].y, u); }
+          flo = (st == 0) ? l : flo + l; fhi = (st == 0) ? u : fhi + u;
+        }
+        sM[i] = observed_pixel<MODE>(T, rec, drec, flo, fhi, av, small_dext, mom, kmin, kmax, has_nan);
+      }
+    }
+  } else {
   // ------------------------------------------------------------------ phase A: stream the rows
   // Each warp owns every NWARP-th contiguous 128-pixel chunk of the region and the observed pixels
   // whose upper bracket falls into it, so the rebinning needs no block-wide barrier and the warps
@@ -923,39 +999,46 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
         const int hl = (int)rec.w - cbase;                            // 0 .. CHUNK-1
         const double flo = seg[seg_slot(hl)];
         const double fhi = seg[seg_slot(hl + 1)];
-        // extinct() on the model grid, then interp1d onto the observed pixel (mft6.py:1162, :1169)
-        const double elo = exp2(av * rec.y);
-        double ehi;
-        if (small_dext) {
-          const double xx = av * rec.z;                                // E_hi = E_lo * exp(xx), |xx| < 4e-3
-          double pz = fma(xx, 1.0 / 120.0, 1.0 / 24.0);
-          pz = fma(pz, xx, 1.0 / 6.0); pz = fma(pz, xx, 0.5); pz = fma(pz, xx, 1.0); pz = fma(pz, xx, 1.0);
-          ehi = elo * pz;
-        } else {
-          ehi = exp2(av * fma(rec.z, 1.4426950408889634, rec.y));   // ext_hi = ext_lo + dext / ln 2
-        }
-        const double ylo = flo * elo, yhi = fhi * ehi;
-        const double m = ylo + (yhi - ylo) * rec.x;
-        sM_dst[i] = m;
-        if constexpr (MODE == MODE_POSTERIOR) {
-          // norm_spec's normal equations in the orthonormal basis, on the unscaled model (mft6.py:194-195)
-          const double frac = drec.y * fast_rcp(m);
-          const double x = drec.x;
-          const double q1 = fma(T.basis[4], x, T.basis[3]);
-          const double q2 = fma(fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
-          mom[0] = fma(T.basis[0], frac, mom[0]); mom[1] = fma(q1, frac, mom[1]); mom[2] = fma(q2, frac, mom[2]);
-        }
-        has_nan |= (m != m);
-        const unsigned long long k = ordered_key(m);
-        kmin = min(kmin, k); kmax = max(kmax, k);
+        sM_dst[i] = observed_pixel<MODE>(T, rec, drec, flo, fhi, av, small_dext, mom, kmin, kmax, has_nan);
       }
       __syncwarp();
     }
   }
+  }  // !FAST
   gsync<NT>(bar);
 
   // ------------------------------------------------------------------ band integrals
   double red[KRED > 0 ? KRED : 1];
+  if constexpr (FAST) {
+    // component band fluxes from the per-row table (only thread 0 needs them, for the final sum)
+#pragma unroll
+    for (int k = 0; k < KRED; ++k) red[k] = 0.0;
+    if (tid == 0) {
+#pragma unroll
+      for (int f = 0; f < NC; ++f) {
+#pragma unroll
+        for (int st = 0; st < NS; ++st) {
+          double acc = 0.0;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) acc = fma(cf[st][r], __ldg(T.bandsum + (long long)sPlan.row[st][r] * BAND_COLS + f), acc);
+          red[NS * f + st] = acc;
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < NP; ++f) {
+        double tot = 0.0;
+#pragma unroll
+        for (int st = 0; st < NS; ++st) {
+          double acc = 0.0;
+#pragma unroll
+          for (int r = 0; r < NR; ++r)
+            acc = fma(cf[st][r], __ldg(T.bandsum + (long long)sPlan.row[st][r] * BAND_COLS + MS_MAX_CONTRAST + f), acc);
+          tot += acc;
+        }
+        red[NS * NC + f] = tot;
+      }
+    }
+  } else {
 #pragma unroll
   for (int f = 0; f < NC; ++f) {
 #pragma unroll
@@ -964,6 +1047,7 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
 #pragma unroll
   for (int f = 0; f < NP; ++f) red[NS * NC + f] = accP[f];
   block_sum<KRED, NWARP>(red, sRed, bar);
+  }
 
   // ------------------------------------------------------------------ phase B: spectral chi-square
   const int n = T.n_data;
@@ -1080,6 +1164,39 @@ lnprob_stream_kernel(const __grid_constant__ DevTables T, const WalkerPlan* __re
     if (parts.lnprior) parts.lnprior[w] = sPlan.lp;
     if (parts.chi2_spec) parts.chi2_spec[w] = iic;
     if (parts.logg) for (int s = 0; s < T.nspec; ++s) parts.logg[w * T.nspec + s] = sPlan.logg[s];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Setup of the bracket-only mode: the two bracketing model pixels of every observed pixel, per grid row, and the
+// band flux of every grid row through every filter.
+// ------------------------------------------------------------------------------------------
+__global__ void bracket_gather_kernel(const double* __restrict__ grid, long long stride, const double* __restrict__ rebin_rec,
+                                      int n_data, double2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = blockIdx.y;
+  if (i >= n_data) return;
+  const int hi = (int)rebin_rec[4 * (long long)i + 3];
+  const double* g = grid + row * stride;
+  out[row * n_data + i] = make_double2(g[hi - 1], g[hi]);
+}
+
+// one CTA per grid row: out[row * BAND_COLS + col] = sum over the band's pixels of w[p] * row[p] (fixed order)
+__global__ void __launch_bounds__(256)
+bandsum_kernel(const double* __restrict__ grid, long long stride, const double* __restrict__ wbase, int p_lo, int p_hi,
+               int col, double* __restrict__ out) {
+  __shared__ double s_part[8];
+  const long long row = blockIdx.x;
+  const double* g = grid + row * stride;
+  double acc = 0.0;
+  for (int p = p_lo + threadIdx.x; p < p_hi; p += 256) acc = fma(wbase[p], g[p], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    out[row * BAND_COLS + col] = t;
   }
 }
 
@@ -1379,6 +1496,7 @@ struct ms_handle {
   int* order = nullptr; unsigned* cell_hist = nullptr; bool use_order = false;
   int pairing = MS_PAIRING_DEFAULT;  // 0: one walker per CTA, 1: two cell-mates per CTA for large batches, -1: automatic
   bool pair_now = false;         // decided per call (evaluate_device)
+  bool fast = false;             // bracket-only evaluation (ms_set_fast)
   int cell_order = -1;           // launch order: -1 automatic (cell-sorted when the grid exceeds L2), 0 natural, 1 cell-sorted
   int max_optin_smem = 0;
   bool nospec = false;           // mft6_nospec.py flavour of the posterior
@@ -1467,7 +1585,7 @@ int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut
   if constexpr (CAN_PAIR) {
     if (h->pair_now) {
       // two cell-mates per CTA (see the kernel's header comment); `order` is the cell-sorted launch order
-      auto kern2 = lnprob_stream_kernel<NR, NC, NP, NT, MODE, NS, 2>;
+      auto kern2 = lnprob_stream_kernel<NR, NC, NP, NT, MODE, NS, 2, 0>;
       CK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * h->smem_bytes)));
       const long long n_pairs = (nw + 1) / 2;
       long long stride = (long long)((double)n_pairs * 0.381966) | 1ll;
@@ -1477,8 +1595,29 @@ int launch_stream_mode(ms_handle* h, long long nw, double* d_lnp, const PartsOut
       launched = true;
     }
   }
+  if constexpr (MODE != MODE_OPTIMIZER) {
+    if (!launched && h->fast) {
+      // bracket-only evaluation: one CTA per walker, no clusters (the work per walker is a few microseconds)
+      auto kernf = lnprob_stream_kernel<NR, NC, NP, NT, MODE, NS, 1, 1>;
+      CK(cudaFuncSetAttribute(kernf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+      if (h->model_global) {
+        const size_t need = (size_t)nw * (size_t)h->T.n_data;
+        if (need > h->model_scratch_cap) {
+          if (need * 8 > (size_t)64 << 30) { set_err(h, "ms_lnprob: batch x observed pixels exceeds the 64 GiB model scratch; evaluate in smaller batches"); return MS_ERR_UNSUPPORTED; }
+          CK(cudaStreamSynchronize(h->stream));
+          if (h->model_scratch) cudaFree(h->model_scratch);
+          h->model_scratch = nullptr; h->model_scratch_cap = 0;
+          CK(cudaMalloc((void**)&h->model_scratch, need * 8));
+          h->model_scratch_cap = need;
+        }
+      }
+      kernf<<<(unsigned)nw, NT, h->smem_bytes, h->stream>>>(h->T, h->plans, order, d_lnp, parts, opt, 1, nw, 1ll,
+                                                            (unsigned)h->smem_bytes, h->model_global ? h->model_scratch : nullptr);
+      launched = true;
+    }
+  }
   if (!launched) {
-    auto kern = lnprob_stream_kernel<NR, NC, NP, NT, MODE, NS, 1>;
+    auto kern = lnprob_stream_kernel<NR, NC, NP, NT, MODE, NS, 1, 0>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     // cluster size: enough CTAs for two per SM, at most 8 per walker (portable limit)
     int csize = h->cluster;
@@ -1579,7 +1718,7 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   // Measured (profiles/): pairing halves the L2->SM traffic (L1 hit rate 53 %), which pays on stream-dominated
   // shapes (C1/C2: +5 %) and costs the pair barriers where the observed-pixel work dominates (C4: -5 %).
   const bool want_pair = h->pairing > 0 || (h->pairing < 0 && (long long)h->T.n_reg >= 16ll * h->T.n_data);
-  h->pair_now = want_pair && !h->model_global && h->cluster <= 1 && mode == MODE_POSTERIOR && h->T.nspec == 2 &&
+  h->pair_now = want_pair && !h->fast && !h->model_global && h->cluster <= 1 && mode == MODE_POSTERIOR && h->T.nspec == 2 &&
                 h->threads == MS_NT_SMALL && h->T.n_cells > 1 && nw >= 8ll * h->num_sms &&
                 2 * h->smem_bytes + 2048 <= (size_t)h->max_optin_smem;
   if (h->pair_now) h->use_order = true;
@@ -1827,6 +1966,28 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     CKC(upload(h, meta.data(), meta.size(), &T.chunk_meta));
   }
 
+  // ---- bracket-only mode tables, built on the device from the (possibly shared) device grid
+  {
+    double2* d_br = nullptr; double* d_bs = nullptr;
+    CKH(cudaMalloc((void**)&d_br, (size_t)n_rows * cfg->n_data * sizeof(double2)));
+    h->allocs.push_back(d_br);
+    CKH(cudaMalloc((void**)&d_bs, (size_t)n_rows * BAND_COLS * sizeof(double)));
+    h->allocs.push_back(d_bs);
+    CKH(cudaMemset(d_bs, 0, (size_t)n_rows * BAND_COLS * sizeof(double)));
+    dim3 gb((unsigned)((cfg->n_data + 255) / 256), (unsigned)n_rows);
+    bracket_gather_kernel<<<gb, 256, 0, h->stream>>>(T.grid, T.stride, T.rebin_rec, cfg->n_data, d_br);
+    for (int f = 0; f < cfg->n_contrast; ++f)
+      if (cfg->c_tile_hi[f] > cfg->c_tile_lo[f])
+        bandsum_kernel<<<(unsigned)n_rows, 256, 0, h->stream>>>(T.grid, T.stride, T.c_wbase[f], cfg->c_tile_lo[f] * TILE,
+                                                                cfg->c_tile_hi[f] * TILE, f, d_bs);
+    for (int f = 0; f < cfg->n_phot; ++f)
+      if (cfg->p_tile_hi[f] > cfg->p_tile_lo[f])
+        bandsum_kernel<<<(unsigned)n_rows, 256, 0, h->stream>>>(T.grid, T.stride, T.p_wbase[f], cfg->p_tile_lo[f] * TILE,
+                                                                cfg->p_tile_hi[f] * TILE, MS_MAX_CONTRAST + f, d_bs);
+    CKH(cudaGetLastError());
+    T.bracket = d_br; T.bandsum = d_bs;
+  }
+
   // ---- isochrone, dust
   CKC(upload(h, cfg->iso_teff, cfg->n_iso, &T.iso_teff));
   CKC(upload(h, cfg->iso_logg, cfg->n_iso, &T.iso_logg));
@@ -1884,6 +2045,12 @@ int ms_set_cluster(ms_handle* h, int ctas_per_walker) {
 int ms_set_pairing(ms_handle* h, int enabled) {
   if (!h) return MS_ERR_INVALID;
   h->pairing = enabled < 0 ? -1 : (enabled != 0);
+  return MS_OK;
+}
+
+int ms_set_fast(ms_handle* h, int enabled) {
+  if (!h) return MS_ERR_INVALID;
+  h->fast = enabled != 0;
   return MS_OK;
 }
 

@@ -23,7 +23,7 @@ _LIB_PATH = os.environ.get('MCMCSPEC_LIB') or os.path.join(os.path.dirname(os.pa
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
            'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_component_mags', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows', 'ms_build_grid',
-           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_cell_order', 'ms_set_timing',
+           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_fast', 'ms_set_cell_order', 'ms_set_timing',
            'ms_kernel_time']
 
 _dp = C.POINTER(C.c_double)
@@ -104,6 +104,7 @@ def load_library(path=None):
     lib.ms_use_own_stream.argtypes = [vp]
     lib.ms_set_cluster.argtypes = [vp, C.c_int]
     lib.ms_set_pairing.argtypes = [vp, C.c_int]
+    lib.ms_set_fast.argtypes = [vp, C.c_int]
     lib.ms_set_cell_order.argtypes = [vp, C.c_int]
     lib.ms_set_timing.argtypes = [vp, C.c_int]
     lib.ms_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -242,6 +243,11 @@ class Engine:
         """Two cell-mates per CTA for large batches: True / False / None (automatic, the default); values are
         bit-identical either way."""
         self._check(self.lib.ms_set_pairing(self._h, -1 if enabled is None else int(bool(enabled))), 'ms_set_pairing')
+
+    def set_fast(self, enabled):
+        """Bracket-only evaluation (reads 2 model pixels per observed pixel and per-row band fluxes instead of
+        streaming whole rows); off by default."""
+        self._check(self.lib.ms_set_fast(self._h, int(bool(enabled))), 'ms_set_fast')
 
     def set_cell_order(self, mode):
         """Launch order of large batches: True grouped by grid cell, False natural, None automatic (default)."""

@@ -27,7 +27,7 @@ from .tables import build_tables
 
 
 class LogPosterior:
-    def __init__(self, problem: Problem, device=0, share_grid_with=None):
+    def __init__(self, problem: Problem, device=0, share_grid_with=None, fast=False):
         """``share_grid_with``: another LogPosterior on the same device, built on the same model grid
         and consumed region, whose device copy of the grid is reused (independent ensembles fitting
         different observed spectra, BASELINE config C3)."""
@@ -36,6 +36,8 @@ class LogPosterior:
         owner = None if share_grid_with is None else share_grid_with.engine
         self.engine = native.Engine(self.tables, device=device, grid_owner=owner)
         self.ndim = self.engine.ndim
+        if fast:
+            self.engine.set_fast(True)         # bracket-only evaluation (ms_set_fast)
 
     def __call__(self, p0):
         p = np.asarray(p0, dtype=np.float64)

@@ -35,7 +35,7 @@ def central_third(prob, nw, seed=1):
     return th
 
 
-def run(name, prob, nw, reps=5, cell_order=None):
+def run(name, prob, nw, reps=5, cell_order=None, fast=False):
     peak = 6455.6
     try:
         peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
@@ -45,6 +45,7 @@ def run(name, prob, nw, reps=5, cell_order=None):
     if os.environ.get('MS_PAIRING') == '0':
         lp.engine.set_pairing(False)
     lp.engine.set_cell_order(cell_order)
+    lp.engine.set_fast(fast)
     th = torch.tensor(central_third(prob, nw), device='cuda')
     out = torch.empty(nw, dtype=torch.float64, device='cuda')
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device='cuda')
@@ -58,9 +59,12 @@ def run(name, prob, nw, reps=5, cell_order=None):
         lp.engine.lnprob_device(th.data_ptr(), nw, out.data_ptr())
     torch.cuda.synchronize()
     ms, nl, nwt = lp.engine.kernel_time()
-    bpe = lp.tables.bytes_per_eval()
-    gbs = nwt * bpe / 1e9 / (ms / 1e3)
     t = lp.tables
+    bpe = lp.tables.bytes_per_eval()
+    if fast:          # bracket-only mode: 2 model pixels per observed pixel + the band table, per row
+        ncorner = t.nspec * (4 if t.feh_nodes.size <= 1 else 8)
+        bpe = ncorner * (2 * t.n_data + t.contrast.n + t.phot.n) * 8 + 8 * lp.ndim + 8
+    gbs = nwt * bpe / 1e9 / (ms / 1e3)
     print(json.dumps({"config": name, "walkers_per_launch": nw, "n_data": t.n_data, "p_reg": t.n_reg,
                       "grid_mb": round(t.grid.nbytes / 1e6, 1), "bytes_per_eval": bpe,
                       "kernel_ms_per_launch": ms / nl, "evals_per_s": nwt / (ms / 1e3), "algorithmic_gbs": gbs,
@@ -172,6 +176,11 @@ def run_c3(n_fits=12, nw=25, reps=50):
 
 if __name__ == '__main__':
     which = sys.argv[1:] or ['c1', 'c1h', 'c1s', 'c3', 'c4', 'c5']
+    if 'fast' in which:
+        run('FAST C1/C2 shape (bracket-only mode), 8192 walkers', synthetic.make_problem(), 8192, fast=True)
+        run('FAST C1/C2 shape, reference walker count (50)', synthetic.make_problem(), 50, reps=20, fast=True)
+        run('FAST C4 (bracket-only mode), 32768 walkers', synthetic.make_problem_c4(), 32768, fast=True)
+        run('FAST C5 fixed [Fe/H] (bracket-only mode), 16384 walkers', synthetic.make_problem_c5(), 16384, reps=3, fast=True)
     if 'c1' in which:
         run('C1/C2 shape: 26x4 grid, 135000-px rows (P_reg ~117k synthetic bands), N=1945', synthetic.make_problem(), 8192)
         run('C1/C2 shape, reference walker count (50)', synthetic.make_problem(), 50, reps=20)

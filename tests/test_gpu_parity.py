@@ -275,6 +275,58 @@ def test_3d_grid_trilinear_16_passbands(native_lib):
         lp.close()
 
 
+def test_bracket_only_mode_equals_streaming(small_problem, small_oracle, native_lib):
+    """ms_set_fast: two model pixels per observed pixel + tabulated per-row band fluxes instead of streaming whole
+    rows (algebraic note).  Model vector bit-identical to the streaming path, chi-square, contrasts
+    and magnitudes to rounding, log-posterior within 1e-12 of it and 1e-9 of the oracle -- for binaries, triples,
+    3-D grids, the nospec flavour, a free [Fe/H] and a spectrum longer than shared memory."""
+    import dataclasses
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    cases = [(small_problem, synthetic.sample_prior_box(small_problem, 512, seed=41)),
+             (dataclasses.replace(small_problem, nospec=True), synthetic.sample_prior_box(small_problem, 128, seed=42))]
+    pt = synthetic.make_problem_triple_small()
+    cases.append((pt, synthetic.sample_prior_box_triple(pt, 128, seed=43)))
+    p3 = synthetic.make_problem_3d_small(feh=0.2)
+    cases.append((p3, synthetic.sample_prior_box(p3, 128, seed=44)))
+    p3f = synthetic.make_problem_3d_small(feh_free=True)
+    cases.append((p3f, synthetic.sample_prior_box(p3f, 128, seed=45)))
+    pl = synthetic.make_problem_small(n_pix=140000, dlam=0.03, n_data=30011, window_um=(0.56, 0.94))
+    cases.append((pl, synthetic.sample_prior_box(pl, 48, seed=46)))
+    for prob, theta in cases:
+        lp = LogPosterior(prob)
+        a = lp.parts(theta)
+        lp.engine.set_fast(True)
+        b = lp.parts(theta)
+        fast = lp(theta)
+        lp.engine.set_fast(False)
+        assert np.array_equal(a['status'], b['status'])
+        ok = a['status'] == 0
+        assert ok.sum() > 20
+        if not prob.nospec:
+            # same model vector (bit for bit); the norm_spec moments are summed in another order
+            assert np.allclose(a['chi2_spec'][ok], b['chi2_spec'][ok], rtol=1e-12, atol=0)
+            k = np.flatnonzero(ok)[:4]
+            lp.engine.set_fast(True); mf = lp.model_spectrum(theta[k])
+            lp.engine.set_fast(False); ms = lp.model_spectrum(theta[k])
+            assert np.array_equal(mf, ms)
+        assert np.allclose(a['contrast'][ok], b['contrast'][ok], rtol=0, atol=1e-11)
+        assert np.allclose(a['phot'][ok], b['phot'][ok], rtol=0, atol=1e-11)
+        assert np.array_equal(np.isfinite(a['lnprob']), np.isfinite(b['lnprob']))
+        f = np.isfinite(a['lnprob'])
+        assert np.max(np.abs(a['lnprob'][f] - b['lnprob'][f]) / np.abs(a['lnprob'][f])) <= 1e-12
+        assert np.array_equal(fast, b['lnprob'])
+        _compare(fast[:32], to_oracle(prob).lnprob_batch(theta[:32]))
+        lp.close()
+    lpf = LogPosterior(small_problem, fast=True)                                   # constructor switch
+    ref = LogPosterior(small_problem)
+    th = cases[0][1][:64]
+    f = np.isfinite(ref(th))
+    assert np.allclose(lpf(th)[f], ref(th)[f], rtol=1e-12) and np.array_equal(np.isfinite(lpf(th)), f)
+    lpf.close(); ref.close()
+
+
 def test_observed_spectrum_longer_than_shared_memory(native_lib):
     """More observed pixels than the shared-memory resident model vector can hold (~27 000): the per-walker model
     vector moves to a global scratch row; same values, same edge behaviour."""
