@@ -32,6 +32,7 @@ if __name__ == '__main__':
     ap.add_argument('--nburn', type=int, default=301)
     ap.add_argument('--nsteps', type=int, default=15001)
     ap.add_argument('--no-converge', action='store_true', help='run all nsteps (skip the autocorrelation stop)')
+    ap.add_argument('--fast', action='store_true', help='sample in the bracket-only mode (ms_set_fast)')
     args = ap.parse_args()
     out = args.outdir or tempfile.mkdtemp(prefix='fit_c1_')
     # truth on the synthetic isochrone (the reference's recipe takes its radii from the real MIST track)
@@ -47,6 +48,7 @@ if __name__ == '__main__':
     t_opt = time.perf_counter() - t0
     n_opt_props = sum(sum(1 for _ in open(os.path.join(out, f'chisq{k}.txt'))) for k in range(args.nwalk))
     msgs = []
+    lp.engine.set_fast(args.fast)
     t1 = time.perf_counter()
     if args.no_converge:
         from mcmc_spec_b200 import optimizer
@@ -67,7 +69,7 @@ if __name__ == '__main__':
     print(json.dumps({
         "config": "C1: 3850 K + 3425 K synthetic binary, koi2298 settings (N=1945, 135000-px rows, 26x4 grid), "
                   "150 optimiser walks x 400 steps -> 50 walkers x (301 + 15001) steps",
-        "optimizer_s": round(t_opt, 2), "optimizer_proposals": n_opt_props,
+        "sampler_mode": "bracket-only" if args.fast else "streaming", "optimizer_s": round(t_opt, 2), "optimizer_proposals": n_opt_props,
         "optimizer_evals_per_s": round(n_opt_props / t_opt),
         "sampler_s": round(t_mc, 2), "sampler_steps_kept": kept, "sampler_evals": n_mc_evals,
         "sampler_evals_per_s": round(n_mc_evals / t_mc), "sampler_ms_per_iteration": round(1e3 * t_mc / (args.nburn + kept), 4),
