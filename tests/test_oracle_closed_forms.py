@@ -255,3 +255,38 @@ def test_correction_factors_closed_form(tmp_path):
     predictive.write_sweep(str(tmp_path), res)
     assert np.allclose(np.loadtxt(tmp_path / 'sec_corr.txt'), sc)
     assert predictive.percentile_summary([-1.0, -2.0, -3.0])[0] == 2.0
+
+
+def test_linearity_identities_behind_the_bracket_only_mode(small_problem, small_oracle):
+    """What ms_set_fast relies on (algebraic note), checked on the oracle itself:
+    (i) a component's band flux equals the interpolation-weighted sum of the band fluxes of its bracketing grid
+        rows (np.trapz and the grid interpolation are linear, the weights do not depend on wavelength);
+    (ii) the rebinned model at an observed pixel depends only on the two model pixels that bracket it."""
+    from oracle import mft6_oracle as mo
+    o = small_oracle.p
+    t = np.array(small_problem.truth, dtype=float)
+    t[0], t[1] = 3733.0, 3541.0                                     # off-node in Teff; log g off-node via the isochrone
+    lg = [float(mo.get_logg(v, o.matrix)) for v in t[:2]]
+    region_um = [min(small_oracle.r) - 0.2, max(small_oracle.r) + 0.2]
+    wl, spec = mo.get_spec(t[0], lg[0], region_um, o.specs, o.temps, o.lgs)
+    # (i) band flux of the interpolated spectrum vs the bilinear combination of node band fluxes
+    ran, tm = np.array(o.ctm[0][0]), np.array(o.ctm[1][0])
+    inb = (wl >= ran.min()) & (wl <= ran.max())
+    tran = np.interp(wl[inb], ran, tm)
+    direct = np.trapezoid(spec[inb] * tran, wl[inb])
+    t1, t2 = mo._bracket(o.temps, t[0]); g1, g2 = mo._bracket(o.lgs, lg[0])
+    wt, wg = (t[0] - t1) / (t2 - t1), (lg[0] - g1) / (g2 - g1)
+    full = np.asarray(o.specs['wl'])
+    keep = (full >= wl[0]) & (full <= wl[-1])
+    node_flux = {k: np.trapezoid(np.asarray(o.specs['{}, {}'.format(*k)])[keep][inb] * tran, wl[inb])
+                 for k in ((t1, g1), (t1, g2), (t2, g1), (t2, g2))}
+    combo = ((1 - wt) * ((1 - wg) * node_flux[(t1, g1)] + wg * node_flux[(t1, g2)])
+             + wt * ((1 - wg) * node_flux[(t2, g1)] + wg * node_flux[(t2, g2)]))
+    assert abs(combo - direct) <= 1e-13 * abs(direct)
+    # (ii) linear rebinning reads two model pixels per observed pixel
+    x_new = np.asarray(small_problem.data[0]) * 1e4
+    ext = mo.extinct(wl, spec, 0.3)
+    hi = np.searchsorted(wl, x_new, side='right'); lo = hi - 1
+    two = ext[lo] + (ext[hi] - ext[lo]) * (x_new - wl[lo]) / (wl[hi] - wl[lo])
+    from scipy.interpolate import interp1d
+    assert np.allclose(two, interp1d(wl, ext)(x_new), rtol=1e-14, atol=0)
