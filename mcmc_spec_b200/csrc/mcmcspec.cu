@@ -252,22 +252,22 @@ __device__ double stefan_boltzmann_radius(double lum, double teff) {
 }
 
 // bayestar(SkyCoord(distance), mode='samples') * 3.1 * 0.884 -> mean, std   (mft6.py:1233-1238)
-__device__ void dust_prior_moments(const DevTables& T, double plx, double* mu, double* sig) {
+__device__ void dust_prior_moments(const double* __restrict__ dust_dm, const double* __restrict__ dust_samples, int n, int ns,
+                                   double plx, double* mu, double* sig) {
   const double d_kpc = (1.0 / plx) / 1.0e3;
   const double dm = 5.0 * (log10(d_kpc) + 2.0);
-  const int n = T.n_dm, ns = T.n_dust_samples;
   int c = 0;                                           // np.searchsorted(edges, dm) (side='left')
-  { int lo = 0, hi = n; while (lo < hi) { int mid = (lo + hi) >> 1; if (T.dust_dm[mid] < dm) lo = mid + 1; else hi = mid; } c = lo; }
+  { int lo = 0, hi = n; while (lo < hi) { int mid = (lo + hi) >> 1; if (dust_dm[mid] < dm) lo = mid + 1; else hi = mid; } c = lo; }
   double s[16];
   double a = 0.0;
-  if (c == 0) a = pow(10.0, 0.2 * (dm - T.dust_dm[0]));
-  else if (c < n) a = (T.dust_dm[c] - dm) / (T.dust_dm[c] - T.dust_dm[c - 1]);
+  if (c == 0) a = pow(10.0, 0.2 * (dm - dust_dm[0]));
+  else if (c < n) a = (dust_dm[c] - dm) / (dust_dm[c] - dust_dm[c - 1]);
   double sum = 0.0;
   for (int k = 0; k < ns; ++k) {
     double e;
-    if (c == 0) e = a * T.dust_samples[k * n];
-    else if (c == n) e = T.dust_samples[k * n + n - 1];
-    else e = (1.0 - a) * T.dust_samples[k * n + c] + a * T.dust_samples[k * n + c - 1];
+    if (c == 0) e = a * dust_samples[k * n];
+    else if (c == n) e = dust_samples[k * n + n - 1];
+    else e = (1.0 - a) * dust_samples[k * n + c] + a * dust_samples[k * n + c - 1];
     e = e * 3.1 * 0.884;
     s[k] = e;
     sum += e;
@@ -285,6 +285,28 @@ __device__ void dust_prior_moments(const DevTables& T, double plx, double* mu, d
 __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__ theta, long long nw,
                                    WalkerPlan* __restrict__ plans_out, unsigned* __restrict__ cell_hist,
                                    const int mode, const OptIn opt) {
+  // The isochrone, node and dust tables (a few KB) are staged in shared memory once per CTA: the searches below
+  // are chains of dependent loads (two bisections of the isochrone per star, the dust slice, three node scans),
+  // ~60 L2 round trips per walker when read from global memory -- which made this kernel 28 us, more than a
+  // third of a 50-walker sampler iteration.
+  extern __shared__ __align__(16) unsigned char prep_smem[];
+  double* s_iso_teff = reinterpret_cast<double*>(prep_smem);
+  double* s_iso_logg = s_iso_teff + T.n_iso;
+  double* s_iso_lum = s_iso_logg + T.n_iso;
+  double* s_teff = s_iso_lum + T.n_iso;
+  double* s_logg = s_teff + T.n_teff;
+  double* s_feh = s_logg + T.n_logg;
+  double* s_dm = s_feh + T.n_feh;
+  double* s_dust = s_dm + T.n_dm;
+  for (int k = threadIdx.x; k < T.n_iso; k += blockDim.x) {
+    s_iso_teff[k] = T.iso_teff[k]; s_iso_logg[k] = T.iso_logg[k]; s_iso_lum[k] = T.iso_lum[k];
+  }
+  for (int k = threadIdx.x; k < T.n_teff; k += blockDim.x) s_teff[k] = T.teff_nodes[k];
+  for (int k = threadIdx.x; k < T.n_logg; k += blockDim.x) s_logg[k] = T.logg_nodes[k];
+  for (int k = threadIdx.x; k < T.n_feh; k += blockDim.x) s_feh[k] = T.feh_nodes[k];
+  for (int k = threadIdx.x; k < T.n_dm; k += blockDim.x) s_dm[k] = T.dust_dm[k];
+  for (int k = threadIdx.x; k < T.n_dm * T.n_dust_samples; k += blockDim.x) s_dust[k] = T.dust_samples[k];
+  __syncthreads();
   const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (w >= nw) return;
   // every exit stores the plan and counts the walker in its cell bin
@@ -347,8 +369,8 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   double lum[MAX_STAR];
   for (int s = 0; s < ns; ++s) {
     double g, l;
-    if (!interp_table(T.iso_teff, T.iso_logg, T.n_iso, temps[s], &g) ||
-        !interp_table(T.iso_teff, T.iso_lum, T.n_iso, temps[s], &l)) {
+    if (!interp_table(s_iso_teff, s_iso_logg, T.n_iso, temps[s], &g) ||
+        !interp_table(s_iso_teff, s_iso_lum, T.n_iso, temps[s], &l)) {
       plan.status = MS_W_OFF_ISOCHRONE; store(plan); return;
     }
     plan.logg[s] = g; lum[s] = l;
@@ -359,7 +381,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   if (mode == MODE_OPTIMIZER) {
     // opt_prior terms in chi-square units (mft6.py:833-854, :1030-1046)
     double mu, sig;
-    dust_prior_moments(T, plx, &mu, &sig);
+    dust_prior_moments(s_dm, s_dust, T.n_dm, T.n_dust_samples, plx, &mu, &sig);
     if (sig == 0.0) sig = 0.05;
     const double avp = opt.av_prior ? opt.av_prior[w] : av;
     { const double z = (avp - mu) / sig; lp += z * z; }
@@ -374,7 +396,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   } else {
     if (T.ext_flag) {
       double mu, sig;
-      dust_prior_moments(T, plx, &mu, &sig);
+      dust_prior_moments(s_dm, s_dust, T.n_dm, T.n_dust_samples, plx, &mu, &sig);
       if (sig == 0.0) sig = 0.05;
       const double z = (av - mu) / sig;
       lp += -0.5 * (z * z);
@@ -400,14 +422,14 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
 
   // ---- grid brackets and coefficients
   int z1 = 0, z2 = 0; double wz = 0.0;
-  if (T.n_feh > 1 && !bracket_nodes(T.feh_nodes, T.n_feh, fehv, &z1, &z2, &wz)) {
+  if (T.n_feh > 1 && !bracket_nodes(s_feh, T.n_feh, fehv, &z1, &z2, &wz)) {
     plan.status = MS_W_OFF_GRID; store(plan); return;
   }
   const double di = 1.0 / plx;                            // mft6.py:690
   for (int s = 0; s < ns; ++s) {
     int t1, t2, g1, g2; double wt, wg;
-    if (!bracket_nodes(T.teff_nodes, T.n_teff, temps[s], &t1, &t2, &wt) ||
-        !bracket_nodes(T.logg_nodes, T.n_logg, plan.logg[s], &g1, &g2, &wg)) {
+    if (!bracket_nodes(s_teff, T.n_teff, temps[s], &t1, &t2, &wt) ||
+        !bracket_nodes(s_logg, T.n_logg, plan.logg[s], &g1, &g2, &wg)) {
       plan.status = MS_W_OFF_GRID; store(plan); return;
     }
     const double base = (s == 0) ? rad[0] * RSUN_CM / (di * PC_CM) : rad[0] * rad[s] * RSUN_CM / (di * PC_CM);
@@ -1723,7 +1745,10 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
                 2 * h->smem_bytes + 2048 <= (size_t)h->max_optin_smem;
   if (h->pair_now) h->use_order = true;
   if (h->use_order) CK(cudaMemsetAsync(h->cell_hist, 0, (size_t)h->T.n_cells * sizeof(unsigned), h->stream));
-  walker_prep_kernel<<<pg, pb, 0, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr, mode, opt);
+  const size_t prep_smem = (size_t)(3 * h->T.n_iso + h->T.n_teff + h->T.n_logg + h->T.n_feh + h->T.n_dm +
+                                    h->T.n_dm * h->T.n_dust_samples) * sizeof(double);
+  if (prep_smem > 48 * 1024) CK(cudaFuncSetAttribute(walker_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+  walker_prep_kernel<<<pg, pb, prep_smem, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr, mode, opt);
   CK(cudaGetLastError());
   h->launches += 1;
   if (h->use_order) {
