@@ -50,6 +50,13 @@ def run():
         return lp
 
     lp = evaluate(synthetic.make_problem_c4(), 32768, 'C4')
+    # the same batch in the bracket-only mode (ms_set_fast)
+    lp.engine.set_fast(True)
+    th = torch.tensor(central_third(lp.problem, 32768), device='cuda')
+    out = torch.empty(32768, dtype=torch.float64, device='cuda')
+    for _ in range(2):
+        lp.engine.lnprob_device(th.data_ptr(), 32768, out.data_ptr())
+    torch.cuda.synchronize()
     lp.close()
     p1 = synthetic.make_problem(truth=synthetic.consistent_truth(3850.0, 3425.0, 0.12, 2.0732e-3))
     lp = evaluate(p1, 8192, 'C1')
