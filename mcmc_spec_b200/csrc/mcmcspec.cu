@@ -387,11 +387,13 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
     { const double z = (avp - mu) / sig; lp += z * z; }
     if (T.dist_fit) { const double z = (plx - T.prior_mu[ndim - 1]) / T.prior_sig[ndim - 1]; lp += z * z; }
     if (T.rad_prior) {
+      // opt_prior(var_par[2], [R1m, R2m/R1m (, R3m/R1m)], si[2])   (mft6.py:1037-1050)
       const double r1m = stefan_boltzmann_radius(lum[0], temps[0]);
-      const double r2m = stefan_boltzmann_radius(lum[1], temps[1]);
-      const double z0 = (rad[0] - r1m) / opt.rad_sigma[w * ns];
-      const double z1 = (rad[1] - r2m / r1m) / opt.rad_sigma[w * ns + 1];
-      lp += z0 * z0 + z1 * z1;
+      for (int s = 0; s < ns; ++s) {
+        const double m = (s == 0) ? r1m : stefan_boltzmann_radius(lum[s], temps[s]) / r1m;
+        const double z = (rad[s] - m) / opt.rad_sigma[w * ns + s];
+        lp += z * z;
+      }
     }
   } else {
     if (T.ext_flag) {
@@ -1688,8 +1690,9 @@ int launch_stream_threads(ms_handle* h, long long nw, double* d_lnp, const Parts
     if constexpr (NR == 4) {
       if (mode == MODE_NOSPEC) return launch_stream_mode<NR, NC, NP, NT, MODE_NOSPEC, 3>(h, nw, d_lnp, parts, opt);
       if (mode == MODE_POSTERIOR) return launch_stream_mode<NR, NC, NP, NT, MODE_POSTERIOR, 3>(h, nw, d_lnp, parts, opt);
+      if (mode == MODE_OPTIMIZER) return launch_stream_mode<NR, NC, NP, NT, MODE_OPTIMIZER, 3>(h, nw, d_lnp, parts, opt);
     }
-    set_err(h, "triples are built for (Teff, log g) grids and the posterior modes only");
+    set_err(h, "triples are built for (Teff, log g) grids only");
     return MS_ERR_UNSUPPORTED;
   }
   if (mode == MODE_OPTIMIZER) return launch_stream_mode<NR, NC, NP, NT, MODE_OPTIMIZER, 2>(h, nw, d_lnp, parts, opt);
@@ -2137,7 +2140,7 @@ int ms_optimizer_chisq(ms_handle* h, const double* theta, const int32_t* set_ind
   if (!h) return MS_ERR_INVALID;
   if (nw < 0 || (nw > 0 && (!theta || !set_index || !rad_sigma || !chisq))) { set_err(h, "ms_optimizer_chisq: null argument"); return MS_ERR_INVALID; }
   if (h->opt_sets < 1) { set_err(h, "ms_optimizer_chisq: call ms_set_optimizer_data first"); return MS_ERR_INVALID; }
-  if (h->T.nspec != 2 || h->T.feh_free) { set_err(h, "ms_optimizer_chisq: the optimiser stage is built for binaries at a fixed [Fe/H]"); return MS_ERR_UNSUPPORTED; }
+  if (h->T.feh_free) { set_err(h, "ms_optimizer_chisq: the optimiser stage is built for a fixed [Fe/H]"); return MS_ERR_UNSUPPORTED; }
   if (nw == 0) return MS_OK;
   for (int64_t w = 0; w < nw; ++w)
     if (set_index[w] < 0 || set_index[w] >= h->opt_sets) { set_err(h, "ms_optimizer_chisq: set_index out of range"); return MS_ERR_INVALID; }

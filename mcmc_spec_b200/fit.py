@@ -178,6 +178,8 @@ def run_fit(lnprob, fp, dirname, optimize=True, emcee=True, seed=0, nthin=100, w
     chisqs = np.genfromtxt(os.path.join(dirname, 'optimize_cs.txt'))
     pars = np.genfromtxt(os.path.join(dirname, 'optimize_res.txt'))
     p0 = optimizer.select_walkers(pars, chisqs)
+    if lnprob.problem.nspec == 3:                                           # mft6.py:3676-3677
+        p0 = p0 + np.random.default_rng(seed).normal(np.zeros(np.shape(p0)), 0.05 * np.abs(p0), np.shape(p0))
     if len(p0) % 2:
         p0 = p0[:-1]                       # the red/blue split needs an even ensemble (emcee requires nwalkers >= 2 ndim)
     sampler = EnsembleSampler(len(p0), lnprob.ndim, CudaBackend(lnprob.engine), seed=seed)

@@ -14,8 +14,12 @@ fix-up loops that only burn ``total_n`` (:1069-1103) -- is kept line for line; t
 process pool and its unseeded ``RandomState`` are replaced by one seeded generator.
 
 ``backend`` supplies two calls (the product one is ``GpuChisq``; tests plug in the oracle):
-    start(theta0 [nw, 6]) -> (init_cs [nw], flux_sets [nw, N])      mft6.py:859-930
-    test(theta [m, 6], walk_index [m], rad_sigma [m, 2]) -> test_cs [m]
+    start(theta0 [nw, ndim]) -> (init_cs [nw], flux_sets [nw, N])      mft6.py:859-930
+    test(theta [m, ndim], walk_index [m], rad_sigma [m, nspec]) -> test_cs [m]
+
+Binaries (ndim = 6: T1, T2, Av, R1, R2/R1, plx) and triples (ndim = 8: T1, T2, T3, Av, R1, R2/R1, R3/R1, plx;
+the ``nspec == 3`` branches at mft6.py:920-922, :952-976, :984-990, :1044-1050, :1718-1741) share the code:
+``ns = (ndim - 2) // 2``.
 """
 from __future__ import annotations
 
@@ -36,7 +40,8 @@ class GpuChisq:
     def start(self, theta0):
         theta0 = np.asarray(theta0, dtype=np.float64)
         bare = theta0.copy()
-        bare[:, 2] = 0.0                                   # the initial model is not extincted (mft6.py:880)
+        ns = (theta0.shape[1] - 2) // 2
+        bare[:, ns] = 0.0                                  # the initial model is not extincted (mft6.py:880)
         if getattr(self.lp.problem, 'nospec', False):
             # mft6_nospec.py: no spectral term, hence no renormalised spectrum (its fit_spec :885-895 commented out)
             sets = np.tile(self.flux, (theta0.shape[0], 1))
@@ -48,9 +53,9 @@ class GpuChisq:
                 sets[k] = self.flux / np.polynomial.Polynomial.fit(self.wl_aa, frac, deg=2)(self.wl_aa)
         self.engine.set_optimizer_data(sets)
         idx = np.arange(theta0.shape[0], dtype=np.int32)
-        rad_sigma = 0.05 * theta0[:, 3:5]                   # mft6.py:916
+        rad_sigma = 0.05 * theta0[:, ns + 1:2 * ns + 1]     # mft6.py:916
         # the starting model stays scaled to the median of the original spectrum (mft6.py:888 precedes :889)
-        init_cs = self.engine.optimizer_chisq(bare, idx, rad_sigma, av_prior=theta0[:, 2],
+        init_cs = self.engine.optimizer_chisq(bare, idx, rad_sigma, av_prior=theta0[:, ns],
                                               ref_median=float(np.median(self.flux)))
         return init_cs, sets
 
@@ -58,50 +63,60 @@ class GpuChisq:
         return self.engine.optimizer_chisq(theta, walk_index, rad_sigma)
 
 
-def draw_starts(nwalk, tmin, tmax, plx, plx_err, rng):
-    """Random starting points of optimize_fit (mft6.py:1712-1741), binary case."""
+def draw_starts(nwalk, tmin, tmax, plx, plx_err, rng, nspec=2):
+    """Random starting points of optimize_fit (mft6.py:1712-1741)."""
     rmin, rmax = 0.05, 1.0
     t1 = rng.uniform(tmin, tmax, nwalk)
     t2 = np.array([rng.uniform(tmin, tt) for tt in t1])
+    temps = [t1, t2]
+    if nspec == 3:
+        temps.append(np.array([rng.uniform(tmin, tt) for tt in t2]))
     e1 = rng.uniform(0.1, 0.5, nwalk)
     rg1 = rng.uniform(rmin, rmax, nwalk)
     rg2 = np.array([rng.uniform(rmin, r) / r for r in rg1])
+    rads = [rg1, rg2]
+    if nspec == 3:
+        rads.append(np.array([rng.uniform(rmin, r) / r for r in rg2]))          # mft6.py:1732-1736 (sic: drawn below rg2)
     dist = np.abs(rng.normal(plx, plx_err, nwalk))
-    return np.column_stack([t1, t2, e1, rg1, rg2, dist])
+    return np.column_stack(temps + [e1] + rads + [dist])
 
 
 def _in_box(v, tlim):
-    """mft6.py:984-985."""
-    return (tlim[0] < v[0] < tlim[1] and tlim[0] < v[1] < tlim[1] and 0 <= v[2] and 0.05 <= v[3] <= 1.5
-            and 0.05 < v[4] < 1 and 1 / 10 > v[5] > 1 / 3000)
+    """mft6.py:984-985 (the test reads only the first two radius entries, for triples too)."""
+    ns = (len(v) - 2) // 2
+    return (all(tlim[0] < t < tlim[1] for t in v[:ns]) and 0 <= v[ns] and 0.05 <= v[ns + 1] <= 1.5
+            and 0.05 < v[ns + 2] < 1 and 1 / 10 > v[2 * ns + 1] > 1 / 3000)
 
 
 def _fixup_calls(v, tlim, total_n, cap):
     """The out-of-box branch (mft6.py:1069-1103): the proposal is nudged back towards the box and thrown
     away; all that survives is the number of calls it is charged.  Returns the new ``total_n``."""
     v = v.copy()
+    ns = (len(v) - 2) // 2
+    temps, rad = v[:ns], v[ns + 1:2 * ns + 1]                      # views
+    ip = 2 * ns + 1
     total_n += 1
-    while (v[0] < tlim[0] or v[1] < tlim[0]) and total_n < cap:
+    while np.any(temps < tlim[0]) and total_n < cap:
         total_n += 1
-        v[:2][v[:2] < tlim[0]] += 100
-    while (v[0] > tlim[1] or v[1] > tlim[1]) and total_n < cap:
+        temps[temps < tlim[0]] += 100
+    while np.any(temps > tlim[1]) and total_n < cap:
         total_n += 1
-        v[:2][v[:2] > tlim[1]] -= 100
+        temps[temps > tlim[1]] -= 100
     while v[0] < v[1] and total_n < cap:
         total_n += 1
         v[1] -= 100
-    while v[2] < 0 and total_n < cap:
+    while v[ns] < 0 and total_n < cap:
         total_n += 1
-        v[2] += 0.1
-    while (v[3] < 0.05 or v[4] < 0.05) and total_n < cap:
+        v[ns] += 0.1
+    while np.any(rad < 0.05) and total_n < cap:
         total_n += 1
-        v[3:5][v[3:5] < 0.05] += 0.01
-    while v[5] > 1 / 100 and total_n < cap:
+        rad[rad < 0.05] += 0.01
+    while v[ip] > 1 / 100 and total_n < cap:
         total_n += 1
-        v[5] -= 0.01 * abs(v[5])
-    while v[5] < 1 / 3000 and total_n < cap:
+        v[ip] -= 0.01 * abs(v[ip])
+    while v[ip] < 1 / 3000 and total_n < cap:
         total_n += 1
-        v[5] += 0.01 * abs(v[5])
+        v[ip] += 0.01 * abs(v[ip])
     return total_n
 
 
@@ -114,8 +129,12 @@ def fit_spec_batch(backend, theta0, tlim, steps, rng, record=False):
     init_cs, _ = backend.start(theta0)
     gi = theta0.copy()
     chi = np.asarray(init_cs, dtype=np.float64).copy()
-    rad0 = theta0[:, 3:5].copy()                                # rad_guess: step sizes hang on the *initial* radii
-    dist0 = theta0[:, 5].copy()                                 # (mft6.py:955, :972)
+    ndim = theta0.shape[1]
+    ns = (ndim - 2) // 2
+    ir, ip = slice(ns + 1, 2 * ns + 1), 2 * ns + 1
+    rad0 = theta0[:, ir].copy()                                 # rad_guess: step sizes hang on the *initial* radii
+    dist0 = theta0[:, ip].copy()                                # (mft6.py:955, :972)
+    d_coarse, d_fine = (0.02, 0.005) if ns == 2 else (0.05, 0.01)      # mft6.py:953-955, :971-974
     n = np.zeros(nw)
     total_n = np.zeros(nw, dtype=np.int64)
     cap = 50 * steps
@@ -125,21 +144,26 @@ def fit_spec_batch(backend, theta0, tlim, steps, rng, record=False):
         if active.size == 0:
             break
         fine = n[active] > steps / 2                               # mft6.py:971
-        si = np.empty((active.size, 6))
-        si[:, 0:2] = np.where(fine, 20.0, 250.0)[:, None]
-        si[:, 2] = np.where(fine, 0.01, 0.05)
-        si[:, 3:5] = np.where(fine, 0.05, 0.1)[:, None] * rad0[active]
-        si[:, 5] = np.where(fine, 0.005, 0.02) * dist0[active]
-        var = gi[active] + si * rng.standard_normal((active.size, 6))   # make_varied_param, mft6.py:211-228
+        si = np.empty((active.size, ndim))
+        si[:, 0:ns] = np.where(fine, 20.0, 250.0)[:, None]
+        si[:, ns] = np.where(fine, 0.01, 0.05)
+        si[:, ir] = np.where(fine, 0.05, 0.1)[:, None] * rad0[active]
+        si[:, ip] = np.where(fine, d_fine, d_coarse) * dist0[active]
+        var = gi[active] + si * rng.standard_normal((active.size, ndim))   # make_varied_param, mft6.py:211-228
         ok = np.array([_in_box(v, tlim) for v in var])
         for k, a in enumerate(active):
             if not ok[k]:
                 total_n[a] = _fixup_calls(var[k], tlim, int(total_n[a]), cap)
+        if ns == 3:
+            # mft6.py:987-988: the tertiary ratio is forced below the secondary's
+            for k in np.flatnonzero(ok):
+                while var[k, ns + 3] >= var[k, ns + 2] or var[k, ns + 3] < 0:
+                    var[k, ns + 3] = var[k, ns + 2] * 0.9
         inbox = active[ok]
         if inbox.size:
             total_n[inbox] += 1
             n[inbox] += 1
-            test_cs = backend.test(var[ok], inbox.astype(np.int32), si[ok][:, 3:5])   # mft6.py:995-1046
+            test_cs = backend.test(var[ok], inbox.astype(np.int32), si[ok][:, ir])   # mft6.py:995-1046
             better = test_cs < chi[inbox]                                               # NaN / +inf never win
             won = inbox[better]
             gi[won] = var[ok][better]
@@ -152,16 +176,17 @@ def fit_spec_batch(backend, theta0, tlim, steps, rng, record=False):
 
 
 def optimize_fit(lnprob, nwalk, nstep, plx, plx_err, seed=None, dirname=None, backend=None, record=None):
-    """Mirror of ``optimize_fit`` (mft6.py:1686-1765) for binaries with a distance.
+    """Mirror of ``optimize_fit`` (mft6.py:1686-1765) for binaries and triples with a distance.
 
     ``lnprob``: a LogPosterior (supplies the problem and the GPU engine).  Writes the reference's
     result files into ``dirname`` when given: optimize_res.txt (one best-fit vector per line),
-    optimize_cs.txt, and per walk params{n}.txt / chisq{n}.txt.  Returns (params [nwalk, 6], chisq [nwalk]).
+    optimize_cs.txt, and per walk params{n}.txt / chisq{n}.txt.  Returns (params [nwalk, ndim], chisq [nwalk]).
     """
     prob = lnprob.problem
     rng = np.random.default_rng(seed)
     tmin, tmax = float(min(prob.temps)), float(max(prob.temps))
-    theta0 = draw_starts(nwalk, tmin, tmax, plx, plx_err, rng)
+    theta0 = draw_starts(nwalk, tmin, tmax, plx, plx_err, rng, nspec=prob.nspec)
+    row = ' '.join(['{}'] * theta0.shape[1]) + '\n'
     backend = backend or GpuChisq(lnprob)
     record = bool(dirname) if record is None else record
     gi, chi, history = fit_spec_batch(backend, theta0, (tmin, tmax), nstep, rng, record=record)
@@ -170,13 +195,13 @@ def optimize_fit(lnprob, nwalk, nstep, plx, plx_err, seed=None, dirname=None, ba
         for k in range(nwalk):
             with open(os.path.join(dirname, f'params{k}.txt'), 'a') as f:       # mft6.py:1107-1110
                 for th, _, _ in history[k]:
-                    f.write('{} {} {} {} {} {}\n'.format(*th))
+                    f.write(row.format(*th))
             with open(os.path.join(dirname, f'chisq{k}.txt'), 'a') as f:        # mft6.py:1112-1115
                 for _, c, t in history[k]:
                     f.write('{} {}\n'.format(c, t))
         with open(os.path.join(dirname, 'optimize_res.txt'), 'a') as f:         # mft6.py:1760-1761
             for th in gi:
-                f.write('{} {} {} {} {} {}\n'.format(*th))
+                f.write(row.format(*th))
         with open(os.path.join(dirname, 'optimize_cs.txt'), 'a') as f:          # mft6.py:1762-1763
             for c in chi:
                 f.write(str(c) + '\n')

@@ -522,7 +522,11 @@ def fit_spec_init(wl_aa, flux, err, reg, t_guess, av, rad_guess, fr_guess, specs
         init_cs += opt_prior([dist], [pprior], [psig])
     if rad_prior == True:                          # noqa: E712
         r1, r2 = get_radius(t_guess[0], matrix), get_radius(t_guess[1], matrix)
-        init_cs += opt_prior(rad_guess, [r1, r2 / r1], [0.05 * r for r in rad_guess])
+        if nspec == 2:                             # mft6.py:917-918
+            init_cs += opt_prior(rad_guess, [r1, r2 / r1], [0.05 * r for r in rad_guess])
+        elif nspec == 3:                           # mft6.py:920-922
+            r3 = get_radius(t_guess[2], matrix)
+            init_cs += opt_prior(rad_guess, [r1, r2 / r1, r3 / r1], [0.05 * r for r in rad_guess])
     mu, sig = _dust_moments(dustmap, dist)
     init_cs += opt_prior([extinct_guess], [mu], [sig])
     return init_cs, flux
@@ -557,6 +561,9 @@ def fit_spec_test_cs(var_par, wl_aa, flux, err, reg, fr_guess, specs, pprior, ps
     if rad_prior == True and nspec == 2:           # noqa: E712
         r1, r2 = get_radius(var_par[0][0], matrix), get_radius(var_par[0][1], matrix)
         test_cs += opt_prior(var_par[2], [r1, r2 / r1], np.array(rad_sigma))
+    elif rad_prior == True and nspec == 3:         # noqa: E712   mft6.py:1044-1050
+        r1, r2, r3 = (get_radius(var_par[0][k], matrix) for k in range(3))
+        test_cs += opt_prior(var_par[2], [r1, r2 / r1, r3 / r1], np.array(rad_sigma))
     return test_cs
 
 

@@ -105,3 +105,37 @@ def test_nospec_optimizer_chisq_matches_oracle(small_problem, native_lib):
     full.start(theta0)
     assert not np.allclose(full.test(theta, idx, rs), got)          # the spectral term really is gone
     lp.close()
+
+
+def test_triple_star_optimizer(native_lib, tmp_path):
+    """fit_spec / optimize_fit for nspec = 3 (mft6.py:920-922, :952-990, :1044-1050, :1718-1741): 8-parameter walks,
+    three radius priors, the tertiary ratio forced below the secondary's; chi-squares against the oracle and a whole
+    walk with the same random draws against the oracle-backed walk."""
+    from mcmc_spec_b200 import optimizer as opt, synthetic
+    from mcmc_spec_b200.optimizer import GpuChisq
+    from mcmc_spec_b200.posterior import LogPosterior
+    from opt_reference import OracleChisq
+    from oracle_adapter import to_oracle
+    prob = synthetic.make_problem_triple_small()
+    orc_p = to_oracle(prob)
+    lp = LogPosterior(prob)
+    plx, plx_err = prob.prior[-2], prob.prior[-1]
+    rng = np.random.default_rng(3)
+    theta0 = opt.draw_starts(12, float(min(prob.temps)), float(max(prob.temps)), plx, plx_err, rng, nspec=3)
+    assert theta0.shape == (12, 8) and np.all(theta0[:, 2] <= theta0[:, 1]) and np.all(theta0[:, 1] <= theta0[:, 0])
+    gpu, orc = GpuChisq(lp), OracleChisq(prob, orc_p)
+    g_cs, g_sets = gpu.start(theta0)
+    o_cs, o_sets = orc.start(theta0)
+    assert np.allclose(g_sets, o_sets, rtol=1e-12) and np.allclose(g_cs, o_cs, rtol=1e-9)
+    theta = theta0[rng.integers(0, 12, 48)] * (1 + 0.02 * rng.standard_normal((48, 8)))
+    theta[:, 3] = np.abs(theta[:, 3])
+    theta[:, 0:3] = np.clip(theta[:, 0:3], min(prob.temps) + 1, max(prob.temps) - 1)
+    idx = rng.integers(0, 12, 48).astype(np.int32)
+    rs = 0.1 * theta0[idx, 4:7]
+    got, want = gpu.test(theta, idx, rs), orc.test(theta, idx, rs)
+    assert np.all(np.isfinite(want)) and np.max(np.abs(got - want) / np.abs(want)) < 1e-9
+    g_par, g_chi = opt.optimize_fit(lp, 6, 6, plx, plx_err, seed=8, dirname=str(tmp_path / 'run'))
+    o_par, o_chi = opt.optimize_fit(lp, 6, 6, plx, plx_err, seed=8, backend=OracleChisq(prob, orc_p))
+    assert g_par.shape == (6, 8) and np.allclose(g_par, o_par, rtol=1e-12) and np.allclose(g_chi, o_chi, rtol=1e-9)
+    assert np.genfromtxt(tmp_path / 'run' / 'optimize_res.txt').shape == (6, 8)
+    lp.close()
