@@ -64,8 +64,8 @@ def main(argv=None):
     fp = paramfile.parse_param_file(parfile)
     if fp.models != 'btsettl':
         raise SystemExit("only models = btsettl is implemented (the hires/PHOENIX reader is out of scope)")
-    if int(fp.nspec) != 2:
-        raise SystemExit("the command-line flow is built for binaries (nspec 2); use the library for triples")
+    if int(fp.nspec) not in (2, 3):
+        raise SystemExit("nspec must be 2 (binary) or 3 (triple)")
     spectrum = o.get('--spectrum', fp.filename)
     if not os.path.isabs(spectrum) and not os.path.exists(spectrum):
         spectrum = os.path.join(root, spectrum)
@@ -86,7 +86,7 @@ def main(argv=None):
     samples = fit.run_fit(lnprob, fp, fp.dirname, optimize=do_opt, emcee=do_mc, seed=seed, nthin=100)
     if do_opt:
         print('optimization complete')                                                            # mft6.py:3664
-    if samples is not None and '--predictive' in o:
+    if samples is not None and '--predictive' in o and int(fp.nspec) == 2:      # the sweep is defined for binaries
         from . import predictive
         sweep = predictive.ComponentSweep(prob, predictive.kepler_curve(fp.res, bps_dir),
                                           predictive.gaia_g_band(fp.res, bps_dir, vega), device=device, share_grid_with=lnprob)
