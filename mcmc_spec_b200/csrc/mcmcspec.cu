@@ -214,18 +214,20 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* scratch /* [NW
 }
 
 // np.interp / interp1d(kind='linear', bounds_error=True) on an ascending table.
-__device__ bool interp_table(const double* __restrict__ x, const double* __restrict__ y, int n, double v,
-                             double* out) {
+// Two ordinates over the same abscissae (isochrone log g and luminosity at one Teff): one bisection.
+__device__ bool interp_table2(const double* __restrict__ x, const double* __restrict__ y1, const double* __restrict__ y2, int n,
+                              double v, double* out1, double* out2) {
   if (!(v >= x[0] && v <= x[n - 1])) return false;
-  if (v == x[n - 1]) { *out = y[n - 1]; return true; }
+  if (v == x[n - 1]) { *out1 = y1[n - 1]; *out2 = y2[n - 1]; return true; }
   int lo = 0, hi = n - 1;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (x[mid] <= v) lo = mid; else hi = mid;
   }
-  if (x[lo] == v) { *out = y[lo]; return true; }
-  const double slope = (y[lo + 1] - y[lo]) / (x[lo + 1] - x[lo]);
-  *out = slope * (v - x[lo]) + y[lo];
+  if (x[lo] == v) { *out1 = y1[lo]; *out2 = y2[lo]; return true; }
+  const double dx = x[lo + 1] - x[lo], dv = v - x[lo];
+  *out1 = ((y1[lo + 1] - y1[lo]) / dx) * dv + y1[lo];
+  *out2 = ((y2[lo + 1] - y2[lo]) / dx) * dv + y2[lo];
   return true;
 }
 
@@ -369,8 +371,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   double lum[MAX_STAR];
   for (int s = 0; s < ns; ++s) {
     double g, l;
-    if (!interp_table(s_iso_teff, s_iso_logg, T.n_iso, temps[s], &g) ||
-        !interp_table(s_iso_teff, s_iso_lum, T.n_iso, temps[s], &l)) {
+    if (!interp_table2(s_iso_teff, s_iso_logg, s_iso_lum, T.n_iso, temps[s], &g, &l)) {
       plan.status = MS_W_OFF_ISOCHRONE; store(plan); return;
     }
     plan.logg[s] = g; lum[s] = l;
