@@ -131,6 +131,15 @@ struct OptIn {
   const double* ref_median;     // [nw] median the model is scaled to, or NULL (= median of the walker's set)
 };
 
+// Stretch-move proposal folded into the prep kernel (ms_stretch_iteration): thread w draws z and its partner,
+// writes the proposal q[w] = theta[w] and the log of the Jacobian factor, then goes on preparing that walker.
+struct ProposeIn {
+  const double* state;          // [nw_total][ncol + 1], or NULL: theta is given
+  const long long* s_idx; const long long* c_idx; long long n_c;
+  double a; unsigned long long seed, iteration; int split; long long gid0;
+  double* q; double* logfac;
+};
+
 struct PartsOut {
   double* chi2_spec; double* contrast; double* phot; double* lnprior; double* logg; int* status;
   double* model;                        // [nw][n_data] median-scaled model
@@ -281,12 +290,16 @@ __device__ void dust_prior_moments(const double* __restrict__ dust_dm, const dou
   *sig = sqrt(var / ns);
 }
 
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x);
+__host__ __device__ __forceinline__ double counter_uniform(unsigned long long seed, unsigned long long iteration,
+                                                           int split, int purpose, unsigned long long gid);
+
 // ------------------------------------------------------------------------------------------
 // walker_prep_kernel
 // ------------------------------------------------------------------------------------------
 __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__ theta, long long nw,
                                    WalkerPlan* __restrict__ plans_out, unsigned* __restrict__ cell_hist,
-                                   const int mode, const OptIn opt) {
+                                   const int mode, const OptIn opt, const ProposeIn prop) {
   // The isochrone, node and dust tables (a few KB) are staged in shared memory once per CTA: the searches below
   // are chains of dependent loads (two bisections of the isochrone per star, the dust slice, three node scans),
   // ~60 L2 round trips per walker when read from global memory -- which made this kernel 28 us, more than a
@@ -319,9 +332,29 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   const int ndim = T.ndim, ns = T.nspec;
   double p[MS_MAX_NDIM];
   bool finite = true;
-  for (int k = 0; k < ndim; ++k) { p[k] = theta[w * T.ncol + k]; finite = finite && isfinite(p[k]); }
-  // 3-D grids: the metallicity is fixed for the fit, or (an extension, for grids beyond L2) a walker parameter
-  const double fehv = T.feh_free ? theta[w * T.ncol + ndim] : T.feh;
+  double fehv = T.feh;
+  if (prop.state) {
+    // emcee StretchMove (a = 2), same arithmetic and random streams as stretch_propose_kernel
+    const unsigned long long gid = (unsigned long long)(prop.gid0 + w);
+    const double u = counter_uniform(prop.seed, prop.iteration, prop.split, 0, gid);
+    const double root = (prop.a - 1.0) * u + 1.0;
+    const double z = root * root / prop.a;
+    long long j = (long long)(counter_uniform(prop.seed, prop.iteration, prop.split, 1, gid) * (double)prop.n_c);
+    if (j >= prop.n_c) j = prop.n_c - 1;
+    const double* x = prop.state + prop.s_idx[w] * (T.ncol + 1);
+    const double* c = prop.state + prop.c_idx[j] * (T.ncol + 1);
+    for (int k = 0; k < T.ncol; ++k) {
+      const double qk = c[k] - (c[k] - x[k]) * z;
+      prop.q[w * T.ncol + k] = qk;
+      if (k < ndim) p[k] = qk; else fehv = qk;
+    }
+    prop.logfac[w] = (double)(T.ncol - 1) * log(z);
+    for (int k = 0; k < ndim; ++k) finite = finite && isfinite(p[k]);
+  } else {
+    for (int k = 0; k < ndim; ++k) { p[k] = theta[w * T.ncol + k]; finite = finite && isfinite(p[k]); }
+    // 3-D grids: the metallicity is fixed for the fit, or (an extension, for grids beyond L2) a walker parameter
+    if (T.feh_free) fehv = theta[w * T.ncol + ndim];
+  }
   finite = finite && isfinite(fehv);
 
   WalkerPlan plan;
@@ -1488,6 +1521,25 @@ __global__ void stretch_accept_kernel(const double* __restrict__ state, const lo
   out[ndim + 1] = acc ? 1.0 : 0.0;
 }
 
+// Single-rank form of accept + scatter: the active half S and its complement C are disjoint, every thread touches
+// only its own row of the state, so the accepted proposal is written in place (no packed buffer, no collective).
+__global__ void stretch_accept_inplace_kernel(double* __restrict__ state, int* __restrict__ naccepted,
+                                              const long long* __restrict__ s_idx, const double* __restrict__ q,
+                                              const double* __restrict__ lnp_q, const double* __restrict__ logfac,
+                                              long long n_s, int ndim, unsigned long long seed, unsigned long long iteration,
+                                              int split, long long gid0) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= n_s) return;
+  double* x = state + s_idx[s] * (ndim + 1);
+  const double u = counter_uniform(seed, iteration, split, 2, (unsigned long long)(gid0 + s));
+  const double lnpdiff = logfac[s] + lnp_q[s] - x[ndim];
+  if (log(u) < lnpdiff) {                                            // -inf proposals never pass; NaN never passes
+    for (int k = 0; k < ndim; ++k) x[k] = q[s * ndim + k];
+    x[ndim] = lnp_q[s];
+    if (naccepted) naccepted[s_idx[s]] += 1;
+  }
+}
+
 // state[idx[k]] = packed[k][0..ndim], naccepted[idx[k]] += packed[k][ndim+1]  (idx: the whole active half)
 __global__ void stretch_scatter_kernel(double* __restrict__ state, int* __restrict__ naccepted,
                                        const long long* __restrict__ idx, const double* __restrict__ packed,
@@ -1727,7 +1779,8 @@ int ensure_plans(ms_handle* h, long long nw) {
 }
 
 int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d_lnp, const PartsOut& parts,
-                    int mode = -1, const OptIn& opt = OptIn{nullptr, nullptr, nullptr, nullptr, nullptr}) {
+                    int mode = -1, const OptIn& opt = OptIn{nullptr, nullptr, nullptr, nullptr, nullptr},
+                    const ProposeIn& prop = ProposeIn{nullptr, nullptr, nullptr, 0, 0.0, 0ull, 0ull, 0, 0, nullptr, nullptr}) {
   if (mode < 0) mode = h->nospec ? MODE_NOSPEC : MODE_POSTERIOR;
   if (nw == 0) return MS_OK;
   int rc = ensure_plans(h, nw);
@@ -1752,7 +1805,7 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   const size_t prep_smem = (size_t)(3 * h->T.n_iso + h->T.n_teff + h->T.n_logg + h->T.n_feh + h->T.n_dm +
                                     h->T.n_dm * h->T.n_dust_samples) * sizeof(double);
   if (prep_smem > 48 * 1024) CK(cudaFuncSetAttribute(walker_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-  walker_prep_kernel<<<pg, pb, prep_smem, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr, mode, opt);
+  walker_prep_kernel<<<pg, pb, prep_smem, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr, mode, opt, prop);
   CK(cudaGetLastError());
   h->launches += 1;
   if (h->use_order) {
@@ -2432,17 +2485,14 @@ int ms_stretch_iteration(ms_handle* h, double* state, int32_t* naccepted, int64_
   for (int split = 0; split < 2; ++split) {
     const long long* s_idx = h->it_half[split];
     const long long* c_idx = h->it_half[1 - split];
-    stretch_propose_kernel<<<g, 128, 0, h->stream>>>(state, s_idx, half, c_idx, half, ndim, a, seed, iteration, split, 0ll,
-                                                     h->it_q, h->it_logfac);
+    // propose + prepare in one kernel, evaluate, accept in place: three launches per half step
+    const ProposeIn prop{state, s_idx, c_idx, half, a, seed, iteration, split, 0ll, h->it_q, h->it_logfac};
+    const int rc = evaluate_device(h, h->it_q, half, h->it_lnp, none, -1, OptIn{nullptr, nullptr, nullptr, nullptr, nullptr}, prop);
+    if (rc) return rc;
+    stretch_accept_inplace_kernel<<<g, 128, 0, h->stream>>>(state, naccepted, s_idx, h->it_q, h->it_lnp, h->it_logfac, half, ndim,
+                                                            seed, iteration, split, 0ll);
     CK(cudaGetLastError());
     h->launches += 1;
-    const int rc = evaluate_device(h, h->it_q, half, h->it_lnp, none);
-    if (rc) return rc;
-    stretch_accept_kernel<<<g, 128, 0, h->stream>>>(state, s_idx, h->it_q, h->it_lnp, h->it_logfac, half, ndim, seed,
-                                                    iteration, split, 0ll, h->it_packed);
-    stretch_scatter_kernel<<<g, 128, 0, h->stream>>>(state, naccepted, s_idx, h->it_packed, half, ndim);
-    CK(cudaGetLastError());
-    h->launches += 2;
   }
   return MS_OK;
 }

@@ -114,7 +114,8 @@ def test_independent_chains_agree_within_monte_carlo_error(small_problem, small_
 @pytest.mark.parametrize('nw,randomize', [(50, True), (32, False), (2048, True), (6, True)])
 def test_fused_iteration_is_the_same_chain(small_problem, small_lp, nw, randomize):
     """ms_stretch_iteration (one call per iteration: in-kernel split sort + both half steps) walks exactly the
-    chain of the per-kernel path (torch argsort + five launches per half step)."""
+    chain of the per-kernel path (torch argsort + five launches per half step): three launches per half step --
+    proposal folded into the prep kernel, streaming kernel, in-place accept."""
     from mcmc_spec_b200.ensemble import CudaBackend, EnsembleSampler
     t = small_problem.truth
     p0 = t * (1 + 0.01 * np.random.default_rng(nw).standard_normal((nw, 6)))
@@ -130,4 +131,4 @@ def test_fused_iteration_is_the_same_chain(small_problem, small_lp, nw, randomiz
     assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
     assert np.array_equal(a.naccepted.cpu().numpy(), b.naccepted.cpu().numpy())
     assert a.naccepted.sum().item() > 0 and a.iteration == b.iteration == 12
-    assert n1 - n0 == 12 * (1 + 2 * 5)                    # split + 2 x (propose, prep, stream, accept, scatter)
+    assert n1 - n0 == 12 * (1 + 2 * 3)                    # split + 2 x (propose+prep, stream, accept in place)
