@@ -19,25 +19,46 @@ def nvcc_path():
     raise RuntimeError('nvcc not found')
 
 
-def build(force=False, verbose=False, defines=(), out=None):
+def build(force=False, verbose=False, defines=(), out=None, split=True):
     """Compile csrc/mcmcspec.cu -> libmcmcspec.so for sm_100a; returns the library path.
-    ``defines`` / ``out``: tuning builds with extra -D macros into another file (scripts/tune_variants.py)."""
+
+    ``split``: the source is compiled three times in parallel (-DMS_TU=1/2/3: the streaming kernel's ~60
+    instantiations are spread over three translation units) and the objects are linked; ``split=False`` is the
+    single-unit build (-DMS_TU=0).  ``defines`` / ``out``: tuning builds with extra -D macros into another file
+    (scripts/tune_variants.py)."""
     lib = out or LIB
     deps = [SRC, os.path.join(ROOT, 'include', 'mcmcspec.h')]
     if (not force and os.path.exists(lib)
             and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps)):
         return lib
-    cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-           '-shared', '-Xcompiler', '-fPIC', '-cudart', 'static', '-I', os.path.join(ROOT, 'include'),
-           '-o', lib, SRC] + ['-D' + d for d in defines]
+    common = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include')] + ['-D' + d for d in defines]
     if verbose:
-        cmd.insert(1, '-Xptxas')
-        cmd.insert(2, '-v')
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed building libmcmcspec.so')
+        common[1:1] = ['-Xptxas', '-v']
+
+    def run(cmd):
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError('nvcc failed building libmcmcspec.so')
+
+    if not split:
+        run(common + ['-shared', '-cudart', 'static', '-DMS_TU=0', '-o', lib, SRC])
+        return lib
+    objdir = os.path.join(HERE, 'build', os.path.basename(lib) + '.obj')
+    os.makedirs(objdir, exist_ok=True)
+    objs = [os.path.join(objdir, f'tu{k}.o') for k in (1, 2, 3)]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(3) as ex:
+        list(ex.map(lambda ko: run(common + ['-c', f'-DMS_TU={ko[0]}', '-o', ko[1], SRC]), zip((1, 2, 3), objs)))
+    run([nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-cudart', 'static', '-Xcompiler', '-fPIC',
+         '-o', lib] + objs)
+    shutil.rmtree(objdir, ignore_errors=True)          # the objects are only needed for the link
+    try:
+        os.rmdir(os.path.dirname(objdir))
+    except OSError:
+        pass
     return lib
 
 

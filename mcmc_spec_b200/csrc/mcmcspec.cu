@@ -36,7 +36,18 @@
 
 namespace cg = cooperative_groups;
 
-namespace {
+// Translation units.  The streaming kernel has ~60 instantiations; `python -m mcmc_spec_b200.build` compiles this file
+// three times in parallel with -DMS_TU=1/2/3 and links the objects (1: the C ABI, all small kernels and the
+// (Teff, log g) grids with <= 2 + 6 bands; 2: (Teff, log g) grids with the wide band set; 3: grids with [Fe/H]).
+// MS_TU = 0 (default, e.g. a plain `nvcc -c mcmcspec.cu`) keeps everything in one unit.
+#ifndef MS_TU
+#define MS_TU 0
+#endif
+#define MS_HAS_MAIN (MS_TU == 0 || MS_TU == 1)
+#define MS_HAS_NR4_WIDE (MS_TU == 0 || MS_TU == 2)
+#define MS_HAS_NR8 (MS_TU == 0 || MS_TU == 3)
+
+namespace msd {   // types shared by the translation units (external linkage)
 
 constexpr int MAXWARP = 16;              // the streaming kernel runs with 256 or 512 threads per CTA
 constexpr int TILE = MS_TILE;           // model pixels per tile (4 per thread)
@@ -145,6 +156,16 @@ struct PartsOut {
   double* model;                        // [nw][n_data] median-scaled model
   double* comp_mag;                     // [nw][n_contrast][nspec] -2.5 log10 of each component's band flux (mft6.py:733)
 };
+
+}  // namespace msd
+using namespace msd;
+
+// launchers of the streaming-kernel families that live in other translation units (see MS_TU)
+struct ms_handle;
+int ms_tu_launch_nr4_wide(ms_handle* h, long long nw, double* d_lnp, const msd::PartsOut& parts, int mode, const msd::OptIn& opt);
+int ms_tu_launch_nr8(ms_handle* h, int wide, long long nw, double* d_lnp, const msd::PartsOut& parts, int mode, const msd::OptIn& opt);
+
+namespace {
 
 // ------------------------------------------------------------------------------------------
 // Small device helpers
@@ -1766,6 +1787,23 @@ size_t stream_smem_bytes(int n_data, int nc, int np, int nwarp, int nstar) {
   return (b + 15) & ~(size_t)15;
 }
 
+}  // namespace
+
+#if MS_HAS_NR4_WIDE
+int ms_tu_launch_nr4_wide(ms_handle* h, long long nw, double* d_lnp, const msd::PartsOut& parts, int mode, const msd::OptIn& opt) {
+  return launch_stream_variant<4, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts, mode, opt);
+}
+#endif
+#if MS_HAS_NR8
+int ms_tu_launch_nr8(ms_handle* h, int wide, long long nw, double* d_lnp, const msd::PartsOut& parts, int mode, const msd::OptIn& opt) {
+  if (wide) return launch_stream_variant<8, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts, mode, opt);
+  return launch_stream_variant<8, 2, 6>(h, nw, d_lnp, parts, mode, opt);
+}
+#endif
+
+#if MS_HAS_MAIN
+namespace {
+
 int ensure_plans(ms_handle* h, long long nw) {
   if (nw <= h->plans_cap) return MS_OK;
   if (h->plans) cudaFree(h->plans);
@@ -1816,10 +1854,9 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   }
   if (h->corners == 4) {
     if (h->variant == 0) return launch_stream_variant<4, 2, 6>(h, nw, d_lnp, parts, mode, opt);
-    return launch_stream_variant<4, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts, mode, opt);
+    return ms_tu_launch_nr4_wide(h, nw, d_lnp, parts, mode, opt);
   }
-  if (h->variant == 0) return launch_stream_variant<8, 2, 6>(h, nw, d_lnp, parts, mode, opt);
-  return launch_stream_variant<8, MS_MAX_CONTRAST, MS_MAX_PHOT>(h, nw, d_lnp, parts, mode, opt);
+  return ms_tu_launch_nr8(h, h->variant != 0, nw, d_lnp, parts, mode, opt);
 }
 
 int ensure_io(ms_handle* h, long long nw) {
@@ -2554,3 +2591,4 @@ int ms_stretch_scatter(ms_handle* h, double* state, int32_t* naccepted, const in
 }
 
 }  // extern "C"
+#endif  // MS_HAS_MAIN
