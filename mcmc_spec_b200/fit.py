@@ -85,21 +85,28 @@ def _auto_window(taus, c):
 
 
 def integrated_autocorr_time(chain, c=5):
-    """emcee ``integrated_time(x, c=5, quiet=True)`` for ``chain`` [nsteps, nwalkers, ndim] -> tau [ndim]."""
-    x = np.asarray(chain, dtype=np.float64)
+    """emcee ``integrated_time(x, c=5, quiet=True)`` for ``chain`` [nsteps, nwalkers, ndim] -> tau [ndim].
+
+    ``chain`` may be a numpy array or a torch tensor; the autocorrelation functions of all (walker, parameter)
+    series are computed by one batched real FFT with torch.fft on the tensor's device -- for the sampler's chain
+    that is the GPU, where it already lives (on the host this estimate, repeated every ``nthin`` steps on a
+    growing chain, was the most expensive part of ``run_emcee``)."""
+    x = chain if torch.is_tensor(chain) else torch.as_tensor(np.asarray(chain, dtype=np.float64))
+    x = x.to(torch.float64)
     if x.ndim == 2:
         x = x[:, :, None]
     n_t, n_w, n_d = x.shape
-    # function_1d for every (walker, parameter) series at once: one batched FFT along the step axis
     n = _next_pow_two(n_t)
-    f = np.fft.fft(x - np.mean(x, axis=0), n=2 * n, axis=0)
-    acf = np.fft.ifft(f * np.conjugate(f), axis=0)[:n_t].real
-    with np.errstate(invalid='ignore', divide='ignore'):
-        acf /= acf[0]
+    series = x.reshape(n_t, n_w * n_d).T.contiguous()                      # [n_w * n_d, n_t], time axis contiguous
+    series = series - series.mean(dim=1, keepdim=True)
+    f = torch.fft.rfft(series, n=2 * n, dim=1)
+    acf = torch.fft.irfft(f * torch.conj(f), n=2 * n, dim=1)[:, :n_t]       # function_1d of every series
+    acf = acf / acf[:, :1]
+    fm = acf.reshape(n_w, n_d, n_t).mean(dim=0)                            # mean over walkers, [n_d, n_t]
+    taus_all = (2.0 * torch.cumsum(fm, dim=1) - 1.0).cpu().numpy()
     tau = np.empty(n_d)
     for d in range(n_d):
-        fm = acf[:, :, d].sum(axis=1) / n_w
-        taus = 2.0 * np.cumsum(fm) - 1.0
+        taus = taus_all[d]
         tau[d] = taus[_auto_window(taus, c)]
     return tau
 
@@ -137,10 +144,9 @@ def run_emcee(dirname, fname, sampler, p0, nsteps, nburn, nthin=10, check_conver
         chain[n].copy_(sampler.coords)
         kept = n + 1
         if n % nthin == 0:
-            host = chain[:kept].cpu().numpy()
-            _dump(os.path.join(dirname, '{}_{}_results.txt'.format(fname, n)), host[-1])
+            _dump(os.path.join(dirname, '{}_{}_results.txt'.format(fname, n)), chain[n].cpu().numpy())
             with np.errstate(invalid='ignore', divide='ignore'):
-                acl = integrated_autocorr_time(host)
+                acl = integrated_autocorr_time(chain[:kept])               # sampler.get_autocorr_time(quiet=True)
             macl = np.mean(acl)
             with open(acf_path, 'a') as f:
                 f.write(str(macl) + '\n')
