@@ -51,7 +51,8 @@ def build(force=False, verbose=False, defines=(), out=None, split=True):
     objs = [os.path.join(objdir, f'tu{k}.o') for k in (1, 2, 3)]
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(3) as ex:
-        list(ex.map(lambda ko: run(common + ['-c', f'-DMS_TU={ko[0]}', '-o', ko[1], SRC]), zip((1, 2, 3), objs)))
+        list(ex.map(lambda ko: run(common + ['-c', '-Xfatbin', '-compress-all', f'-DMS_TU={ko[0]}', '-o', ko[1], SRC]),
+                    zip((1, 2, 3), objs)))
     run([nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-cudart', 'static', '-Xcompiler', '-fPIC',
          '-o', lib] + objs)
     shutil.rmtree(objdir, ignore_errors=True)          # the objects are only needed for the link
