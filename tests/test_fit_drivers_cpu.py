@@ -77,3 +77,23 @@ def test_assemble_problem_from_the_reference_param_file():
     assert list(prob.fr[2]) == fp.cfilt and len(prob.fr[3]) == 6
     t = build_tables(prob)
     assert t.n_reg == 93245 and t.n_data == 1945          # P_reg and N of config C2
+
+
+def test_command_line_argument_checks(tmp_path):
+    """python -m mcmc_spec_b200: usage text without -f, explicit paths for what the reference hard-codes, and the
+    MIST loader's exponentiation of the Teff / luminosity columns (mft6.py:3487-3490)."""
+    from mcmc_spec_b200.__main__ import load_mist, main
+    from mcmc_spec_b200 import synthetic
+    with pytest.raises(SystemExit) as e:
+        main(['mcmc_spec_b200'])
+    assert 'python -m mcmc_spec_b200 -f paramfile' in str(e.value)
+    par = tmp_path / 'p.txt'
+    par.write_text('models btsettl\n')
+    with pytest.raises(SystemExit) as e:
+        main(['mcmc_spec_b200', '-f', str(par), '-o', 'True'])
+    assert '--models-dir is required' in str(e.value)
+    m = synthetic.make_isochrone_matrix()
+    logs = m.copy(); logs[:, 4], logs[:, 6] = np.log10(m[:, 4]), np.log10(m[:, 6])
+    np.savetxt(tmp_path / 'mist.cmd', logs)
+    back = load_mist(str(tmp_path / 'mist.cmd'))
+    assert np.allclose(back[:, 4], m[:, 4], rtol=1e-12) and np.allclose(back[:, 6], m[:, 6], rtol=1e-12)
