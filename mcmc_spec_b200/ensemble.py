@@ -110,6 +110,7 @@ class EnsembleSampler:
         self._fixed = [torch.arange(0, nwalkers, 2, device=self.device), torch.arange(1, nwalkers, 2, device=self.device)]
         self._side, self._next = None, None
         self.fused = True                       # allow the one-call iteration where the backend offers it
+        self._stored, self._iter0 = None, 0
 
     # ------------------------------------------------------------------ state
     def initialize(self, p0):
@@ -127,6 +128,7 @@ class EnsembleSampler:
             self.state = torch.empty((self.nwalkers, self.ndim + 1), dtype=torch.float64, device=self.device)
             dist.all_gather_into_tensor(self.state, packed, group=self.group)
         self.iteration = 0
+        self._iter0 = 0
         self.naccepted.zero_()
 
     @property
@@ -139,7 +141,7 @@ class EnsembleSampler:
 
     @property
     def acceptance_fraction(self):
-        return (self.naccepted.to(torch.float64) / max(self.iteration, 1)).cpu().numpy()
+        return (self.naccepted.to(torch.float64) / max(self.iteration - self._iter0, 1)).cpu().numpy()
 
     # ------------------------------------------------------------------ one iteration
     def _compute_halves(self, iteration):
@@ -201,6 +203,56 @@ class EnsembleSampler:
             if thin and n % thin == 0:
                 self.chain.append(self.state.detach().cpu().numpy().copy())
         return self.state
+
+    # ------------------------------------------------------------------ the emcee calls the reference makes
+    # (mft6.py:1491-1527: sampler.sample(pos, iterations=n) yielding a state with .coords, get_last_sample(),
+    #  reset(), get_autocorr_time(quiet=True), acceptance_fraction, chain)
+    def sample(self, initial_state=None, iterations=1, store=True):
+        """Generator over iterations, like ``emcee.EnsembleSampler.sample``: yields the sampler itself after every
+        step (``.coords`` and ``.log_prob`` are the current ensemble).  ``initial_state``: positions [nw, ndim], or
+        the object returned by ``get_last_sample()``.  With ``store`` the positions of every step are kept (on the
+        device) for ``chain`` / ``get_autocorr_time``."""
+        if initial_state is not None and initial_state is not self:
+            pos = initial_state.coords if hasattr(initial_state, 'coords') else initial_state
+            if torch.is_tensor(pos):
+                pos = pos.detach().clone()
+            it = self.iteration
+            self.initialize(pos)
+            self.iteration = self._iter0 = it        # the random streams go on, they never repeat an iteration index
+        if store and self._stored is None:
+            self._stored = []
+        for _ in range(int(iterations)):
+            self.step()
+            if store:
+                self._stored.append(self.coords.detach().clone())
+            yield self
+
+    def get_last_sample(self):
+        return self
+
+    def reset(self):
+        """Forget the stored chain and the acceptance counts; positions stay (emcee ``reset``)."""
+        self._stored = None
+        self.naccepted.zero_()
+        self._iter0 = self.iteration
+
+    def get_chain(self, flat=False):
+        """Stored positions [nsteps, nwalkers, ndim] (``flat``: [nsteps * nwalkers, ndim]) as a numpy array."""
+        if not self._stored:
+            return np.empty((0, self.nwalkers, self.ndim))
+        x = torch.stack(self._stored).cpu().numpy()
+        return x.reshape(-1, self.ndim) if flat else x
+
+    @property
+    def stored_chain(self):
+        """emcee's legacy ``sampler.chain``: [nwalkers, nsteps, ndim] (what mft6.py:1527 flattens into samples.txt)."""
+        return np.swapaxes(self.get_chain(), 0, 1)
+
+    def get_autocorr_time(self, quiet=True, c=5):
+        from .fit import integrated_autocorr_time
+        if not self._stored:
+            return np.full(self.ndim, np.nan)
+        return integrated_autocorr_time(torch.stack(self._stored), c=c)
 
     # ------------------------------------------------------------------ emcee-style file dumps
     def save_coords(self, path):

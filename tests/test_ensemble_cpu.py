@@ -98,3 +98,36 @@ def test_two_rank_gloo_chain_is_bit_identical_to_single_process(tmp_path):
     got = np.load(out)
     assert np.array_equal(got[:, :NDIM + 1], single.state.numpy())        # independent of the number of ranks
     assert np.array_equal(got[:, NDIM + 1], single.naccepted.numpy())
+
+
+def test_emcee_style_calls_of_the_reference(tmp_path):
+    """The commented sampling block of the reference (mft6.py:1491-1527) written against this sampler: sample()
+    generator with .coords, get_last_sample(), reset(), get_autocorr_time(quiet=True), acceptance_fraction and the
+    [nwalkers, nsteps, ndim] chain."""
+    nw = 24
+    sampler = EnsembleSampler(nw, NDIM, sr.NumpyBackend(gauss_lnprob, NDIM), seed=4)
+    n_dumps = 0
+    for n, s in enumerate(sampler.sample(_p0(nw), iterations=30)):
+        if n % 10 == 0:
+            with open(tmp_path / 'x_{}_burnin.txt'.format(n), 'ab') as f:
+                f.write(b"\\n"); np.savetxt(f, s.coords)
+            n_dumps += 1
+    assert n_dumps == 3
+    state = sampler.get_last_sample()
+    before = state.coords.clone()
+    sampler.reset()
+    assert sampler.get_chain().shape == (0, nw, NDIM) and np.all(sampler.acceptance_fraction == 0)
+    assert torch.equal(sampler.coords, before)
+    for n, s in enumerate(sampler.sample(state, iterations=200)):
+        pass
+    acl = sampler.get_autocorr_time(quiet=True)
+    assert acl.shape == (NDIM,) and np.all(np.isfinite(acl)) and np.all(acl > 0.5)
+    assert 0.2 < np.mean(sampler.acceptance_fraction) < 0.9
+    chain = sampler.stored_chain
+    assert chain.shape == (nw, 200, NDIM)
+    samples = chain[:, :, :].reshape((-1, NDIM))                      # mft6.py:1527
+    assert np.array_equal(samples[-1], sampler.coords.numpy()[-1])
+    # same chain as run_mcmc with the same seed and start
+    ref = EnsembleSampler(nw, NDIM, sr.NumpyBackend(gauss_lnprob, NDIM), seed=4)
+    ref.initialize(_p0(nw)); ref.run_mcmc(30)
+    assert np.array_equal(ref.coords.numpy(), before.numpy())
