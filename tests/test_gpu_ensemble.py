@@ -132,3 +132,23 @@ def test_fused_iteration_is_the_same_chain(small_problem, small_lp, nw, randomiz
     assert np.array_equal(a.naccepted.cpu().numpy(), b.naccepted.cpu().numpy())
     assert a.naccepted.sum().item() > 0 and a.iteration == b.iteration == 12
     assert n1 - n0 == 12 * (1 + 2 * 3)                    # split + 2 x (propose+prep, stream, accept in place)
+
+
+def test_emcee_style_calls_on_the_device_sampler(small_problem, small_lp):
+    """sample() / get_last_sample() / reset() / get_autocorr_time() / stored_chain on the CUDA backend."""
+    from mcmc_spec_b200.ensemble import CudaBackend, EnsembleSampler
+    t = small_problem.truth
+    p0 = t * (1 + 0.01 * np.random.default_rng(3).standard_normal((50, 6)))
+    p0[:, 2] = np.abs(p0[:, 2])
+    sampler = EnsembleSampler(50, 6, CudaBackend(small_lp.engine), seed=12)
+    for n, s in enumerate(sampler.sample(p0, iterations=40)):
+        assert s.coords.shape == (50, 6)
+    state = sampler.get_last_sample()
+    sampler.reset()
+    for n, s in enumerate(sampler.sample(state, iterations=300)):
+        pass
+    acl = sampler.get_autocorr_time(quiet=True)
+    chain = sampler.stored_chain
+    assert chain.shape == (50, 300, 6) and acl.shape == (6,) and np.all(np.isfinite(acl))
+    assert 0.1 < sampler.acceptance_fraction.mean() < 0.9 and sampler.iteration == 340
+    assert np.allclose(small_lp(chain[:, -1]), sampler.log_prob.cpu().numpy(), rtol=0, atol=0)
