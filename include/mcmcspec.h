@@ -311,6 +311,24 @@ int ms_set_fast(ms_handle* h, int enabled);
  */
 int ms_set_cell_order(ms_handle* h, int mode);
 
+/*
+ * Group evaluation of large posterior batches (binaries on a (Teff, log g) grid).  Walkers are sorted by grid
+ * cell on the device and handed out in groups of up to 8 cell-mates; one persistent CTA streams the group's
+ * 2 * 2^D bracketing rows ONCE through a 4-stage shared-memory ring filled by bulk tensor copies (TMA, mbarrier
+ * completion), integrates the staged rows through the passbands, gathers the bracketing model pixels of the
+ * observed pixels, and one warp per walker does that walker's extinction, rebinning, quadratic renormalisation,
+ * exact median and chi-square.  The reference's per-walker contract is unchanged (get_spec / make_composite /
+ * loglikelihood of mft6.py are linear in the grid rows up to the extinction, which stays per walker and per
+ * model pixel); values agree with the one-CTA-per-walker kernel to rounding (summation order of the band
+ * integrals), and a walker's value does not depend on which other walkers share its group.
+ * mode: -1 (default) automatic -- batches of at least `min_walkers` (default 1024; <= 0 keeps the current
+ * threshold) on handles whose tables fit the ring; 0 never; 1 whenever the tables fit.
+ * ms_group_supported: 1 when this handle's tables fit (at most 4 passbands overlapping on a 128-pixel stage, at
+ * most 64 observed pixels per stage, nspec = 2, no [Fe/H] axis).
+ */
+int ms_set_group(ms_handle* h, int mode, int64_t min_walkers);
+int ms_group_supported(const ms_handle* h);
+
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 int64_t ms_launch_count(const ms_handle* h);
 

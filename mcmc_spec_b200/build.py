@@ -22,12 +22,12 @@ def nvcc_path():
 def build(force=False, verbose=False, defines=(), out=None, split=True):
     """Compile csrc/mcmcspec.cu -> libmcmcspec.so for sm_100a; returns the library path.
 
-    ``split``: the source is compiled three times in parallel (-DMS_TU=1/2/3: the streaming kernel's ~60
-    instantiations are spread over three translation units) and the objects are linked; ``split=False`` is the
+    ``split``: the source is compiled four times in parallel (-DMS_TU=1/2/3/4: the streaming kernel's ~60
+    instantiations are spread over three translation units, the group kernel is the fourth) and the objects are linked; ``split=False`` is the
     single-unit build (-DMS_TU=0).  ``defines`` / ``out``: tuning builds with extra -D macros into another file
     (scripts/tune_variants.py)."""
     lib = out or LIB
-    deps = [SRC, os.path.join(ROOT, 'include', 'mcmcspec.h')]
+    deps = [SRC, os.path.join(HERE, 'csrc', 'group_kernel.cuh'), os.path.join(ROOT, 'include', 'mcmcspec.h')]
     if (not force and os.path.exists(lib)
             and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps)):
         return lib
@@ -48,11 +48,11 @@ def build(force=False, verbose=False, defines=(), out=None, split=True):
         return lib
     objdir = os.path.join(HERE, 'build', os.path.basename(lib) + '.obj')
     os.makedirs(objdir, exist_ok=True)
-    objs = [os.path.join(objdir, f'tu{k}.o') for k in (1, 2, 3)]
+    objs = [os.path.join(objdir, f'tu{k}.o') for k in (1, 2, 3, 4)]
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(3) as ex:
+    with ThreadPoolExecutor(4) as ex:
         list(ex.map(lambda ko: run(common + ['-c', '-Xfatbin', '-compress-all', f'-DMS_TU={ko[0]}', '-o', ko[1], SRC]),
-                    zip((1, 2, 3), objs)))
+                    zip((1, 2, 3, 4), objs)))
     run([nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-cudart', 'static', '-Xcompiler', '-fPIC',
          '-o', lib] + objs)
     shutil.rmtree(objdir, ignore_errors=True)          # the objects are only needed for the link

@@ -46,6 +46,16 @@ namespace cg = cooperative_groups;
 #define MS_HAS_MAIN (MS_TU == 0 || MS_TU == 1)
 #define MS_HAS_NR4_WIDE (MS_TU == 0 || MS_TU == 2)
 #define MS_HAS_NR8 (MS_TU == 0 || MS_TU == 3)
+#define MS_HAS_GROUP (MS_TU == 0 || MS_TU == 4)      // lnprob_group_kernel (group_kernel.cuh)
+#ifndef MS_GROUP_WALKERS
+#define MS_GROUP_WALKERS 8                           // walkers (walker warps) per CTA of the group kernel
+#endif
+#ifndef MS_GROUP_WSLOTS
+#define MS_GROUP_WSLOTS 4                            // passbands that may overlap on one 128-pixel stage
+#endif
+#ifndef MS_GROUP_RCAP
+#define MS_GROUP_RCAP 64                             // observed pixels per 128-pixel stage the ring is sized for
+#endif
 
 namespace msd {   // types shared by the translation units (external linkage)
 
@@ -164,6 +174,7 @@ using namespace msd;
 struct ms_handle;
 int ms_tu_launch_nr4_wide(ms_handle* h, long long nw, double* d_lnp, const msd::PartsOut& parts, int mode, const msd::OptIn& opt);
 int ms_tu_launch_nr8(ms_handle* h, int wide, long long nw, double* d_lnp, const msd::PartsOut& parts, int mode, const msd::OptIn& opt);
+int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::PartsOut& parts);
 
 namespace {
 
@@ -391,6 +402,10 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   const double av = p[ns];
   const double* rad = p + ns + 1;          // rad[0] = R1, rad[1] = R2/R1
   const double plx = p[2 * ns + 1];
+  // What logprior calls `rad`.  The 6-parameter dist_fit branch with ext == False slices p0[nspec:2*nspec]
+  // (mft6.py:1219-1221), i.e. the Av slot and R1, for its bounds and its radius prior; every other branch reads the
+  // radii where the likelihood does (mft6.py:1216, :1278-1279, :1340-1342, :1400-1402).
+  const double* prad = (ns == 2 && T.dist_fit && !T.ext_flag && mode != MODE_OPTIMIZER) ? p + ns : rad;
 
   // ---- logprior bounds (mft6.py:1227-1230 / :1287-1290).  fit_spec keeps its proposals inside its own
   // box on the host (mft6.py:984-985, :1069-1103), so the optimiser mode has none here.
@@ -400,8 +415,8 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
     if (ns == 2) {
       if (T.dist_fit) {
         const double plx_hi = (mode == MODE_NOSPEC) ? 1.0 / 100.0 : 1.0 / 4.0;     // mft6_nospec.py:1228
-        for (int s = 0; s < ns; ++s) out = out || (rad[s] < 0.05);
-        out = out || (rad[0] > 1.5) || (plx < 1.0 / 3000.0) || (plx > plx_hi);
+        for (int s = 0; s < ns; ++s) out = out || (prad[s] < 0.05);
+        out = out || (prad[0] > 1.5) || (plx < 1.0 / 3000.0) || (plx > plx_hi);
       } else {
         out = out || (rad[1] < 0.05) || (rad[0] < 0.05);
       }
@@ -470,18 +485,28 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
       const double r1m = stefan_boltzmann_radius(lum[0], temps[0]);
       for (int s = 0; s < ns; ++s) {
         const double m = (s == 0) ? r1m : stefan_boltzmann_radius(lum[s], temps[s]) / r1m;
-        const double z = (rad[s] - m) / (0.02 * m);
+        const double z = (prad[s] - m) / (0.02 * m);
         lp += -0.5 * (z * z);
       }
     }
   }
   if (!isfinite(lp)) { plan.status = MS_W_NONFINITE; store(plan); return; }   // mft6.py:1465
 
-  // ---- grid brackets and coefficients
+  // ---- grid brackets and coefficients.  The corners are stored in a canonical order -- lower node first on every
+  // axis -- so that all walkers of one grid cell carry the same row list (the group kernel streams those rows once
+  // for the whole group); find_nearest's "nearest node first" order (mft6.py:439-453) only decides which weight
+  // goes with which node.  A walker exactly on a node gets the node above as its (weight 0) partner.
+  auto canon = [](int i1, int i2, double w2, int n, int* lo, int* hi, double* wlo, double* whi) {
+    if (i1 == i2) { *lo = i1; *hi = min(i1 + 1, n - 1); *wlo = 1.0; *whi = 0.0; }
+    else if (i1 < i2) { *lo = i1; *hi = i2; *wlo = 1.0 - w2; *whi = w2; }
+    else { *lo = i2; *hi = i1; *wlo = w2; *whi = 1.0 - w2; }
+  };
   int z1 = 0, z2 = 0; double wz = 0.0;
   if (T.n_feh > 1 && !bracket_nodes(s_feh, T.n_feh, fehv, &z1, &z2, &wz)) {
     plan.status = MS_W_OFF_GRID; store(plan); return;
   }
+  int zlo = 0, zhi = 0; double czl = 1.0, czh = 0.0;
+  if (T.n_feh > 1) canon(z1, z2, wz, T.n_feh, &zlo, &zhi, &czl, &czh);
   const double di = 1.0 / plx;                            // mft6.py:690
   for (int s = 0; s < ns; ++s) {
     int t1, t2, g1, g2; double wt, wg;
@@ -491,9 +516,12 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
     }
     const double base = (s == 0) ? rad[0] * RSUN_CM / (di * PC_CM) : rad[0] * rad[s] * RSUN_CM / (di * PC_CM);
     const double scale = base * base;                     // mft6.py:691, :700
-    // corners: (t1,g1) (t1,g2) (t2,g1) (t2,g2) [x z1, z2]
-    const double ct[2] = {1.0 - wt, wt}, cg[2] = {1.0 - wg, wg}, cz[2] = {1.0 - wz, wz};
-    const int it[2] = {t1, t2}, ig[2] = {g1, g2}, iz[2] = {z1, z2};
+    int it[2], ig[2]; double ct[2], cg[2];
+    canon(t1, t2, wt, T.n_teff, &it[0], &it[1], &ct[0], &ct[1]);
+    canon(g1, g2, wg, T.n_logg, &ig[0], &ig[1], &cg[0], &cg[1]);
+    const double cz[2] = {czl, czh};
+    const int iz[2] = {zlo, zhi};
+    // corners: (t_lo,g_lo) (t_lo,g_hi) (t_hi,g_lo) (t_hi,g_hi) [x z_lo, z_hi]
     const int nz = (T.n_feh > 1) ? 2 : 1;
     int c = 0;
     for (int a = 0; a < nz; ++a)
@@ -513,7 +541,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
       const int tl = min(r_a % T.n_teff, r_b % T.n_teff), gl = min(r_a / T.n_teff, r_b / T.n_teff);
       key = key * per_star + gl * T.n_teff + tl;
     }
-    if (T.n_feh > 1) key = key * T.n_feh + min(z1, z2);
+    if (T.n_feh > 1) key = key * T.n_feh + zlo;
     plan.cell = (T.n_cells > 1) ? min(key, T.n_cells - 2) : 0;
   }
   plan.av = ((T.ext_flag || mode == MODE_OPTIMIZER) && av > 0.0) ? av : 0.0;   // mft6.py:1161, :1001
@@ -806,6 +834,8 @@ __device__ __forceinline__ double observed_pixel(const DevTables& T, const dbl4&
   kmin = min(kmin, k); kmax = max(kmax, k);
   return m;
 }
+
+#include "group_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------
 // lnprob_stream_kernel: one thread group of NT threads per walker, G groups per CTA.
@@ -1608,6 +1638,15 @@ struct ms_handle {
   long long* it_half[2] = {nullptr, nullptr}; double* it_q = nullptr; double* it_logfac = nullptr; double* it_lnp = nullptr;
   double* it_packed = nullptr; long long it_cap = 0;
   bool model_global = false; double* model_scratch = nullptr; size_t model_scratch_cap = 0;   // observed spectra beyond shared memory
+  // group kernel (group_kernel.cuh): tables, per-call group list, model-vector scratch slots
+  grp::GroupTables GT{};
+  bool group_ok = false;         // the tables fit the kernel's shared-memory ring (weight slots, records per stage)
+  int group_mode = -1;           // -1 automatic (large posterior batches), 0 never, 1 whenever possible
+  bool group_now = false;        // decided per call
+  long long group_min_walkers = 1024;
+  grp::GroupDesc* groups = nullptr; long long groups_cap = 0;
+  unsigned* cell_start = nullptr; unsigned* group_off = nullptr; int* n_groups = nullptr;
+  double* group_scratch = nullptr; int* group_counter = nullptr; int group_ctas = 0;
   unsigned char* scratch = nullptr; size_t scratch_cap = 0;   // per-call inputs of ms_optimizer_chisq (grown on demand)
   cudaStream_t own_stream = nullptr;
   // optional device-side timing of the streaming kernel
@@ -1801,6 +1840,31 @@ int ms_tu_launch_nr8(ms_handle* h, int wide, long long nw, double* d_lnp, const 
 }
 #endif
 
+#if MS_HAS_GROUP
+int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::PartsOut& parts) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing) {
+    if (h->ev_used + 2 > h->ev_pool.size()) {
+      for (int k = 0; k < 2; ++k) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
+    }
+    e0 = h->ev_pool[h->ev_used]; e1 = h->ev_pool[h->ev_used + 1];
+    h->ev_used += 2; h->timed_walkers += nw;
+    CK(cudaEventRecord(e0, h->stream));
+  }
+  auto kern = grp::lnprob_group_kernel<4>;
+  const int smem = grp::NSTAGE * grp::StageLayout<8>::bytes;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long max_groups = (nw + grp::GW - 1) / grp::GW + std::min<long long>(h->T.n_cells, nw);
+  const unsigned ctas = (unsigned)std::min<long long>(h->group_ctas, max_groups);
+  kern<<<ctas, grp::NTHREADS, smem, h->stream>>>(h->T, h->GT, h->plans, h->order, h->groups, h->n_groups, h->group_counter,
+                                                 d_lnp, parts, h->group_scratch);
+  CK(cudaGetLastError());
+  if (h->timing) CK(cudaEventRecord(e1, h->stream));
+  h->launches += 1;
+  return MS_OK;
+}
+#endif
+
 #if MS_HAS_MAIN
 namespace {
 
@@ -1821,6 +1885,12 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
                     const ProposeIn& prop = ProposeIn{nullptr, nullptr, nullptr, 0, 0.0, 0ull, 0ull, 0, 0, nullptr, nullptr}) {
   if (mode < 0) mode = h->nospec ? MODE_NOSPEC : MODE_POSTERIOR;
   if (nw == 0) return MS_OK;
+  if (mode != MODE_OPTIMIZER && h->T.nspec == 3 && h->T.dist_fit && !h->T.rad_prior) {
+    // mft6.py:1381-1393: the 8-parameter dist_fit branch only returns inside `if rad_prior == True`; without it
+    // logprior returns None and logposterior's np.isfinite(None) raises.  There is no value to reproduce.
+    set_err(h, "logprior is undefined for a triple with dist_fit and without rad_prior (mft6.py:1381-1393 returns None)");
+    return MS_ERR_UNSUPPORTED;
+  }
   int rc = ensure_plans(h, nw);
   if (rc) return rc;
   const int pb = 128;
@@ -1839,6 +1909,11 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
                 h->threads == MS_NT_SMALL && h->T.n_cells > 1 && nw >= 8ll * h->num_sms &&
                 2 * h->smem_bytes + 2048 <= (size_t)h->max_optin_smem;
   if (h->pair_now) h->use_order = true;
+  // Large posterior batches of binaries on a (Teff, log g) grid: groups of cell-mates share one stream of their
+  // rows (group_kernel.cuh).  Needs the cell-sorted order and the group table.
+  h->group_now = h->group_ok && h->group_mode != 0 && mode == MODE_POSTERIOR && !h->fast && h->cluster <= 1 &&
+                 h->corners == 4 && (h->group_mode > 0 || nw >= h->group_min_walkers);
+  if (h->group_now) { h->use_order = true; h->pair_now = false; }
   if (h->use_order) CK(cudaMemsetAsync(h->cell_hist, 0, (size_t)h->T.n_cells * sizeof(unsigned), h->stream));
   const size_t prep_smem = (size_t)(3 * h->T.n_iso + h->T.n_teff + h->T.n_logg + h->T.n_feh + h->T.n_dm +
                                     h->T.n_dm * h->T.n_dust_samples) * sizeof(double);
@@ -1846,6 +1921,23 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   walker_prep_kernel<<<pg, pb, prep_smem, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr, mode, opt, prop);
   CK(cudaGetLastError());
   h->launches += 1;
+  if (h->group_now) {
+    const long long max_groups = (nw + grp::GW - 1) / grp::GW + std::min<long long>(h->T.n_cells, nw);
+    if (max_groups > h->groups_cap) {
+      CK(cudaStreamSynchronize(h->stream));
+      if (h->groups) cudaFree(h->groups);
+      h->groups = nullptr; h->groups_cap = 0;
+      CK(cudaMalloc((void**)&h->groups, (size_t)(max_groups + max_groups / 4) * sizeof(grp::GroupDesc)));
+      h->groups_cap = max_groups + max_groups / 4;
+    }
+    grp::group_scan_kernel<<<1, 1024, 0, h->stream>>>(h->cell_hist, h->T.n_cells, h->cell_start, h->group_off, h->n_groups,
+                                                      h->group_counter);
+    cell_scatter_kernel<<<pg, pb, 0, h->stream>>>(h->plans, nw, h->cell_hist, h->order);
+    grp::group_table_kernel<<<pg, pb, 0, h->stream>>>(h->plans, h->order, nw, h->cell_start, h->group_off, h->groups);
+    CK(cudaGetLastError());
+    h->launches += 3;
+    return ms_tu_launch_group(h, nw, d_lnp, parts);
+  }
   if (h->use_order) {
     cell_scan_kernel<<<1, 1024, 0, h->stream>>>(h->cell_hist, h->T.n_cells);
     cell_scatter_kernel<<<pg, pb, 0, h->stream>>>(h->plans, nw, h->cell_hist, h->order);
@@ -1915,6 +2007,12 @@ int ms_destroy(ms_handle* h) {
   if (h->h_lnp) cudaFreeHost(h->h_lnp);
   if (h->scratch) cudaFree(h->scratch);
   if (h->model_scratch) cudaFree(h->model_scratch);
+  if (h->groups) cudaFree(h->groups);
+  if (h->cell_start) cudaFree(h->cell_start);
+  if (h->group_off) cudaFree(h->group_off);
+  if (h->n_groups) cudaFree(h->n_groups);
+  if (h->group_scratch) cudaFree(h->group_scratch);
+  if (h->group_counter) cudaFree(h->group_counter);
   if (h->it_half[0]) cudaFree(h->it_half[0]);
   if (h->it_half[1]) cudaFree(h->it_half[1]);
   if (h->it_q) cudaFree(h->it_q);
@@ -1998,13 +2096,15 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     T.grid = grid_owner->T.grid;
     h->grid_bytes = grid_owner->grid_bytes; h->l2_bytes = grid_owner->l2_bytes;
   } else {
+    // 256 bytes of zeros in front of row 0: the group kernel's bulk copies start two pixels before a stage
     void* p = nullptr;
-    CKH(cudaMalloc(&p, (size_t)n_rows * T.stride * 8));
+    CKH(cudaMalloc(&p, (size_t)n_rows * T.stride * 8 + 256));
     h->allocs.push_back(p);
-    CKH(cudaMemset(p, 0, (size_t)n_rows * T.stride * 8));
-    CKH(cudaMemcpy2D(p, (size_t)T.stride * 8, cfg->grid + cfg->reg_lo, (size_t)cfg->row_len * 8,
+    CKH(cudaMemset(p, 0, (size_t)n_rows * T.stride * 8 + 256));
+    double* g0 = static_cast<double*>(p) + 32;
+    CKH(cudaMemcpy2D(g0, (size_t)T.stride * 8, cfg->grid + cfg->reg_lo, (size_t)cfg->row_len * 8,
                      (size_t)cfg->n_reg * 8, (size_t)n_rows, cudaMemcpyHostToDevice));
-    T.grid = static_cast<const double*>(p);
+    T.grid = g0;
     h->grid_bytes = (size_t)n_rows * T.stride * 8;
     int l2 = 0;
     CKH(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
@@ -2107,6 +2207,102 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     T.bracket = d_br; T.bandsum = d_bs;
   }
 
+  // ---- group kernel tables (group_kernel.cuh): 128-pixel stages
+  {
+    using namespace grp;
+    const int n = cfg->n_data;
+    const int n_stages = (cfg->n_reg + TP - 1) / TP;
+    const double LN2 = 0.69314718055994530942;
+    bool ok = (cfg->nspec == 2) && (T.n_cells > 1);
+    // observed pixels per stage (rebin_hi ascending): [sd[s], sd[s+1])
+    std::vector<int> sd((size_t)n_stages + 1);
+    {
+      int i = 0;
+      for (int s = 0; s <= n_stages; ++s) {
+        while (i < n && cfg->rebin_hi[i] < s * TP) ++i;
+        sd[s] = i;
+      }
+      for (int s = 0; s < n_stages; ++s) ok = ok && (sd[s + 1] - sd[s] <= RCAP);
+    }
+    // tight stage range of every band (first / last non-zero weight), then one weight slot per band such that
+    // bands overlapping on a stage sit in different slots (interval colouring in order of first stage)
+    struct Band { int col, s_lo, s_hi, slot; };
+    std::vector<Band> bands;
+    auto add_band = [&](int col, const double* w, int lo_t, int hi_t) {
+      long long first = -1, last = -1;
+      const long long len = (long long)(hi_t - lo_t) * TILE;
+      for (long long k = 0; k < len; ++k) if (w[k] != 0.0) { if (first < 0) first = k; last = k; }
+      if (first < 0) return;
+      const long long p_lo = (long long)lo_t * TILE + first, p_hi = (long long)lo_t * TILE + last + 1;
+      Band b; b.col = col; b.s_lo = (int)(p_lo / TP); b.s_hi = std::min((int)((p_hi + TP - 1) / TP), n_stages); b.slot = -1;
+      if (b.s_hi > b.s_lo) bands.push_back(b);
+    };
+    for (int f = 0; f < cfg->n_contrast; ++f) add_band(f, cfg->c_weights + cfg->c_offset[f], cfg->c_tile_lo[f], cfg->c_tile_hi[f]);
+    for (int f = 0; f < cfg->n_phot; ++f) add_band(MS_MAX_CONTRAST + f, cfg->p_weights + cfg->p_offset[f], cfg->p_tile_lo[f], cfg->p_tile_hi[f]);
+    std::sort(bands.begin(), bands.end(), [](const Band& a, const Band& b) { return a.s_lo < b.s_lo || (a.s_lo == b.s_lo && a.col < b.col); });
+    {
+      int free_at[WS];
+      for (int q = 0; q < WS; ++q) free_at[q] = 0;
+      for (auto& b : bands) {
+        for (int q = 0; q < WS && b.slot < 0; ++q) if (free_at[q] <= b.s_lo) { b.slot = q; free_at[q] = b.s_hi; }
+        if (b.slot < 0) ok = false;
+      }
+    }
+    std::vector<int4> meta((size_t)n_stages);
+    for (int s = 0; s < n_stages; ++s) meta[s] = make_int4(sd[s], sd[s + 1], -1, 0);
+    if (ok) {
+      for (const auto& b : bands) {
+        for (int s = b.s_lo; s < b.s_hi; ++s) {
+          unsigned z = (unsigned)meta[s].z;
+          z = (z & ~(0xffu << (8 * b.slot))) | ((unsigned)b.col << (8 * b.slot));
+          meta[s].z = (int)z;
+        }
+        meta[b.s_hi - 1].w |= 1 << b.slot;
+      }
+    }
+    // records: x = (ext - anchor of the stage) ln 2; d q_k(x) of norm_spec's orthonormal quadratic basis
+    std::vector<double> anchor((size_t)n_stages + 32, 0.0);
+    std::vector<double2> ra((size_t)n + 4), rb((size_t)n + 4), rc((size_t)n + 4);
+    std::vector<int> hl((size_t)n + 8, 0);
+    std::vector<double> dr2(4 * (size_t)n);
+    double xmax = 0.0;
+    for (int s = 0; s < n_stages; ++s) {
+      if (sd[s + 1] > sd[s]) anchor[s] = 0.5 * (cfg->ext_lo[sd[s]] + cfg->ext_hi[sd[s + 1] - 1]);
+      for (int i = sd[s]; i < sd[s + 1]; ++i) {
+        const double xlo = (cfg->ext_lo[i] - anchor[s]) * LN2, xhi = (cfg->ext_hi[i] - anchor[s]) * LN2;
+        xmax = std::max(xmax, std::max(std::fabs(xlo), std::fabs(xhi)));
+        const double x = cfg->data_x[i], d = cfg->data_flux[i];
+        const double q0 = T.basis[0], q1 = std::fma(T.basis[4], x, T.basis[3]);
+        const double q2 = std::fma(std::fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
+        ra[i] = make_double2(cfg->rebin_t[i], xlo);
+        rb[i] = make_double2(xhi, d * q0);
+        rc[i] = make_double2(d * q1, d * q2);
+        hl[i] = cfg->rebin_hi[i] - s * TP;
+        dr2[4 * (size_t)i] = q1; dr2[4 * (size_t)i + 1] = q2; dr2[4 * (size_t)i + 2] = d;
+        dr2[4 * (size_t)i + 3] = 1.0 / (cfg->data_err[i] * cfg->data_err[i]);
+      }
+    }
+    for (int k = 0; k < 4; ++k) { ra[(size_t)n + k] = rb[(size_t)n + k] = rc[(size_t)n + k] = make_double2(0.0, 0.0); }
+    grp::GroupTables& GT = h->GT;
+    GT.n_stages = n_stages; GT.xmax = xmax;
+    CKC(upload(h, meta.data(), meta.size(), &GT.stage_meta));
+    CKC(upload(h, ra.data(), ra.size(), &GT.recA));
+    CKC(upload(h, rb.data(), rb.size(), &GT.recB));
+    CKC(upload(h, rc.data(), rc.size(), &GT.recC));
+    CKC(upload(h, hl.data(), hl.size(), &GT.hl));
+    CKC(upload(h, anchor.data(), anchor.size(), &GT.anchor));
+    CKC(upload(h, dr2.data(), dr2.size(), &GT.drec2));
+    for (int c = 0; c < BAND_COLS; ++c) GT.wbase[c] = (c < MS_MAX_CONTRAST) ? T.c_wbase[c] : T.p_wbase[c - MS_MAX_CONTRAST];
+    h->group_ok = ok;
+    // persistent CTAs, two per SM; scratch: one model vector per walker warp of every CTA
+    h->group_ctas = 2 * h->num_sms;
+    CKH(cudaMalloc((void**)&h->cell_start, ((size_t)T.n_cells + 1) * sizeof(unsigned)));
+    CKH(cudaMalloc((void**)&h->group_off, (size_t)T.n_cells * sizeof(unsigned)));
+    CKH(cudaMalloc((void**)&h->n_groups, sizeof(int)));
+    CKH(cudaMalloc((void**)&h->group_counter, sizeof(int)));
+    if (ok) CKH(cudaMalloc((void**)&h->group_scratch, (size_t)h->group_ctas * GW * (size_t)n * sizeof(double)));
+  }
+
   // ---- isochrone, dust
   CKC(upload(h, cfg->iso_teff, cfg->n_iso, &T.iso_teff));
   CKC(upload(h, cfg->iso_logg, cfg->n_iso, &T.iso_logg));
@@ -2172,6 +2368,15 @@ int ms_set_fast(ms_handle* h, int enabled) {
   h->fast = enabled != 0;
   return MS_OK;
 }
+
+int ms_set_group(ms_handle* h, int mode, int64_t min_walkers) {
+  if (!h) return MS_ERR_INVALID;
+  h->group_mode = mode < 0 ? -1 : (mode != 0);
+  if (min_walkers > 0) h->group_min_walkers = min_walkers;
+  return MS_OK;
+}
+
+int ms_group_supported(const ms_handle* h) { return (h && h->group_ok && h->corners == 4) ? 1 : 0; }
 
 int ms_set_cell_order(ms_handle* h, int mode) {
   if (!h) return MS_ERR_INVALID;

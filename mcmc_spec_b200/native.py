@@ -23,7 +23,7 @@ _LIB_PATH = os.environ.get('MCMCSPEC_LIB') or os.path.join(os.path.dirname(os.pa
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
            'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_component_mags', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows', 'ms_build_grid',
-           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_fast', 'ms_set_cell_order', 'ms_set_timing',
+           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_fast', 'ms_set_cell_order', 'ms_set_group', 'ms_group_supported', 'ms_set_timing',
            'ms_kernel_time']
 
 _dp = C.POINTER(C.c_double)
@@ -106,6 +106,8 @@ def load_library(path=None):
     lib.ms_set_pairing.argtypes = [vp, C.c_int]
     lib.ms_set_fast.argtypes = [vp, C.c_int]
     lib.ms_set_cell_order.argtypes = [vp, C.c_int]
+    lib.ms_set_group.argtypes = [vp, C.c_int, C.c_int64]
+    lib.ms_group_supported.argtypes = [vp]
     lib.ms_set_timing.argtypes = [vp, C.c_int]
     lib.ms_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     for name in EXPORTS:
@@ -252,6 +254,15 @@ class Engine:
     def set_cell_order(self, mode):
         """Launch order of large batches: True grouped by grid cell, False natural, None automatic (default)."""
         self._check(self.lib.ms_set_cell_order(self._h, -1 if mode is None else int(bool(mode))), 'ms_set_cell_order')
+
+    def set_group(self, mode, min_walkers=0):
+        """Group evaluation of large posterior batches (cell-mates share one TMA-staged stream of their grid rows):
+        True whenever the tables fit, False never, None automatic (batches >= ``min_walkers``, default 1024)."""
+        self._check(self.lib.ms_set_group(self._h, -1 if mode is None else int(bool(mode)), int(min_walkers)), 'ms_set_group')
+
+    @property
+    def group_supported(self):
+        return bool(self.lib.ms_group_supported(self._h))
 
     def set_timing(self, enabled):
         self._check(self.lib.ms_set_timing(self._h, int(bool(enabled))), 'ms_set_timing')

@@ -42,9 +42,11 @@ def lnprob(t, theta, tile=1024):
     if not np.all(np.isfinite(p)):
         return -np.inf
     temps, av, rad, plx = p[:ns], p[ns], p[ns + 1:2 * ns + 1], p[2 * ns + 1]
+    # logprior's own `rad`: p0[nspec:2*nspec] in the dist_fit branch when ext is False (mft6.py:1219-1221)
+    prad = p[ns:2 * ns] if (ns == 2 and t.dist_fit and not t.ext_flag) else rad
     out = any(temps > t.tmax) or any(temps < t.tmin)
     if t.dist_fit:
-        out = out or any(rad < 0.05) or rad[0] > 1.5 or plx < 1 / 3000 or plx > 1 / 4
+        out = out or any(prad < 0.05) or prad[0] > 1.5 or plx < 1 / 3000 or plx > 1 / 4
     else:
         out = out or rad[1] < 0.05 or rad[0] < 0.05
     if t.ext_flag and av < 0:
@@ -78,7 +80,7 @@ def lnprob(t, theta, tile=1024):
             lp += -0.5 * ((p[k] - t.prior_mu[k]) / t.prior_sig[k]) ** 2
     if t.rad_prior:
         rm = [np.sqrt(lum[s] * LSUN / (4 * np.pi * SIGMA_SB * temps[s] ** 4)) / RSUN for s in range(2)]
-        for val, m in ((rad[0], rm[0]), (rad[1], rm[1] / rm[0])):
+        for val, m in ((prad[0], rm[0]), (prad[1], rm[1] / rm[0])):
             lp += -0.5 * ((val - m) / (0.02 * m)) ** 2
     grid = t.grid.reshape(-1, t.row_len)[:, t.reg_lo:t.reg_lo + t.n_reg]
     comps = []

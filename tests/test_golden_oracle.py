@@ -40,3 +40,23 @@ def test_oracle_matches_c3_golden():
         want = fx['oracle_lnprob'][k][:3]
         f = np.isfinite(want)
         assert np.array_equal(np.isfinite(got), f) and np.allclose(got[f], want[f], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize('name', ['c1', 'c2', 'c3', 'c4', 'c5'])
+def test_oracle_matches_10k_fixture(name):
+    """tests/golden/c*_10k.npz (make_theta10k.py): the oracle reproduces a spot sample of each file on the CPU,
+    so a stale fixture or a changed oracle is caught without a GPU."""
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_theta10k
+    fx = np.load(os.path.join(GOLD, name + '_10k.npz'))
+    assert len(fx['theta']) >= 10000 and fx['theta'].shape[1] == 6
+    assert 9000 < np.isfinite(fx['oracle_lnprob']).sum() < len(fx['theta'])       # edge cases give -inf
+    idx = [0, 8, 9, 4001, 8500, 9999] if name != 'c3' else [0, 8, 700]
+    k = int(fx['problem'][idx[0]]) if name == 'c3' else 0
+    orc = to_oracle(make_theta10k.problem_for(name, k))
+    got = orc.lnprob_batch(fx['theta'][idx])
+    want = fx['oracle_lnprob'][idx]
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    f = np.isfinite(want)
+    assert np.allclose(got[f], want[f], rtol=1e-12, atol=0)

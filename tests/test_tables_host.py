@@ -52,6 +52,35 @@ def test_device_plan_matches_oracle(small_problem, small_oracle):
     assert np.max(np.abs(got[f] - want[f]) / np.abs(want[f])) < 1e-11
 
 
+@pytest.mark.parametrize('dist_fit', [True, False])
+@pytest.mark.parametrize('rad_prior', [True, False])
+@pytest.mark.parametrize('av', [True, False])
+def test_device_plan_prior_flags(dist_fit, rad_prior, av):
+    """Every (dist_fit, rad_prior, a) branch of the 6-parameter logprior (mft6.py:1212-1327), including
+    ext == False where the reference slices p0[nspec:2*nspec] as its radii (mft6.py:1219-1221)."""
+    import dataclasses
+    from oracle_adapter import to_oracle
+    prob = dataclasses.replace(synthetic.make_problem_small(dist_fit=dist_fit, rad_prior=rad_prior), av=av)
+    t = build_tables(prob)
+    theta = flag_thetas(prob, 96, seed=33)
+    want = to_oracle(prob).lnprob_batch(theta)
+    got = np.array([tables_emulator.lnprob(t, th) for th in theta])
+    assert np.array_equal(np.isfinite(want), np.isfinite(got))
+    f = np.isfinite(want)
+    assert 10 <= f.sum() < len(theta)
+    assert np.max(np.abs(got[f] - want[f]) / np.abs(want[f])) < 1e-11
+
+
+def flag_thetas(prob, n, seed):
+    """Prior-box sample whose Av column also covers [0.05, 1.5] x the radius bounds: with ext == False the Av slot
+    is what the reference bounds and weighs as `R1` (mft6.py:1219-1227), so both signs of each test are hit."""
+    th = synthetic.sample_prior_box(prob, n, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    k = np.arange(n) % 4 == 1
+    th[k, 2] = rng.uniform(0.0, 1.7, k.sum())
+    return th
+
+
 def test_unsorted_filter_curve_is_stably_sorted():
     # lp600-like digitised curve: descending steps and a duplicated abscissa (SURVEY.md section 7)
     w = np.array([6000., 6100., 6050., 6200., 6200., 6300.]); tr = np.array([0., .5, .4, .8, .7, 0.])
