@@ -1,75 +1,101 @@
 // group_kernel.cuh -- lnprob_group_kernel: the large-batch form of the streaming evaluation (included by
-// mcmcspec.cu; translation unit MS_TU = 4).
+// mcmcspec.cu; instantiated in translation unit MS_TU = 4).
 //
-// One CTA evaluates a *group* of up to GW walkers that sit in the same grid cell, i.e. whose 2 * 2^D bracketing
-// grid rows (mft6.py:439-519) are the same rows.  The rows are streamed ONCE per group:
+// One persistent CTA evaluates *groups* of up to 32 walkers that sit in the same grid cell, i.e. whose 2 * 2^D
+// bracketing grid rows (mft6.py:439-519) are the same rows.  The rows are streamed ONCE per group, 128 model pixels
+// (one stage) at a time, through a shared-memory ring:
 //
-//   warp 0      producer   -- per 128-pixel stage one elected set of lanes issues 1-D bulk tensor copies
-//                             (cp.async.bulk ... mbarrier::complete_tx: SASS UBLKCP) of the bracketing row segments,
-//                             of the weight tiles of the passbands that touch the stage and of the per-observed-pixel
-//                             records into a 4-stage shared-memory ring; `full` / `empty` mbarriers per stage.
-//   warp 1      gather     -- picks, for every observed pixel whose upper bracketing model pixel lies in the stage,
-//                             the two bracketing pixels of every row out of the staged segments (mft6.py:1169:
-//                             interp1d onto the observed wavelengths) into a compact table B[row][pixel] that all
-//                             walkers of the group read coalesced; `bready` mbarrier.
+//   warp 0      producer   -- per stage ONE 3-D tiled tensor copy per star (cp.async.bulk.tensor, SASS UTMALDG: box =
+//                             130 pixels x 2 Teff nodes x 2 log g nodes = the star's four bracketing rows), one bulk
+//                             copy (UBLKCP) per passband weight tile that touches the stage and one for the stage's
+//                             block of per-observed-pixel records; completion is counted in bytes on the stage's
+//                             `full` mbarrier, `empty` mbarriers hand slots back.  After the stream: bulk copies of
+//                             the chi-square pass's per-pixel records through two slots of the same ring.
+//   warp 1      gather     -- for every observed pixel whose upper bracketing model pixel lies in the stage, the two
+//                             bracketing pixels of every row out of the staged segments (mft6.py:1169: interp1d onto
+//                             the observed wavelengths) into a compact table B[row][pixel]; `bready` mbarrier.
 //   warps 2,3   band       -- integrate every staged ROW through the passbands that touch the stage
-//                             (sum_p w_f[p] * row[p]: np.trapz of mft6.py:731 resp. pyphot get_flux, mft6.py:776, which
-//                             are linear in the spectrum); a walker's band fluxes are the same linear combination of
-//                             these row integrals as its spectrum is of the rows (mft6.py:507-519, :689-700).
-//   warps 4..   walkers    -- one warp per walker: forms the composite at the two bracketing pixels of each observed
-//                             pixel (FMA chain over the rows, then the sum over the stars, mft6.py:744), extincts both
-//                             (mft6.py:1162), rebins (mft6.py:1169), accumulates norm_spec's moments (mft6.py:193-196)
-//                             and the key range for the median, and writes the model vector to its scratch row.
-//                             After the stream the same warp finishes alone: exact median by MSD radix select fused
-//                             with the chi-square pass (mft6.py:1173-1179), contrasts, magnitudes, priors, final sum
-//                             (mft6.py:1182-1205).  No block-wide barrier inside either phase.
+//                             (sum_p w_f[p] * row[p]: np.trapz of mft6.py:731 resp. pyphot get_flux, mft6.py:776, both
+//                             linear in the spectrum); a walker's band fluxes are the same linear combination of these
+//                             row integrals as its spectrum is of the rows (mft6.py:507-519, :689-700).
+//   warps 4..7  walkers    -- LANE = WALKER: lane l of every walker warp serves walker l of the group and keeps its
+//                             eight row coefficients and Av in registers; the four warps split the observed pixels of
+//                             each stage between them.  B and the records are the same for all lanes, so every
+//                             shared-memory read is a one-wavefront broadcast.  Per pixel and lane: composite at the
+//                             two bracketing pixels (FMA chain over the rows, then the sum over the stars,
+//                             mft6.py:744), extinction of both (mft6.py:1162), linear rebin (mft6.py:1169),
+//                             norm_spec's moments (mft6.py:193-196), key range and a scale-free 64-bin histogram for
+//                             the median; the model value goes to a transposed scratch row [pixel][lane] (coalesced).
+//                             After the stream the partial sums of the four warps are combined in a fixed order, the
+//                             warps split one pass over the scratch for the chi-square (mft6.py:1178-1179) that also
+//                             collects the keys of the median's histogram bin, and the first walker warp finishes:
+//                             exact selection on those keys (mft6.py:1173, np.median convention), contrasts,
+//                             magnitudes, priors, final sum (mft6.py:1182-1205).  No shuffles, no atomics.
 //
-// Consumer warps never touch global memory for grid rows, weights or records (LDS only), so their stalls are
-// shared-memory latency (~30 cycles) instead of L2 latency (~800), and L2 -> SM traffic drops by the group size.
-// Extinction: exp2(Av * ext(p)) = A_s * exp(Av * x_p) with A_s = exp2(Av * anchor_s) computed once per stage and
-// walker (32 stages at a time, one per lane) and a 7th-order polynomial on |Av * x_p| < 0.02 (x^8/8! < 7e-19);
-// larger exponents take the exp2 path.
+// Extinction: exp2(Av * ext(p)) = A_s * exp(Av * x_p) with A_s = exp2(Av * anchor_s) once per stage and walker and a
+// 7th-order polynomial on |Av * x_p| <= 0.02 (x^8/8! < 7e-19); larger exponents take the exp2 path (whole warp).
 
 namespace grp {
 
+// -DMS_GROUP_DEBUG: CTA 0 prints, per group, how long each role spent in total and inside mbarrier waits
+#ifdef MS_GROUP_DEBUG
+#define GDBG_DECL long long gdbg_wait = 0, gdbg_t0 = clock64();
+#define GDBG_WAIT(stmt) { const long long t__ = clock64(); stmt; gdbg_wait += clock64() - t__; }
+#define GDBG_REPORT(name) if (blockIdx.x == 0 && lane == 0) printf("%s warp %d: group %d of %d (%d walkers) total %lld wait %lld cycles\n", name, warp, g, total_groups, count, clock64() - gdbg_t0, gdbg_wait);
+#else
+#define GDBG_DECL
+#define GDBG_WAIT(stmt) stmt;
+#define GDBG_REPORT(name)
+#endif
+
 constexpr int TP = 128;                    // model pixels per stage
 constexpr int ROWPX = TP + 2;              // staged pixels per row: the tile and the two pixels before it (16-byte
-                                           // alignment of the bulk copy; the second one is the lower bracket of an
+                                           // alignment of the box; the second one is the lower bracket of an
                                            // observed pixel whose upper bracket is the first pixel of the tile)
-constexpr int ROWB = ROWPX * 8;            // 1040 bytes = 16 (mod 128): the 8 rows of one gather land in distinct banks
+constexpr int ROWB = ROWPX * 8;            // 1040 bytes
 constexpr int WS = MS_GROUP_WSLOTS;        // weight slots: passbands that may overlap on one stage
 constexpr int RCAP = MS_GROUP_RCAP;        // observed pixels per stage the ring is sized for
-constexpr int NSTAGE = 4;
-constexpr int GW = MS_GROUP_WALKERS;       // walkers (= walker warps) per CTA
+constexpr int NSTAGE = 3;
+constexpr int NWW = 4;                     // walker warps per CTA: they split the observed pixels of the group's 32 walkers
+constexpr int GMAX = 32;                   // walkers per group (one per lane)
 constexpr int NSERVICE = 4;                // producer, gather, 2 x band
-constexpr int NTHREADS = (GW + NSERVICE) * 32;
+constexpr int NTHREADS = (NWW + NSERVICE) * 32;
 constexpr int BROWB = RCAP * 16 + 16;      // stride of a B row (one pad slot: conflict-free stores from 8 rows)
-constexpr int LIST_MAX = 1024;             // keys of the median bin a warp keeps in shared memory
+constexpr int HBITS = 6;
+constexpr int HBINS = 1 << HBITS;          // per-lane histogram bins
+constexpr int CHI_CHUNK = 64;              // observed pixels per ring slot in the chi-square pass: 32-byte records + the
+                                           // group's model values [pixel][lane]
+constexpr int LISTCAP = 1024;              // keys of the median's bin a lane collects (per walker warp)
+constexpr int PIX = 4;                     // observed pixels a walker lane keeps in flight (independent FMA chains)
+constexpr int CAND = 8;                    // keys of the median's second-level bin per lane and walker warp (fast finish)
 constexpr double POLY_XMAX = 0.02;
+constexpr int REC_BYTES = (RCAP * 52 + 15) & ~15;   // record block of one stage: 3 double2 + one int32 per observed pixel
 
-template <int NROW> struct StageLayout {
+template <int NR> struct StageLayout {
+  static constexpr int NROW = 2 * NR;
+  static constexpr int box = (NR * ROWB + 127) & ~127;     // one star's rows, written by one tensor copy (128-byte aligned)
   static constexpr int rows = 0;
-  static constexpr int weights = NROW * ROWB;
-  static constexpr int recA = weights + WS * TP * 8;       // double2 {t, x_lo}
-  static constexpr int recB = recA + RCAP * 16;            // double2 {x_hi, d q0}
-  static constexpr int recC = recB + RCAP * 16;            // double2 {d q1, d q2}
-  static constexpr int hl = recC + RCAP * 16;              // int32[RCAP + 4]: upper bracket, tile-local
-  static constexpr int meta = hl + (RCAP + 4) * 4;
+  static constexpr int weights = 2 * box;
+  static constexpr int rec = weights + WS * TP * 8;        // {t, x_lo}[n] | {x_hi, d q0}[n] | {d q1, d q2}[n] | int32 upper bracket[n]
+  static constexpr int meta = rec + REC_BYTES;
   static constexpr int B = meta + 16;
-  static constexpr int bytes = B + NROW * BROWB;
-  static_assert(weights % 16 == 0 && meta % 16 == 0 && B % 16 == 0 && bytes % 16 == 0, "bulk copies need 16-byte alignment");
+  static constexpr int bytes = (B + NROW * BROWB + 127) & ~127;
+  static_assert(weights % 128 == 0 && rec % 16 == 0 && meta % 16 == 0 && B % 16 == 0, "bulk copies need aligned destinations");
+  static_assert(CHI_CHUNK * (32 + 256) <= bytes, "a chi-square chunk fits a ring slot");
+  __device__ static constexpr int row_off(int r) { return (r / NR) * box + (r % NR) * ROWB; }
 };
 
 // What the group kernel needs beyond DevTables (built once in ms_create).
 struct GroupTables {
-  const int4* stage_meta;       // [n_stages] {d0, d1, 4 x uint8 band column per weight slot (0xff: free), flush mask}
-  const double2* recA; const double2* recB; const double2* recC;   // [n_data (+pad)]
-  const int* hl;                // [n_data (+pad)]
-  const double* anchor;         // [n_stages + 32] extinction exponent the stage's x values are relative to
+  const int4* stage_meta;       // [n_stages] {first observed pixel, observed pixels, 4 x uint8 band column per weight slot
+                                //  (0xff: free), flush mask | (offset of the record block / 16) << 8}
+  const unsigned char* recblk;  // per stage: {t, x_lo}[n] | {x_hi, d q0}[n] | {d q1, d q2}[n] | int32 tile-local upper bracket[n]
+  const double* anchor;         // [n_stages] extinction exponent the stage's x values are relative to
   const double* drec2;          // [n_data][4] {q1(x), q2(x), flux, 1/err^2}: phase B
   const double* wbase[BAND_COLS];   // weight of region pixel p for band column c: wbase[c][p]
   double xmax;                  // max |x| over all records (x = (ext - anchor) ln 2)
   int n_stages;
+  int n_teff;
 };
 
 struct GroupDesc { int start, count; };
@@ -95,10 +121,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n"
       "}\n" :: "r"(bar), "r"(parity) : "memory");
 }
-// 1-D bulk tensor copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, SASS UBLKCP)
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, SASS UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// 3-D tiled tensor copy (pixel, Teff node, log g node) global -> shared: the four bracketing rows of one star in
+// one request (TMA, SASS UTMALDG); out-of-range coordinates are filled with zeros
+__device__ __forceinline__ void tensor_g2s_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               :: "r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
@@ -128,274 +160,160 @@ __device__ __forceinline__ unsigned hi_key(double v) {
   return (unsigned)h ^ ((unsigned)(h >> 31) | 0x80000000u);
 }
 
-// ---- warp-level exact selection --------------------------------------------------------------
-// Locate the bin of `hist` (256 bins in shared memory) that holds rank `rank`; every lane returns the same
-// (bin, elements below the bin, elements in the bin).
-__device__ __forceinline__ void warp_locate_bin(const unsigned* hist, unsigned rank, int lane, unsigned& bin, unsigned& below,
-                                                unsigned& in_bin) {
-  unsigned c[8]; unsigned tot = 0;
-  const uint4 a = *reinterpret_cast<const uint4*>(hist + lane * 8);
-  const uint4 b = *reinterpret_cast<const uint4*>(hist + lane * 8 + 4);
-  c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) tot += c[j];
-  unsigned incl = tot;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-  const unsigned excl = incl - tot;
-  const bool mine = rank >= excl && rank < incl;
-  unsigned mb = 0, mbelow = 0, mcnt = 0;
-  if (mine) {
-    unsigned run = excl;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (rank >= run && rank < run + c[j]) { mb = (unsigned)(lane * 8 + j); mbelow = run; mcnt = c[j]; }
-      run += c[j];
-    }
-  }
-  const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-  bin = __shfl_sync(0xffffffffu, mb, src);
-  below = __shfl_sync(0xffffffffu, mbelow, src);
-  in_bin = __shfl_sync(0xffffffffu, mcnt, src);
+// ---- per-lane exact selection --------------------------------------------------------------------------
+// Every lane selects on its own column of a transposed array (element t of lane l at [t * 32 + l]) with its own
+// histogram column hist[bin * 32 + l] (uint16 counts: at most 65 535 elements), so there is nothing to share.
+struct LaneSel {
+  unsigned long long prefix;    // the top `bits` bits of the wanted key
+  unsigned long long above;     // smallest key seen so far that is larger than every key with this prefix
+  unsigned rank;                // rank of the wanted key among the keys with this prefix
+  unsigned cnt;                 // how many keys have this prefix
+  int bits;
+};
+
+__device__ __forceinline__ void lane_hist_zero(unsigned short* hist, int lane) {
+#pragma unroll 8
+  for (int b = 0; b < HBINS; ++b) hist[b * 32 + lane] = 0;
 }
 
-__device__ __forceinline__ void warp_hist_add(unsigned* hist, unsigned digit, int lane) {
-  // warp-aggregated shared-memory atomics (neighbouring pixels of a smooth spectrum share a bin); digit
-  // 0xffffffff = no element
-  const unsigned peers = __match_any_sync(0xffffffffu, digit);
-  if (digit != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(hist + digit, (unsigned)__popc(peers));
+// Scan the bins in the order first + t (mod HBINS), t = 0, 1, ..., for the one holding `rank`.
+__device__ __forceinline__ void lane_locate(const unsigned short* hist, int lane, unsigned first, unsigned rank, unsigned& bin_t,
+                                            unsigned& below, unsigned& in_bin) {
+  unsigned cum = 0;
+  bool found = false;
+  bin_t = 0; below = 0; in_bin = 0;
+#pragma unroll 4
+  for (unsigned t = 0; t < (unsigned)HBINS; ++t) {
+    const unsigned c = hist[((first + t) & (HBINS - 1)) * 32 + lane];
+    if (!found && rank < cum + c) { found = true; bin_t = t; below = cum; in_bin = c; }
+    cum += c;
+  }
 }
 
-// Median of sM[0..n) (np.median convention) by one warp; also returns through *chi_out
-// sum_i (m_i - d_i / p(x_i))^2 / e_i^2 with p = a0 q0 + a1 q1 + a2 q2 (mft6.py:196, :120 on the unscaled model).
-// hist: 256 unsigned, list: LIST_MAX keys, both warp-private shared memory.  [kmin32, kmax32]: range of hi_key().
-__device__ double warp_median_chi(const double* __restrict__ sM, int n, unsigned* hist, unsigned long long* list,
-                                  unsigned kmin32, unsigned kmax32, const double* __restrict__ drec2, double a0q0, double a1,
-                                  double a2, double* chi_out, int lane) {
-  const unsigned long long kmin = (unsigned long long)kmin32 << 32, kmax = ((unsigned long long)kmax32 << 32) | 0xffffffffull;
-  unsigned rank = (unsigned)((n - 1) >> 1);
-  int bits_done = __clzll((long long)(kmin ^ kmax));                 // < 64: the low words differ
-  unsigned long long prefix = (bits_done == 0) ? 0ull : (kmin & (~0ull << (64 - bits_done)));
-  int width = min(8, 64 - bits_done);
-  int shift = 64 - bits_done - width;
-
-  // ---- pass 1: chi-square terms + histogram of the first differing key bits
-#pragma unroll
-  for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0u;
-  __syncwarp();
-  double chi = 0.0;
-  constexpr int U = 4;
-  for (int i0 = 0; i0 < n; i0 += 32 * U) {
-    double m[U]; dbl4 rec[U]; bool v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * 32 + lane;
-      v[u] = i < n;
-      m[u] = 0.0; rec[u].x = rec[u].y = rec[u].z = rec[u].w = 0.0;
-      if (v[u]) { m[u] = sM[i]; rec[u] = ldg_cached4(drec2 + 4 * (long long)i); }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      unsigned dg = 0xffffffffu;
-      if (v[u]) {
-        const double pfit = fma(a2, rec[u].y, fma(a1, rec[u].x, a0q0));
-        const double res = m[u] - rec[u].z * fast_rcp(pfit);
-        chi = fma(res * res, rec[u].w, chi);
-        dg = (unsigned)((ordered_key(m[u]) >> shift) & ((1u << width) - 1u));
-      }
-      warp_hist_add(hist, dg, lane);
+// One more HBITS-bit digit on the elements [0, n_l) of the lane's column: histogram of the keys that carry the lane's
+// prefix, then new prefix / rank / count.  VALUES: the column holds doubles (keys are derived), else it holds keys.
+// Lanes with n_l == 0 or all 64 bits fixed only take part in the warp-wide trip count.
+template <bool VALUES>
+__device__ __forceinline__ void lane_narrow(const void* col, unsigned n_l, LaneSel& S, unsigned short* hist, int lane) {
+  const bool active = S.bits < 64 && n_l > 0;
+  const int width = min(HBITS, 64 - S.bits);
+  const int shift = max(64 - S.bits - width, 0);
+  const unsigned long long himask = (S.bits == 0) ? 0ull : (~0ull << (64 - S.bits));
+  lane_hist_zero(hist, lane);
+  const unsigned n_max = __reduce_max_sync(0xffffffffu, active ? n_l : 0u);
+  for (unsigned t = 0; t < n_max; ++t) {
+    if (active && t < n_l) {
+      const unsigned long long k = VALUES ? ordered_key(reinterpret_cast<const double*>(col)[(size_t)t * 32 + lane])
+                                          : reinterpret_cast<const unsigned long long*>(col)[(size_t)t * 32 + lane];
+      if ((k & himask) == S.prefix) hist[(unsigned)((k >> shift) & ((1u << width) - 1u)) * 32 + lane] += 1;
     }
   }
-  *chi_out = warp_sum(chi);
-  __syncwarp();
-
-  // ---- narrow down on the full vector until the bin fits the list
-  unsigned bin, below, in_bin;
-  while (true) {
-    warp_locate_bin(hist, rank, lane, bin, below, in_bin);
-    rank -= below;
-    prefix |= ((unsigned long long)bin) << shift;
-    bits_done += width;
-    if (in_bin <= (unsigned)LIST_MAX || bits_done >= 64) break;
-    width = min(8, 64 - bits_done);
-    shift = 64 - bits_done - width;
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0u;
-    __syncwarp();
-    const unsigned long long himask = ~0ull << (64 - bits_done);
-    for (int i0 = 0; i0 < n; i0 += 32) {
-      const int i = i0 + lane;
-      unsigned dg = 0xffffffffu;
-      if (i < n) {
-        const unsigned long long k = ordered_key(sM[i]);
-        if ((k & himask) == prefix) dg = (unsigned)((k >> shift) & ((1u << width) - 1u));
-      }
-      warp_hist_add(hist, dg, lane);
-    }
-    __syncwarp();
+  if (active) {
+    unsigned bin, below, in_bin;
+    lane_locate(hist, lane, 0u, S.rank, bin, below, in_bin);
+    S.rank -= below; S.cnt = in_bin;
+    S.prefix |= ((unsigned long long)bin) << shift;
+    S.bits += width;
   }
-
-  double v1, v2;
-  bool need_next;
-  if (bits_done >= 64) {
-    v1 = key_value(prefix); v2 = v1;                                 // in_bin copies of one value
-    need_next = (rank + 1 >= in_bin);
-  } else {
-    // ---- compact the bin's keys (in index order), then keep narrowing on the list
-    const unsigned long long himask = ~0ull << (64 - bits_done);
-    unsigned cnt = 0;
-    for (int i0 = 0; i0 < n; i0 += 32 * U) {
-      unsigned long long k[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * 32 + lane;
-        k[u] = (i < n) ? ordered_key(sM[i]) : ~prefix;               // ~prefix never matches
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool hit = (k[u] & himask) == prefix;
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) list[cnt + __popc(bal & ((1u << lane) - 1u))] = k[u];
-        cnt += __popc(bal);
-      }
-    }
-    __syncwarp();
-    while (cnt > 64u && bits_done < 64) {
-      width = min(8, 64 - bits_done);
-      shift = 64 - bits_done - width;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0u;
-      __syncwarp();
-      for (unsigned t0 = 0; t0 < cnt; t0 += 32) {
-        const unsigned t = t0 + lane;
-        warp_hist_add(hist, t < cnt ? (unsigned)((list[t] >> shift) & ((1u << width) - 1u)) : 0xffffffffu, lane);
-      }
-      __syncwarp();
-      warp_locate_bin(hist, rank, lane, bin, below, in_bin);
-      rank -= below;
-      prefix |= ((unsigned long long)bin) << shift;
-      bits_done += width;
-      const unsigned long long hm = (bits_done >= 64) ? ~0ull : (~0ull << (64 - bits_done));
-      unsigned out = 0;                                              // in-place compaction: out <= t0 always
-      for (unsigned t0 = 0; t0 < cnt; t0 += 32) {
-        const unsigned t = t0 + lane;
-        const unsigned long long k = t < cnt ? list[t] : ~prefix;
-        const bool hit = t < cnt && (k & hm) == prefix;
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        __syncwarp();
-        if (hit) list[out + __popc(bal & ((1u << lane) - 1u))] = k;
-        out += __popc(bal);
-        __syncwarp();
-      }
-      cnt = out;
-    }
-    // ---- rank the remaining keys by counting
-    unsigned long long r1 = 0ull, r2 = 0ull;
-    bool f1 = false, f2 = false;
-    for (unsigned t = lane; t < cnt; t += 32) {
-      const unsigned long long mine = list[t];
-      unsigned b = 0;
-      for (unsigned j = 0; j < cnt; ++j) {
-        const unsigned long long o = list[j];
-        b += (o < mine) || (o == mine && j < t);
-      }
-      if (b == rank) { r1 = mine; f1 = true; }
-      if (b == rank + 1) { r2 = mine; f2 = true; }
-    }
-    const unsigned b1 = __ballot_sync(0xffffffffu, f1), b2 = __ballot_sync(0xffffffffu, f2);
-    r1 = __shfl_sync(0xffffffffu, r1, __ffs(b1) - 1);
-    need_next = (b2 == 0u);
-    r2 = __shfl_sync(0xffffffffu, r2, need_next ? 0 : __ffs(b2) - 1);
-    v1 = key_value(r1); v2 = key_value(r2);
-  }
-  if (n & 1) return v1;
-  if (need_next) {
-    // rare: the lower median is the largest element of its bin -> upper median = min{key > key(v1)}
-    const unsigned long long k1 = ordered_key(v1);
-    unsigned long long kgt = ~0ull;
-    for (int i = lane; i < n; i += 32) {
-      const unsigned long long k = ordered_key(sM[i]);
-      if (k > k1) kgt = min(kgt, k);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) kgt = min(kgt, __shfl_xor_sync(0xffffffffu, kgt, o));
-    v2 = key_value(kgt);
-  }
-  return (v1 + v2) / 2.0;
 }
+
+// In-place compaction of a lane's key column to the keys carrying its (new) prefix; dropped keys above the prefix
+// feed `above`.
+__device__ __forceinline__ unsigned lane_compact(unsigned long long* col, unsigned n_l, LaneSel& S, int lane) {
+  const unsigned long long himask = (S.bits >= 64) ? ~0ull : (~0ull << (64 - S.bits));
+  const unsigned n_max = __reduce_max_sync(0xffffffffu, n_l);
+  unsigned out = 0;
+  for (unsigned t = 0; t < n_max; ++t) {
+    if (t < n_l) {
+      const unsigned long long k = col[(size_t)t * 32 + lane];
+      if ((k & himask) == S.prefix) { col[(size_t)out * 32 + lane] = k; ++out; }
+      else if (k > S.prefix) S.above = min(S.above, k);
+    }
+  }
+  return out;
+}
+
+// Sum of the NWW walker warps' histogram columns, scanned in the order first + t (mod HBINS).
+__device__ __forceinline__ void lane_locate_merged(const unsigned short* hist_all, int lane, unsigned first, unsigned rank,
+                                                   unsigned& bin_t, unsigned& below, unsigned& in_bin) {
+  unsigned cum = 0;
+  bool found = false;
+  bin_t = 0; below = 0; in_bin = 0;
+#pragma unroll 2
+  for (unsigned t = 0; t < (unsigned)HBINS; ++t) {
+    const unsigned b = (first + t) & (HBINS - 1);
+    unsigned c = 0;
+#pragma unroll
+    for (int j = 0; j < NWW; ++j) c += hist_all[(j * HBINS + b) * 32 + lane];
+    if (!found && rank < cum + c) { found = true; bin_t = t; below = cum; in_bin = c; }
+    cum += c;
+  }
+}
+
+__device__ __forceinline__ void walker_bar() { asm volatile("bar.sync 1, %0;" :: "n"(NWW * 32) : "memory"); }
 
 // ------------------------------------------------------------------------------------------
-// NR: grid rows per star (4 or 8).  Binaries, posterior mode.
+// NR: grid rows per star (4; 8 with [Fe/H] is not instantiated yet).  Binaries, posterior mode.
 // ------------------------------------------------------------------------------------------
 template <int NR>
-__global__ void __launch_bounds__(NTHREADS, (NR == 4) ? 2 : 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__ GroupTables GT,
-                    const WalkerPlan* __restrict__ plans, const int* __restrict__ order,
-                    const GroupDesc* __restrict__ groups, const int* __restrict__ n_groups,
+                    const __grid_constant__ CUtensorMap grid_map, const WalkerPlan* __restrict__ plans,
+                    const int* __restrict__ order, const GroupDesc* __restrict__ groups, const int* __restrict__ n_groups,
                     int* __restrict__ group_counter, double* __restrict__ lnprob, const PartsOut parts,
-                    double* __restrict__ scratch) {
+                    double* __restrict__ scratch, unsigned long long* __restrict__ list_scratch) {
   constexpr int NS = 2;
   constexpr int NROW = NS * NR;
-  using L = StageLayout<NROW>;
+  using L = StageLayout<NR>;
   extern __shared__ __align__(128) unsigned char gsm[];
-  __shared__ __align__(8) unsigned long long s_full[NSTAGE], s_empty[NSTAGE], s_bready[NSTAGE];
+  unsigned short* const hist_all = reinterpret_cast<unsigned short*>(gsm + NSTAGE * L::bytes);   // [NWW][HBINS][32]
+  __shared__ __align__(8) unsigned long long s_full[NSTAGE], s_empty[NSTAGE], s_bready[NSTAGE], s_cfull[NSTAGE], s_cempty[NSTAGE];
   __shared__ double s_band[BAND_COLS * NROW];            // row integrals through every band
-  __shared__ double s_cf[GW][NROW];
-  __shared__ double s_av[GW], s_lp[GW], s_logg[GW][NS];
-  __shared__ int s_w[GW];
+  __shared__ double s_part[NWW][4][32];                  // per walker warp and lane: three moments / chi-square
+  __shared__ unsigned long long s_above[NWW][32];
+  __shared__ unsigned s_kmin[NWW][32], s_kmax[NWW][32], s_nl[NWW][32], s_nc[NWW][32];
   __shared__ int s_row[NROW];
   __shared__ int s_group, s_status;
-  static_assert(GW * (1024 + LIST_MAX * 8) <= NSTAGE * L::bytes, "phase-B scratch aliases the ring");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 32) {
+  if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(smem_u32(&s_full[s]), 1);
-      mbar_init(smem_u32(&s_empty[s]), (unsigned)(GW + 3));        // every walker warp + gather + 2 band warps
+      mbar_init(smem_u32(&s_empty[s]), (unsigned)(NWW + 3));       // every walker warp + gather + 2 band warps
       mbar_init(smem_u32(&s_bready[s]), 1);
     }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(smem_u32(&s_cfull[s]), 1); mbar_init(smem_u32(&s_cempty[s]), (unsigned)NWW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const int n_stages = GT.n_stages;
-  const int n_data = T.n_data;
+  const int n = T.n_data;
+  const int n_chunks = (n + CHI_CHUNK - 1) / CHI_CHUNK;
   const int total_groups = *n_groups;
   const uint32_t ring = smem_u32(gsm);
-  // this CTA's model vectors: one scratch row per walker warp, reused by every group the CTA takes
-  double* const sM = scratch + ((size_t)blockIdx.x * GW + (size_t)max(warp - NSERVICE, 0)) * (size_t)n_data;
-  unsigned it0 = 0;                         // stages this CTA has streamed so far: ring slot and mbarrier parity go on
+  const int wj = warp - NSERVICE;                                  // walker warp index, < 0 for the service warps
+  // the CTA's scratch, reused by every group it takes: model values [pixel][lane], key lists [warp][slot][lane]
+  double* const sMT = scratch + (size_t)blockIdx.x * (size_t)n * 32;
+  unsigned long long* const list0 = list_scratch + (size_t)blockIdx.x * (NWW + 1) * (size_t)LISTCAP * 32;   // + a spare list
+  unsigned long long* const listT = list0 + (size_t)max(wj, 0) * LISTCAP * 32;
+  unsigned short* const hist = hist_all + (size_t)max(wj, 0) * HBINS * 32;
+  unsigned it0 = 0, cit0 = 0;               // ring uses so far (stages / chi-square chunks): slot and mbarrier parity go on
 
   // Persistent CTA: groups are handed out by an atomic counter (reset by group_scan_kernel).
   while (true) {
     if (tid == 0) s_group = atomicAdd(group_counter, 1);
-    __syncthreads();                                                // also: the previous group's phase B is over
+    __syncthreads();                                                // also: the previous group is completely done
     const int g = s_group;
     if (g >= total_groups) break;
     const GroupDesc gd = groups[g];
     const int count = gd.count;
 
-    // ---- group prologue: plans of the members, rows of the cell
-    if (tid < GW) {
-      const bool live = tid < count;
-      const int w = live ? order[gd.start + tid] : -1;
-      s_w[tid] = w;
-      if (live) {
-        const WalkerPlan& p = plans[w];
+    if (tid == 0) {
+      const WalkerPlan& p = plans[order[gd.start]];
+      s_status = p.status;
 #pragma unroll
-        for (int st = 0; st < NS; ++st) {
+      for (int st = 0; st < NS; ++st) {
 #pragma unroll
-          for (int r = 0; r < NR; ++r) s_cf[tid][st * NR + r] = p.coef[st][r];
-          s_logg[tid][st] = p.logg[st];
-        }
-        s_av[tid] = p.av; s_lp[tid] = p.lp;
-        if (tid == 0) {
-          s_status = p.status;
-#pragma unroll
-          for (int st = 0; st < NS; ++st) {
-#pragma unroll
-            for (int r = 0; r < NR; ++r) s_row[st * NR + r] = p.row[st][r];
-          }
-        }
+        for (int r = 0; r < NR; ++r) s_row[st * NR + r] = p.row[st][r];
       }
     }
     for (int k = tid; k < BAND_COLS * NROW; k += NTHREADS) s_band[k] = 0.0;
@@ -403,8 +321,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
 
     if (s_status != 0) {
       // the walkers that never reach the grid are sorted into their own cell: nothing to stream (mft6.py:1465-1466)
-      if (tid < count) {
-        const int w = s_w[tid];
+      for (int k = tid; k < count; k += NTHREADS) {
+        const int w = order[gd.start + k];
         const WalkerPlan& p = plans[w];
         lnprob[w] = -CUDART_INF;
         if (parts.status) parts.status[w] = p.status;
@@ -414,78 +332,82 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         if (parts.contrast) for (int c = 0; c < T.n_contrast; ++c) parts.contrast[w * T.n_contrast + c] = CUDART_NAN;
         if (parts.phot) for (int f = 0; f < T.n_phot; ++f) parts.phot[w * T.n_phot + f] = CUDART_NAN;
         if (parts.comp_mag) for (int f = 0; f < T.n_contrast * NS; ++f) parts.comp_mag[w * T.n_contrast * NS + f] = CUDART_NAN;
+        if (parts.model) for (int i = 0; i < n; ++i) parts.model[(long long)w * n + i] = CUDART_NAN;
       }
-      if (parts.model)
-        for (int k = 0; k < count; ++k)
-          for (int i = tid; i < n_data; i += NTHREADS) parts.model[(long long)s_w[k] * n_data + i] = CUDART_NAN;
       continue;
     }
 
-    // walker-warp state that survives the stream
-    double mom0 = 0.0, mom1 = 0.0, mom2 = 0.0;
-    unsigned kmin = 0xffffffffu, kmax = 0u;
+    // ---- walker-lane state (walker warps only): lane l serves walker l of the group in every walker warp; idle
+    // lanes shadow walker 0 (same arithmetic, nothing stored)
+    const bool live = lane < count;
+    const int w = order[gd.start + (live ? lane : 0)];
+    double cf[NROW];
+#pragma unroll
+    for (int r = 0; r < NROW; ++r) cf[r] = 0.0;
+    double av = 0.0;
 
     if (warp == 0) {
       // ================================================================= producer
-      const double* rowp = nullptr;
-      if (lane < NROW) rowp = T.grid + (long long)s_row[lane] * T.stride - 2;    // tile pixel 0 = region pixel px0 - 2
+      // box origin of each star: its lower (Teff, log g) nodes (the plan's corners are in box order)
+      const int t0[NS] = {s_row[0] % GT.n_teff, s_row[NR] % GT.n_teff};
+      const int g0[NS] = {s_row[0] / GT.n_teff, s_row[NR] / GT.n_teff};
+      int4 meta = __ldg(GT.stage_meta);
+      GDBG_DECL
       for (int s = 0; s < n_stages; ++s) {
         const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs & (NSTAGE - 1));
-        const unsigned use = gs / NSTAGE;
-        mbar_wait(smem_u32(&s_empty[slot]), (use & 1u) ^ 1u);
-        const int4 meta = __ldg(GT.stage_meta + s);
-        const int n_obs = meta.y - meta.x;
+        const int slot = (int)(gs % NSTAGE);
+        const int4 meta_next = __ldg(GT.stage_meta + min(s + 1, n_stages - 1));      // in flight while the slot frees up
+        GDBG_WAIT(mbar_wait(smem_u32(&s_empty[slot]), ((gs / NSTAGE) & 1u) ^ 1u))
+        const int n_obs = meta.y;
         const uint32_t st = ring + (uint32_t)slot * L::bytes;
         const uint32_t bar = smem_u32(&s_full[slot]);
-        // bytes of this stage (uniform): rows, active weight tiles, records
-        const int hl_lo = meta.x & ~3;
-        const int hl_n = n_obs > 0 ? ((meta.y - hl_lo + 3) & ~3) : 0;
+        // bytes of this stage (uniform): two row boxes, active weight tiles, the record block
+        const unsigned rec_bytes = (unsigned)(n_obs * 52 + 15) & ~15u;
         int n_w = 0;
 #pragma unroll
         for (int q = 0; q < WS; ++q) n_w += (((unsigned)meta.z >> (8 * q)) & 0xffu) != 0xffu;
-        const unsigned total = (unsigned)(NROW * ROWB + n_w * TP * 8 + 3 * n_obs * 16 + hl_n * 4);
+        const unsigned total = (unsigned)(NS * NR * ROWB + n_w * TP * 8) + rec_bytes;
         if (lane == 0) {
           *reinterpret_cast<int4*>(gsm + (size_t)slot * L::bytes + L::meta) = meta;
           mbar_expect_tx(bar, total);
         }
         __syncwarp();
-        const long long px0 = (long long)s * TP;
-        if (lane < NROW) {
-          bulk_g2s(st + L::rows + lane * ROWB, rowp + px0, ROWB, bar);
-        } else if (lane < NROW + WS) {
-          const int q = lane - NROW;
+        const int px0 = s * TP;
+        if (lane < NS) {
+          tensor_g2s_3d(st + L::rows + lane * L::box, &grid_map, px0 - 2, t0[lane], g0[lane], bar);
+        } else if (lane < NS + WS) {
+          const int q = lane - NS;
           const unsigned col = ((unsigned)meta.z >> (8 * q)) & 0xffu;
           if (col != 0xffu) bulk_g2s(st + L::weights + q * TP * 8, GT.wbase[col] + px0, TP * 8, bar);
-        } else if (n_obs > 0) {
-          const int j = lane - NROW - WS;
-          if (j == 0) bulk_g2s(st + L::recA, GT.recA + meta.x, n_obs * 16, bar);
-          else if (j == 1) bulk_g2s(st + L::recB, GT.recB + meta.x, n_obs * 16, bar);
-          else if (j == 2) bulk_g2s(st + L::recC, GT.recC + meta.x, n_obs * 16, bar);
-          else if (j == 3) bulk_g2s(st + L::hl, GT.hl + hl_lo, hl_n * 4, bar);
+        } else if (lane == NS + WS && n_obs > 0) {
+          bulk_g2s(st + L::rec, GT.recblk + (size_t)((unsigned)meta.w >> 8) * 16, rec_bytes, bar);
         }
+        meta = meta_next;
       }
+      GDBG_REPORT("producer")
     } else if (warp == 1) {
       // ================================================================= gather
+      GDBG_DECL
       for (int s = 0; s < n_stages; ++s) {
         const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs & (NSTAGE - 1));
-        const unsigned par = (gs / NSTAGE) & 1u;
-        mbar_wait(smem_u32(&s_full[slot]), par);
+        const int slot = (int)(gs % NSTAGE);
+        GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NSTAGE) & 1u))
         const uint32_t st = ring + (uint32_t)slot * L::bytes;
         const int4 meta = *reinterpret_cast<const int4*>(gsm + (size_t)slot * L::bytes + L::meta);
-        const int n_obs = meta.y - meta.x;
-        const int hoff = meta.x & 3;
+        const int n_obs = meta.y;
         const int r = lane & 7;
+        const uint32_t hlp = st + L::rec + (uint32_t)n_obs * 48;
+#pragma unroll 4
         for (int k0 = 0; k0 < n_obs; k0 += 4) {
           const int k = k0 + (lane >> 3);
           if (k < n_obs) {
-            const int hl = *reinterpret_cast<const int*>(gsm + (size_t)slot * L::bytes + L::hl + 4 * (k + hoff));
+            int hl;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(hl) : "r"(hlp + 4 * k));
             const int j1 = hl + 1;                          // tile index of the lower bracket (upper: hl + 2)
             const int e = j1 & ~1;
 #pragma unroll
             for (int rr = 0; rr < NROW; rr += 8) {
-              const uint32_t rp = st + L::rows + (uint32_t)(rr + r) * ROWB + (uint32_t)e * 8;
+              const uint32_t rp = st + L::rows + (uint32_t)L::row_off(rr + r) + (uint32_t)e * 8;
               const double2 v01 = lds128(rp);
               const double v2 = lds64(rp + 16);
               double2 pr;
@@ -498,6 +420,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         __syncwarp();
         if (lane == 0) { mbar_arrive(smem_u32(&s_bready[slot])); mbar_arrive(smem_u32(&s_empty[slot])); }
       }
+      GDBG_REPORT("gather")
     } else if (warp < NSERVICE) {
       // ================================================================= band integration (rows [r0, r0 + NROW/2))
       constexpr int HR = NROW / 2;
@@ -508,14 +431,14 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < WS; ++q) acc[r][q] = 0.0;
       }
+      GDBG_DECL
       for (int s = 0; s < n_stages; ++s) {
         const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs & (NSTAGE - 1));
-        const unsigned par = (gs / NSTAGE) & 1u;
-        mbar_wait(smem_u32(&s_full[slot]), par);
+        const int slot = (int)(gs % NSTAGE);
+        GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NSTAGE) & 1u))
         const uint32_t st = ring + (uint32_t)slot * L::bytes;
         const int4 meta = *reinterpret_cast<const int4*>(gsm + (size_t)slot * L::bytes + L::meta);
-        const unsigned slots = (unsigned)meta.z, flush = (unsigned)meta.w;
+        const unsigned slots = (unsigned)meta.z, flush = (unsigned)meta.w & 0xffu;
         if (slots != 0xffffffffu) {
           // this lane's pixels of the tile: {2l, 2l+1} and {64 + 2l, 65 + 2l} (16-byte accesses, lanes contiguous)
 #pragma unroll
@@ -526,7 +449,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
               const double2 w1 = lds128(st + L::weights + q * TP * 8 + 512 + lane * 16);
 #pragma unroll
               for (int r = 0; r < HR; ++r) {
-                const uint32_t rp = st + L::rows + (uint32_t)(r0 + r) * ROWB + 16 + lane * 16;
+                const uint32_t rp = st + L::rows + (uint32_t)L::row_off(r0 + r) + 16 + lane * 16;
                 const double2 v0 = lds128(rp);
                 const double2 v1 = lds128(rp + 512);
                 double a = acc[r][q];
@@ -547,99 +470,353 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_empty[slot]));
       }
+      GDBG_REPORT("band")
     } else {
-      // ================================================================= walker warp: phase A
-      const int j = warp - NSERVICE;
-      const bool live = j < count;                         // idle walker warps only keep the ring's arrival counts
-      double cf[NROW];
+      // ================================================================= walker warps, phase A: lane = walker; warp wj
+      // takes the observed pixel quadruples wj, wj + NWW, ... of every stage
+      double mom0 = 0.0, mom1 = 0.0, mom2 = 0.0;
+      unsigned kmin = 0xffffffffu, kmax = 0u;
+      {
+        const WalkerPlan& p = plans[w];
 #pragma unroll
-      for (int r = 0; r < NROW; ++r) cf[r] = live ? s_cf[j][r] : 0.0;
-      const double av = live ? s_av[j] : 0.0;
-      const bool poly_ok = av * GT.xmax <= POLY_XMAX;
-      double a_lane = 1.0;
+        for (int st = 0; st < NS; ++st) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) cf[st * NR + r] = p.coef[st][r];
+        }
+        av = p.av;
+        lane_hist_zero(hist, lane);
+      }
+      const bool poly_ok = __all_sync(0xffffffffu, av * GT.xmax <= POLY_XMAX);
+      GDBG_DECL
       for (int s = 0; s < n_stages; ++s) {
         const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs & (NSTAGE - 1));
-        const unsigned par = (gs / NSTAGE) & 1u;
-        if (live && (s & 31) == 0) a_lane = exp2(av * __ldg(GT.anchor + s + lane));   // A of stages s .. s+31, one per lane
-        mbar_wait(smem_u32(&s_bready[slot]), par);          // B is ready (the gather warp saw `full`)
-        mbar_wait(smem_u32(&s_full[slot]), par);            // records: acquire on the barrier the bulk copies signal
-        const uint32_t st = ring + (uint32_t)slot * L::bytes;
-        const int4 meta = *reinterpret_cast<const int4*>(gsm + (size_t)slot * L::bytes + L::meta);
-        const int n_obs = meta.y - meta.x;
-        if (live && n_obs > 0) {
-          const double A = __shfl_sync(0xffffffffu, a_lane, s & 31);
-          for (int k = lane; k < n_obs; k += 32) {
-            const double2 ra = lds128(st + L::recA + k * 16);        // t, x_lo
-            const double2 rb = lds128(st + L::recB + k * 16);        // x_hi, d q0
-            const double2 rc = lds128(st + L::recC + k * 16);        // d q1, d q2
+        const int slot = (int)(gs % NSTAGE);
+        // the gather warp observed `full` (the copies' barrier) before it wrote B and arrived here, so the staged
+        // records are visible too (release / acquire chain)
+        GDBG_WAIT(mbar_wait(smem_u32(&s_bready[slot]), (gs / NSTAGE) & 1u))
+        const unsigned char* stp = gsm + (size_t)slot * L::bytes;
+        const int4 meta = *reinterpret_cast<const int4*>(stp + L::meta);
+        const int n_obs = meta.y;
+        if (PIX * wj < n_obs) {
+          const double anc = __ldg(GT.anchor + s);
+          const double A = exp2(av * anc);                                  // the stage's common extinction factor
+          double* dst = sMT + (size_t)meta.x * 32 + lane;
+          const double2* recA = reinterpret_cast<const double2*>(stp + L::rec);
+          const double2* recB = recA + n_obs;
+          const double2* recC = recB + n_obs;
+          // one observed pixel for this lane's walker; every shared-memory operand is the same address in all
+          // lanes (one-wavefront broadcasts)
+          auto pixel = [&](auto poly, int k, double& rm_out) -> double {
+            const double2 ra = recA[k];                                      // t, x_lo
+            const double xhi = recB[k].x;
             double flo = 0.0, fhi = 0.0;
 #pragma unroll
             for (int stx = 0; stx < NS; ++stx) {
-              const double2 b0 = lds128(st + L::B + (uint32_t)(stx * NR) * BROWB + k * 16);
+              const double2 b0 = *reinterpret_cast<const double2*>(stp + L::B + (stx * NR) * BROWB + k * 16);
               double l = cf[stx * NR] * b0.x, u = cf[stx * NR] * b0.y;
 #pragma unroll
               for (int r = 1; r < NR; ++r) {
-                const double2 b = lds128(st + L::B + (uint32_t)(stx * NR + r) * BROWB + k * 16);
+                const double2 b = *reinterpret_cast<const double2*>(stp + L::B + (stx * NR + r) * BROWB + k * 16);
                 l = fma(cf[stx * NR + r], b.x, l); u = fma(cf[stx * NR + r], b.y, u);
               }
-              flo = (stx == 0) ? l : flo + l; fhi = (stx == 0) ? u : fhi + u;    // mft6.py:744
+              flo = (stx == 0) ? l : flo + l; fhi = (stx == 0) ? u : fhi + u;        // mft6.py:744
             }
             double elo, ehi, scale_a = A;
-            if (poly_ok) {
-              elo = exp_small(av * ra.y); ehi = exp_small(av * rb.x);
+            if constexpr (decltype(poly)::value) {
+              elo = exp_small(av * ra.y); ehi = exp_small(av * xhi);
             } else {
               // exponent too large for the polynomial: exp2 of the whole exponent (1/ln 2 = 1.4426950408889634)
-              const double anc = __ldg(GT.anchor + s);
               elo = exp2(av * fma(ra.y, 1.4426950408889634, anc));
-              ehi = exp2(av * fma(rb.x, 1.4426950408889634, anc));
+              ehi = exp2(av * fma(xhi, 1.4426950408889634, anc));
               scale_a = 1.0;
             }
             const double ylo = flo * elo, yhi = fhi * ehi;                 // extinct() at both brackets, mft6.py:1162
             const double m = scale_a * fma(yhi - ylo, ra.x, ylo);          // interp1d onto the observed pixel, mft6.py:1169
-            const double rm = fast_rcp(m);                                 // norm_spec moments, mft6.py:194-195
-            mom0 = fma(rb.y, rm, mom0); mom1 = fma(rc.x, rm, mom1); mom2 = fma(rc.y, rm, mom2);
+            rm_out = fast_rcp(m);
+            return m;
+          };
+          auto tally = [&](int k, double m, double rm) {
+            const double dq0 = recB[k].y; const double2 rc = recC[k];      // d q0, d q1, d q2
+            mom0 = fma(dq0, rm, mom0); mom1 = fma(rc.x, rm, mom1); mom2 = fma(rc.y, rm, mom2);   // norm_spec moments, mft6.py:194-195
             const unsigned hk = hi_key(m);
             kmin = min(kmin, hk); kmax = max(kmax, hk);
-            sM[meta.x + k] = m;
-          }
+            hist[((hk >> (20 - (HBITS - 3))) & (HBINS - 1)) * 32 + lane] += 1;   // 3 exponent bits + HBITS - 3 mantissa bits
+            dst[(size_t)k * 32] = m;
+          };
+          auto run = [&](auto poly) {
+            for (int k = PIX * wj; k < n_obs; k += PIX * NWW) {             // PIX independent pixels in flight
+              double mv[PIX], rmv[PIX];
+#pragma unroll
+              for (int u = 0; u < PIX; ++u) mv[u] = pixel(poly, min(k + u, n_obs - 1), rmv[u]);   // no branch: the chains interleave
+#pragma unroll
+              for (int u = 0; u < PIX; ++u)
+                if (k + u < n_obs) tally(k + u, mv[u], rmv[u]);
+            }
+          };
+          if (poly_ok) run(std::true_type{}); else run(std::false_type{});
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_empty[slot]));
       }
+      s_part[wj][0][lane] = mom0; s_part[wj][1][lane] = mom1; s_part[wj][2][lane] = mom2;
+      s_kmin[wj][lane] = kmin; s_kmax[wj][lane] = kmax;
+      asm volatile("fence.proxy.async;" ::: "memory");                  // the model values are read back by bulk copies
+      GDBG_REPORT("walker")
     }
     it0 += (unsigned)n_stages;
 
-    __syncthreads();          // band integrals complete; the ring is idle and becomes phase-B scratch
+    __syncthreads();          // band integrals and the walker warps' partial sums complete
 
-    // ================================================================= walker warp: phase B + final sum
-    if (warp >= NSERVICE && warp - NSERVICE < count) {
-      const int j = warp - NSERVICE;
-      const int w = s_w[j];
-      const int n = n_data;
-      unsigned* hist = reinterpret_cast<unsigned*>(gsm + (size_t)j * (1024 + LIST_MAX * 8));
-      unsigned long long* list = reinterpret_cast<unsigned long long*>(gsm + (size_t)j * (1024 + LIST_MAX * 8) + 1024);
-      mom0 = warp_sum(mom0); mom1 = warp_sum(mom1); mom2 = warp_sum(mom2);
-      kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
-      __syncwarp();
-      bool has_nan = false;
-      if (kmax >= 0xfff00000u || kmin <= 0x000fffffu) {
-        // an infinity or a NaN is in the vector: look for NaNs exactly (mft6.py:1202)
-        int f = 0;
-        for (int i = lane; i < n; i += 32) { const double m = sM[i]; f |= (m != m); }
-        has_nan = __any_sync(0xffffffffu, f);
+    // ================================================================= the chi-square pass's inputs through the ring: per
+    // chunk of 64 observed pixels the records {q1, q2, d, 1/e^2} and the group's model values [pixel][lane]
+    if (warp == 0) {
+      for (int c = 0; c < n_chunks; ++c) {
+        const unsigned gs = cit0 + (unsigned)c;
+        const int slot = (int)(gs % NSTAGE);
+        mbar_wait(smem_u32(&s_cempty[slot]), ((gs / NSTAGE) & 1u) ^ 1u);
+        const unsigned npx = (unsigned)min(CHI_CHUNK, n - c * CHI_CHUNK);
+        const uint32_t dstb = ring + (uint32_t)slot * L::bytes;
+        if (lane == 0) mbar_expect_tx(smem_u32(&s_cfull[slot]), npx * (32u + 256u));
+        __syncwarp();
+        if (lane == 0) bulk_g2s(dstb, GT.drec2 + (size_t)c * CHI_CHUNK * 4, npx * 32u, smem_u32(&s_cfull[slot]));
+        else if (lane == 1) bulk_g2s(dstb + CHI_CHUNK * 32, sMT + (size_t)c * CHI_CHUNK * 32, npx * 256u, smem_u32(&s_cfull[slot]));
       }
-      double chi_un = CUDART_NAN, med = CUDART_NAN;
-      if (!has_nan) med = warp_median_chi(sM, n, hist, list, kmin, kmax, GT.drec2, mom0 * T.basis[0], mom1, mom2, &chi_un, lane);
-      const double scale = T.data_median / med;                            // mft6.py:1173
-      if (parts.model) for (int i = lane; i < n; i += 32) parts.model[(long long)w * n + i] = sM[i] * scale;
-
-      if (lane == 0) {
-        const double av = s_av[j], lp = s_lp[j];
-        double cf[NROW];
+    } else if (wj >= 0) {
+      // ================================================================= walker warps, phase B: lane = walker
+      GDBG_DECL
+      // ---- the walker's sums over all its pixels, combined in a fixed order (every warp ends up with the same values)
+      double mom[3];
 #pragma unroll
-        for (int r = 0; r < NROW; ++r) cf[r] = s_cf[j][r];
-        const double iic = (scale * scale) * chi_un / (double)n;          // mft6.py:1173-1179
+      for (int c = 0; c < 3; ++c) {
+        double a = s_part[0][c][lane];
+#pragma unroll
+        for (int j = 1; j < NWW; ++j) a += s_part[j][c][lane];
+        mom[c] = a;
+      }
+      unsigned kmin = s_kmin[0][lane], kmax = s_kmax[0][lane];
+#pragma unroll
+      for (int j = 1; j < NWW; ++j) { kmin = min(kmin, s_kmin[j][lane]); kmax = max(kmax, s_kmax[j][lane]); }
+      // ---- the bin of the median.  The phase-A histograms are indexed by 3 exponent + HBITS - 3 mantissa bits of the
+      // key; their sum orders the keys as long as a walker's values span fewer than 8 binades and are finite
+      LaneSel S;
+      S.rank = (unsigned)((n - 1) >> 1); S.above = ~0ull; S.cnt = (unsigned)n; S.prefix = 0ull; S.bits = 0;
+      int has_nan = 0;
+      const bool suspicious = kmax >= 0xfff00000u || kmin <= 0x000fffffu;   // an infinity or a NaN may be present
+      if (__any_sync(0xffffffffu, suspicious)) {
+        for (int i = 0; i < n; ++i) { const double m = sMT[(size_t)i * 32 + lane]; has_nan |= (m != m); }   // mft6.py:1202
+      }
+      const bool fast_hist = ((kmax >> 20) - (kmin >> 20)) < 8u && !suspicious;
+      const bool all_fast = __all_sync(0xffffffffu, fast_hist);
+      if (all_fast) {
+        constexpr int SH = 20 - (HBITS - 3);                                // hi-key bits below the histogram digit
+        unsigned bin_t, below, in_bin;
+        const unsigned first = (kmin >> SH) & ~((1u << (HBITS - 3)) - 1u);     // lowest binade, mantissa bits 0
+        lane_locate_merged(hist_all, lane, first, S.rank, bin_t, below, in_bin);
+        S.prefix = (unsigned long long)(first + bin_t) << (32 + SH); S.bits = 32 - SH;
+        S.rank -= below; S.cnt = in_bin;
+      }
+      walker_bar();                                                         // every warp has read the phase-A histograms
+      if (!all_fast) {
+        // general case: digits below the common prefix of the lane's key range, from the scratch column
+        const unsigned long long k0 = (unsigned long long)kmin << 32, k1 = ((unsigned long long)kmax << 32) | 0xffffffffull;
+        S.bits = __clzll((long long)(k0 ^ k1));
+        S.prefix = (S.bits == 0) ? 0ull : (k0 & (~0ull << (64 - S.bits)));
+        lane_narrow<true>(sMT, (unsigned)n, S, hist, lane);
+      }
+      while (__any_sync(0xffffffffu, S.cnt > (unsigned)LISTCAP && S.bits < 64)) {
+        LaneSel S2 = S;
+        if (!(S.cnt > (unsigned)LISTCAP && S.bits < 64)) S2.bits = 64;     // this lane is done: trip count only
+        lane_narrow<true>(sMT, (unsigned)n, S2, hist, lane);
+        if (S.cnt > (unsigned)LISTCAP && S.bits < 64) S = S2;
+      }
+      // ---- one pass over the model vector, split between the warps in blocks of 8 pixels: chi-square terms
+      // (mft6.py:196, :120 on the unscaled model) + the keys of the median's bin into the warp's list, a second-level
+      // histogram of those keys (the next HBITS key bits) and the smallest key above the bin.  The per-pixel records
+      // {q1, q2, d, 1/e^2} arrive through the ring (bulk copies by the producer warp), the model values are read one
+      // block ahead.  Branch free: eight independent pixels are in flight per lane.
+      const double a0q0 = mom[0] * T.basis[0], a1 = mom[1], a2 = mom[2];
+      double chi = 0.0;
+      unsigned nl = 0;
+      unsigned long long above = ~0ull;
+      const bool collect = S.cnt <= (unsigned)LISTCAP && S.bits < 64;      // per lane; otherwise the slow path below
+      const int width2 = min(HBITS, 64 - S.bits);
+      const int shift2 = max(64 - S.bits - width2, 0);
+      lane_hist_zero(hist, lane);
+      {
+        const unsigned long long himask = (S.bits >= 64) ? ~0ull : (S.bits == 0 ? 0ull : (~0ull << (64 - S.bits)));
+        const unsigned long long prefix = S.prefix;
+        constexpr int U = 8;
+        constexpr int PER_WARP = CHI_CHUNK / NWW;                           // pixels of a chunk per walker warp
+        static_assert(PER_WARP % U == 0, "a warp's share of a chunk is whole blocks");
+        for (int c = 0; c < n_chunks; ++c) {
+          const unsigned gs = cit0 + (unsigned)c;
+          const int slot = (int)(gs % NSTAGE);
+          GDBG_WAIT(mbar_wait(smem_u32(&s_cfull[slot]), (gs / NSTAGE) & 1u))
+          const dbl4* rec = reinterpret_cast<const dbl4*>(gsm + (size_t)slot * L::bytes);
+          const double* mch = reinterpret_cast<const double*>(gsm + (size_t)slot * L::bytes + CHI_CHUNK * 32) + lane;
+          const int npx = min(CHI_CHUNK, n - c * CHI_CHUNK);
+          for (int p0 = wj * PER_WARP; p0 < (wj + 1) * PER_WARP && p0 < npx; p0 += U) {
+            double res[U]; unsigned long long key[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const bool valid = p0 + u < npx;
+              const int pp = min(p0 + u, npx - 1);
+              const double m = mch[pp * 32];
+              const dbl4 r4 = rec[pp];                                      // same address in every lane
+              const double pfit = fma(a2, r4.y, fma(a1, r4.x, a0q0));
+              const double r = m - r4.z * fast_rcp(pfit);
+              res[u] = valid ? (r * r) * r4.w : 0.0;
+              key[u] = ordered_key(m);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              chi += res[u];
+              const bool valid = p0 + u < npx;
+              const bool hit = valid && (key[u] & himask) == prefix;
+              if (hit && collect) {
+                listT[(size_t)nl * 32 + lane] = key[u];
+                hist[(unsigned)((key[u] >> shift2) & ((1u << width2) - 1u)) * 32 + lane] += 1;
+              }
+              nl += hit ? 1u : 0u;
+              if (valid && !hit && key[u] > prefix) above = min(above, key[u]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s_cempty[slot]));
+        }
+      }
+      s_part[wj][3][lane] = chi; s_nl[wj][lane] = collect ? nl : 0u;
+      walker_bar();
+      // ---- second level: every warp locates the sub-bin in the summed second-level histograms, then filters its own
+      // list into a small candidate buffer
+      unsigned long long* const cand_all = reinterpret_cast<unsigned long long*>(hist_all + NWW * HBINS * 32);   // [NWW][CAND][32]
+      unsigned long long* const cand = cand_all + (size_t)wj * CAND * 32;
+      LaneSel S2 = S;
+      unsigned nc = 0;
+      bool overflow = !collect;
+      {
+        unsigned bin, below, in_bin;
+        lane_locate_merged(hist_all, lane, 0u, S.rank, bin, below, in_bin);
+        S2.rank = S.rank - below; S2.cnt = in_bin;
+        S2.prefix = S.prefix | (((unsigned long long)bin) << shift2);
+        S2.bits = S.bits + width2;
+        const unsigned long long hm2 = (S2.bits >= 64) ? ~0ull : (~0ull << (64 - S2.bits));
+        const unsigned nl_eff = collect ? nl : 0u;
+        const unsigned nmax = __reduce_max_sync(0xffffffffu, nl_eff);
+        for (unsigned t0 = 0; t0 < nmax; t0 += 8) {                        // eight loads in flight
+          unsigned long long kb[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) kb[u] = (t0 + u < nl_eff) ? listT[(size_t)(t0 + u) * 32 + lane] : 0ull;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (t0 + u < nl_eff) {
+              const unsigned long long k = kb[u];
+              if ((k & hm2) == S2.prefix) {
+                if (nc < (unsigned)CAND) cand[(size_t)nc * 32 + lane] = k; else overflow = true;
+                ++nc;
+              } else if (k > S2.prefix) {
+                above = min(above, k);
+              }
+            }
+          }
+        }
+      }
+      s_above[wj][lane] = above; s_nc[wj][lane] = overflow ? 0xffffffffu : nc;
+      __threadfence_block();
+      walker_bar();
+      if (wj == 0) {
+        // ---- the first walker warp finishes: merge, rank the candidates, final sum
+#pragma unroll
+        for (int j = 1; j < NWW; ++j) { chi += s_part[j][3][lane]; above = min(above, s_above[j][lane]); }
+        bool any_overflow = false;
+#pragma unroll
+        for (int j = 0; j < NWW; ++j) any_overflow = any_overflow || s_nc[j][lane] == 0xffffffffu;
+        double v1, v2;
+        if (!__any_sync(0xffffffffu, any_overflow)) {
+          // at most NWW * CAND keys carry the prefix: rank them by counting (ties by position)
+          unsigned long long r1 = 0ull, r2 = above;
+          unsigned total = 0;
+#pragma unroll
+          for (int j = 0; j < NWW; ++j) total += s_nc[j][lane];
+          const unsigned tmax = __reduce_max_sync(0xffffffffu, total);
+          // candidate t of this lane: (warp ja, index ia) in the concatenation of the four buffers
+          for (unsigned t = 0; t < tmax; ++t) {
+            if (t < total) {
+              unsigned rem = t; int ja = 0;
+#pragma unroll
+              for (int j = 0; j < NWW - 1; ++j) { const unsigned cj = s_nc[j][lane]; if (ja == j && rem >= cj) { rem -= cj; ja = j + 1; } }
+              const unsigned long long mine = cand_all[((size_t)ja * CAND + rem) * 32 + lane];
+              unsigned below = 0, pos = 0;
+#pragma unroll
+              for (int j = 0; j < NWW; ++j) {
+                const unsigned cj = s_nc[j][lane];
+                for (unsigned i = 0; i < cj; ++i, ++pos) {
+                  const unsigned long long o = cand_all[((size_t)j * CAND + i) * 32 + lane];
+                  below += (o < mine) || (o == mine && pos < t);
+                }
+              }
+              if (below == S2.rank) r1 = mine;
+              if (below == S2.rank + 1) r2 = mine;
+            }
+          }
+          v1 = key_value(r1); v2 = key_value(r2);
+        } else {
+          // ---- slow path (a lane's second-level bin holds more keys than the buffers take, or all its values are
+          // equal): the keys with the second-level prefix of all four lists go to a spare list, then digit by digit
+          unsigned long long* const spare = list0 + (size_t)NWW * LISTCAP * 32;
+          unsigned cnt = 0u;
+          const unsigned long long hm2 = (S2.bits >= 64) ? ~0ull : (~0ull << (64 - S2.bits));
+          for (int j = 0; j < NWW; ++j) {
+            const unsigned long long* lj = list0 + (size_t)j * LISTCAP * 32;
+            const unsigned nj = collect ? s_nl[j][lane] : 0u;
+            const unsigned nmax = __reduce_max_sync(0xffffffffu, nj);
+            for (unsigned t0 = 0; t0 < nmax; t0 += 8) {
+              unsigned long long kb[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) kb[u] = (t0 + u < nj) ? lj[(size_t)(t0 + u) * 32 + lane] : 0ull;
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (t0 + u < nj && (kb[u] & hm2) == S2.prefix) { spare[(size_t)cnt * 32 + lane] = kb[u]; ++cnt; }
+            }
+          }
+          __syncwarp();
+          if (collect) { S = S2; S.above = above; }                          // `above` already has the keys dropped so far
+          else S.above = above;
+          unsigned long long* const listT = spare;
+          if (S.bits >= 64) cnt = 0u;
+          while (__any_sync(0xffffffffu, cnt > 8u && S.bits < 64)) {
+            const bool go = cnt > 8u && S.bits < 64;
+            LaneSel S3 = S;
+            if (!go) S3.bits = 64;                                          // trip count only
+            lane_narrow<false>(listT, go ? cnt : 0u, S3, hist, lane);
+            const unsigned out = lane_compact(listT, go ? cnt : 0u, S3, lane);
+            if (go) { S = S3; cnt = out; }
+          }
+          if (S.bits >= 64) {
+            v1 = key_value(S.prefix);                                       // S.cnt copies of one value
+            v2 = (S.rank + 1 < S.cnt) ? v1 : key_value(S.above);
+          } else {
+            unsigned long long r1 = 0ull, r2 = S.above;
+            for (unsigned t = 0; t < cnt; ++t) {
+              const unsigned long long mine = listT[(size_t)t * 32 + lane];
+              unsigned b2 = 0;
+              for (unsigned j = 0; j < cnt; ++j) {
+                const unsigned long long o = listT[(size_t)j * 32 + lane];
+                b2 += (o < mine) || (o == mine && j < t);
+              }
+              if (b2 == S.rank) r1 = mine;
+              if (b2 == S.rank + 1) r2 = mine;
+            }
+            v1 = key_value(r1); v2 = key_value(r2);
+          }
+        }
+        const double med = has_nan ? CUDART_NAN : ((n & 1) ? v1 : (v1 + v2) / 2.0);   // np.median, mft6.py:1173
+        const double chi_un = has_nan ? CUDART_NAN : chi;
+        const double scale = T.data_median / med;
+        if (parts.model && live) for (int i = 0; i < n; ++i) parts.model[(long long)w * n + i] = sMT[(size_t)i * 32 + lane] * scale;
+
+        // ---- final sum (mft6.py:1178-1205), every lane for its own walker
+        const double iic = (scale * scale) * chi_un / (double)n;            // mft6.py:1173-1179
         double icontrast = 0.0, iphot = 0.0;
         for (int f = 0; f < T.n_contrast; ++f) {
           double fl[NS];
@@ -651,11 +828,11 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             fl[stx] = a;
           }
           const double m0 = -2.5 * log10(fl[0]), m1 = -2.5 * log10(fl[1]);
-          const double con = m1 - m0;                                      // mft6.py:741
+          const double con = m1 - m0;                                        // mft6.py:741
           const double d = con - T.c_mag[f];
           icontrast += (d * d) / (T.c_err[f] * T.c_err[f]);
-          if (parts.contrast) parts.contrast[w * T.n_contrast + f] = con;
-          if (parts.comp_mag) { parts.comp_mag[(w * T.n_contrast + f) * NS] = m0; parts.comp_mag[(w * T.n_contrast + f) * NS + 1] = m1; }
+          if (live && parts.contrast) parts.contrast[w * T.n_contrast + f] = con;
+          if (live && parts.comp_mag) { parts.comp_mag[(w * T.n_contrast + f) * NS] = m0; parts.comp_mag[(w * T.n_contrast + f) * NS + 1] = m1; }
         }
         for (int f = 0; f < T.n_phot; ++f) {
           double tot = 0.0;
@@ -666,29 +843,34 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             for (int r = 0; r < NR; ++r) a = fma(cf[stx * NR + r], s_band[(MS_MAX_CONTRAST + f) * NROW + stx * NR + r], a);
             tot += a;
           }
-          double mag = -2.5 * log10(tot * T.p_norm[f]);                   // mft6.py:780-782
-          mag += av * T.p_ext[f];                                         // mft6.py:1163 (av == 0 when skipped)
+          double mag = -2.5 * log10(tot * T.p_norm[f]);                     // mft6.py:780-782
+          mag += av * T.p_ext[f];                                           // mft6.py:1163 (av == 0 when skipped)
           const double d = mag - T.p_mag[f];
           iphot += (d * d) / (T.p_err[f] * T.p_err[f]);
-          if (parts.phot) parts.phot[w * T.n_phot + f] = mag;
+          if (live && parts.phot) parts.phot[w * T.n_phot + f] = mag;
         }
-        const double init_cs = iic * (double)(T.n_contrast + T.n_phot) + icontrast + iphot;   // mft6.py:1191
-        const double lnl = (init_cs != init_cs) ? -CUDART_INF : -0.5 * init_cs;                // mft6.py:1202-1205
-        double out = lp + lnl;
-        if (out != out) out = -CUDART_INF;
-        lnprob[w] = out;
-        if (parts.status) parts.status[w] = (init_cs != init_cs) ? MS_W_NONFINITE : 0;
-        if (parts.lnprior) parts.lnprior[w] = lp;
-        if (parts.chi2_spec) parts.chi2_spec[w] = iic;
-        if (parts.logg) for (int s = 0; s < NS; ++s) parts.logg[w * NS + s] = s_logg[j][s];
+        if (live) {
+          const WalkerPlan& p = plans[w];
+          const double init_cs = iic * (double)(T.n_contrast + T.n_phot) + icontrast + iphot;   // mft6.py:1191
+          const double lnl = (init_cs != init_cs) ? -CUDART_INF : -0.5 * init_cs;                // mft6.py:1202-1205
+          double out = p.lp + lnl;
+          if (out != out) out = -CUDART_INF;
+          lnprob[w] = out;
+          if (parts.status) parts.status[w] = (init_cs != init_cs) ? MS_W_NONFINITE : 0;
+          if (parts.lnprior) parts.lnprior[w] = p.lp;
+          if (parts.chi2_spec) parts.chi2_spec[w] = iic;
+          if (parts.logg) for (int s = 0; s < NS; ++s) parts.logg[w * NS + s] = p.logg[s];
+        }
       }
+      GDBG_REPORT("phaseB")
     }
+    cit0 += (unsigned)n_chunks;
   }
 }
 
-// ---- group table: contiguous runs of at most GW cell-sorted walkers that share a cell ----------------------
+// ---- group table: contiguous runs of at most GMAX cell-sorted walkers that share a cell --------------------
 // cell_start: exclusive prefix of the cell histogram (n_cells + 1 entries); group_off: exclusive prefix of
-// ceil(count / GW).  One thread per walker (after the counting sort has placed it): the first walker of every
+// ceil(count / GMAX).  One thread per walker (after the counting sort has placed it): the first walker of every
 // group writes the descriptor.
 __global__ void group_table_kernel(const WalkerPlan* __restrict__ plans, const int* __restrict__ order, long long nw,
                                    const unsigned* __restrict__ cell_start, const unsigned* __restrict__ group_off,
@@ -697,10 +879,10 @@ __global__ void group_table_kernel(const WalkerPlan* __restrict__ plans, const i
   if (pos >= nw) return;
   const int cell = plans[order[pos]].cell;
   const unsigned local = (unsigned)pos - cell_start[cell];
-  if (local % GW == 0) {
+  if (local % GMAX == 0) {
     const unsigned cnt = cell_start[cell + 1] - cell_start[cell];
-    GroupDesc g; g.start = (int)pos; g.count = (int)min((unsigned)GW, cnt - local);
-    groups[group_off[cell] + local / GW] = g;
+    GroupDesc g; g.start = (int)pos; g.count = (int)min((unsigned)GMAX, cnt - local);
+    groups[group_off[cell] + local / GMAX] = g;
   }
 }
 
@@ -717,7 +899,7 @@ __global__ void __launch_bounds__(1024) group_scan_kernel(unsigned* __restrict__
   for (int base = 0; base < n_cells; base += 1024) {
     const int i = base + tid;
     const unsigned v = (i < n_cells) ? hist_offsets[i] : 0u;
-    const unsigned g = (v + GW - 1) / GW;
+    const unsigned g = (v + GMAX - 1) / GMAX;
     unsigned ia = v, ib = g;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {

@@ -21,6 +21,7 @@
 #include "mcmcspec.h"
 
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <nvtx3/nvToolsExt.h>
@@ -32,6 +33,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace cg = cooperative_groups;
@@ -495,9 +497,14 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   // ---- grid brackets and coefficients.  The corners are stored in a canonical order -- lower node first on every
   // axis -- so that all walkers of one grid cell carry the same row list (the group kernel streams those rows once
   // for the whole group); find_nearest's "nearest node first" order (mft6.py:439-453) only decides which weight
-  // goes with which node.  A walker exactly on a node gets the node above as its (weight 0) partner.
+  // goes with which node.
   auto canon = [](int i1, int i2, double w2, int n, int* lo, int* hi, double* wlo, double* whi) {
-    if (i1 == i2) { *lo = i1; *hi = min(i1 + 1, n - 1); *wlo = 1.0; *whi = 0.0; }
+    if (i1 == i2) {
+      // on a node: the node above is the (weight 0) partner; on the last node the one below is, so that the
+      // corners are always the 2 x 2 (x 2) block starting at the lower node (one tensor-copy box)
+      if (i1 < n - 1 || n == 1) { *lo = i1; *hi = min(i1 + 1, n - 1); *wlo = 1.0; *whi = 0.0; }
+      else { *lo = n - 2; *hi = n - 1; *wlo = 0.0; *whi = 1.0; }
+    }
     else if (i1 < i2) { *lo = i1; *hi = i2; *wlo = 1.0 - w2; *whi = w2; }
     else { *lo = i2; *hi = i1; *wlo = w2; *whi = 1.0 - w2; }
   };
@@ -521,12 +528,13 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
     canon(g1, g2, wg, T.n_logg, &ig[0], &ig[1], &cg[0], &cg[1]);
     const double cz[2] = {czl, czh};
     const int iz[2] = {zlo, zhi};
-    // corners: (t_lo,g_lo) (t_lo,g_hi) (t_hi,g_lo) (t_hi,g_hi) [x z_lo, z_hi]
+    // corners in the order a (pixel, Teff, log g[, Fe/H]) tensor box lands in shared memory, Teff fastest:
+    // (t_lo,g_lo) (t_hi,g_lo) (t_lo,g_hi) (t_hi,g_hi) [x z_lo, z_hi]
     const int nz = (T.n_feh > 1) ? 2 : 1;
     int c = 0;
     for (int a = 0; a < nz; ++a)
-      for (int b = 0; b < 2; ++b)
-        for (int d = 0; d < 2; ++d) {
+      for (int d = 0; d < 2; ++d)
+        for (int b = 0; b < 2; ++b) {
           plan.row[s][c] = (iz[a] * T.n_logg + ig[d]) * T.n_teff + it[b];
           plan.coef[s][c] = ((nz == 2) ? cz[a] : 1.0) * ct[b] * cg[d] * scale;
           ++c;
@@ -1640,13 +1648,14 @@ struct ms_handle {
   bool model_global = false; double* model_scratch = nullptr; size_t model_scratch_cap = 0;   // observed spectra beyond shared memory
   // group kernel (group_kernel.cuh): tables, per-call group list, model-vector scratch slots
   grp::GroupTables GT{};
+  CUtensorMap grid_map{};         // (pixel, Teff, log g) view of the device grid for the group kernel's row boxes
   bool group_ok = false;         // the tables fit the kernel's shared-memory ring (weight slots, records per stage)
   int group_mode = -1;           // -1 automatic (large posterior batches), 0 never, 1 whenever possible
   bool group_now = false;        // decided per call
   long long group_min_walkers = 1024;
   grp::GroupDesc* groups = nullptr; long long groups_cap = 0;
   unsigned* cell_start = nullptr; unsigned* group_off = nullptr; int* n_groups = nullptr;
-  double* group_scratch = nullptr; int* group_counter = nullptr; int group_ctas = 0;
+  double* group_scratch = nullptr; unsigned long long* group_list = nullptr; int* group_counter = nullptr; int group_ctas = 0;
   unsigned char* scratch = nullptr; size_t scratch_cap = 0;   // per-call inputs of ms_optimizer_chisq (grown on demand)
   cudaStream_t own_stream = nullptr;
   // optional device-side timing of the streaming kernel
@@ -1852,12 +1861,12 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
     CK(cudaEventRecord(e0, h->stream));
   }
   auto kern = grp::lnprob_group_kernel<4>;
-  const int smem = grp::NSTAGE * grp::StageLayout<8>::bytes;
+  const int smem = grp::NSTAGE * grp::StageLayout<4>::bytes + grp::NWW * grp::HBINS * 32 * 2 + grp::NWW * grp::CAND * 32 * 8;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const long long max_groups = (nw + grp::GW - 1) / grp::GW + std::min<long long>(h->T.n_cells, nw);
+  const long long max_groups = (nw + grp::GMAX - 1) / grp::GMAX + std::min<long long>(h->T.n_cells, nw);
   const unsigned ctas = (unsigned)std::min<long long>(h->group_ctas, max_groups);
-  kern<<<ctas, grp::NTHREADS, smem, h->stream>>>(h->T, h->GT, h->plans, h->order, h->groups, h->n_groups, h->group_counter,
-                                                 d_lnp, parts, h->group_scratch);
+  kern<<<ctas, grp::NTHREADS, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups, h->group_counter,
+                                                 d_lnp, parts, h->group_scratch, h->group_list);
   CK(cudaGetLastError());
   if (h->timing) CK(cudaEventRecord(e1, h->stream));
   h->launches += 1;
@@ -1922,7 +1931,7 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   CK(cudaGetLastError());
   h->launches += 1;
   if (h->group_now) {
-    const long long max_groups = (nw + grp::GW - 1) / grp::GW + std::min<long long>(h->T.n_cells, nw);
+    const long long max_groups = (nw + grp::GMAX - 1) / grp::GMAX + std::min<long long>(h->T.n_cells, nw);
     if (max_groups > h->groups_cap) {
       CK(cudaStreamSynchronize(h->stream));
       if (h->groups) cudaFree(h->groups);
@@ -2013,6 +2022,7 @@ int ms_destroy(ms_handle* h) {
   if (h->n_groups) cudaFree(h->n_groups);
   if (h->group_scratch) cudaFree(h->group_scratch);
   if (h->group_counter) cudaFree(h->group_counter);
+  if (h->group_list) cudaFree(h->group_list);
   if (h->it_half[0]) cudaFree(h->it_half[0]);
   if (h->it_half[1]) cudaFree(h->it_half[1]);
   if (h->it_q) cudaFree(h->it_q);
@@ -2213,7 +2223,7 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     const int n = cfg->n_data;
     const int n_stages = (cfg->n_reg + TP - 1) / TP;
     const double LN2 = 0.69314718055994530942;
-    bool ok = (cfg->nspec == 2) && (T.n_cells > 1);
+    bool ok = (cfg->nspec == 2) && (T.n_cells > 1) && (cfg->n_data <= 65535);     // uint16 histogram counts
     // observed pixels per stage (rebin_hi ascending): [sd[s], sd[s+1])
     std::vector<int> sd((size_t)n_stages + 1);
     {
@@ -2249,7 +2259,7 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
       }
     }
     std::vector<int4> meta((size_t)n_stages);
-    for (int s = 0; s < n_stages; ++s) meta[s] = make_int4(sd[s], sd[s + 1], -1, 0);
+    for (int s = 0; s < n_stages; ++s) meta[s] = make_int4(sd[s], sd[s + 1] - sd[s], -1, 0);
     if (ok) {
       for (const auto& b : bands) {
         for (int s = b.s_lo; s < b.s_hi; ++s) {
@@ -2260,47 +2270,84 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
         meta[b.s_hi - 1].w |= 1 << b.slot;
       }
     }
-    // records: x = (ext - anchor of the stage) ln 2; d q_k(x) of norm_spec's orthonormal quadratic basis
+    // records, one block per stage: x = (ext - anchor of the stage) ln 2; d q_k(x) of norm_spec's orthonormal
+    // quadratic basis; tile-local upper bracket
     std::vector<double> anchor((size_t)n_stages + 32, 0.0);
-    std::vector<double2> ra((size_t)n + 4), rb((size_t)n + 4), rc((size_t)n + 4);
-    std::vector<int> hl((size_t)n + 8, 0);
+    std::vector<unsigned char> blk;
     std::vector<double> dr2(4 * (size_t)n);
     double xmax = 0.0;
     for (int s = 0; s < n_stages; ++s) {
-      if (sd[s + 1] > sd[s]) anchor[s] = 0.5 * (cfg->ext_lo[sd[s]] + cfg->ext_hi[sd[s + 1] - 1]);
-      for (int i = sd[s]; i < sd[s + 1]; ++i) {
+      const int d0 = sd[s], ns_ = sd[s + 1] - sd[s];
+      const size_t off = blk.size();
+      meta[s].x = d0; meta[s].y = ns_;
+      meta[s].w = (meta[s].w & 0xff) | (int)((off / 16) << 8);
+      if (ns_ == 0) continue;
+      anchor[s] = 0.5 * (cfg->ext_lo[d0] + cfg->ext_hi[d0 + ns_ - 1]);
+      const size_t bytes = ((size_t)ns_ * 52 + 15) & ~(size_t)15;
+      blk.resize(off + bytes, 0);
+      double2* pa = reinterpret_cast<double2*>(blk.data() + off);
+      double2* pb = pa + ns_; double2* pc = pb + ns_;
+      int* ph = reinterpret_cast<int*>(pc + ns_);
+      for (int k = 0; k < ns_; ++k) {
+        const int i = d0 + k;
         const double xlo = (cfg->ext_lo[i] - anchor[s]) * LN2, xhi = (cfg->ext_hi[i] - anchor[s]) * LN2;
         xmax = std::max(xmax, std::max(std::fabs(xlo), std::fabs(xhi)));
         const double x = cfg->data_x[i], d = cfg->data_flux[i];
         const double q0 = T.basis[0], q1 = std::fma(T.basis[4], x, T.basis[3]);
         const double q2 = std::fma(std::fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
-        ra[i] = make_double2(cfg->rebin_t[i], xlo);
-        rb[i] = make_double2(xhi, d * q0);
-        rc[i] = make_double2(d * q1, d * q2);
-        hl[i] = cfg->rebin_hi[i] - s * TP;
+        pa[k] = make_double2(cfg->rebin_t[i], xlo);
+        pb[k] = make_double2(xhi, d * q0);
+        pc[k] = make_double2(d * q1, d * q2);
+        ph[k] = cfg->rebin_hi[i] - s * TP;
         dr2[4 * (size_t)i] = q1; dr2[4 * (size_t)i + 1] = q2; dr2[4 * (size_t)i + 2] = d;
         dr2[4 * (size_t)i + 3] = 1.0 / (cfg->data_err[i] * cfg->data_err[i]);
       }
     }
-    for (int k = 0; k < 4; ++k) { ra[(size_t)n + k] = rb[(size_t)n + k] = rc[(size_t)n + k] = make_double2(0.0, 0.0); }
+    if (blk.size() / 16 >= (1u << 23)) ok = false;
+    blk.resize(blk.size() + 64, 0);
     grp::GroupTables& GT = h->GT;
-    GT.n_stages = n_stages; GT.xmax = xmax;
+    GT.n_stages = n_stages; GT.xmax = xmax; GT.n_teff = cfg->n_teff;
     CKC(upload(h, meta.data(), meta.size(), &GT.stage_meta));
-    CKC(upload(h, ra.data(), ra.size(), &GT.recA));
-    CKC(upload(h, rb.data(), rb.size(), &GT.recB));
-    CKC(upload(h, rc.data(), rc.size(), &GT.recC));
-    CKC(upload(h, hl.data(), hl.size(), &GT.hl));
+    CKC(upload(h, blk.data(), blk.size(), &GT.recblk));
     CKC(upload(h, anchor.data(), anchor.size(), &GT.anchor));
     CKC(upload(h, dr2.data(), dr2.size(), &GT.drec2));
     for (int c = 0; c < BAND_COLS; ++c) GT.wbase[c] = (c < MS_MAX_CONTRAST) ? T.c_wbase[c] : T.p_wbase[c - MS_MAX_CONTRAST];
+    // (pixel, Teff, log g) tensor map of the device grid: one box = the 2 x 2 bracketing rows of a star
+    if (ok && cfg->n_feh == 1 && cfg->n_teff >= 2 && cfg->n_logg >= 2) {
+      typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+          qres != cudaDriverEntryPointSuccess) {
+        ok = false;
+      } else {
+        const cuuint64_t gdim[3] = {(cuuint64_t)T.stride, (cuuint64_t)cfg->n_teff, (cuuint64_t)cfg->n_logg};
+        const cuuint64_t gstr[2] = {(cuuint64_t)T.stride * 8, (cuuint64_t)T.stride * 8 * (cuuint64_t)cfg->n_teff};
+        const cuuint32_t box[3] = {(cuuint32_t)ROWPX, 2u, 2u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult cr = reinterpret_cast<EncodeFn>(fn)(&h->grid_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(T.grid),
+                                                          gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) ok = false;
+      }
+    } else {
+      ok = false;
+    }
     h->group_ok = ok;
-    // persistent CTAs, two per SM; scratch: one model vector per walker warp of every CTA
+    // persistent CTAs, two per SM
     h->group_ctas = 2 * h->num_sms;
     CKH(cudaMalloc((void**)&h->cell_start, ((size_t)T.n_cells + 1) * sizeof(unsigned)));
     CKH(cudaMalloc((void**)&h->group_off, (size_t)T.n_cells * sizeof(unsigned)));
     CKH(cudaMalloc((void**)&h->n_groups, sizeof(int)));
     CKH(cudaMalloc((void**)&h->group_counter, sizeof(int)));
-    if (ok) CKH(cudaMalloc((void**)&h->group_scratch, (size_t)h->group_ctas * GW * (size_t)n * sizeof(double)));
+    if (ok) {
+      // per CTA: the transposed model vectors [n][32] and the walker warps' key lists [NWW][LISTCAP][32]
+      CKH(cudaMalloc((void**)&h->group_scratch, (size_t)h->group_ctas * (size_t)n * 32 * sizeof(double)));
+      CKH(cudaMalloc((void**)&h->group_list, (size_t)h->group_ctas * (NWW + 1) * (size_t)LISTCAP * 32 * sizeof(unsigned long long)));
+    }
   }
 
   // ---- isochrone, dust

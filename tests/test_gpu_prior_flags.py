@@ -66,3 +66,33 @@ def test_prior_flag_combination(native_lib, nspec, dist_fit, rad_prior, a):
     assert 64 <= f.sum() < N                                     # both finite and -inf vectors are present
     rel = np.abs(got[f] - want[f]) / np.abs(want[f])
     assert rel.max() <= 1e-9, f"max rel err {rel.max():.3e}"
+
+
+def test_device_bayestar_rule_documented_cases(native_lib):
+    """walker_prep_kernel's Av prior against the dustmaps rule written out by hand (tests/test_published_known_answers.py
+    cites it): exactly on a distance slice, half-way in DM between two slices, nearer than the first slice (linear in
+    distance), beyond the last slice -- with every other prior term switched off."""
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    prob = synthetic.make_problem_small(rad_prior=False)
+    prob.prior = [0.0] * len(prob.prior)
+    edges, samples = prob.dust_dm_edges, prob.dust_samples
+    k10 = int(round((10.0 - edges[0]) / (edges[1] - edges[0])))
+    cases = {
+        1000.0: samples[:, k10],
+        10 ** ((10.0 + 0.0625) / 5 + 1): 0.5 * (samples[:, k10] + samples[:, k10 + 1]),
+        0.5 * 10 ** (edges[0] / 5 + 1): 0.5 * samples[:, 0],
+        2900.0: None,
+    }
+    theta = np.tile(np.asarray(prob.truth, dtype=float), (len(cases), 1))
+    for k, d in enumerate(cases):
+        theta[k, 5] = 1.0 / d
+    lp = LogPosterior(prob)
+    got = lp.parts(theta)['lnprior']
+    lp.close()
+    for k, (d, e) in enumerate(cases.items()):
+        if e is None:
+            continue
+        e = e * 3.1 * 0.884
+        want = -0.5 * ((theta[k, 2] - e.mean()) / (e.std() if e.std() else 0.05)) ** 2
+        assert got[k] == pytest.approx(want, rel=1e-11, abs=1e-13), d
