@@ -131,7 +131,10 @@ def test_fused_iteration_is_the_same_chain(small_problem, small_lp, nw, randomiz
     assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
     assert np.array_equal(a.naccepted.cpu().numpy(), b.naccepted.cpu().numpy())
     assert a.naccepted.sum().item() > 0 and a.iteration == b.iteration == 12
-    assert n1 - n0 == 12 * (1 + 2 * 3)                    # split + 2 x (propose+prep, stream, accept in place)
+    # split + 2 x (propose+prep, stream, accept in place); half steps of >= 1024 walkers go through the group kernel,
+    # which adds the cell sort and the group table (scan, scatter, table)
+    per_half = 3 + (3 if nw // 2 >= 1024 and small_lp.engine.group_supported else 0)
+    assert n1 - n0 == 12 * (1 + 2 * per_half)
 
 
 def test_emcee_style_calls_on_the_device_sampler(small_problem, small_lp):
