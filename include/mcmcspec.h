@@ -253,6 +253,19 @@ int ms_stretch_scatter(ms_handle* h, double* state, int32_t* naccepted, const in
                        int64_t n, int32_t ndim);
 
 /*
+ * One half step of the stretch move for ensembles of any size, sharded or not, in one call: the proposal for the
+ * n_s walkers state[s_idx[k]] (partners drawn from state[c_idx[0..n_c)]; random streams keyed by (seed, iteration,
+ * split, gid0 + k), as ms_stretch_propose) is folded into the preparation kernel, the proposals are evaluated, and the
+ * acceptance test is applied -- in place when `packed` is NULL (this rank owns the whole active half), otherwise into
+ * packed[n_s][ncol + 2] = new position | new log-prob | accepted, the rows the ranks exchange (one all-gather) and
+ * ms_stretch_scatter applies.  q [n_s][ncol], logfac [n_s], lnp_q [n_s] are device scratch owned by the caller.
+ * All pointers are device pointers; work is enqueued on the handle's stream.
+ */
+int ms_stretch_halfstep(ms_handle* h, double* state, int32_t* naccepted, const int64_t* s_idx, int64_t n_s,
+                        const int64_t* c_idx, int64_t n_c, double a, uint64_t seed, uint64_t iteration, int32_t split,
+                        int64_t gid0, double* q, double* logfac, double* lnp_q, double* packed);
+
+/*
  * One whole ensemble iteration (both half steps) for a single-rank ensemble of at most 2048 walkers, enqueued
  * from one call: the iteration's red/blue split (hashed keys sorted in one CTA; randomize_split = 0 gives
  * evens/odds), then per half: propose, evaluate (prep + streaming kernel), accept, scatter -- in place on
@@ -328,6 +341,14 @@ int ms_set_cell_order(ms_handle* h, int mode);
  */
 int ms_set_group(ms_handle* h, int mode, int64_t min_walkers);
 int ms_group_supported(const ms_handle* h);
+
+/*
+ * Evaluations that were cut short before any grid row was read (outside the prior box, off the isochrone or the
+ * grid, non-finite input: -inf per mft6.py:1227-1230, :1465-1466) since the handle was created or the counter was
+ * last reset.  Synchronises the handle's stream.  bench.py reports it so that a throughput figure cannot hide
+ * skipped work.
+ */
+int ms_short_circuited(ms_handle* h, int64_t* count, int reset);
 
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 int64_t ms_launch_count(const ms_handle* h);

@@ -11,15 +11,15 @@
 //                             block of per-observed-pixel records; completion is counted in bytes on the stage's
 //                             `full` mbarrier, `empty` mbarriers hand slots back.  After the stream: bulk copies of
 //                             the chi-square pass's per-pixel records through two slots of the same ring.
-//   warp 1      gather     -- for every observed pixel whose upper bracketing model pixel lies in the stage, the two
-//                             bracketing pixels of every row out of the staged segments (mft6.py:1169: interp1d onto
-//                             the observed wavelengths) into a compact table B[row][pixel]; `bready` mbarrier.
-//   warps 2,3   band       -- integrate every staged ROW through the passbands that touch the stage
+//   warps 1..3  service    -- gather: for every observed pixel whose upper bracketing model pixel lies in the stage, the
+//                             two bracketing pixels of every row out of the staged segments (mft6.py:1169: interp1d
+//                             onto the observed wavelengths) into a compact table B[row][pixel]; `bready` mbarrier.
+//                             Warps 2, 3 also integrate every staged ROW through the passbands that touch the stage
 //                             (sum_p w_f[p] * row[p]: np.trapz of mft6.py:731 resp. pyphot get_flux, mft6.py:776, both
 //                             linear in the spectrum); a walker's band fluxes are the same linear combination of these
 //                             row integrals as its spectrum is of the rows (mft6.py:507-519, :689-700).
-//   warps 4..7  walkers    -- LANE = WALKER: lane l of every walker warp serves walker l of the group and keeps its
-//                             eight row coefficients and Av in registers; the four warps split the observed pixels of
+//   warps 4..   walkers    -- LANE = WALKER: lane l of every walker warp serves walker l of the group and keeps its
+//                             eight row coefficients and Av in registers; the 4 or 8 warps split the observed pixels of
 //                             each stage between them.  B and the records are the same for all lanes, so every
 //                             shared-memory read is a one-wavefront broadcast.  Per pixel and lane: composite at the
 //                             two bracketing pixels (FMA chain over the rows, then the sum over the stars,
@@ -56,16 +56,19 @@ constexpr int ROWB = ROWPX * 8;            // 1040 bytes
 constexpr int WS = MS_GROUP_WSLOTS;        // weight slots: passbands that may overlap on one stage
 constexpr int RCAP = MS_GROUP_RCAP;        // observed pixels per stage the ring is sized for
 constexpr int NSTAGE = 3;
-constexpr int NWW = 4;                     // walker warps per CTA: they split the observed pixels of the group's 32 walkers
+constexpr int NWW_MAX = 8;                 // walker warps per CTA (template parameter NWW: 4 with two CTAs per SM, 8 with
+                                           // one): they split the observed pixels of the group's 32 walkers
 constexpr int GMAX = 32;                   // walkers per group (one per lane)
 constexpr int NSERVICE = 4;                // producer, gather, 2 x band
-constexpr int NTHREADS = (NWW + NSERVICE) * 32;
 constexpr int BROWB = RCAP * 16 + 16;      // stride of a B row (one pad slot: conflict-free stores from 8 rows)
 constexpr int HBITS = 6;
 constexpr int HBINS = 1 << HBITS;          // per-lane histogram bins
 constexpr int CHI_CHUNK = 64;              // observed pixels per ring slot in the chi-square pass: 32-byte records + the
                                            // group's model values [pixel][lane]
 constexpr int LISTCAP = 1024;              // keys of the median's bin a lane collects (per walker warp)
+constexpr int VW = 8;                      // partial sums per walker: quadruple q of a stage / block b of a chunk goes to partial
+                                           // q mod 8 resp. b mod 8 whatever the number of walker warps, so that a walker's value
+                                           // does not depend on the kernel variant
 constexpr int PIX = 4;                     // observed pixels a walker lane keeps in flight (independent FMA chains)
 constexpr int CAND = 8;                    // keys of the median's second-level bin per lane and walker warp (fast finish)
 constexpr double POLY_XMAX = 0.02;
@@ -234,6 +237,7 @@ __device__ __forceinline__ unsigned lane_compact(unsigned long long* col, unsign
 }
 
 // Sum of the NWW walker warps' histogram columns, scanned in the order first + t (mod HBINS).
+template <int NWW>
 __device__ __forceinline__ void lane_locate_merged(const unsigned short* hist_all, int lane, unsigned first, unsigned rank,
                                                    unsigned& bin_t, unsigned& below, unsigned& in_bin) {
   unsigned cum = 0;
@@ -250,13 +254,14 @@ __device__ __forceinline__ void lane_locate_merged(const unsigned short* hist_al
   }
 }
 
+template <int NWW>
 __device__ __forceinline__ void walker_bar() { asm volatile("bar.sync 1, %0;" :: "n"(NWW * 32) : "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // NR: grid rows per star (4; 8 with [Fe/H] is not instantiated yet).  Binaries, posterior mode.
 // ------------------------------------------------------------------------------------------
-template <int NR>
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <int NR, int NWW, int CTAS_PER_SM>
+__global__ void __launch_bounds__((NWW + NSERVICE) * 32, CTAS_PER_SM)
 lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__ GroupTables GT,
                     const __grid_constant__ CUtensorMap grid_map, const WalkerPlan* __restrict__ plans,
                     const int* __restrict__ order, const GroupDesc* __restrict__ groups, const int* __restrict__ n_groups,
@@ -264,12 +269,15 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
                     double* __restrict__ scratch, unsigned long long* __restrict__ list_scratch) {
   constexpr int NS = 2;
   constexpr int NROW = NS * NR;
+  constexpr int NTHREADS = (NWW + NSERVICE) * 32;
+  static_assert(NWW <= NWW_MAX && VW % NWW == 0, "scratch is sized for NWW_MAX walker warps; partial sums are dealt to the warps");
+  constexpr int NV = VW / NWW;                                     // partial sums a walker warp carries
   using L = StageLayout<NR>;
   extern __shared__ __align__(128) unsigned char gsm[];
   unsigned short* const hist_all = reinterpret_cast<unsigned short*>(gsm + NSTAGE * L::bytes);   // [NWW][HBINS][32]
   __shared__ __align__(8) unsigned long long s_full[NSTAGE], s_empty[NSTAGE], s_bready[NSTAGE], s_cfull[NSTAGE], s_cempty[NSTAGE];
   __shared__ double s_band[BAND_COLS * NROW];            // row integrals through every band
-  __shared__ double s_part[NWW][4][32];                  // per walker warp and lane: three moments / chi-square
+  __shared__ double s_part[VW][4][32];                   // per partial sum and lane: three moments / chi-square
   __shared__ unsigned long long s_above[NWW][32];
   __shared__ unsigned s_kmin[NWW][32], s_kmax[NWW][32], s_nl[NWW][32], s_nc[NWW][32];
   __shared__ int s_row[NROW];
@@ -279,8 +287,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(smem_u32(&s_full[s]), 1);
-      mbar_init(smem_u32(&s_empty[s]), (unsigned)(NWW + 3));       // every walker warp + gather + 2 band warps
-      mbar_init(smem_u32(&s_bready[s]), 1);
+      mbar_init(smem_u32(&s_empty[s]), (unsigned)(NWW + 3));       // every walker warp + the three service workers
+      mbar_init(smem_u32(&s_bready[s]), 3);                         // the three service workers each gather a share
     }
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(smem_u32(&s_cfull[s]), 1); mbar_init(smem_u32(&s_cempty[s]), (unsigned)NWW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -293,7 +301,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
   const int wj = warp - NSERVICE;                                  // walker warp index, < 0 for the service warps
   // the CTA's scratch, reused by every group it takes: model values [pixel][lane], key lists [warp][slot][lane]
   double* const sMT = scratch + (size_t)blockIdx.x * (size_t)n * 32;
-  unsigned long long* const list0 = list_scratch + (size_t)blockIdx.x * (NWW + 1) * (size_t)LISTCAP * 32;   // + a spare list
+  unsigned long long* const list0 = list_scratch + (size_t)blockIdx.x * (NWW_MAX + 1) * (size_t)LISTCAP * 32;   // + a spare list
   unsigned long long* const listT = list0 + (size_t)max(wj, 0) * LISTCAP * 32;
   unsigned short* const hist = hist_all + (size_t)max(wj, 0) * HBINS * 32;
   unsigned it0 = 0, cit0 = 0;               // ring uses so far (stages / chi-square chunks): slot and mbarrier parity go on
@@ -385,46 +393,13 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         meta = meta_next;
       }
       GDBG_REPORT("producer")
-    } else if (warp == 1) {
-      // ================================================================= gather
-      GDBG_DECL
-      for (int s = 0; s < n_stages; ++s) {
-        const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs % NSTAGE);
-        GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NSTAGE) & 1u))
-        const uint32_t st = ring + (uint32_t)slot * L::bytes;
-        const int4 meta = *reinterpret_cast<const int4*>(gsm + (size_t)slot * L::bytes + L::meta);
-        const int n_obs = meta.y;
-        const int r = lane & 7;
-        const uint32_t hlp = st + L::rec + (uint32_t)n_obs * 48;
-#pragma unroll 4
-        for (int k0 = 0; k0 < n_obs; k0 += 4) {
-          const int k = k0 + (lane >> 3);
-          if (k < n_obs) {
-            int hl;
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(hl) : "r"(hlp + 4 * k));
-            const int j1 = hl + 1;                          // tile index of the lower bracket (upper: hl + 2)
-            const int e = j1 & ~1;
-#pragma unroll
-            for (int rr = 0; rr < NROW; rr += 8) {
-              const uint32_t rp = st + L::rows + (uint32_t)L::row_off(rr + r) + (uint32_t)e * 8;
-              const double2 v01 = lds128(rp);
-              const double v2 = lds64(rp + 16);
-              double2 pr;
-              pr.x = (j1 & 1) ? v01.y : v01.x;
-              pr.y = (j1 & 1) ? v2 : v01.y;
-              sts128(st + L::B + (uint32_t)(rr + r) * BROWB + (uint32_t)k * 16, pr);
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(smem_u32(&s_bready[slot])); mbar_arrive(smem_u32(&s_empty[slot])); }
-      }
-      GDBG_REPORT("gather")
     } else if (warp < NSERVICE) {
-      // ================================================================= band integration (rows [r0, r0 + NROW/2))
+      // ================================================================= service workers (warps 1..3): gather + band
+      // integration.  Each takes every third quadruple of observed pixels of the gather; warps 2 and 3 also integrate
+      // half of the rows each through the passbands.
       constexpr int HR = NROW / 2;
-      const int r0 = (warp - 2) * HR;
+      const int sw = warp - 1;                                        // 0, 1, 2
+      const int r0 = (warp == 3) ? HR : 0;
       double acc[HR][WS];
 #pragma unroll
       for (int r = 0; r < HR; ++r) {
@@ -438,8 +413,35 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NSTAGE) & 1u))
         const uint32_t st = ring + (uint32_t)slot * L::bytes;
         const int4 meta = *reinterpret_cast<const int4*>(gsm + (size_t)slot * L::bytes + L::meta);
+        const int n_obs = meta.y;
+        {
+          const int r = lane & 7;
+          const uint32_t hlp = st + L::rec + (uint32_t)n_obs * 48;
+#pragma unroll 2
+          for (int k0 = 4 * sw; k0 < n_obs; k0 += 12) {
+            const int k = k0 + (lane >> 3);
+            if (k < n_obs) {
+              int hl;
+              asm volatile("ld.shared.s32 %0, [%1];" : "=r"(hl) : "r"(hlp + 4 * k));
+              const int j1 = hl + 1;                          // tile index of the lower bracket (upper: hl + 2)
+              const int e = j1 & ~1;
+#pragma unroll
+              for (int rr = 0; rr < NROW; rr += 8) {
+                const uint32_t rp = st + L::rows + (uint32_t)L::row_off(rr + r) + (uint32_t)e * 8;
+                const double2 v01 = lds128(rp);
+                const double v2 = lds64(rp + 16);
+                double2 pr;
+                pr.x = (j1 & 1) ? v01.y : v01.x;
+                pr.y = (j1 & 1) ? v2 : v01.y;
+                sts128(st + L::B + (uint32_t)(rr + r) * BROWB + (uint32_t)k * 16, pr);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_bready[slot]));           // this worker's share of B is written
         const unsigned slots = (unsigned)meta.z, flush = (unsigned)meta.w & 0xffu;
-        if (slots != 0xffffffffu) {
+        if (warp >= 2 && slots != 0xffffffffu) {
           // this lane's pixels of the tile: {2l, 2l+1} and {64 + 2l, 65 + 2l} (16-byte accesses, lanes contiguous)
 #pragma unroll
           for (int q = 0; q < WS; ++q) {
@@ -470,11 +472,13 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_empty[slot]));
       }
-      GDBG_REPORT("band")
+      GDBG_REPORT("service")
     } else {
       // ================================================================= walker warps, phase A: lane = walker; warp wj
       // takes the observed pixel quadruples wj, wj + NWW, ... of every stage
-      double mom0 = 0.0, mom1 = 0.0, mom2 = 0.0;
+      double momv[NV][3];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { momv[v][0] = 0.0; momv[v][1] = 0.0; momv[v][2] = 0.0; }
       unsigned kmin = 0xffffffffu, kmax = 0u;
       {
         const WalkerPlan& p = plans[w];
@@ -497,7 +501,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         const unsigned char* stp = gsm + (size_t)slot * L::bytes;
         const int4 meta = *reinterpret_cast<const int4*>(stp + L::meta);
         const int n_obs = meta.y;
-        if (PIX * wj < n_obs) {
+        if (PIX * wj < n_obs) {                                            // this warp has pixels in the stage
           const double anc = __ldg(GT.anchor + s);
           const double A = exp2(av * anc);                                  // the stage's common extinction factor
           double* dst = sMT + (size_t)meta.x * 32 + lane;
@@ -535,22 +539,30 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             rm_out = fast_rcp(m);
             return m;
           };
-          auto tally = [&](int k, double m, double rm) {
+          auto tally = [&](int k, double m, double rm, double (&mom)[3]) {
             const double dq0 = recB[k].y; const double2 rc = recC[k];      // d q0, d q1, d q2
-            mom0 = fma(dq0, rm, mom0); mom1 = fma(rc.x, rm, mom1); mom2 = fma(rc.y, rm, mom2);   // norm_spec moments, mft6.py:194-195
+            mom[0] = fma(dq0, rm, mom[0]); mom[1] = fma(rc.x, rm, mom[1]); mom[2] = fma(rc.y, rm, mom[2]);   // norm_spec moments, mft6.py:194-195
             const unsigned hk = hi_key(m);
             kmin = min(kmin, hk); kmax = max(kmax, hk);
             hist[((hk >> (20 - (HBITS - 3))) & (HBINS - 1)) * 32 + lane] += 1;   // 3 exponent bits + HBITS - 3 mantissa bits
             dst[(size_t)k * 32] = m;
           };
           auto run = [&](auto poly) {
-            for (int k = PIX * wj; k < n_obs; k += PIX * NWW) {             // PIX independent pixels in flight
-              double mv[PIX], rmv[PIX];
+            // quadruple q of the stage (pixels 4q .. 4q+3) belongs to partial sum q mod VW; this warp carries the
+            // partials wj, wj + NWW, ...
+            for (int q0 = 0; q0 * PIX < n_obs; q0 += VW) {
 #pragma unroll
-              for (int u = 0; u < PIX; ++u) mv[u] = pixel(poly, min(k + u, n_obs - 1), rmv[u]);   // no branch: the chains interleave
+              for (int v = 0; v < NV; ++v) {
+                const int k = (q0 + wj + v * NWW) * PIX;
+                if (k < n_obs) {                                             // warp-uniform
+                  double mv[PIX], rmv[PIX];
 #pragma unroll
-              for (int u = 0; u < PIX; ++u)
-                if (k + u < n_obs) tally(k + u, mv[u], rmv[u]);
+                  for (int u = 0; u < PIX; ++u) mv[u] = pixel(poly, min(k + u, n_obs - 1), rmv[u]);   // no branch: the chains interleave
+#pragma unroll
+                  for (int u = 0; u < PIX; ++u)
+                    if (k + u < n_obs) tally(k + u, mv[u], rmv[u], momv[v]);
+                }
+              }
             }
           };
           if (poly_ok) run(std::true_type{}); else run(std::false_type{});
@@ -558,7 +570,11 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_empty[slot]));
       }
-      s_part[wj][0][lane] = mom0; s_part[wj][1][lane] = mom1; s_part[wj][2][lane] = mom2;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s_part[wj + v * NWW][c][lane] = momv[v][c];
+      }
       s_kmin[wj][lane] = kmin; s_kmax[wj][lane] = kmax;
       asm volatile("fence.proxy.async;" ::: "memory");                  // the model values are read back by bulk copies
       GDBG_REPORT("walker")
@@ -590,7 +606,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       for (int c = 0; c < 3; ++c) {
         double a = s_part[0][c][lane];
 #pragma unroll
-        for (int j = 1; j < NWW; ++j) a += s_part[j][c][lane];
+        for (int j = 1; j < VW; ++j) a += s_part[j][c][lane];
         mom[c] = a;
       }
       unsigned kmin = s_kmin[0][lane], kmax = s_kmax[0][lane];
@@ -611,11 +627,11 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         constexpr int SH = 20 - (HBITS - 3);                                // hi-key bits below the histogram digit
         unsigned bin_t, below, in_bin;
         const unsigned first = (kmin >> SH) & ~((1u << (HBITS - 3)) - 1u);     // lowest binade, mantissa bits 0
-        lane_locate_merged(hist_all, lane, first, S.rank, bin_t, below, in_bin);
+        lane_locate_merged<NWW>(hist_all, lane, first, S.rank, bin_t, below, in_bin);
         S.prefix = (unsigned long long)(first + bin_t) << (32 + SH); S.bits = 32 - SH;
         S.rank -= below; S.cnt = in_bin;
       }
-      walker_bar();                                                         // every warp has read the phase-A histograms
+      walker_bar<NWW>();                                                         // every warp has read the phase-A histograms
       if (!all_fast) {
         // general case: digits below the common prefix of the lane's key range, from the scratch column
         const unsigned long long k0 = (unsigned long long)kmin << 32, k1 = ((unsigned long long)kmax << 32) | 0xffffffffull;
@@ -635,58 +651,87 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       // {q1, q2, d, 1/e^2} arrive through the ring (bulk copies by the producer warp), the model values are read one
       // block ahead.  Branch free: eight independent pixels are in flight per lane.
       const double a0q0 = mom[0] * T.basis[0], a1 = mom[1], a2 = mom[2];
-      double chi = 0.0;
+      double chiv[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) chiv[v] = 0.0;
       unsigned nl = 0;
-      unsigned long long above = ~0ull;
+      unsigned long long above = ~0ull;                                     // smallest key above the wanted (sub-)bin seen so far
       const bool collect = S.cnt <= (unsigned)LISTCAP && S.bits < 64;      // per lane; otherwise the slow path below
       const int width2 = min(HBITS, 64 - S.bits);
       const int shift2 = max(64 - S.bits - width2, 0);
       lane_hist_zero(hist, lane);
       {
-        const unsigned long long himask = (S.bits >= 64) ? ~0ull : (S.bits == 0 ? 0ull : (~0ull << (64 - S.bits)));
-        const unsigned long long prefix = S.prefix;
         constexpr int U = 8;
-        constexpr int PER_WARP = CHI_CHUNK / NWW;                           // pixels of a chunk per walker warp
-        static_assert(PER_WARP % U == 0, "a warp's share of a chunk is whole blocks");
-        for (int c = 0; c < n_chunks; ++c) {
-          const unsigned gs = cit0 + (unsigned)c;
-          const int slot = (int)(gs % NSTAGE);
-          GDBG_WAIT(mbar_wait(smem_u32(&s_cfull[slot]), (gs / NSTAGE) & 1u))
-          const dbl4* rec = reinterpret_cast<const dbl4*>(gsm + (size_t)slot * L::bytes);
-          const double* mch = reinterpret_cast<const double*>(gsm + (size_t)slot * L::bytes + CHI_CHUNK * 32) + lane;
-          const int npx = min(CHI_CHUNK, n - c * CHI_CHUNK);
-          for (int p0 = wj * PER_WARP; p0 < (wj + 1) * PER_WARP && p0 < npx; p0 += U) {
-            double res[U]; unsigned long long key[U];
+        static_assert(CHI_CHUNK == VW * U, "block b of a chunk belongs to partial sum b");
+        // HI32: every lane's prefix sits in the high word of the key (always so on the histogram path): 32-bit tests
+        auto chi_pass = [&](auto hi32) {
+          constexpr bool HI32 = decltype(hi32)::value;
+          const unsigned long long himask = (S.bits >= 64) ? ~0ull : (S.bits == 0 ? 0ull : (~0ull << (64 - S.bits)));
+          const unsigned long long prefix = S.prefix;
+          const unsigned himask_h = (unsigned)(himask >> 32), prefix_h = (unsigned)(prefix >> 32);
+          const unsigned bound_h = prefix_h | ~himask_h;                   // high word of the bin's largest key
+          unsigned above_h = 0xffffffffu;
+          for (int c = 0; c < n_chunks; ++c) {
+            const unsigned gs = cit0 + (unsigned)c;
+            const int slot = (int)(gs % NSTAGE);
+            GDBG_WAIT(mbar_wait(smem_u32(&s_cfull[slot]), (gs / NSTAGE) & 1u))
+            const dbl4* rec = reinterpret_cast<const dbl4*>(gsm + (size_t)slot * L::bytes);
+            const double* mch = reinterpret_cast<const double*>(gsm + (size_t)slot * L::bytes + CHI_CHUNK * 32) + lane;
+            const int npx = min(CHI_CHUNK, n - c * CHI_CHUNK);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const bool valid = p0 + u < npx;
-              const int pp = min(p0 + u, npx - 1);
-              const double m = mch[pp * 32];
-              const dbl4 r4 = rec[pp];                                      // same address in every lane
-              const double pfit = fma(a2, r4.y, fma(a1, r4.x, a0q0));
-              const double r = m - r4.z * fast_rcp(pfit);
-              res[u] = valid ? (r * r) * r4.w : 0.0;
-              key[u] = ordered_key(m);
-            }
+            for (int v = 0; v < NV; ++v) {
+              const int p0 = (wj + v * NWW) * U;
+              if (p0 < npx) {                                                // warp-uniform
+                double res[U], mval[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              chi += res[u];
-              const bool valid = p0 + u < npx;
-              const bool hit = valid && (key[u] & himask) == prefix;
-              if (hit && collect) {
-                listT[(size_t)nl * 32 + lane] = key[u];
-                hist[(unsigned)((key[u] >> shift2) & ((1u << width2) - 1u)) * 32 + lane] += 1;
+                for (int u = 0; u < U; ++u) {
+                  const bool valid = p0 + u < npx;
+                  const int pp = min(p0 + u, npx - 1);
+                  const double m = mch[pp * 32];
+                  const dbl4 r4 = rec[pp];                                  // same address in every lane
+                  const double pfit = fma(a2, r4.y, fma(a1, r4.x, a0q0));
+                  const double r = m - r4.z * fast_rcp(pfit);
+                  res[u] = valid ? (r * r) * r4.w : 0.0;
+                  mval[u] = m;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                  chiv[v] += res[u];
+                  const bool valid = p0 + u < npx;
+                  bool hit;
+                  if constexpr (HI32) hit = valid && (hi_key(mval[u]) & himask_h) == prefix_h;
+                  else hit = valid && (ordered_key(mval[u]) & himask) == prefix;
+                  if (hit && collect) {
+                    const unsigned long long key = ordered_key(mval[u]);
+                    listT[(size_t)nl * 32 + lane] = key;
+                    hist[(unsigned)((key >> shift2) & ((1u << width2) - 1u)) * 32 + lane] += 1;
+                  }
+                  nl += hit ? 1u : 0u;
+                  // smallest key above the bin (the upper median of an even-sized vector when the lower one is the
+                  // bin's largest key): the high words are compared first, the running minimum rarely changes
+                  if constexpr (HI32) {
+                    const unsigned hk = hi_key(mval[u]);
+                    if (valid && hk > bound_h && hk <= above_h) {
+                      above = min(above, ordered_key(mval[u]));
+                      above_h = (unsigned)(above >> 32);
+                    }
+                  } else {
+                    const unsigned long long key = ordered_key(mval[u]);
+                    if (valid && !hit && key > prefix) above = min(above, key);
+                  }
+                }
               }
-              nl += hit ? 1u : 0u;
-              if (valid && !hit && key[u] > prefix) above = min(above, key[u]);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_cempty[slot]));
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&s_cempty[slot]));
-        }
+        };
+        if (__all_sync(0xffffffffu, S.bits <= 32)) chi_pass(std::true_type{}); else chi_pass(std::false_type{});
       }
-      s_part[wj][3][lane] = chi; s_nl[wj][lane] = collect ? nl : 0u;
-      walker_bar();
+#pragma unroll
+      for (int v = 0; v < NV; ++v) s_part[wj + v * NWW][3][lane] = chiv[v];
+      s_nl[wj][lane] = collect ? nl : 0u;
+      walker_bar<NWW>();
       // ---- second level: every warp locates the sub-bin in the summed second-level histograms, then filters its own
       // list into a small candidate buffer
       unsigned long long* const cand_all = reinterpret_cast<unsigned long long*>(hist_all + NWW * HBINS * 32);   // [NWW][CAND][32]
@@ -696,7 +741,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       bool overflow = !collect;
       {
         unsigned bin, below, in_bin;
-        lane_locate_merged(hist_all, lane, 0u, S.rank, bin, below, in_bin);
+        lane_locate_merged<NWW>(hist_all, lane, 0u, S.rank, bin, below, in_bin);
         S2.rank = S.rank - below; S2.cnt = in_bin;
         S2.prefix = S.prefix | (((unsigned long long)bin) << shift2);
         S2.bits = S.bits + width2;
@@ -723,11 +768,15 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       }
       s_above[wj][lane] = above; s_nc[wj][lane] = overflow ? 0xffffffffu : nc;
       __threadfence_block();
-      walker_bar();
+      walker_bar<NWW>();
       if (wj == 0) {
         // ---- the first walker warp finishes: merge, rank the candidates, final sum
 #pragma unroll
-        for (int j = 1; j < NWW; ++j) { chi += s_part[j][3][lane]; above = min(above, s_above[j][lane]); }
+        double chi = s_part[0][3][lane];
+#pragma unroll
+        for (int j = 1; j < VW; ++j) chi += s_part[j][3][lane];
+#pragma unroll
+        for (int j = 1; j < NWW; ++j) above = min(above, s_above[j][lane]);
         bool any_overflow = false;
 #pragma unroll
         for (int j = 0; j < NWW; ++j) any_overflow = any_overflow || s_nc[j][lane] == 0xffffffffu;
@@ -763,7 +812,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         } else {
           // ---- slow path (a lane's second-level bin holds more keys than the buffers take, or all its values are
           // equal): the keys with the second-level prefix of all four lists go to a spare list, then digit by digit
-          unsigned long long* const spare = list0 + (size_t)NWW * LISTCAP * 32;
+          unsigned long long* const spare = list0 + (size_t)NWW_MAX * LISTCAP * 32;
           unsigned cnt = 0u;
           const unsigned long long hm2 = (S2.bits >= 64) ? ~0ull : (~0ull << (64 - S2.bits));
           for (int j = 0; j < NWW; ++j) {

@@ -333,7 +333,8 @@ __host__ __device__ __forceinline__ double counter_uniform(unsigned long long se
 // ------------------------------------------------------------------------------------------
 __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__ theta, long long nw,
                                    WalkerPlan* __restrict__ plans_out, unsigned* __restrict__ cell_hist,
-                                   const int mode, const OptIn opt, const ProposeIn prop) {
+                                   const int mode, const OptIn opt, const ProposeIn prop,
+                                   unsigned long long* __restrict__ short_circuited) {
   // The isochrone, node and dust tables (a few KB) are staged in shared memory once per CTA: the searches below
   // are chains of dependent loads (two bisections of the isochrone per star, the dust slice, three node scans),
   // ~60 L2 round trips per walker when read from global memory -- which made this kernel 28 us, more than a
@@ -362,6 +363,7 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   auto store = [&](const WalkerPlan& p) {
     plans_out[w] = p;
     if (cell_hist) atomicAdd(cell_hist + p.cell, 1u);
+    if (p.status != 0) atomicAdd(short_circuited, 1ull);      // never reaches the grid: -inf without streaming
   };
   const int ndim = T.ndim, ns = T.nspec;
   double p[MS_MAX_NDIM];
@@ -1656,6 +1658,8 @@ struct ms_handle {
   grp::GroupDesc* groups = nullptr; long long groups_cap = 0;
   unsigned* cell_start = nullptr; unsigned* group_off = nullptr; int* n_groups = nullptr;
   double* group_scratch = nullptr; unsigned long long* group_list = nullptr; int* group_counter = nullptr; int group_ctas = 0;
+  unsigned long long* short_circuited = nullptr;   // device counter: evaluations cut short by the prior box / tables
+  int* h_n_groups = nullptr;     // pinned: group count of a recent call (picks the kernel variant of the next one)
   unsigned char* scratch = nullptr; size_t scratch_cap = 0;   // per-call inputs of ms_optimizer_chisq (grown on demand)
   cudaStream_t own_stream = nullptr;
   // optional device-side timing of the streaming kernel
@@ -1860,15 +1864,37 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
     h->ev_used += 2; h->timed_walkers += nw;
     CK(cudaEventRecord(e0, h->stream));
   }
-  auto kern = grp::lnprob_group_kernel<4>;
-  const int smem = grp::NSTAGE * grp::StageLayout<4>::bytes + grp::NWW * grp::HBINS * 32 * 2 + grp::NWW * grp::CAND * 32 * 8;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const long long max_groups = (nw + grp::GMAX - 1) / grp::GMAX + std::min<long long>(h->T.n_cells, nw);
-  const unsigned ctas = (unsigned)std::min<long long>(h->group_ctas, max_groups);
-  kern<<<ctas, grp::NTHREADS, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups, h->group_counter,
-                                                 d_lnp, parts, h->group_scratch, h->group_list);
+  // Few groups (at most one per SM): one CTA per SM with eight walker warps per group shortens the time a group takes;
+  // otherwise two CTAs per SM with four walker warps each.  The number of groups depends on how the walkers spread over
+  // the grid cells and is only known on the device: the count of a recent call of the same batch size (copied back
+  // asynchronously, never waited for) stands in for it -- successive half steps of a chain look alike.
+  const long long min_groups = (nw + grp::GMAX - 1) / grp::GMAX;
+  const long long max_groups = min_groups + std::min<long long>(h->T.n_cells, nw);
+  const size_t ring = (size_t)grp::NSTAGE * grp::StageLayout<4>::bytes;
+  const int seen = *reinterpret_cast<volatile int*>(h->h_n_groups);
+  const long long seen_nw = *reinterpret_cast<volatile int*>(h->h_n_groups + 1);
+  const long long expect_groups = (seen > 0 && seen_nw == nw) ? (long long)seen : min_groups + min_groups / 3;
+  if (expect_groups <= h->num_sms) {
+    constexpr int NWW = 8;
+    auto kern = grp::lnprob_group_kernel<4, NWW, 1>;
+    const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2 + NWW * grp::CAND * 32 * 8);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const unsigned ctas = (unsigned)std::min<long long>(h->num_sms, max_groups);
+    kern<<<ctas, (NWW + grp::NSERVICE) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
+                                                               h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
+  } else {
+    constexpr int NWW = 4;
+    auto kern = grp::lnprob_group_kernel<4, NWW, 2>;
+    const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2 + NWW * grp::CAND * 32 * 8);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const unsigned ctas = (unsigned)std::min<long long>(h->group_ctas, max_groups);
+    kern<<<ctas, (NWW + grp::NSERVICE) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
+                                                               h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
+  }
   CK(cudaGetLastError());
   if (h->timing) CK(cudaEventRecord(e1, h->stream));
+  h->h_n_groups[1] = (int)std::min<long long>(nw, 0x7fffffff);
+  CK(cudaMemcpyAsync(h->h_n_groups, h->n_groups, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   h->launches += 1;
   return MS_OK;
 }
@@ -1927,7 +1953,8 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   const size_t prep_smem = (size_t)(3 * h->T.n_iso + h->T.n_teff + h->T.n_logg + h->T.n_feh + h->T.n_dm +
                                     h->T.n_dm * h->T.n_dust_samples) * sizeof(double);
   if (prep_smem > 48 * 1024) CK(cudaFuncSetAttribute(walker_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-  walker_prep_kernel<<<pg, pb, prep_smem, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr, mode, opt, prop);
+  walker_prep_kernel<<<pg, pb, prep_smem, h->stream>>>(h->T, d_theta, nw, h->plans, h->use_order ? h->cell_hist : nullptr, mode, opt, prop,
+                                                       h->short_circuited);
   CK(cudaGetLastError());
   h->launches += 1;
   if (h->group_now) {
@@ -2023,6 +2050,8 @@ int ms_destroy(ms_handle* h) {
   if (h->group_scratch) cudaFree(h->group_scratch);
   if (h->group_counter) cudaFree(h->group_counter);
   if (h->group_list) cudaFree(h->group_list);
+  if (h->h_n_groups) cudaFreeHost(h->h_n_groups);
+  if (h->short_circuited) cudaFree(h->short_circuited);
   if (h->it_half[0]) cudaFree(h->it_half[0]);
   if (h->it_half[1]) cudaFree(h->it_half[1]);
   if (h->it_q) cudaFree(h->it_q);
@@ -2343,10 +2372,14 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     CKH(cudaMalloc((void**)&h->group_off, (size_t)T.n_cells * sizeof(unsigned)));
     CKH(cudaMalloc((void**)&h->n_groups, sizeof(int)));
     CKH(cudaMalloc((void**)&h->group_counter, sizeof(int)));
+    CKH(cudaMalloc((void**)&h->short_circuited, sizeof(unsigned long long)));
+    CKH(cudaMemset(h->short_circuited, 0, sizeof(unsigned long long)));
+    CKH(cudaMallocHost((void**)&h->h_n_groups, 2 * sizeof(int)));
+    h->h_n_groups[0] = -1; h->h_n_groups[1] = 0;
     if (ok) {
-      // per CTA: the transposed model vectors [n][32] and the walker warps' key lists [NWW][LISTCAP][32]
+      // per CTA: the transposed model vectors [n][32] and the walker warps' key lists [NWW_MAX + 1][LISTCAP][32]
       CKH(cudaMalloc((void**)&h->group_scratch, (size_t)h->group_ctas * (size_t)n * 32 * sizeof(double)));
-      CKH(cudaMalloc((void**)&h->group_list, (size_t)h->group_ctas * (NWW + 1) * (size_t)LISTCAP * 32 * sizeof(unsigned long long)));
+      CKH(cudaMalloc((void**)&h->group_list, (size_t)h->group_ctas * (NWW_MAX + 1) * (size_t)LISTCAP * 32 * sizeof(unsigned long long)));
     }
   }
 
@@ -2413,6 +2446,17 @@ int ms_set_pairing(ms_handle* h, int enabled) {
 int ms_set_fast(ms_handle* h, int enabled) {
   if (!h) return MS_ERR_INVALID;
   h->fast = enabled != 0;
+  return MS_OK;
+}
+
+int ms_short_circuited(ms_handle* h, int64_t* count, int reset) {
+  if (!h || !count) return MS_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  unsigned long long v = 0;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(&v, h->short_circuited, sizeof(v), cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(h->short_circuited, 0, sizeof(v)));
+  *count = (int64_t)v;
   return MS_OK;
 }
 
@@ -2783,6 +2827,36 @@ int ms_stretch_iteration(ms_handle* h, double* state, int32_t* naccepted, int64_
     CK(cudaGetLastError());
     h->launches += 1;
   }
+  return MS_OK;
+}
+
+int ms_stretch_halfstep(ms_handle* h, double* state, int32_t* naccepted, const int64_t* s_idx, int64_t n_s,
+                        const int64_t* c_idx, int64_t n_c, double a, uint64_t seed, uint64_t iteration, int32_t split,
+                        int64_t gid0, double* q, double* logfac, double* lnp_q, double* packed) {
+  NvtxRange nvtx_range("ms_stretch_halfstep");
+  if (!h) return MS_ERR_INVALID;
+  if (n_s < 0 || n_c < 1 || !state || !s_idx || !c_idx || !q || !logfac || !lnp_q) {
+    set_err(h, "ms_stretch_halfstep: invalid argument"); return MS_ERR_INVALID;
+  }
+  if (n_s == 0) return MS_OK;
+  CK(cudaSetDevice(h->device));
+  const int ndim = h->T.ncol;
+  // proposal folded into the prep kernel, evaluation, then the acceptance test: in place (one rank owns the whole
+  // half) or into the packed rows the ranks exchange
+  const ProposeIn prop{state, (const long long*)s_idx, (const long long*)c_idx, n_c, a, seed, iteration, split, (long long)gid0, q, logfac};
+  const PartsOut none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const int rc = evaluate_device(h, q, n_s, lnp_q, none, -1, OptIn{nullptr, nullptr, nullptr, nullptr, nullptr}, prop);
+  if (rc) return rc;
+  const unsigned g = (unsigned)((n_s + 127) / 128);
+  if (packed) {
+    stretch_accept_kernel<<<g, 128, 0, h->stream>>>(state, (const long long*)s_idx, q, lnp_q, logfac, n_s, ndim, seed, iteration,
+                                                    split, gid0, packed);
+  } else {
+    stretch_accept_inplace_kernel<<<g, 128, 0, h->stream>>>(state, naccepted, (const long long*)s_idx, q, lnp_q, logfac, n_s, ndim,
+                                                            seed, iteration, split, gid0);
+  }
+  CK(cudaGetLastError());
+  h->launches += 1;
   return MS_OK;
 }
 

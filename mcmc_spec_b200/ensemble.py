@@ -16,7 +16,8 @@ contiguous shard of the active half, in place, and the shards are exchanged by O
 half step (NCCL over NVLink; the only collective of the path).  Random numbers -- the split
 permutation, z, the partner and the acceptance draw -- come from a counter-based generator keyed
 by (seed, iteration, split, slot in the half), so the chain does not depend on the number of
-ranks.  Positions never leave the device; a half step is five kernel launches plus the collective.
+ranks.  Positions never leave the device; a half step is one C call (proposal folded into the preparation kernel,
+evaluation, acceptance) plus, when sharded, the collective and the scatter of the gathered rows.
 
 ``backend`` supplies the five primitives on torch tensors.  The product backend is
 ``CudaBackend`` (the C ABI kernels); tests plug in a numpy mirror to exercise the sharding logic
@@ -69,6 +70,13 @@ class CudaBackend:
         self._bind()
         self.engine.stretch_scatter(state.data_ptr(), naccepted.data_ptr(), idx.data_ptr(), packed.data_ptr(),
                                     idx.shape[0])
+
+    def halfstep(self, state, naccepted, s_idx, c_idx, a, seed, iteration, split, gid0, q, logfac, lnp_q, packed=None):
+        """Propose, evaluate and accept one rank's share of a half step in one C call; ``packed`` None: in place."""
+        self._bind()
+        self.engine.stretch_halfstep(state.data_ptr(), naccepted.data_ptr(), s_idx.data_ptr(), s_idx.shape[0], c_idx.data_ptr(),
+                                     c_idx.shape[0], a, seed, iteration, split, gid0, q.data_ptr(), logfac.data_ptr(),
+                                     lnp_q.data_ptr(), None if packed is None else packed.data_ptr())
 
     FUSED_MAX_WALKERS = 2048
 
@@ -139,6 +147,12 @@ class EnsembleSampler:
     def log_prob(self):
         return self.state[:, self.ndim]
 
+    def checksum(self):
+        """Order-independent exact fingerprint of the ensemble (positions and log-probs): the sum of the state's
+        64-bit patterns modulo 2^64.  The random streams do not depend on the number of ranks and a walker's
+        log-posterior does not depend on its batch, so the value is the same at 1, 2, 4 and 8 GPUs."""
+        return int(self.state.contiguous().view(torch.int64).sum().item()) & 0xFFFFFFFFFFFFFFFF
+
     @property
     def acceptance_fraction(self):
         return (self.naccepted.to(torch.float64) / max(self.iteration - self._iter0, 1)).cpu().numpy()
@@ -188,10 +202,20 @@ class EnsembleSampler:
             s_idx, c_idx = halves[split], halves[1 - split]
             lo = self.rank * self.shard
             mine = s_idx[lo:lo + self.shard]
-            be.propose(self.state, mine, c_idx, self.a, self.seed, self.iteration, split, lo, self._q, self._logfac)
-            be.lnprob(self._q, out=self._lnp_q)
-            be.accept(self.state, mine, self._q, self._lnp_q, self._logfac, self.seed, self.iteration, split, lo,
-                      self._packed)
+            if hasattr(be, 'halfstep'):
+                # one C call: proposal folded into the preparation kernel, evaluation, acceptance -- in place when this
+                # rank owns the whole half, else into the packed rows of the all-gather
+                if self.world_size == 1:
+                    be.halfstep(self.state, self.naccepted, mine, c_idx, self.a, self.seed, self.iteration, split, lo,
+                                self._q, self._logfac, self._lnp_q)
+                    continue
+                be.halfstep(self.state, self.naccepted, mine, c_idx, self.a, self.seed, self.iteration, split, lo,
+                            self._q, self._logfac, self._lnp_q, self._packed)
+            else:
+                be.propose(self.state, mine, c_idx, self.a, self.seed, self.iteration, split, lo, self._q, self._logfac)
+                be.lnprob(self._q, out=self._lnp_q)
+                be.accept(self.state, mine, self._q, self._lnp_q, self._logfac, self.seed, self.iteration, split, lo,
+                          self._packed)
             if self.world_size > 1:
                 dist.all_gather_into_tensor(self._full, self._packed, group=self.group)   # slot order
             be.scatter(self.state, self.naccepted, s_idx, self._full)

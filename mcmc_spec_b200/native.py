@@ -23,7 +23,7 @@ _LIB_PATH = os.environ.get('MCMCSPEC_LIB') or os.path.join(os.path.dirname(os.pa
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
            'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_component_mags', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows', 'ms_build_grid',
-           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_fast', 'ms_set_cell_order', 'ms_set_group', 'ms_group_supported', 'ms_set_timing',
+           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_stretch_halfstep', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_fast', 'ms_set_cell_order', 'ms_set_group', 'ms_group_supported', 'ms_short_circuited', 'ms_set_timing',
            'ms_kernel_time']
 
 _dp = C.POINTER(C.c_double)
@@ -98,6 +98,8 @@ def load_library(path=None):
                                       C.c_int32, C.c_int64, vp]
     lib.ms_stretch_scatter.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_int32]
     lib.ms_stretch_iteration.argtypes = [vp, vp, vp, C.c_int64, C.c_double, C.c_uint64, C.c_uint64, C.c_int32]
+    lib.ms_stretch_halfstep.argtypes = [vp, vp, vp, vp, C.c_int64, vp, C.c_int64, C.c_double, C.c_uint64, C.c_uint64, C.c_int32,
+                                        C.c_int64, vp, vp, vp, vp]
     lib.ms_launch_count.argtypes = [vp]
     lib.ms_launch_count.restype = C.c_int64
     lib.ms_set_stream.argtypes = [vp, vp]
@@ -108,6 +110,7 @@ def load_library(path=None):
     lib.ms_set_cell_order.argtypes = [vp, C.c_int]
     lib.ms_set_group.argtypes = [vp, C.c_int, C.c_int64]
     lib.ms_group_supported.argtypes = [vp]
+    lib.ms_short_circuited.argtypes = [vp, C.POINTER(C.c_int64), C.c_int]
     lib.ms_set_timing.argtypes = [vp, C.c_int]
     lib.ms_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     for name in EXPORTS:
@@ -264,6 +267,12 @@ class Engine:
     def group_supported(self):
         return bool(self.lib.ms_group_supported(self._h))
 
+    def short_circuited(self, reset=False):
+        """Evaluations cut short by the prior box / tables (no grid row read) since creation or the last reset."""
+        c = C.c_int64(0)
+        self._check(self.lib.ms_short_circuited(self._h, C.byref(c), int(bool(reset))), 'ms_short_circuited')
+        return int(c.value)
+
     def set_timing(self, enabled):
         self._check(self.lib.ms_set_timing(self._h, int(bool(enabled))), 'ms_set_timing')
 
@@ -353,6 +362,14 @@ class Engine:
     def stretch_iteration(self, state_ptr, naccepted_ptr, nw, a, seed, iteration, randomize_split=True):
         self._check(self.lib.ms_stretch_iteration(self._h, state_ptr, naccepted_ptr, nw, a, seed, iteration,
                                                   int(bool(randomize_split))), 'ms_stretch_iteration')
+
+    def stretch_halfstep(self, state_ptr, naccepted_ptr, s_idx_ptr, n_s, c_idx_ptr, n_c, a, seed, iteration, split, gid0,
+                         q_ptr, logfac_ptr, lnp_ptr, packed_ptr=None):
+        """Propose + evaluate + accept for one rank's share of a half step (ms_stretch_halfstep); ``packed_ptr`` None:
+        the accepted rows are written in place."""
+        self._check(self.lib.ms_stretch_halfstep(self._h, state_ptr, naccepted_ptr, s_idx_ptr, n_s, c_idx_ptr, n_c, a, seed,
+                                                 iteration, split, gid0, q_ptr, logfac_ptr, lnp_ptr, packed_ptr),
+                    'ms_stretch_halfstep')
 
     def stretch_scatter(self, state_ptr, naccepted_ptr, idx_ptr, packed_ptr, n):
         self._check(self.lib.ms_stretch_scatter(self._h, state_ptr, naccepted_ptr, idx_ptr, packed_ptr, n, self.ndim),
