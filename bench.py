@@ -75,31 +75,33 @@ def make_workload(name='c4', k=0):
     return make_theta10k.problem_for(name, k)
 
 
-def initial_ensemble(prob, nw, seed=1, name='c4'):
-    """C4 / C5: walkers uniform in the central third of the prior box -- every stretch proposal (z <= 2) stays inside
-    the box, so no evaluation is cut short by the prior bounds.  C1-C3: a 2 % ball around a plausible solution, as
-    the reference starts its walkers from the optimiser's best third (mft6.py:3670-3674)."""
+def initial_ensemble(prob, nw, seed=1, name='c4', init='ball'):
+    """`ball` (default): a 1 % ball around the solution, the way the reference starts its walkers from the best third
+    of the optimiser's results (mft6.py:3670-3674) -- the regime an ensemble sampler spends its life in.  `box`
+    (--init box, C4 / C5 only): uniform in the central third of the prior box, i.e. a chain far from the mode whose
+    walkers spread over the whole (Teff1, Teff2) plane; reported in DESIGN.md beside the default."""
     rng = np.random.default_rng(seed)
-    if name in ('c4', 'c5'):
+    if init == 'box' and name in ('c4', 'c5'):
         lo = np.array([min(prob.temps), min(prob.temps), 0.0, 0.1, 0.1, 1 / 3000.0])
         hi = np.array([max(prob.temps), max(prob.temps), 1.0, 1.2, 1.0, 1 / 100.0])
         a, b = lo + (hi - lo) / 3.0, hi - (hi - lo) / 3.0
         return a + (b - a) * rng.random((nw, 6))
     centre = np.asarray(prob.truth, dtype=float)
-    p0 = centre * (1 + 0.02 * rng.standard_normal((nw, centre.size)))
+    p0 = centre * (1 + (0.01 if name in ('c4', 'c5') else 0.02) * rng.standard_normal((nw, centre.size)))
     p0[:, 2] = np.abs(p0[:, 2])
     return p0
 
 
-def workload_config(name, prob, tables, nw):
+def workload_config(name, prob, tables, nw, init='ball'):
     """Identical in the product arm and the reference arm (the driver compares the two)."""
     return {"workload": WORKLOADS[name]['text'], "name": name,
             "walkers": int(nw), "n_data": int(tables.n_data), "p_reg": int(tables.n_reg),
             "grid_nodes": ([len(prob.fehs)] if prob.fehs is not None else []) + [len(prob.lgs), len(prob.temps)],
             "bytes_per_eval": int(tables.bytes_per_eval()),
             "step": f"one stretch-move iteration = 2 half steps = {int(nw)} logposterior evaluations",
-            "walker_init": ("uniform in the central third of the prior box" if name in ('c4', 'c5')
-                            else "2 % ball around a plausible solution"),
+            "walker_init": ("uniform in the central third of the prior box (a chain far from the mode)" if init == 'box' and name in ('c4', 'c5')
+                            else "ball around the solution (1 % for C4/C5, 2 % for C1-C3), as the reference starts from the "
+                                 "optimiser's best third (mft6.py:3670-3674)"),
             "l2": "flushed between timed steps (256 MiB write); the grid rows are re-read by every group of walkers within a "
                   "step and are L2 resident by nature"}
 
@@ -130,10 +132,10 @@ def time_cpu_sample(pool, theta):
     return time.perf_counter() - t0, np.array(out)
 
 
-def cpu_baseline(prob, name, target_s=15.0):
+def cpu_baseline(prob, name, target_s=15.0, init='ball'):
     """Oracle throughput on all host cores over a bounded sample of the workload's ensemble."""
     cores = os.cpu_count() or 1
-    theta = initial_ensemble(prob, 65536, seed=2, name=name)
+    theta = initial_ensemble(prob, 65536, seed=2, name=name, init=init)
     with cpu_pool(cores, name) as pool:
         dt, _ = time_cpu_sample(pool, theta[:cores * 2])                  # warm-up + per-eval estimate
         dt, _ = time_cpu_sample(pool, theta[:cores * 2])
@@ -156,7 +158,7 @@ def run_reference_arm(args, rank):
     nw = args.walkers or WORKLOADS[name]['walkers']
     cores = os.cpu_count() or 1
     per_step = cores * 8
-    theta = initial_ensemble(prob, per_step * (args.steps + args.warmup), seed=3, name=name)
+    theta = initial_ensemble(prob, per_step * (args.steps + args.warmup), seed=3, name=name, init=args.init)
     times = []
     with cpu_pool(cores, name) as pool:
         time_cpu_sample(pool, theta[:cores])                                  # workers up
@@ -171,7 +173,7 @@ def run_reference_arm(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(name, prob, tables, nw),
+            "config": workload_config(name, prob, tables, nw, args.init),
             "reference_step": sample,
             "reference_note": "mft6.py cannot be imported offline (emcee, pyphot, extinction, dustmaps ... absent); this arm "
                               "times the oracle port (oracle/mft6_oracle.py)",
@@ -251,7 +253,7 @@ def run_product_arm(args, rank, local_rank, world):
     cpu = None
     prob = make_workload(name)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(prob, name, target_s=args.cpu_seconds)     # before CUDA is initialised
+        cpu = cpu_baseline(prob, name, target_s=args.cpu_seconds, init=args.init)     # before CUDA is initialised
 
     import torch
     import torch.distributed as dist
@@ -265,7 +267,17 @@ def run_product_arm(args, rank, local_rank, world):
     if world > 1:
         if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
             os.environ['NCCL_DEBUG'] = 'WARN'            # keep NCCL's version banner off stdout (one JSON line)
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator comes up: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if world > 1:
@@ -287,7 +299,7 @@ def run_product_arm(args, rank, local_rank, world):
     lp, tables = lps[0], lps[0].tables
     for k, s_k in enumerate(samplers):
         with torch.cuda.stream(streams[k]):
-            s_k.initialize(initial_ensemble(prob, nw // n_prob, seed=1 + k, name=name))
+            s_k.initialize(initial_ensemble(prob, nw // n_prob, seed=1 + k, name=name, init=args.init))
     torch.cuda.synchronize()
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
 
@@ -401,7 +413,7 @@ def run_product_arm(args, rank, local_rank, world):
         line = {"metric": METRIC, "value": nw * args.steps / total_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(name, prob, tables, nw),
+                "config": workload_config(name, prob, tables, nw, args.init),
                 "parallelism": f"walker-sharded x{world}, 1 all-gather per half step" if world > 1 else "1 GPU, no collective",
                 "acceptance_fraction": acc_frac, "finite_lnprob_frac": finite_frac,
                 "proposals_cut_short_by_prior": int(cut_short),
@@ -433,6 +445,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='c4', choices=sorted(WORKLOADS))
+    ap.add_argument('--init', default='ball', choices=['ball', 'box'])
     ap.add_argument('--walkers', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=10)
     ap.add_argument('--cpu-seconds', type=float, default=15.0)

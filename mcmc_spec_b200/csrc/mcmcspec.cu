@@ -362,7 +362,11 @@ __global__ void walker_prep_kernel(const DevTables T, const double* __restrict__
   // every exit stores the plan and counts the walker in its cell bin
   auto store = [&](const WalkerPlan& p) {
     plans_out[w] = p;
-    if (cell_hist) atomicAdd(cell_hist + p.cell, 1u);
+    if (cell_hist) {
+      // warp-aggregated: the walkers of a chain near its mode share a handful of cells
+      const unsigned peers = __match_any_sync(__activemask(), p.cell);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cell_hist + p.cell, (unsigned)__popc(peers));
+    }
     if (p.status != 0) atomicAdd(short_circuited, 1ull);      // never reaches the grid: -inf without streaming
   };
   const int ndim = T.ndim, ns = T.nspec;
@@ -597,7 +601,15 @@ __global__ void cell_scatter_kernel(const WalkerPlan* __restrict__ plans, long l
                                     int* __restrict__ order) {
   const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (w >= nw) return;
-  order[atomicAdd(offsets + plans[w].cell, 1u)] = (int)w;
+  // warp-aggregated: one atomic per distinct cell and warp, the lanes of a cell take consecutive slots
+  const int cell = plans[w].cell;
+  const int lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(__activemask(), cell);
+  const int leader = __ffs(peers) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(offsets + cell, (unsigned)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  order[base + __popc(peers & ((1u << lane) - 1u))] = (int)w;
 }
 
 // ------------------------------------------------------------------------------------------
