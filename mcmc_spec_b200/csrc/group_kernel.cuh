@@ -149,6 +149,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, double2 v) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
 
+// ++(uint16 counter in shared memory), invisible to the compiler's alias analysis (the caller brackets the phase with
+// barriers that are compiler fences)
+__device__ __forceinline__ void hist_inc(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  v = (unsigned short)(v + 1);
+  asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"(v));
+}
+
 // exp(y) for |y| <= POLY_XMAX: Taylor to y^7 (remainder y^8/40320 < 7e-19 relative)
 __device__ __forceinline__ double exp_small(double y) {
   double p = fma(y, 1.0 / 5040.0, 1.0 / 720.0);
@@ -505,6 +514,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
           const double anc = __ldg(GT.anchor + s);
           const double A = exp2(av * anc);                                  // the stage's common extinction factor
           double* dst = sMT + (size_t)meta.x * 32 + lane;
+          const uint32_t hist_s = smem_u32(hist);
           const double2* recA = reinterpret_cast<const double2*>(stp + L::rec);
           const double2* recB = recA + n_obs;
           const double2* recC = recB + n_obs;
@@ -544,7 +554,9 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             mom[0] = fma(dq0, rm, mom[0]); mom[1] = fma(rc.x, rm, mom[1]); mom[2] = fma(rc.y, rm, mom[2]);   // norm_spec moments, mft6.py:194-195
             const unsigned hk = hi_key(m);
             kmin = min(kmin, hk); kmax = max(kmax, hk);
-            hist[((hk >> (20 - (HBITS - 3))) & (HBINS - 1)) * 32 + lane] += 1;   // 3 exponent bits + HBITS - 3 mantissa bits
+            // 3 exponent bits + HBITS - 3 mantissa bits.  The counter update goes through asm without a memory clobber so
+            // that the compiler does not order the next pixels' (plain) shared-memory loads behind it
+            hist_inc(hist_s + (((hk >> (20 - (HBITS - 3))) & (HBINS - 1)) * 32 + lane) * 2);
             dst[(size_t)k * 32] = m;
           };
           auto run = [&](auto poly) {
