@@ -5,8 +5,12 @@ cannot be imported offline (emcee, PyAstronomy, extinction, pyphot, synphot, ast
 corner, matplotlib and the BT-Settl / MIST / bayestar2019 data are all absent), and it ships no
 golden vectors for this path, so this module *is* the statement of truth for the parity tests.
 
-PARITY UNPINNED for the third-party numerics (oracle/thirdparty.py); numpy/scipy calls
-(``interp1d``, ``Polynomial.fit``, ``np.median``, ``np.trapezoid``) are the real libraries.
+PARITY UNPINNED for the third-party numerics (oracle/thirdparty.py) in the sense that the reference
+holds no vectors for them and cannot be run; they are held instead to published known answers from
+outside this repository (tests/test_published_known_answers.py: the extinction package's documented
+ccm89 vector, CCM89 Table 3, PyAstronomy's FWHM / sigma / tap rule, the 3631 Jy AB zero point, the
+Cohen et al. 2003 2MASS zero points, dustmaps' distance rule).  numpy/scipy calls (``interp1d``,
+``Polynomial.fit``, ``np.median``, ``np.trapezoid``) are the real libraries.
 
 Every function names the reference lines it follows (``/root/reference/mft6.py``).  Argument
 order follows the reference where that is meaningful; arguments the reference passes but never
