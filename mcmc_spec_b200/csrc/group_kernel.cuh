@@ -47,6 +47,13 @@ namespace grp {
 #define GDBG_WAIT(stmt) stmt;
 #define GDBG_REPORT(name)
 #endif
+// -DMS_GROUP_TIMING: the first eight CTAs print, when they run out of groups, where the first and last walker warps'
+// cycles went: waiting for a group, phase A, the barrier after it, phase B, the finish (first warp only)
+#ifdef MS_GROUP_TIMING
+#define GTIME(i) { const long long t__ = clock64(); gt_acc[i] += t__ - gt_last; gt_last = t__; }
+#else
+#define GTIME(i)
+#endif
 
 constexpr int TP = 128;                    // model pixels per stage
 constexpr int ROWPX = TP + 2;              // staged pixels per row: the tile and the two pixels before it (16-byte
@@ -158,11 +165,18 @@ __device__ __forceinline__ void hist_inc(uint32_t addr) {
   asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"(v));
 }
 
-// exp(y) for |y| <= POLY_XMAX: Taylor to y^7 (remainder y^8/40320 < 7e-19 relative)
+// *p = v for the lanes whose predicate is set, as one predicated store (no branch)
+__device__ __forceinline__ void store_if(unsigned long long* p, double v, bool pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f64 [%0], %1;\n\t}" :: "l"(p), "d"(v), "r"((unsigned)pred));
+}
+
+// exp(y) for |y| <= POLY_XMAX: Taylor to y^7 (remainder y^8/40320 < 7e-19 relative).  The coefficients sit in constant
+// memory so that every FMA takes its coefficient as a constant-bank operand (no register moves to build 64-bit immediates).
+__constant__ double EXP_C[6] = {1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
 __device__ __forceinline__ double exp_small(double y) {
-  double p = fma(y, 1.0 / 5040.0, 1.0 / 720.0);
-  p = fma(p, y, 1.0 / 120.0); p = fma(p, y, 1.0 / 24.0); p = fma(p, y, 1.0 / 6.0);
-  p = fma(p, y, 0.5); p = fma(p, y, 1.0); p = fma(p, y, 1.0);
+  double p = fma(y, EXP_C[0], EXP_C[1]);
+  p = fma(p, y, EXP_C[2]); p = fma(p, y, EXP_C[3]); p = fma(p, y, EXP_C[4]);
+  p = fma(p, y, EXP_C[5]); p = fma(p, y, 1.0); p = fma(p, y, 1.0);
   return p;
 }
 
@@ -315,12 +329,20 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
   unsigned short* const hist = hist_all + (size_t)max(wj, 0) * HBINS * 32;
   unsigned it0 = 0, cit0 = 0;               // ring uses so far (stages / chi-square chunks): slot and mbarrier parity go on
 
+#ifdef MS_GROUP_TIMING
+  long long gt_acc[6] = {0, 0, 0, 0, 0, 0}, gt_last = clock64();
+  int gt_groups = 0;
+#endif
   // Persistent CTA: groups are handed out by an atomic counter (reset by group_scan_kernel).
   while (true) {
     if (tid == 0) s_group = atomicAdd(group_counter, 1);
     __syncthreads();                                                // also: the previous group is completely done
     const int g = s_group;
+    GTIME(0)
     if (g >= total_groups) break;
+#ifdef MS_GROUP_TIMING
+    ++gt_groups;
+#endif
     const GroupDesc gd = groups[g];
     const int count = gd.count;
 
@@ -592,8 +614,10 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       GDBG_REPORT("walker")
     }
     it0 += (unsigned)n_stages;
+    GTIME(1)
 
     __syncthreads();          // band integrals and the walker warps' partial sums complete
+    GTIME(2)
 
     // ================================================================= the chi-square pass's inputs through the ring: per
     // chunk of 64 observed pixels the records {q1, q2, d, 1/e^2} and the group's model values [pixel][lane]
@@ -706,31 +730,38 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
                   res[u] = valid ? (r * r) * r4.w : 0.0;
                   mval[u] = m;
                 }
+                // keys of the median's bin: predicated stores of the raw values to the lane's list column, no branch
+                // (a pixel is a hit for a few lanes at most; a branch would run its body once per hit with one lane on)
+                bool touch = false;                                         // a value between the bin and `above` was seen
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                   chiv[v] += res[u];
                   const bool valid = p0 + u < npx;
                   bool hit;
-                  if constexpr (HI32) hit = valid && (hi_key(mval[u]) & himask_h) == prefix_h;
-                  else hit = valid && (ordered_key(mval[u]) & himask) == prefix;
-                  if (hit && collect) {
-                    const unsigned long long key = ordered_key(mval[u]);
-                    listT[(size_t)nl * 32 + lane] = key;
-                    hist[(unsigned)((key >> shift2) & ((1u << width2) - 1u)) * 32 + lane] += 1;
-                  }
-                  nl += hit ? 1u : 0u;
-                  // smallest key above the bin (the upper median of an even-sized vector when the lower one is the
-                  // bin's largest key): the high words are compared first, the running minimum rarely changes
                   if constexpr (HI32) {
                     const unsigned hk = hi_key(mval[u]);
-                    if (valid && hk > bound_h && hk <= above_h) {
-                      above = min(above, ordered_key(mval[u]));
-                      above_h = (unsigned)(above >> 32);
-                    }
+                    hit = valid && (hk & himask_h) == prefix_h;
+                    touch = touch || (valid && hk > bound_h && hk <= above_h);
                   } else {
                     const unsigned long long key = ordered_key(mval[u]);
-                    if (valid && !hit && key > prefix) above = min(above, key);
+                    hit = valid && (key & himask) == prefix;
+                    touch = touch || (valid && !hit && key > prefix && key < above);
                   }
+                  store_if(listT + (size_t)nl * 32 + lane, mval[u], hit && collect);
+                  nl += hit ? 1u : 0u;
+                }
+                // smallest key above the bin (the upper median of an even-sized vector when the lower one is the bin's
+                // largest key): the running minimum rarely changes, one warp-uniform branch per block
+                if (__any_sync(0xffffffffu, touch)) {
+#pragma unroll
+                  for (int u = 0; u < U; ++u) {
+                    const unsigned long long key = ordered_key(mval[u]);
+                    bool over;
+                    if constexpr (HI32) over = (unsigned)(key >> 32) > bound_h;
+                    else over = (key & himask) != prefix && key > prefix;
+                    if (p0 + u < npx && over) above = min(above, key);
+                  }
+                  above_h = (unsigned)(above >> 32);
                 }
               }
             }
@@ -739,6 +770,25 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
           }
         };
         if (__all_sync(0xffffffffu, S.bits <= 32)) chi_pass(std::true_type{}); else chi_pass(std::false_type{});
+      }
+      // ---- the warp's list: raw values become ordered keys in place, second-level histogram of the next key bits
+      // (every lane walks its own column)
+      {
+        const unsigned nl_eff = collect ? nl : 0u;
+        const unsigned nmax = __reduce_max_sync(0xffffffffu, nl_eff);
+        for (unsigned t0 = 0; t0 < nmax; t0 += 8) {
+          unsigned long long kb[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) kb[u] = (t0 + u < nl_eff) ? listT[(size_t)(t0 + u) * 32 + lane] : 0ull;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (t0 + u < nl_eff) {
+              const unsigned long long key = ordered_key(__longlong_as_double((long long)kb[u]));
+              listT[(size_t)(t0 + u) * 32 + lane] = key;
+              hist[(unsigned)((key >> shift2) & ((1u << width2) - 1u)) * 32 + lane] += 1;
+            }
+          }
+        }
       }
 #pragma unroll
       for (int v = 0; v < NV; ++v) s_part[wj + v * NWW][3][lane] = chiv[v];
@@ -780,7 +830,9 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       }
       s_above[wj][lane] = above; s_nc[wj][lane] = overflow ? 0xffffffffu : nc;
       __threadfence_block();
+      GTIME(3)
       walker_bar<NWW>();
+      GTIME(4)
       if (wj == 0) {
         // ---- the first walker warp finishes: merge, rank the candidates, final sum
 #pragma unroll
@@ -924,9 +976,15 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         }
       }
       GDBG_REPORT("phaseB")
+      GTIME(5)
     }
     cit0 += (unsigned)n_chunks;
   }
+#ifdef MS_GROUP_TIMING
+  if (blockIdx.x < 8 && lane == 0 && (warp == 1 || wj == 0 || wj == NWW - 1))
+    printf("cta %d warp %d groups %d: idle %lld A %lld sync %lld B %lld bar %lld finish %lld\n", blockIdx.x, warp, gt_groups,
+           gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[3], gt_acc[4], gt_acc[5]);
+#endif
 }
 
 // ---- group table: contiguous runs of at most GMAX cell-sorted walkers that share a cell --------------------
