@@ -44,7 +44,11 @@ namespace grp {
 #define GDBG_REPORT(name) if (blockIdx.x == 0 && lane == 0) printf("%s warp %d: group %d of %d (%d walkers) total %lld wait %lld cycles\n", name, warp, g, total_groups, count, clock64() - gdbg_t0, gdbg_wait);
 #else
 #define GDBG_DECL
+#ifdef MS_GROUP_TIMING
+#define GDBG_WAIT(stmt) { const long long t__ = clock64(); stmt; gt_wait += clock64() - t__; }
+#else
 #define GDBG_WAIT(stmt) stmt;
+#endif
 #define GDBG_REPORT(name)
 #endif
 // -DMS_GROUP_TIMING: the first eight CTAs print, when they run out of groups, where the first and last walker warps'
@@ -62,36 +66,62 @@ constexpr int ROWPX = TP + 2;              // staged pixels per row: the tile an
 constexpr int ROWB = ROWPX * 8;            // 1040 bytes
 constexpr int WS = MS_GROUP_WSLOTS;        // weight slots: passbands that may overlap on one stage
 constexpr int RCAP = MS_GROUP_RCAP;        // observed pixels per stage the ring is sized for
-constexpr int NSTAGE = 3;
-constexpr int NWW_MAX = 8;                 // walker warps per CTA (template parameter NWW: 4 with two CTAs per SM, 8 with
+#ifndef MS_GROUP_NRS
+#define MS_GROUP_NRS 2
+#endif
+#ifndef MS_GROUP_NBS
+#define MS_GROUP_NBS 3
+#endif
+#ifndef MS_GROUP_NRC
+#define MS_GROUP_NRC 5
+#endif
+constexpr int NRS = MS_GROUP_NRS;          // row slots: a stage's staged rows + weight tiles, dead once gathered and integrated
+constexpr int NBS = MS_GROUP_NBS;          // B slots: a stage's bracket table, written by the gather once the walker warps are
+                                           // through with the stage NBS back
+constexpr int NRC = MS_GROUP_NRC;          // record slots: a stage's per-pixel records + meta; copied in NRC stages ahead of the
+                                           // walker warps, so that only the gather sits between a freed B slot and the next table
+constexpr int ANCHOR_REFRESH = 8;          // the stage's common extinction factor is updated incrementally, exactly every 8th
+constexpr int NWW_MAX = 12;                // walker warps per CTA (template parameter NWW: 6 with two CTAs per SM, 12 with
                                            // one): they split the observed pixels of the group's 32 walkers
 constexpr int GMAX = 32;                   // walkers per group (one per lane)
-constexpr int NSERVICE = 4;                // producer, gather, 2 x band
 constexpr int BROWB = RCAP * 16 + 16;      // stride of a B row (one pad slot: conflict-free stores from 8 rows)
 constexpr int HBITS = 6;
 constexpr int HBINS = 1 << HBITS;          // per-lane histogram bins
-constexpr int CHI_CHUNK = 64;              // observed pixels per ring slot in the chi-square pass: 32-byte records + the
-                                           // group's model values [pixel][lane]
 constexpr int LISTCAP = 1024;              // keys of the median's bin a lane collects (per walker warp)
-constexpr int VW = 8;                      // partial sums per walker: quadruple q of a stage / block b of a chunk goes to partial
-                                           // q mod 8 resp. b mod 8 whatever the number of walker warps, so that a walker's value
-                                           // does not depend on the kernel variant
+constexpr int VW = 12;                     // partial sums per walker: the quadruples of observed pixels (counted along the whole
+                                           // vector) resp. the blocks of a chi-square chunk are dealt to partial sum (index mod 12)
+                                           // whatever the number of walker warps, so that a walker's value does not depend on
+                                           // the kernel variant
 constexpr int PIX = 4;                     // observed pixels a walker lane keeps in flight (independent FMA chains)
+constexpr int CHI_U = 4;                   // observed pixels per block of the chi-square pass
+constexpr int CHI_CHUNK = VW * CHI_U;      // observed pixels per chunk of the chi-square pass: 32-byte records + the group's
+                                           // model values [pixel][lane]
+constexpr int CHI_BYTES = CHI_CHUNK * (32 + 256);
 constexpr int CAND = 8;                    // keys of the median's second-level bin per lane and walker warp (fast finish)
 constexpr double POLY_XMAX = 0.02;
 constexpr int REC_BYTES = (RCAP * 52 + 15) & ~15;   // record block of one stage: 3 double2 + one int32 per observed pixel
 
+// The ring: NRS row slots {star 0 rows | star 1 rows | weight tiles}, NBS B slots {B}, NRC record slots {records | meta}.
 template <int NR> struct StageLayout {
   static constexpr int NROW = 2 * NR;
   static constexpr int box = (NR * ROWB + 127) & ~127;     // one star's rows, written by one tensor copy (128-byte aligned)
+  // row slot
   static constexpr int rows = 0;
   static constexpr int weights = 2 * box;
-  static constexpr int rec = weights + WS * TP * 8;        // {t, x_lo}[n] | {x_hi, d q0}[n] | {d q1, d q2}[n] | int32 upper bracket[n]
+  static constexpr int rbytes = weights + WS * TP * 8;
+  // B slot
+  static constexpr int bbytes = (NROW * BROWB + 127) & ~127;
+  // record slot
+  static constexpr int rec = 0;                            // {t, x_lo}[n] | {x_hi, d q0}[n] | {d q1, d q2}[n] | int32 upper bracket[n]
   static constexpr int meta = rec + REC_BYTES;
-  static constexpr int B = meta + 16;
-  static constexpr int bytes = (B + NROW * BROWB + 127) & ~127;
-  static_assert(weights % 128 == 0 && rec % 16 == 0 && meta % 16 == 0 && B % 16 == 0, "bulk copies need aligned destinations");
-  static_assert(CHI_CHUNK * (32 + 256) <= bytes, "a chi-square chunk fits a ring slot");
+  static constexpr int cbytes = (meta + 16 + 127) & ~127;
+  static constexpr int b0 = NRS * rbytes;                  // offset of the first B slot
+  static constexpr int c0 = b0 + NBS * bbytes;             // offset of the first record slot
+  static constexpr int bytes = c0 + NRC * cbytes;          // the whole ring
+  static_assert(weights % 128 == 0 && rbytes % 128 == 0 && meta % 16 == 0, "bulk copies need aligned destinations");
+  static_assert(NRC > NBS, "the records run ahead of the tables");
+  static constexpr int cslots = bytes / CHI_BYTES;          // the chi-square pass cuts the same ring into chunk slots
+  static_assert(CHI_BYTES % 128 == 0 && cslots >= 2, "chi-square chunks: aligned, at least two in flight");
   __device__ static constexpr int row_off(int r) { return (r / NR) * box + (r % NR) * ROWB; }
 };
 
@@ -100,7 +130,9 @@ struct GroupTables {
   const int4* stage_meta;       // [n_stages] {first observed pixel, observed pixels, 4 x uint8 band column per weight slot
                                 //  (0xff: free), flush mask | (offset of the record block / 16) << 8}
   const unsigned char* recblk;  // per stage: {t, x_lo}[n] | {x_hi, d q0}[n] | {d q1, d q2}[n] | int32 tile-local upper bracket[n]
-  const double* anchor;         // [n_stages] extinction exponent the stage's x values are relative to
+  const double2* anchor;        // [n_stages] {extinction exponent the stage's x values are relative to, (its step from the
+                                //  previous non-empty stage) ln 2, or +inf: take the exact factor here}
+  double dxmax;                 // max |step|
   const double* drec2;          // [n_data][4] {q1(x), q2(x), flux, 1/err^2}: phase B
   const double* wbase[BAND_COLS];   // weight of region pixel p for band column c: wbase[c][p]
   double xmax;                  // max |x| over all records (x = (ext - anchor) ln 2)
@@ -280,11 +312,50 @@ __device__ __forceinline__ void lane_locate_merged(const unsigned short* hist_al
 template <int NWW>
 __device__ __forceinline__ void walker_bar() { asm volatile("bar.sync 1, %0;" :: "n"(NWW * 32) : "memory"); }
 
+// Integrate the staged rows [r0, r0 + NRB) through the passbands that touch the stage (one warp; acc carries the sums
+// of a band over the stages it spans, flushed to s_band on its last stage).
+template <int NR, int NRB>
+__device__ __forceinline__ void band_stage(uint32_t st, unsigned slots, unsigned flush, int r0, double (&acc)[NRB][WS],
+                                           double* s_band, int lane) {
+  using L = StageLayout<NR>;
+  constexpr int NROW = 2 * NR;
+  if (slots == 0xffffffffu) return;
+  // this lane's pixels of the tile: {2l, 2l+1} and {64 + 2l, 65 + 2l} (16-byte accesses, lanes contiguous)
+#pragma unroll
+  for (int q = 0; q < WS; ++q) {
+    const unsigned col = (slots >> (8 * q)) & 0xffu;
+    if (col != 0xffu) {                                // warp-uniform
+      const double2 w0 = lds128(st + L::weights + q * TP * 8 + lane * 16);
+      const double2 w1 = lds128(st + L::weights + q * TP * 8 + 512 + lane * 16);
+#pragma unroll
+      for (int r = 0; r < NRB; ++r) {
+        const uint32_t rp = st + L::rows + (uint32_t)L::row_off(r0 + r) + 16 + lane * 16;
+        const double2 v0 = lds128(rp);
+        const double2 v1 = lds128(rp + 512);
+        double a = acc[r][q];
+        a = fma(w0.x, v0.x, a); a = fma(w0.y, v0.y, a); a = fma(w1.x, v1.x, a); a = fma(w1.y, v1.y, a);
+        acc[r][q] = a;
+      }
+      if ((flush >> q) & 1u) {
+#pragma unroll
+        for (int r = 0; r < NRB; ++r) {
+          const double tot = warp_sum(acc[r][q]);
+          if (lane == 0) s_band[col * NROW + r0 + r] = tot;
+          acc[r][q] = 0.0;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // NR: grid rows per star (4; 8 with [Fe/H] is not instantiated yet).  Binaries, posterior mode.
+// NWW walker warps and NSV service warps per CTA:
+//   NSV == 2: warp 0 issues the copies and integrates the rows through the passbands one stage behind, warp 1 gathers;
+//   NSV == 4: warp 0 issues the copies, warps 1..3 split the gather, warps 2 and 3 integrate half of the rows each.
 // ------------------------------------------------------------------------------------------
-template <int NR, int NWW, int CTAS_PER_SM>
-__global__ void __launch_bounds__((NWW + NSERVICE) * 32, CTAS_PER_SM)
+template <int NR, int NWW, int NSV, int CTAS_PER_SM>
+__global__ void __launch_bounds__((NWW + NSV) * 32, CTAS_PER_SM)
 lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__ GroupTables GT,
                     const __grid_constant__ CUtensorMap grid_map, const WalkerPlan* __restrict__ plans,
                     const int* __restrict__ order, const GroupDesc* __restrict__ groups, const int* __restrict__ n_groups,
@@ -292,13 +363,17 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
                     double* __restrict__ scratch, unsigned long long* __restrict__ list_scratch) {
   constexpr int NS = 2;
   constexpr int NROW = NS * NR;
-  constexpr int NTHREADS = (NWW + NSERVICE) * 32;
+  constexpr int NTHREADS = (NWW + NSV) * 32;
+  static_assert(NSV == 2 || NSV == 4, "service roles");
   static_assert(NWW <= NWW_MAX && VW % NWW == 0, "scratch is sized for NWW_MAX walker warps; partial sums are dealt to the warps");
   constexpr int NV = VW / NWW;                                     // partial sums a walker warp carries
+  constexpr int NG = NSV - 1;                                      // warps that gather
+  constexpr int NARRIVE = (NSV == 2) ? 2 : 3;                      // service warps that hand a slot back
   using L = StageLayout<NR>;
+  constexpr int CSLOTS = L::cslots;
   extern __shared__ __align__(128) unsigned char gsm[];
-  unsigned short* const hist_all = reinterpret_cast<unsigned short*>(gsm + NSTAGE * L::bytes);   // [NWW][HBINS][32]
-  __shared__ __align__(8) unsigned long long s_full[NSTAGE], s_empty[NSTAGE], s_bready[NSTAGE], s_cfull[NSTAGE], s_cempty[NSTAGE];
+  unsigned short* const hist_all = reinterpret_cast<unsigned short*>(gsm + L::bytes);   // [NWW][HBINS][32]
+  __shared__ __align__(8) unsigned long long s_full[NRS], s_rempty[NRS], s_bready[NBS], s_done[NRC], s_cfull[CSLOTS], s_cempty[CSLOTS];
   __shared__ double s_band[BAND_COLS * NROW];            // row integrals through every band
   __shared__ double s_part[VW][4][32];                   // per partial sum and lane: three moments / chi-square
   __shared__ unsigned long long s_above[NWW][32];
@@ -308,12 +383,13 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < NRS; ++s) {
       mbar_init(smem_u32(&s_full[s]), 1);
-      mbar_init(smem_u32(&s_empty[s]), (unsigned)(NWW + 3));       // every walker warp + the three service workers
-      mbar_init(smem_u32(&s_bready[s]), 3);                         // the three service workers each gather a share
+      mbar_init(smem_u32(&s_rempty[s]), (unsigned)NARRIVE);         // the service warps that read the rows
     }
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(smem_u32(&s_cfull[s]), 1); mbar_init(smem_u32(&s_cempty[s]), (unsigned)NWW); }
+    for (int s = 0; s < NBS; ++s) mbar_init(smem_u32(&s_bready[s]), (unsigned)NG);   // every gathering warp has written its share of B
+    for (int s = 0; s < NRC; ++s) mbar_init(smem_u32(&s_done[s]), (unsigned)NWW);    // every walker warp is through with the stage
+    for (int s = 0; s < CSLOTS; ++s) { mbar_init(smem_u32(&s_cfull[s]), 1); mbar_init(smem_u32(&s_cempty[s]), (unsigned)NWW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const int n_stages = GT.n_stages;
@@ -321,17 +397,18 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
   const int n_chunks = (n + CHI_CHUNK - 1) / CHI_CHUNK;
   const int total_groups = *n_groups;
   const uint32_t ring = smem_u32(gsm);
-  const int wj = warp - NSERVICE;                                  // walker warp index, < 0 for the service warps
+  const int wj = warp - NSV;                                       // walker warp index, < 0 for the service warps
   // the CTA's scratch, reused by every group it takes: model values [pixel][lane], key lists [warp][slot][lane]
   double* const sMT = scratch + (size_t)blockIdx.x * (size_t)n * 32;
-  unsigned long long* const list0 = list_scratch + (size_t)blockIdx.x * (NWW_MAX + 1) * (size_t)LISTCAP * 32;   // + a spare list
+  unsigned long long* const list0 = list_scratch + (size_t)blockIdx.x * (NWW + 1) * (size_t)LISTCAP * 32;       // + a spare list
   unsigned long long* const listT = list0 + (size_t)max(wj, 0) * LISTCAP * 32;
   unsigned short* const hist = hist_all + (size_t)max(wj, 0) * HBINS * 32;
   unsigned it0 = 0, cit0 = 0;               // ring uses so far (stages / chi-square chunks): slot and mbarrier parity go on
 
 #ifdef MS_GROUP_TIMING
-  long long gt_acc[6] = {0, 0, 0, 0, 0, 0}, gt_last = clock64();
+  long long gt_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, gt_last = clock64();
   int gt_groups = 0;
+  long long gt_wait = 0, gt_wait_a = 0;
 #endif
   // Persistent CTA: groups are handed out by an atomic counter (reset by group_scan_kernel).
   while (true) {
@@ -391,118 +468,136 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       const int t0[NS] = {s_row[0] % GT.n_teff, s_row[NR] % GT.n_teff};
       const int g0[NS] = {s_row[0] / GT.n_teff, s_row[NR] / GT.n_teff};
       int4 meta = __ldg(GT.stage_meta);
-      GDBG_DECL
-      for (int s = 0; s < n_stages; ++s) {
-        const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs % NSTAGE);
-        const int4 meta_next = __ldg(GT.stage_meta + min(s + 1, n_stages - 1));      // in flight while the slot frees up
-        GDBG_WAIT(mbar_wait(smem_u32(&s_empty[slot]), ((gs / NSTAGE) & 1u) ^ 1u))
-        const int n_obs = meta.y;
-        const uint32_t st = ring + (uint32_t)slot * L::bytes;
-        const uint32_t bar = smem_u32(&s_full[slot]);
-        // bytes of this stage (uniform): two row boxes, active weight tiles, the record block
-        const unsigned rec_bytes = (unsigned)(n_obs * 52 + 15) & ~15u;
-        int n_w = 0;
+      // NSV == 2: this warp also integrates the rows through the passbands, LAG stages behind its own copies (by then
+      // the stage has landed, and the walker warps are still busy with it)
+      constexpr int LAG = (NSV == 2) ? NRS - 1 : 0;
+      constexpr int NRB = (NSV == 2) ? NROW : 1;
+      double acc[NRB][WS];
 #pragma unroll
-        for (int q = 0; q < WS; ++q) n_w += (((unsigned)meta.z >> (8 * q)) & 0xffu) != 0xffu;
-        const unsigned total = (unsigned)(NS * NR * ROWB + n_w * TP * 8) + rec_bytes;
-        if (lane == 0) {
-          *reinterpret_cast<int4*>(gsm + (size_t)slot * L::bytes + L::meta) = meta;
-          mbar_expect_tx(bar, total);
+      for (int r = 0; r < NRB; ++r) {
+#pragma unroll
+        for (int q = 0; q < WS; ++q) acc[r][q] = 0.0;
+      }
+      GDBG_DECL
+      for (int s = 0; s < n_stages + LAG; ++s) {
+        GTIME(8)
+        if (s < n_stages) {
+          const unsigned gs = it0 + (unsigned)s;
+          const int slot = (int)(gs % NRS), cslot = (int)(gs % NRC);
+          const int4 meta_next = __ldg(GT.stage_meta + min(s + 1, n_stages - 1));      // in flight while the slots free up
+          GDBG_WAIT(mbar_wait(smem_u32(&s_rempty[slot]), ((gs / NRS) & 1u) ^ 1u))
+          GDBG_WAIT(mbar_wait(smem_u32(&s_done[cslot]), ((gs / NRC) & 1u) ^ 1u))        // the walker warps are through with stage gs - NRC
+          const int n_obs = meta.y;
+          const uint32_t st = ring + (uint32_t)slot * L::rbytes;
+          const uint32_t stc = ring + (uint32_t)(L::c0 + cslot * L::cbytes);
+          const uint32_t bar = smem_u32(&s_full[slot]);
+          // bytes of this stage (uniform): two row boxes, active weight tiles, the record block
+          const unsigned rec_bytes = (unsigned)(n_obs * 52 + 15) & ~15u;
+          int n_w = 0;
+#pragma unroll
+          for (int q = 0; q < WS; ++q) n_w += (((unsigned)meta.z >> (8 * q)) & 0xffu) != 0xffu;
+          const unsigned total = (unsigned)(NS * NR * ROWB + n_w * TP * 8) + rec_bytes;
+          if (lane == 0) {
+            *reinterpret_cast<int4*>(gsm + L::c0 + (size_t)cslot * L::cbytes + L::meta) = meta;
+            mbar_expect_tx(bar, total);
+          }
+          __syncwarp();
+          const int px0 = s * TP;
+          if (lane < NS) {
+            tensor_g2s_3d(st + L::rows + lane * L::box, &grid_map, px0 - 2, t0[lane], g0[lane], bar);
+          } else if (lane < NS + WS) {
+            const int q = lane - NS;
+            const unsigned col = ((unsigned)meta.z >> (8 * q)) & 0xffu;
+            if (col != 0xffu) bulk_g2s(st + L::weights + q * TP * 8, GT.wbase[col] + px0, TP * 8, bar);
+          } else if (lane == NS + WS && n_obs > 0) {
+            bulk_g2s(stc + L::rec, GT.recblk + (size_t)((unsigned)meta.w >> 8) * 16, rec_bytes, bar);
+          }
+          meta = meta_next;
         }
-        __syncwarp();
-        const int px0 = s * TP;
-        if (lane < NS) {
-          tensor_g2s_3d(st + L::rows + lane * L::box, &grid_map, px0 - 2, t0[lane], g0[lane], bar);
-        } else if (lane < NS + WS) {
-          const int q = lane - NS;
-          const unsigned col = ((unsigned)meta.z >> (8 * q)) & 0xffu;
-          if (col != 0xffu) bulk_g2s(st + L::weights + q * TP * 8, GT.wbase[col] + px0, TP * 8, bar);
-        } else if (lane == NS + WS && n_obs > 0) {
-          bulk_g2s(st + L::rec, GT.recblk + (size_t)((unsigned)meta.w >> 8) * 16, rec_bytes, bar);
+        GTIME(6)
+        if constexpr (NSV == 2) {
+          if (s >= LAG) {
+            const unsigned gs = it0 + (unsigned)(s - LAG);
+            const int slot = (int)(gs % NRS), cslot = (int)(gs % NRC);
+            GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NRS) & 1u))
+            const int4 mb = *reinterpret_cast<const int4*>(gsm + L::c0 + (size_t)cslot * L::cbytes + L::meta);
+            band_stage<NR, NRB>(ring + (uint32_t)slot * L::rbytes, (unsigned)mb.z, (unsigned)mb.w & 0xffu, 0, acc, s_band, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_rempty[slot]));
+          }
         }
-        meta = meta_next;
+        GTIME(7)
       }
       GDBG_REPORT("producer")
-    } else if (warp < NSERVICE) {
-      // ================================================================= service workers (warps 1..3): gather + band
-      // integration.  Each takes every third quadruple of observed pixels of the gather; warps 2 and 3 also integrate
-      // half of the rows each through the passbands.
+    } else if (warp < NSV) {
+      // ================================================================= service warps 1 .. NSV - 1: the gather, split by
+      // quadruples of observed pixels; with four service warps, warps 2 and 3 also integrate half of the rows each
+      // through the passbands
       constexpr int HR = NROW / 2;
-      const int sw = warp - 1;                                        // 0, 1, 2
+      const int sw = warp - 1;
       const int r0 = (warp == 3) ? HR : 0;
-      double acc[HR][WS];
+      constexpr int NRB = (NSV == 4) ? HR : 1;
+      double acc[NRB][WS];
 #pragma unroll
-      for (int r = 0; r < HR; ++r) {
+      for (int r = 0; r < NRB; ++r) {
 #pragma unroll
         for (int q = 0; q < WS; ++q) acc[r][q] = 0.0;
       }
       GDBG_DECL
       for (int s = 0; s < n_stages; ++s) {
         const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs % NSTAGE);
-        GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NSTAGE) & 1u))
-        const uint32_t st = ring + (uint32_t)slot * L::bytes;
-        const int4 meta = *reinterpret_cast<const int4*>(gsm + (size_t)slot * L::bytes + L::meta);
+        const int slot = (int)(gs % NRS), bslot = (int)(gs % NBS), cslot = (int)(gs % NRC);
+        GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NRS) & 1u))
+        // the B slot is free once the walker warps are through with stage gs - NBS (its `done` barrier cannot have moved
+        // on by another phase: that takes the stage gs - NBS + NRC, which waits for this table)
+        if (gs >= (unsigned)NBS) { GDBG_WAIT(mbar_wait(smem_u32(&s_done[(gs - NBS) % NRC]), ((gs - NBS) / NRC) & 1u)) }
+        const uint32_t st = ring + (uint32_t)slot * L::rbytes;
+        const unsigned char* strow = gsm + (size_t)slot * L::rbytes + L::rows;
+        unsigned char* stB = gsm + L::b0 + (size_t)bslot * L::bbytes;
+        const unsigned char* stc = gsm + L::c0 + (size_t)cslot * L::cbytes;
+        const int4 meta = *reinterpret_cast<const int4*>(stc + L::meta);
         const int n_obs = meta.y;
         {
+          // lane -> (row r, pixel k0 + lane / 8 + 4 j): four independent load chains per lane and trip
+          constexpr int GI = 4;
           const int r = lane & 7;
-          const uint32_t hlp = st + L::rec + (uint32_t)n_obs * 48;
-#pragma unroll 2
-          for (int k0 = 4 * sw; k0 < n_obs; k0 += 12) {
-            const int k = k0 + (lane >> 3);
-            if (k < n_obs) {
-              int hl;
-              asm volatile("ld.shared.s32 %0, [%1];" : "=r"(hl) : "r"(hlp + 4 * k));
-              const int j1 = hl + 1;                          // tile index of the lower bracket (upper: hl + 2)
-              const int e = j1 & ~1;
+          const int* hlp = reinterpret_cast<const int*>(stc + L::rec + (size_t)n_obs * 48);
+          for (int k0 = 4 * GI * sw; k0 < n_obs; k0 += 4 * GI * NG) {
+            int j1[GI];
 #pragma unroll
-              for (int rr = 0; rr < NROW; rr += 8) {
-                const uint32_t rp = st + L::rows + (uint32_t)L::row_off(rr + r) + (uint32_t)e * 8;
-                const double2 v01 = lds128(rp);
-                const double v2 = lds64(rp + 16);
+            for (int j = 0; j < GI; ++j) {
+              const int k = min(k0 + 4 * j + (lane >> 3), n_obs - 1);
+              j1[j] = hlp[k] + 1;                            // tile index of the lower bracket (upper: + 1)
+            }
+#pragma unroll
+            for (int rr = 0; rr < NROW; rr += 8) {
+              double2 v01[GI]; double v2[GI];
+#pragma unroll
+              for (int j = 0; j < GI; ++j) {
+                const unsigned char* rp = strow + L::row_off(rr + r) + (size_t)(j1[j] & ~1) * 8;
+                v01[j] = *reinterpret_cast<const double2*>(rp);
+                v2[j] = *reinterpret_cast<const double*>(rp + 16);
+              }
+#pragma unroll
+              for (int j = 0; j < GI; ++j) {
+                const int k = k0 + 4 * j + (lane >> 3);
                 double2 pr;
-                pr.x = (j1 & 1) ? v01.y : v01.x;
-                pr.y = (j1 & 1) ? v2 : v01.y;
-                sts128(st + L::B + (uint32_t)(rr + r) * BROWB + (uint32_t)k * 16, pr);
+                pr.x = (j1[j] & 1) ? v01[j].y : v01[j].x;
+                pr.y = (j1[j] & 1) ? v2[j] : v01[j].y;
+                if (k < n_obs) *reinterpret_cast<double2*>(stB + (size_t)(rr + r) * BROWB + (size_t)k * 16) = pr;
               }
             }
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_bready[slot]));           // this worker's share of B is written
-        const unsigned slots = (unsigned)meta.z, flush = (unsigned)meta.w & 0xffu;
-        if (warp >= 2 && slots != 0xffffffffu) {
-          // this lane's pixels of the tile: {2l, 2l+1} and {64 + 2l, 65 + 2l} (16-byte accesses, lanes contiguous)
-#pragma unroll
-          for (int q = 0; q < WS; ++q) {
-            const unsigned col = (slots >> (8 * q)) & 0xffu;
-            if (col != 0xffu) {                                // warp-uniform
-              const double2 w0 = lds128(st + L::weights + q * TP * 8 + lane * 16);
-              const double2 w1 = lds128(st + L::weights + q * TP * 8 + 512 + lane * 16);
-#pragma unroll
-              for (int r = 0; r < HR; ++r) {
-                const uint32_t rp = st + L::rows + (uint32_t)L::row_off(r0 + r) + 16 + lane * 16;
-                const double2 v0 = lds128(rp);
-                const double2 v1 = lds128(rp + 512);
-                double a = acc[r][q];
-                a = fma(w0.x, v0.x, a); a = fma(w0.y, v0.y, a); a = fma(w1.x, v1.x, a); a = fma(w1.y, v1.y, a);
-                acc[r][q] = a;
-              }
-              if ((flush >> q) & 1u) {
-#pragma unroll
-                for (int r = 0; r < HR; ++r) {
-                  const double tot = warp_sum(acc[r][q]);
-                  if (lane == 0) s_band[col * NROW + r0 + r] = tot;
-                  acc[r][q] = 0.0;
-                }
-              }
-            }
-          }
+        if (lane == 0) mbar_arrive(smem_u32(&s_bready[bslot]));          // this warp's share of B is written
+        if constexpr (NSV == 4) {
+          if (warp >= 2) band_stage<NR, NRB>(st, (unsigned)meta.z, (unsigned)meta.w & 0xffu, r0, acc, s_band, lane);
+          __syncwarp();
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_empty[slot]));
+        if (lane == 0) mbar_arrive(smem_u32(&s_rempty[slot]));
       }
+      asm volatile("fence.proxy.async;" ::: "memory");                  // B is overwritten by the chi-square pass's bulk copies
       GDBG_REPORT("service")
     } else {
       // ================================================================= walker warps, phase A: lane = walker; warp wj
@@ -522,19 +617,30 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         lane_hist_zero(hist, lane);
       }
       const bool poly_ok = __all_sync(0xffffffffu, av * GT.xmax <= POLY_XMAX);
+      const bool inc_ok = __all_sync(0xffffffffu, av * GT.dxmax <= POLY_XMAX);
+      double A = 1.0;
+      double2 anc_next = __ldg(GT.anchor);
+      int qrot = 0;                       // quadruples of the stages so far, mod VW: where this stage's first one is dealt
       GDBG_DECL
       for (int s = 0; s < n_stages; ++s) {
         const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs % NSTAGE);
+        const int slot = (int)(gs % NBS), cslot = (int)(gs % NRC);
+        const double2 anc2 = anc_next;
+        anc_next = __ldg(GT.anchor + min(s + 1, n_stages - 1));           // in flight during this stage
         // the gather warp observed `full` (the copies' barrier) before it wrote B and arrived here, so the staged
         // records are visible too (release / acquire chain)
-        GDBG_WAIT(mbar_wait(smem_u32(&s_bready[slot]), (gs / NSTAGE) & 1u))
-        const unsigned char* stp = gsm + (size_t)slot * L::bytes;
+        GDBG_WAIT(mbar_wait(smem_u32(&s_bready[slot]), (gs / NBS) & 1u))
+        const unsigned char* stB = gsm + L::b0 + (size_t)slot * L::bbytes;
+        const unsigned char* stp = gsm + L::c0 + (size_t)cslot * L::cbytes;
         const int4 meta = *reinterpret_cast<const int4*>(stp + L::meta);
         const int n_obs = meta.y;
-        if (PIX * wj < n_obs) {                                            // this warp has pixels in the stage
-          const double anc = __ldg(GT.anchor + s);
-          const double A = exp2(av * anc);                                  // the stage's common extinction factor
+        {
+          // the stage's common extinction factor exp2(av * anchor): exact on every ANCHOR_REFRESH-th non-empty stage, from
+          // the previous stage's by the polynomial in between (the same sequence in every warp and kernel variant)
+          const double anc = anc2.x;
+          if (n_obs > 0) {
+            if (inc_ok && anc2.y < CUDART_INF) A *= exp_small(av * anc2.y); else A = exp2(av * anc);
+          }
           double* dst = sMT + (size_t)meta.x * 32 + lane;
           const uint32_t hist_s = smem_u32(hist);
           const double2* recA = reinterpret_cast<const double2*>(stp + L::rec);
@@ -548,11 +654,11 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             double flo = 0.0, fhi = 0.0;
 #pragma unroll
             for (int stx = 0; stx < NS; ++stx) {
-              const double2 b0 = *reinterpret_cast<const double2*>(stp + L::B + (stx * NR) * BROWB + k * 16);
+              const double2 b0 = *reinterpret_cast<const double2*>(stB + (stx * NR) * BROWB + k * 16);
               double l = cf[stx * NR] * b0.x, u = cf[stx * NR] * b0.y;
 #pragma unroll
               for (int r = 1; r < NR; ++r) {
-                const double2 b = *reinterpret_cast<const double2*>(stp + L::B + (stx * NR + r) * BROWB + k * 16);
+                const double2 b = *reinterpret_cast<const double2*>(stB + (stx * NR + r) * BROWB + k * 16);
                 l = fma(cf[stx * NR + r], b.x, l); u = fma(cf[stx * NR + r], b.y, u);
               }
               flo = (stx == 0) ? l : flo + l; fhi = (stx == 0) ? u : fhi + u;        // mft6.py:744
@@ -582,13 +688,14 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             dst[(size_t)k * 32] = m;
           };
           auto run = [&](auto poly) {
-            // quadruple q of the stage (pixels 4q .. 4q+3) belongs to partial sum q mod VW; this warp carries the
-            // partials wj, wj + NWW, ...
-            for (int q0 = 0; q0 * PIX < n_obs; q0 += VW) {
+            // quadruple q of the stage (pixels 4q .. 4q+3) belongs to partial sum (qrot + q) mod VW: the quadruples are
+            // dealt round robin along the whole vector, so the warps' shares even out over the stages whatever the number
+            // of observed pixels per stage; this warp carries the partials wj, wj + NWW, ...
+            for (int q0 = -qrot; q0 * PIX < n_obs; q0 += VW) {
 #pragma unroll
               for (int v = 0; v < NV; ++v) {
                 const int k = (q0 + wj + v * NWW) * PIX;
-                if (k < n_obs) {                                             // warp-uniform
+                if (k >= 0 && k < n_obs) {                                   // warp-uniform
                   double mv[PIX], rmv[PIX];
 #pragma unroll
                   for (int u = 0; u < PIX; ++u) mv[u] = pixel(poly, min(k + u, n_obs - 1), rmv[u]);   // no branch: the chains interleave
@@ -601,8 +708,9 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
           };
           if (poly_ok) run(std::true_type{}); else run(std::false_type{});
         }
+        qrot = (qrot + (n_obs + PIX - 1) / PIX) % VW;
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_empty[slot]));
+        if (lane == 0) mbar_arrive(smem_u32(&s_done[cslot]));
       }
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
@@ -615,6 +723,9 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
     }
     it0 += (unsigned)n_stages;
     GTIME(1)
+#ifdef MS_GROUP_TIMING
+    gt_wait_a += gt_wait; gt_wait = 0;
+#endif
 
     __syncthreads();          // band integrals and the walker warps' partial sums complete
     GTIME(2)
@@ -624,10 +735,10 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
     if (warp == 0) {
       for (int c = 0; c < n_chunks; ++c) {
         const unsigned gs = cit0 + (unsigned)c;
-        const int slot = (int)(gs % NSTAGE);
-        mbar_wait(smem_u32(&s_cempty[slot]), ((gs / NSTAGE) & 1u) ^ 1u);
+        const int slot = (int)(gs % CSLOTS);
+        mbar_wait(smem_u32(&s_cempty[slot]), ((gs / CSLOTS) & 1u) ^ 1u);
         const unsigned npx = (unsigned)min(CHI_CHUNK, n - c * CHI_CHUNK);
-        const uint32_t dstb = ring + (uint32_t)slot * L::bytes;
+        const uint32_t dstb = ring + (uint32_t)slot * CHI_BYTES;
         if (lane == 0) mbar_expect_tx(smem_u32(&s_cfull[slot]), npx * (32u + 256u));
         __syncwarp();
         if (lane == 0) bulk_g2s(dstb, GT.drec2 + (size_t)c * CHI_CHUNK * 4, npx * 32u, smem_u32(&s_cfull[slot]));
@@ -696,9 +807,9 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       const int width2 = min(HBITS, 64 - S.bits);
       const int shift2 = max(64 - S.bits - width2, 0);
       lane_hist_zero(hist, lane);
+      GTIME(6)
       {
-        constexpr int U = 8;
-        static_assert(CHI_CHUNK == VW * U, "block b of a chunk belongs to partial sum b");
+        constexpr int U = CHI_U;
         // HI32: every lane's prefix sits in the high word of the key (always so on the histogram path): 32-bit tests
         auto chi_pass = [&](auto hi32) {
           constexpr bool HI32 = decltype(hi32)::value;
@@ -709,60 +820,67 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
           unsigned above_h = 0xffffffffu;
           for (int c = 0; c < n_chunks; ++c) {
             const unsigned gs = cit0 + (unsigned)c;
-            const int slot = (int)(gs % NSTAGE);
-            GDBG_WAIT(mbar_wait(smem_u32(&s_cfull[slot]), (gs / NSTAGE) & 1u))
-            const dbl4* rec = reinterpret_cast<const dbl4*>(gsm + (size_t)slot * L::bytes);
-            const double* mch = reinterpret_cast<const double*>(gsm + (size_t)slot * L::bytes + CHI_CHUNK * 32) + lane;
+            const int slot = (int)(gs % CSLOTS);
+            GDBG_WAIT(mbar_wait(smem_u32(&s_cfull[slot]), (gs / CSLOTS) & 1u))
+            const dbl4* rec = reinterpret_cast<const dbl4*>(gsm + (size_t)slot * CHI_BYTES);
+            const double* mch = reinterpret_cast<const double*>(gsm + (size_t)slot * CHI_BYTES + CHI_CHUNK * 32) + lane;
             const int npx = min(CHI_CHUNK, n - c * CHI_CHUNK);
+            // block b of the chunk (pixels b * U ...) belongs to partial sum b; this warp's blocks: wj, wj + NWW, ...
+            if (wj * U < npx) {                                              // warp-uniform
+              double res[NV][U], mval[NV][U];
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              const int p0 = (wj + v * NWW) * U;
-              if (p0 < npx) {                                                // warp-uniform
-                double res[U], mval[U];
+              for (int v = 0; v < NV; ++v) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                  const bool valid = p0 + u < npx;
-                  const int pp = min(p0 + u, npx - 1);
+                  const int px = (wj + v * NWW) * U + u;
+                  const bool valid = px < npx;
+                  const int pp = min(px, npx - 1);
                   const double m = mch[pp * 32];
                   const dbl4 r4 = rec[pp];                                  // same address in every lane
                   const double pfit = fma(a2, r4.y, fma(a1, r4.x, a0q0));
                   const double r = m - r4.z * fast_rcp(pfit);
-                  res[u] = valid ? (r * r) * r4.w : 0.0;
-                  mval[u] = m;
+                  res[v][u] = valid ? (r * r) * r4.w : 0.0;
+                  mval[v][u] = m;
                 }
-                // keys of the median's bin: predicated stores of the raw values to the lane's list column, no branch
-                // (a pixel is a hit for a few lanes at most; a branch would run its body once per hit with one lane on)
-                bool touch = false;                                         // a value between the bin and `above` was seen
+              }
+              // keys of the median's bin: predicated stores of the raw values to the lane's list column, no branch
+              // (a pixel is a hit for a few lanes at most; a branch would run its body once per hit with one lane on)
+              bool touch = false;                                         // a value between the bin and `above` was seen
+#pragma unroll
+              for (int v = 0; v < NV; ++v) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                  chiv[v] += res[u];
-                  const bool valid = p0 + u < npx;
+                  chiv[v] += res[v][u];
+                  const bool valid = (wj + v * NWW) * U + u < npx;
                   bool hit;
                   if constexpr (HI32) {
-                    const unsigned hk = hi_key(mval[u]);
+                    const unsigned hk = hi_key(mval[v][u]);
                     hit = valid && (hk & himask_h) == prefix_h;
                     touch = touch || (valid && hk > bound_h && hk <= above_h);
                   } else {
-                    const unsigned long long key = ordered_key(mval[u]);
+                    const unsigned long long key = ordered_key(mval[v][u]);
                     hit = valid && (key & himask) == prefix;
                     touch = touch || (valid && !hit && key > prefix && key < above);
                   }
-                  store_if(listT + (size_t)nl * 32 + lane, mval[u], hit && collect);
+                  store_if(listT + (size_t)nl * 32 + lane, mval[v][u], hit && collect);
                   nl += hit ? 1u : 0u;
                 }
-                // smallest key above the bin (the upper median of an even-sized vector when the lower one is the bin's
-                // largest key): the running minimum rarely changes, one warp-uniform branch per block
-                if (__any_sync(0xffffffffu, touch)) {
+              }
+              // smallest key above the bin (the upper median of an even-sized vector when the lower one is the bin's
+              // largest key): the running minimum rarely changes, one warp-uniform branch per chunk
+              if (__any_sync(0xffffffffu, touch)) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
 #pragma unroll
                   for (int u = 0; u < U; ++u) {
-                    const unsigned long long key = ordered_key(mval[u]);
+                    const unsigned long long key = ordered_key(mval[v][u]);
                     bool over;
                     if constexpr (HI32) over = (unsigned)(key >> 32) > bound_h;
                     else over = (key & himask) != prefix && key > prefix;
-                    if (p0 + u < npx && over) above = min(above, key);
+                    if ((wj + v * NWW) * U + u < npx && over) above = min(above, key);
                   }
-                  above_h = (unsigned)(above >> 32);
                 }
+                above_h = (unsigned)(above >> 32);
               }
             }
             __syncwarp();
@@ -771,6 +889,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         };
         if (__all_sync(0xffffffffu, S.bits <= 32)) chi_pass(std::true_type{}); else chi_pass(std::false_type{});
       }
+      GTIME(7)
       // ---- the warp's list: raw values become ordered keys in place, second-level histogram of the next key bits
       // (every lane walks its own column)
       {
@@ -796,7 +915,9 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       walker_bar<NWW>();
       // ---- second level: every warp locates the sub-bin in the summed second-level histograms, then filters its own
       // list into a small candidate buffer
-      unsigned long long* const cand_all = reinterpret_cast<unsigned long long*>(hist_all + NWW * HBINS * 32);   // [NWW][CAND][32]
+      // [NWW][CAND][32], on the ring: every walker warp is past the chi-square pass, its chunks are consumed
+      static_assert(NWW * CAND * 32 * 8 <= L::bytes, "the candidate buffers fit the ring");
+      unsigned long long* const cand_all = reinterpret_cast<unsigned long long*>(gsm);
       unsigned long long* const cand = cand_all + (size_t)wj * CAND * 32;
       LaneSel S2 = S;
       unsigned nc = 0;
@@ -876,7 +997,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         } else {
           // ---- slow path (a lane's second-level bin holds more keys than the buffers take, or all its values are
           // equal): the keys with the second-level prefix of all four lists go to a spare list, then digit by digit
-          unsigned long long* const spare = list0 + (size_t)NWW_MAX * LISTCAP * 32;
+          unsigned long long* const spare = list0 + (size_t)NWW * LISTCAP * 32;
           unsigned cnt = 0u;
           const unsigned long long hm2 = (S2.bits >= 64) ? ~0ull : (~0ull << (64 - S2.bits));
           for (int j = 0; j < NWW; ++j) {
@@ -981,9 +1102,9 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
     cit0 += (unsigned)n_chunks;
   }
 #ifdef MS_GROUP_TIMING
-  if (blockIdx.x < 8 && lane == 0 && (warp == 1 || wj == 0 || wj == NWW - 1))
-    printf("cta %d warp %d groups %d: idle %lld A %lld sync %lld B %lld bar %lld finish %lld\n", blockIdx.x, warp, gt_groups,
-           gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[3], gt_acc[4], gt_acc[5]);
+  if (blockIdx.x < 8 && lane == 0 && (warp <= 1 || wj == 0 || wj == NWW - 1))
+    printf("cta %d warp %d groups %d: idle %lld A %lld sync %lld B: locate %lld chi %lld lists %lld bar %lld finish %lld | mbarrier waits A %lld B %lld\n", blockIdx.x, warp,
+           gt_groups, gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[6], gt_acc[7], gt_acc[3], gt_acc[4], gt_acc[5], gt_wait_a, gt_wait);
 #endif
 }
 

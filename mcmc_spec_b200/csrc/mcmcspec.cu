@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <new>
 #include <string>
 #include <type_traits>
@@ -54,6 +55,15 @@ namespace cg = cooperative_groups;
 #endif
 #ifndef MS_GROUP_WSLOTS
 #define MS_GROUP_WSLOTS 4                            // passbands that may overlap on one 128-pixel stage
+#endif
+#ifndef MS_GROUP_NWW
+#define MS_GROUP_NWW 6                               // walker warps of the group kernel with two CTAs per SM ...
+#endif
+#ifndef MS_GROUP_NSV
+#define MS_GROUP_NSV 2                               // ... and its service warps (2 or 4)
+#endif
+#ifndef MS_GROUP_NWW_WIDE
+#define MS_GROUP_NWW_WIDE 12                         // walker warps of the variant with one CTA per SM (four service warps)
 #endif
 #ifndef MS_GROUP_RCAP
 #define MS_GROUP_RCAP 64                             // observed pixels per 128-pixel stage the ring is sized for
@@ -1876,31 +1886,31 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
     h->ev_used += 2; h->timed_walkers += nw;
     CK(cudaEventRecord(e0, h->stream));
   }
-  // Few groups (at most one per SM): one CTA per SM with eight walker warps per group shortens the time a group takes;
-  // otherwise two CTAs per SM with four walker warps each.  The number of groups depends on how the walkers spread over
+  // Few groups (at most one per SM): one CTA per SM with twelve walker warps per group shortens the time a group takes;
+  // otherwise two CTAs per SM with six walker warps each.  The number of groups depends on how the walkers spread over
   // the grid cells and is only known on the device: the count of a recent call of the same batch size (copied back
   // asynchronously, never waited for) stands in for it -- successive half steps of a chain look alike.
   const long long min_groups = (nw + grp::GMAX - 1) / grp::GMAX;
   const long long max_groups = min_groups + std::min<long long>(h->T.n_cells, nw);
-  const size_t ring = (size_t)grp::NSTAGE * grp::StageLayout<4>::bytes;
+  const size_t ring = (size_t)grp::StageLayout<4>::bytes;
   const int seen = *reinterpret_cast<volatile int*>(h->h_n_groups);
   const long long seen_nw = *reinterpret_cast<volatile int*>(h->h_n_groups + 1);
   const long long expect_groups = (seen > 0 && seen_nw == nw) ? (long long)seen : min_groups + min_groups / 3;
   if (expect_groups <= h->num_sms) {
-    constexpr int NWW = 8;
-    auto kern = grp::lnprob_group_kernel<4, NWW, 1>;
-    const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2 + NWW * grp::CAND * 32 * 8);
+    constexpr int NWW = MS_GROUP_NWW_WIDE, NSV = 4;
+    auto kern = grp::lnprob_group_kernel<4, NWW, NSV, 1>;
+    const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned ctas = (unsigned)std::min<long long>(h->num_sms, max_groups);
-    kern<<<ctas, (NWW + grp::NSERVICE) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
+    kern<<<ctas, (NWW + NSV) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
                                                                h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
   } else {
-    constexpr int NWW = 4;
-    auto kern = grp::lnprob_group_kernel<4, NWW, 2>;
-    const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2 + NWW * grp::CAND * 32 * 8);
+    constexpr int NWW = MS_GROUP_NWW, NSV = MS_GROUP_NSV;
+    auto kern = grp::lnprob_group_kernel<4, NWW, NSV, 2>;
+    const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned ctas = (unsigned)std::min<long long>(h->group_ctas, max_groups);
-    kern<<<ctas, (NWW + grp::NSERVICE) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
+    kern<<<ctas, (NWW + NSV) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
                                                                h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
   }
   CK(cudaGetLastError());
@@ -2314,6 +2324,9 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     // records, one block per stage: x = (ext - anchor of the stage) ln 2; d q_k(x) of norm_spec's orthonormal
     // quadratic basis; tile-local upper bracket
     std::vector<double> anchor((size_t)n_stages + 32, 0.0);
+    std::vector<double2> anchor2((size_t)n_stages + 32, make_double2(0.0, std::numeric_limits<double>::infinity()));
+    double dxmax = 0.0;
+    int n_nonempty = 0, prev_nonempty = -1;
     std::vector<unsigned char> blk;
     std::vector<double> dr2(4 * (size_t)n);
     double xmax = 0.0;
@@ -2324,6 +2337,14 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
       meta[s].w = (meta[s].w & 0xff) | (int)((off / 16) << 8);
       if (ns_ == 0) continue;
       anchor[s] = 0.5 * (cfg->ext_lo[d0] + cfg->ext_hi[d0 + ns_ - 1]);
+      // the stage's common factor exp2(av * anchor) follows from the previous non-empty stage's by exp(av * step); every
+      // ANCHOR_REFRESH-th one is taken exactly (step = +inf)
+      anchor2[s].x = anchor[s];
+      if (prev_nonempty >= 0 && n_nonempty % grp::ANCHOR_REFRESH != 0) {
+        anchor2[s].y = (anchor[s] - anchor[prev_nonempty]) * LN2;
+        dxmax = std::max(dxmax, std::fabs(anchor2[s].y));
+      }
+      prev_nonempty = s; ++n_nonempty;
       const size_t bytes = ((size_t)ns_ * 52 + 15) & ~(size_t)15;
       blk.resize(off + bytes, 0);
       double2* pa = reinterpret_cast<double2*>(blk.data() + off);
@@ -2347,10 +2368,10 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     if (blk.size() / 16 >= (1u << 23)) ok = false;
     blk.resize(blk.size() + 64, 0);
     grp::GroupTables& GT = h->GT;
-    GT.n_stages = n_stages; GT.xmax = xmax; GT.n_teff = cfg->n_teff;
+    GT.n_stages = n_stages; GT.xmax = xmax; GT.dxmax = dxmax; GT.n_teff = cfg->n_teff;
     CKC(upload(h, meta.data(), meta.size(), &GT.stage_meta));
     CKC(upload(h, blk.data(), blk.size(), &GT.recblk));
-    CKC(upload(h, anchor.data(), anchor.size(), &GT.anchor));
+    CKC(upload(h, anchor2.data(), anchor2.size(), &GT.anchor));
     CKC(upload(h, dr2.data(), dr2.size(), &GT.drec2));
     for (int c = 0; c < BAND_COLS; ++c) GT.wbase[c] = (c < MS_MAX_CONTRAST) ? T.c_wbase[c] : T.p_wbase[c - MS_MAX_CONTRAST];
     // (pixel, Teff, log g) tensor map of the device grid: one box = the 2 x 2 bracketing rows of a star
@@ -2391,7 +2412,8 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     if (ok) {
       // per CTA: the transposed model vectors [n][32] and the walker warps' key lists [NWW_MAX + 1][LISTCAP][32]
       CKH(cudaMalloc((void**)&h->group_scratch, (size_t)h->group_ctas * (size_t)n * 32 * sizeof(double)));
-      CKH(cudaMalloc((void**)&h->group_list, (size_t)h->group_ctas * (NWW_MAX + 1) * (size_t)LISTCAP * 32 * sizeof(unsigned long long)));
+      const size_t n_lists = std::max<size_t>((size_t)h->group_ctas * (MS_GROUP_NWW + 1), (size_t)h->num_sms * (MS_GROUP_NWW_WIDE + 1));
+      CKH(cudaMalloc((void**)&h->group_list, n_lists * (size_t)LISTCAP * 32 * sizeof(unsigned long long)));
     }
   }
 
