@@ -2,96 +2,72 @@
 // mcmcspec.cu; instantiated in translation unit MS_TU = 4).
 //
 // One persistent CTA evaluates *groups* of up to 32 walkers that sit in the same grid cell, i.e. whose 2 * 2^D
-// bracketing grid rows (mft6.py:439-519) are the same rows.  The rows are streamed ONCE per group, 128 model pixels
-// (one stage) at a time, through a shared-memory ring:
+// bracketing grid rows (mft6.py:439-519) are the same rows.  What a walker needs of a row is, per observed pixel, the
+// row's two model pixels that bracket it (mft6.py:1169: interp1d onto the observed wavelengths) -- the bracket table
+// T.bracket[row][pixel] built once in ms_create -- and the row's integrals through the passbands (T.bandsum; np.trapz
+// of mft6.py:731 resp. pyphot get_flux, mft6.py:776, both linear in the spectrum, so a walker's band fluxes are the
+// same linear combination of the row integrals as its spectrum is of the rows, mft6.py:507-519, :689-700).  The
+// bracket rows are streamed ONCE per group, KP observed pixels (one stage) at a time, through a shared-memory ring:
 //
 //   warp 0      producer   -- per stage ONE 3-D tiled tensor copy per star (cp.async.bulk.tensor, SASS UTMALDG: box =
-//                             130 pixels x 2 Teff nodes x 2 log g nodes = the star's four bracketing rows), one bulk
-//                             copy (UBLKCP) per passband weight tile that touches the stage and one for the stage's
-//                             block of per-observed-pixel records; completion is counted in bytes on the stage's
-//                             `full` mbarrier, `empty` mbarriers hand slots back.  After the stream: bulk copies of
-//                             the chi-square pass's per-pixel records through two slots of the same ring.
-//   warps 1..3  service    -- gather: for every observed pixel whose upper bracketing model pixel lies in the stage, the
-//                             two bracketing pixels of every row out of the staged segments (mft6.py:1169: interp1d
-//                             onto the observed wavelengths) into a compact table B[row][pixel]; `bready` mbarrier.
-//                             Warps 2, 3 also integrate every staged ROW through the passbands that touch the stage
-//                             (sum_p w_f[p] * row[p]: np.trapz of mft6.py:731 resp. pyphot get_flux, mft6.py:776, both
-//                             linear in the spectrum); a walker's band fluxes are the same linear combination of these
-//                             row integrals as its spectrum is of the rows (mft6.py:507-519, :689-700).
-//   warps 4..   walkers    -- LANE = WALKER: lane l of every walker warp serves walker l of the group and keeps its
-//                             eight row coefficients and Av in registers; the 4 or 8 warps split the observed pixels of
-//                             each stage between them.  B and the records are the same for all lanes, so every
-//                             shared-memory read is a one-wavefront broadcast.  Per pixel and lane: composite at the
-//                             two bracketing pixels (FMA chain over the rows, then the sum over the stars,
+//                             KP bracket pairs x 2 Teff nodes x 2 log g nodes = the star's four bracketing rows) and one
+//                             bulk copy (UBLKCP) of the stage's per-observed-pixel records; completion is counted in
+//                             bytes on the stage's `full` mbarrier, `done` mbarriers hand slots back.  After the stream:
+//                             bulk copies of the chi-square pass's inputs through the same ring.
+//   warps 1..   walkers    -- LANE = WALKER: lane l of every walker warp serves walker l of the group and keeps its
+//                             eight row coefficients and Av in registers; the warps split the observed pixels of
+//                             each stage between them.  The staged table and the records are the same for all lanes, so
+//                             every shared-memory read is a one-wavefront broadcast.  Per pixel and lane: composite at
+//                             the two bracketing pixels (FMA chain over the rows, then the sum over the stars,
 //                             mft6.py:744), extinction of both (mft6.py:1162), linear rebin (mft6.py:1169),
 //                             norm_spec's moments (mft6.py:193-196), key range and a scale-free 64-bin histogram for
 //                             the median; the model value goes to a transposed scratch row [pixel][lane] (coalesced).
-//                             After the stream the partial sums of the four warps are combined in a fixed order, the
+//                             After the stream the partial sums of the warps are combined in a fixed order, the
 //                             warps split one pass over the scratch for the chi-square (mft6.py:1178-1179) that also
 //                             collects the keys of the median's histogram bin, and the first walker warp finishes:
 //                             exact selection on those keys (mft6.py:1173, np.median convention), contrasts,
 //                             magnitudes, priors, final sum (mft6.py:1182-1205).  No shuffles, no atomics.
 //
-// Extinction: exp2(Av * ext(p)) = A_s * exp(Av * x_p) with A_s = exp2(Av * anchor_s) once per stage and walker and a
-// 7th-order polynomial on |Av * x_p| <= 0.02 (x^8/8! < 7e-19); larger exponents take the exp2 path (whole warp).
+// Extinction: exp2(Av * ext(p)) = A_s * exp(Av * x_p) with A_s = exp2(Av * anchor_s) per stage and walker and a
+// 7th-order polynomial on |Av * x_p| <= 0.02 (x^8/8! < 7e-19); walkers with larger exponents take exp2 of the whole exponent.  A_s
+// itself is taken exactly on every 8th stage and follows from the previous stage's by the same polynomial in between.
 
 namespace grp {
 
-// -DMS_GROUP_DEBUG: CTA 0 prints, per group, how long each role spent in total and inside mbarrier waits
-#ifdef MS_GROUP_DEBUG
-#define GDBG_DECL long long gdbg_wait = 0, gdbg_t0 = clock64();
-#define GDBG_WAIT(stmt) { const long long t__ = clock64(); stmt; gdbg_wait += clock64() - t__; }
-#define GDBG_REPORT(name) if (blockIdx.x == 0 && lane == 0) printf("%s warp %d: group %d of %d (%d walkers) total %lld wait %lld cycles\n", name, warp, g, total_groups, count, clock64() - gdbg_t0, gdbg_wait);
-#else
-#define GDBG_DECL
-#ifdef MS_GROUP_TIMING
-#define GDBG_WAIT(stmt) { const long long t__ = clock64(); stmt; gt_wait += clock64() - t__; }
-#else
-#define GDBG_WAIT(stmt) stmt;
-#endif
-#define GDBG_REPORT(name)
-#endif
-// -DMS_GROUP_TIMING: the first eight CTAs print, when they run out of groups, where the first and last walker warps'
-// cycles went: waiting for a group, phase A, the barrier after it, phase B, the finish (first warp only)
+// -DMS_GROUP_TIMING: the first eight CTAs print, when they run out of groups, where the producer's and the first and
+// last walker warps' cycles went: waiting for a group, phase A, the barrier after it, phase B (bin of the median,
+// chi-square pass, lists), the finish (first warp only), and the time inside mbarrier waits
 #ifdef MS_GROUP_TIMING
 #define GTIME(i) { const long long t__ = clock64(); gt_acc[i] += t__ - gt_last; gt_last = t__; }
+#define GDBG_WAIT(stmt) { const long long t__ = clock64(); stmt; gt_wait += clock64() - t__; }
 #else
 #define GTIME(i)
+#define GDBG_WAIT(stmt) stmt;
 #endif
+#define GDBG_DECL
+#define GDBG_REPORT(name)
 
-constexpr int TP = 128;                    // model pixels per stage
-constexpr int ROWPX = TP + 2;              // staged pixels per row: the tile and the two pixels before it (16-byte
-                                           // alignment of the box; the second one is the lower bracket of an
-                                           // observed pixel whose upper bracket is the first pixel of the tile)
-constexpr int ROWB = ROWPX * 8;            // 1040 bytes
-constexpr int WS = MS_GROUP_WSLOTS;        // weight slots: passbands that may overlap on one stage
-constexpr int RCAP = MS_GROUP_RCAP;        // observed pixels per stage the ring is sized for
-#ifndef MS_GROUP_NRS
-#define MS_GROUP_NRS 2
+#ifndef MS_GROUP_KP
+#define MS_GROUP_KP 32
 #endif
-#ifndef MS_GROUP_NBS
-#define MS_GROUP_NBS 3
+#ifndef MS_GROUP_NST
+#define MS_GROUP_NST 10
 #endif
-#ifndef MS_GROUP_NRC
-#define MS_GROUP_NRC 5
+#ifndef MS_GROUP_VW
+#define MS_GROUP_VW 14
 #endif
-constexpr int NRS = MS_GROUP_NRS;          // row slots: a stage's staged rows + weight tiles, dead once gathered and integrated
-constexpr int NBS = MS_GROUP_NBS;          // B slots: a stage's bracket table, written by the gather once the walker warps are
-                                           // through with the stage NBS back
-constexpr int NRC = MS_GROUP_NRC;          // record slots: a stage's per-pixel records + meta; copied in NRC stages ahead of the
-                                           // walker warps, so that only the gather sits between a freed B slot and the next table
-constexpr int ANCHOR_REFRESH = 8;          // the stage's common extinction factor is updated incrementally, exactly every 8th
-constexpr int NWW_MAX = 12;                // walker warps per CTA (template parameter NWW: 6 with two CTAs per SM, 12 with
+constexpr int KP = MS_GROUP_KP;            // observed pixels per stage
+constexpr int NST = MS_GROUP_NST;          // ring slots: stages in flight ahead of the walker warps
+constexpr int ANCHOR_REFRESH = 8;          // the stage's common extinction factor is taken exactly on every 8th stage
+constexpr int NWW_MAX = MS_GROUP_VW;       // walker warps per CTA (template parameter NWW: 7 with two CTAs per SM, 14 with
                                            // one): they split the observed pixels of the group's 32 walkers
 constexpr int GMAX = 32;                   // walkers per group (one per lane)
-constexpr int BROWB = RCAP * 16 + 16;      // stride of a B row (one pad slot: conflict-free stores from 8 rows)
 constexpr int HBITS = 6;
 constexpr int HBINS = 1 << HBITS;          // per-lane histogram bins
 constexpr int LISTCAP = 1024;              // keys of the median's bin a lane collects (per walker warp)
-constexpr int VW = 12;                     // partial sums per walker: the quadruples of observed pixels (counted along the whole
-                                           // vector) resp. the blocks of a chi-square chunk are dealt to partial sum (index mod 12)
-                                           // whatever the number of walker warps, so that a walker's value does not depend on
-                                           // the kernel variant
+constexpr int VW = MS_GROUP_VW;            // partial sums per walker: the quadruples of observed pixels resp. the blocks of a
+                                           // chi-square chunk are dealt to partial sum (index mod VW) whatever the number of
+                                           // walker warps, so that a walker's value does not depend on the kernel variant
 constexpr int PIX = 4;                     // observed pixels a walker lane keeps in flight (independent FMA chains)
 constexpr int CHI_U = 4;                   // observed pixels per block of the chi-square pass
 constexpr int CHI_CHUNK = VW * CHI_U;      // observed pixels per chunk of the chi-square pass: 32-byte records + the group's
@@ -99,43 +75,30 @@ constexpr int CHI_CHUNK = VW * CHI_U;      // observed pixels per chunk of the c
 constexpr int CHI_BYTES = CHI_CHUNK * (32 + 256);
 constexpr int CAND = 8;                    // keys of the median's second-level bin per lane and walker warp (fast finish)
 constexpr double POLY_XMAX = 0.02;
-constexpr int REC_BYTES = (RCAP * 52 + 15) & ~15;   // record block of one stage: 3 double2 + one int32 per observed pixel
+static_assert(KP % PIX == 0, "a stage is a whole number of quadruples");
 
-// The ring: NRS row slots {star 0 rows | star 1 rows | weight tiles}, NBS B slots {B}, NRC record slots {records | meta}.
+// One ring slot: the bracket table of the stage {star 0: [log g][Teff][KP] double2 | star 1} and its records.
 template <int NR> struct StageLayout {
   static constexpr int NROW = 2 * NR;
-  static constexpr int box = (NR * ROWB + 127) & ~127;     // one star's rows, written by one tensor copy (128-byte aligned)
-  // row slot
-  static constexpr int rows = 0;
-  static constexpr int weights = 2 * box;
-  static constexpr int rbytes = weights + WS * TP * 8;
-  // B slot
-  static constexpr int bbytes = (NROW * BROWB + 127) & ~127;
-  // record slot
-  static constexpr int rec = 0;                            // {t, x_lo}[n] | {x_hi, d q0}[n] | {d q1, d q2}[n] | int32 upper bracket[n]
-  static constexpr int meta = rec + REC_BYTES;
-  static constexpr int cbytes = (meta + 16 + 127) & ~127;
-  static constexpr int b0 = NRS * rbytes;                  // offset of the first B slot
-  static constexpr int c0 = b0 + NBS * bbytes;             // offset of the first record slot
-  static constexpr int bytes = c0 + NRC * cbytes;          // the whole ring
-  static_assert(weights % 128 == 0 && rbytes % 128 == 0 && meta % 16 == 0, "bulk copies need aligned destinations");
-  static_assert(NRC > NBS, "the records run ahead of the tables");
-  static constexpr int cslots = bytes / CHI_BYTES;          // the chi-square pass cuts the same ring into chunk slots
+  static constexpr int rowb = KP * 16;                     // one row of the stage
+  static constexpr int box = NR * rowb;                    // one star's rows, written by one tensor copy
+  static constexpr int B = 0;
+  static constexpr int rec = 2 * box;                      // {t, x_lo}[KP] | {x_hi, d q0}[KP] | {d q1, d q2}[KP]
+  static constexpr int bytes = rec + KP * 48;
+  static constexpr int ring = NST * bytes;
+  static_assert(box % 128 == 0 && bytes % 128 == 0, "bulk copies need aligned destinations");
+  static constexpr int cslots = ring / CHI_BYTES;          // the chi-square pass cuts the same ring into chunk slots
   static_assert(CHI_BYTES % 128 == 0 && cslots >= 2, "chi-square chunks: aligned, at least two in flight");
-  __device__ static constexpr int row_off(int r) { return (r / NR) * box + (r % NR) * ROWB; }
 };
 
 // What the group kernel needs beyond DevTables (built once in ms_create).
 struct GroupTables {
-  const int4* stage_meta;       // [n_stages] {first observed pixel, observed pixels, 4 x uint8 band column per weight slot
-                                //  (0xff: free), flush mask | (offset of the record block / 16) << 8}
-  const unsigned char* recblk;  // per stage: {t, x_lo}[n] | {x_hi, d q0}[n] | {d q1, d q2}[n] | int32 tile-local upper bracket[n]
+  const double2* recblk;        // per stage: {t, x_lo}[KP] | {x_hi, d q0}[KP] | {d q1, d q2}[KP]
   const double2* anchor;        // [n_stages] {extinction exponent the stage's x values are relative to, (its step from the
-                                //  previous non-empty stage) ln 2, or +inf: take the exact factor here}
-  double dxmax;                 // max |step|
+                                //  previous stage) ln 2, or +inf: take the exact factor here}
   const double* drec2;          // [n_data][4] {q1(x), q2(x), flux, 1/err^2}: phase B
-  const double* wbase[BAND_COLS];   // weight of region pixel p for band column c: wbase[c][p]
   double xmax;                  // max |x| over all records (x = (ext - anchor) ln 2)
+  double dxmax;                 // max |step|
   int n_stages;
   int n_teff;
 };
@@ -312,68 +275,27 @@ __device__ __forceinline__ void lane_locate_merged(const unsigned short* hist_al
 template <int NWW>
 __device__ __forceinline__ void walker_bar() { asm volatile("bar.sync 1, %0;" :: "n"(NWW * 32) : "memory"); }
 
-// Integrate the staged rows [r0, r0 + NRB) through the passbands that touch the stage (one warp; acc carries the sums
-// of a band over the stages it spans, flushed to s_band on its last stage).
-template <int NR, int NRB>
-__device__ __forceinline__ void band_stage(uint32_t st, unsigned slots, unsigned flush, int r0, double (&acc)[NRB][WS],
-                                           double* s_band, int lane) {
-  using L = StageLayout<NR>;
-  constexpr int NROW = 2 * NR;
-  if (slots == 0xffffffffu) return;
-  // this lane's pixels of the tile: {2l, 2l+1} and {64 + 2l, 65 + 2l} (16-byte accesses, lanes contiguous)
-#pragma unroll
-  for (int q = 0; q < WS; ++q) {
-    const unsigned col = (slots >> (8 * q)) & 0xffu;
-    if (col != 0xffu) {                                // warp-uniform
-      const double2 w0 = lds128(st + L::weights + q * TP * 8 + lane * 16);
-      const double2 w1 = lds128(st + L::weights + q * TP * 8 + 512 + lane * 16);
-#pragma unroll
-      for (int r = 0; r < NRB; ++r) {
-        const uint32_t rp = st + L::rows + (uint32_t)L::row_off(r0 + r) + 16 + lane * 16;
-        const double2 v0 = lds128(rp);
-        const double2 v1 = lds128(rp + 512);
-        double a = acc[r][q];
-        a = fma(w0.x, v0.x, a); a = fma(w0.y, v0.y, a); a = fma(w1.x, v1.x, a); a = fma(w1.y, v1.y, a);
-        acc[r][q] = a;
-      }
-      if ((flush >> q) & 1u) {
-#pragma unroll
-        for (int r = 0; r < NRB; ++r) {
-          const double tot = warp_sum(acc[r][q]);
-          if (lane == 0) s_band[col * NROW + r0 + r] = tot;
-          acc[r][q] = 0.0;
-        }
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // NR: grid rows per star (4; 8 with [Fe/H] is not instantiated yet).  Binaries, posterior mode.
-// NWW walker warps and NSV service warps per CTA:
-//   NSV == 2: warp 0 issues the copies and integrates the rows through the passbands one stage behind, warp 1 gathers;
-//   NSV == 4: warp 0 issues the copies, warps 1..3 split the gather, warps 2 and 3 integrate half of the rows each.
+// NWW walker warps per CTA + the producer warp.
 // ------------------------------------------------------------------------------------------
-template <int NR, int NWW, int NSV, int CTAS_PER_SM>
-__global__ void __launch_bounds__((NWW + NSV) * 32, CTAS_PER_SM)
+template <int NR, int NWW, int CTAS_PER_SM>
+__global__ void __launch_bounds__((NWW + 1) * 32, CTAS_PER_SM)
 lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__ GroupTables GT,
-                    const __grid_constant__ CUtensorMap grid_map, const WalkerPlan* __restrict__ plans,
+                    const __grid_constant__ CUtensorMap bracket_map, const WalkerPlan* __restrict__ plans,
                     const int* __restrict__ order, const GroupDesc* __restrict__ groups, const int* __restrict__ n_groups,
                     int* __restrict__ group_counter, double* __restrict__ lnprob, const PartsOut parts,
                     double* __restrict__ scratch, unsigned long long* __restrict__ list_scratch) {
   constexpr int NS = 2;
   constexpr int NROW = NS * NR;
-  constexpr int NTHREADS = (NWW + NSV) * 32;
-  static_assert(NSV == 2 || NSV == 4, "service roles");
+  constexpr int NTHREADS = (NWW + 1) * 32;
   static_assert(NWW <= NWW_MAX && VW % NWW == 0, "scratch is sized for NWW_MAX walker warps; partial sums are dealt to the warps");
   constexpr int NV = VW / NWW;                                     // partial sums a walker warp carries
-  constexpr int NG = NSV - 1;                                      // warps that gather
-  constexpr int NARRIVE = (NSV == 2) ? 2 : 3;                      // service warps that hand a slot back
   using L = StageLayout<NR>;
   constexpr int CSLOTS = L::cslots;
   extern __shared__ __align__(128) unsigned char gsm[];
-  unsigned short* const hist_all = reinterpret_cast<unsigned short*>(gsm + L::bytes);   // [NWW][HBINS][32]
-  __shared__ __align__(8) unsigned long long s_full[NRS], s_rempty[NRS], s_bready[NBS], s_done[NRC], s_cfull[CSLOTS], s_cempty[CSLOTS];
+  unsigned short* const hist_all = reinterpret_cast<unsigned short*>(gsm + L::ring);   // [NWW][HBINS][32]
+  __shared__ __align__(8) unsigned long long s_full[NST], s_done[NST], s_cfull[CSLOTS], s_cempty[CSLOTS];
   __shared__ double s_band[BAND_COLS * NROW];            // row integrals through every band
   __shared__ double s_part[VW][4][32];                   // per partial sum and lane: three moments / chi-square
   __shared__ unsigned long long s_above[NWW][32];
@@ -383,12 +305,10 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < NRS; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(smem_u32(&s_full[s]), 1);
-      mbar_init(smem_u32(&s_rempty[s]), (unsigned)NARRIVE);         // the service warps that read the rows
+      mbar_init(smem_u32(&s_done[s]), (unsigned)NWW);              // every walker warp is through with the stage
     }
-    for (int s = 0; s < NBS; ++s) mbar_init(smem_u32(&s_bready[s]), (unsigned)NG);   // every gathering warp has written its share of B
-    for (int s = 0; s < NRC; ++s) mbar_init(smem_u32(&s_done[s]), (unsigned)NWW);    // every walker warp is through with the stage
     for (int s = 0; s < CSLOTS; ++s) { mbar_init(smem_u32(&s_cfull[s]), 1); mbar_init(smem_u32(&s_cempty[s]), (unsigned)NWW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -397,7 +317,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
   const int n_chunks = (n + CHI_CHUNK - 1) / CHI_CHUNK;
   const int total_groups = *n_groups;
   const uint32_t ring = smem_u32(gsm);
-  const int wj = warp - NSV;                                       // walker warp index, < 0 for the service warps
+  const int wj = warp - 1;                                         // walker warp index, < 0 for the producer
   // the CTA's scratch, reused by every group it takes: model values [pixel][lane], key lists [warp][slot][lane]
   double* const sMT = scratch + (size_t)blockIdx.x * (size_t)n * 32;
   unsigned long long* const list0 = list_scratch + (size_t)blockIdx.x * (NWW + 1) * (size_t)LISTCAP * 32;       // + a spare list
@@ -432,7 +352,6 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         for (int r = 0; r < NR; ++r) s_row[st * NR + r] = p.row[st][r];
       }
     }
-    for (int k = tid; k < BAND_COLS * NROW; k += NTHREADS) s_band[k] = 0.0;
     __syncthreads();
 
     if (s_status != 0) {
@@ -452,6 +371,9 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       }
       continue;
     }
+    // the rows' integrals through the passbands (read by the finishing warp, after the barriers below)
+    for (int k = tid; k < BAND_COLS * NROW; k += NTHREADS)
+      s_band[k] = __ldg(T.bandsum + (long long)s_row[k % NROW] * BAND_COLS + k / NROW);
 
     // ---- walker-lane state (walker warps only): lane l serves walker l of the group in every walker warp; idle
     // lanes shadow walker 0 (same arithmetic, nothing stored)
@@ -467,141 +389,22 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       // box origin of each star: its lower (Teff, log g) nodes (the plan's corners are in box order)
       const int t0[NS] = {s_row[0] % GT.n_teff, s_row[NR] % GT.n_teff};
       const int g0[NS] = {s_row[0] / GT.n_teff, s_row[NR] / GT.n_teff};
-      int4 meta = __ldg(GT.stage_meta);
-      // NSV == 2: this warp also integrates the rows through the passbands, LAG stages behind its own copies (by then
-      // the stage has landed, and the walker warps are still busy with it)
-      constexpr int LAG = (NSV == 2) ? NRS - 1 : 0;
-      constexpr int NRB = (NSV == 2) ? NROW : 1;
-      double acc[NRB][WS];
-#pragma unroll
-      for (int r = 0; r < NRB; ++r) {
-#pragma unroll
-        for (int q = 0; q < WS; ++q) acc[r][q] = 0.0;
-      }
-      GDBG_DECL
-      for (int s = 0; s < n_stages + LAG; ++s) {
-        GTIME(8)
-        if (s < n_stages) {
-          const unsigned gs = it0 + (unsigned)s;
-          const int slot = (int)(gs % NRS), cslot = (int)(gs % NRC);
-          const int4 meta_next = __ldg(GT.stage_meta + min(s + 1, n_stages - 1));      // in flight while the slots free up
-          GDBG_WAIT(mbar_wait(smem_u32(&s_rempty[slot]), ((gs / NRS) & 1u) ^ 1u))
-          GDBG_WAIT(mbar_wait(smem_u32(&s_done[cslot]), ((gs / NRC) & 1u) ^ 1u))        // the walker warps are through with stage gs - NRC
-          const int n_obs = meta.y;
-          const uint32_t st = ring + (uint32_t)slot * L::rbytes;
-          const uint32_t stc = ring + (uint32_t)(L::c0 + cslot * L::cbytes);
-          const uint32_t bar = smem_u32(&s_full[slot]);
-          // bytes of this stage (uniform): two row boxes, active weight tiles, the record block
-          const unsigned rec_bytes = (unsigned)(n_obs * 52 + 15) & ~15u;
-          int n_w = 0;
-#pragma unroll
-          for (int q = 0; q < WS; ++q) n_w += (((unsigned)meta.z >> (8 * q)) & 0xffu) != 0xffu;
-          const unsigned total = (unsigned)(NS * NR * ROWB + n_w * TP * 8) + rec_bytes;
-          if (lane == 0) {
-            *reinterpret_cast<int4*>(gsm + L::c0 + (size_t)cslot * L::cbytes + L::meta) = meta;
-            mbar_expect_tx(bar, total);
-          }
-          __syncwarp();
-          const int px0 = s * TP;
-          if (lane < NS) {
-            tensor_g2s_3d(st + L::rows + lane * L::box, &grid_map, px0 - 2, t0[lane], g0[lane], bar);
-          } else if (lane < NS + WS) {
-            const int q = lane - NS;
-            const unsigned col = ((unsigned)meta.z >> (8 * q)) & 0xffu;
-            if (col != 0xffu) bulk_g2s(st + L::weights + q * TP * 8, GT.wbase[col] + px0, TP * 8, bar);
-          } else if (lane == NS + WS && n_obs > 0) {
-            bulk_g2s(stc + L::rec, GT.recblk + (size_t)((unsigned)meta.w >> 8) * 16, rec_bytes, bar);
-          }
-          meta = meta_next;
-        }
-        GTIME(6)
-        if constexpr (NSV == 2) {
-          if (s >= LAG) {
-            const unsigned gs = it0 + (unsigned)(s - LAG);
-            const int slot = (int)(gs % NRS), cslot = (int)(gs % NRC);
-            GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NRS) & 1u))
-            const int4 mb = *reinterpret_cast<const int4*>(gsm + L::c0 + (size_t)cslot * L::cbytes + L::meta);
-            band_stage<NR, NRB>(ring + (uint32_t)slot * L::rbytes, (unsigned)mb.z, (unsigned)mb.w & 0xffu, 0, acc, s_band, lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_rempty[slot]));
-          }
-        }
-        GTIME(7)
-      }
-      GDBG_REPORT("producer")
-    } else if (warp < NSV) {
-      // ================================================================= service warps 1 .. NSV - 1: the gather, split by
-      // quadruples of observed pixels; with four service warps, warps 2 and 3 also integrate half of the rows each
-      // through the passbands
-      constexpr int HR = NROW / 2;
-      const int sw = warp - 1;
-      const int r0 = (warp == 3) ? HR : 0;
-      constexpr int NRB = (NSV == 4) ? HR : 1;
-      double acc[NRB][WS];
-#pragma unroll
-      for (int r = 0; r < NRB; ++r) {
-#pragma unroll
-        for (int q = 0; q < WS; ++q) acc[r][q] = 0.0;
-      }
-      GDBG_DECL
       for (int s = 0; s < n_stages; ++s) {
         const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs % NRS), bslot = (int)(gs % NBS), cslot = (int)(gs % NRC);
-        GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NRS) & 1u))
-        // the B slot is free once the walker warps are through with stage gs - NBS (its `done` barrier cannot have moved
-        // on by another phase: that takes the stage gs - NBS + NRC, which waits for this table)
-        if (gs >= (unsigned)NBS) { GDBG_WAIT(mbar_wait(smem_u32(&s_done[(gs - NBS) % NRC]), ((gs - NBS) / NRC) & 1u)) }
-        const uint32_t st = ring + (uint32_t)slot * L::rbytes;
-        const unsigned char* strow = gsm + (size_t)slot * L::rbytes + L::rows;
-        unsigned char* stB = gsm + L::b0 + (size_t)bslot * L::bbytes;
-        const unsigned char* stc = gsm + L::c0 + (size_t)cslot * L::cbytes;
-        const int4 meta = *reinterpret_cast<const int4*>(stc + L::meta);
-        const int n_obs = meta.y;
-        {
-          // lane -> (row r, pixel k0 + lane / 8 + 4 j): four independent load chains per lane and trip
-          constexpr int GI = 4;
-          const int r = lane & 7;
-          const int* hlp = reinterpret_cast<const int*>(stc + L::rec + (size_t)n_obs * 48);
-          for (int k0 = 4 * GI * sw; k0 < n_obs; k0 += 4 * GI * NG) {
-            int j1[GI];
-#pragma unroll
-            for (int j = 0; j < GI; ++j) {
-              const int k = min(k0 + 4 * j + (lane >> 3), n_obs - 1);
-              j1[j] = hlp[k] + 1;                            // tile index of the lower bracket (upper: + 1)
-            }
-#pragma unroll
-            for (int rr = 0; rr < NROW; rr += 8) {
-              double2 v01[GI]; double v2[GI];
-#pragma unroll
-              for (int j = 0; j < GI; ++j) {
-                const unsigned char* rp = strow + L::row_off(rr + r) + (size_t)(j1[j] & ~1) * 8;
-                v01[j] = *reinterpret_cast<const double2*>(rp);
-                v2[j] = *reinterpret_cast<const double*>(rp + 16);
-              }
-#pragma unroll
-              for (int j = 0; j < GI; ++j) {
-                const int k = k0 + 4 * j + (lane >> 3);
-                double2 pr;
-                pr.x = (j1[j] & 1) ? v01[j].y : v01[j].x;
-                pr.y = (j1[j] & 1) ? v2[j] : v01[j].y;
-                if (k < n_obs) *reinterpret_cast<double2*>(stB + (size_t)(rr + r) * BROWB + (size_t)k * 16) = pr;
-              }
-            }
-          }
-        }
+        const int slot = (int)(gs % NST);
+        GDBG_WAIT(mbar_wait(smem_u32(&s_done[slot]), ((gs / NST) & 1u) ^ 1u))     // the walker warps are through with stage gs - NST
+        const uint32_t st = ring + (uint32_t)slot * L::bytes;
+        const uint32_t bar = smem_u32(&s_full[slot]);
+        if (lane == 0) mbar_expect_tx(bar, (unsigned)L::bytes);         // pixels past the end of the spectrum are zero-filled
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_bready[bslot]));          // this warp's share of B is written
-        if constexpr (NSV == 4) {
-          if (warp >= 2) band_stage<NR, NRB>(st, (unsigned)meta.z, (unsigned)meta.w & 0xffu, r0, acc, s_band, lane);
-          __syncwarp();
+        if (lane < NS) {
+          tensor_g2s_3d(st + L::B + lane * L::box, &bracket_map, 2 * KP * s, t0[lane], g0[lane], bar);
+        } else if (lane == NS) {
+          bulk_g2s(st + L::rec, GT.recblk + (size_t)s * 3 * KP, KP * 48, bar);
         }
-        if (lane == 0) mbar_arrive(smem_u32(&s_rempty[slot]));
       }
-      asm volatile("fence.proxy.async;" ::: "memory");                  // B is overwritten by the chi-square pass's bulk copies
-      GDBG_REPORT("service")
     } else {
-      // ================================================================= walker warps, phase A: lane = walker; warp wj
-      // takes the observed pixel quadruples wj, wj + NWW, ... of every stage
+      // ================================================================= walker warps, phase A: lane = walker
       double momv[NV][3];
 #pragma unroll
       for (int v = 0; v < NV; ++v) { momv[v][0] = 0.0; momv[v][1] = 0.0; momv[v][2] = 0.0; }
@@ -616,36 +419,31 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         av = p.av;
         lane_hist_zero(hist, lane);
       }
-      const bool poly_ok = __all_sync(0xffffffffu, av * GT.xmax <= POLY_XMAX);
-      const bool inc_ok = __all_sync(0xffffffffu, av * GT.dxmax <= POLY_XMAX);
+      // which form of the extinction factor a walker gets depends on its own Av only (never on its companions in the
+      // group): the polynomial where it is accurate, exp2 of the whole exponent otherwise
+      const bool lane_poly = av * GT.xmax <= POLY_XMAX, lane_inc = av * GT.dxmax <= POLY_XMAX;
+      const bool poly_ok = __all_sync(0xffffffffu, lane_poly);
       double A = 1.0;
       double2 anc_next = __ldg(GT.anchor);
       int qrot = 0;                       // quadruples of the stages so far, mod VW: where this stage's first one is dealt
-      GDBG_DECL
+      const uint32_t hist_s = smem_u32(hist);
       for (int s = 0; s < n_stages; ++s) {
         const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs % NBS), cslot = (int)(gs % NRC);
+        const int slot = (int)(gs % NST);
         const double2 anc2 = anc_next;
         anc_next = __ldg(GT.anchor + min(s + 1, n_stages - 1));           // in flight during this stage
-        // the gather warp observed `full` (the copies' barrier) before it wrote B and arrived here, so the staged
-        // records are visible too (release / acquire chain)
-        GDBG_WAIT(mbar_wait(smem_u32(&s_bready[slot]), (gs / NBS) & 1u))
-        const unsigned char* stB = gsm + L::b0 + (size_t)slot * L::bbytes;
-        const unsigned char* stp = gsm + L::c0 + (size_t)cslot * L::cbytes;
-        const int4 meta = *reinterpret_cast<const int4*>(stp + L::meta);
-        const int n_obs = meta.y;
+        // the stage's common extinction factor exp2(av * anchor): exact on every ANCHOR_REFRESH-th stage, from the
+        // previous stage's by the polynomial in between (the same sequence in every warp and kernel variant)
+        const double anc = anc2.x;
+        if (lane_inc && anc2.y < CUDART_INF) A = __dmul_rn(A, exp_small(__dmul_rn(av, anc2.y))); else A = exp2(__dmul_rn(av, anc));
+        const int n_obs = min(KP, n - s * KP);
+        GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NST) & 1u))
+        const unsigned char* stB = gsm + (size_t)slot * L::bytes + L::B;
         {
-          // the stage's common extinction factor exp2(av * anchor): exact on every ANCHOR_REFRESH-th non-empty stage, from
-          // the previous stage's by the polynomial in between (the same sequence in every warp and kernel variant)
-          const double anc = anc2.x;
-          if (n_obs > 0) {
-            if (inc_ok && anc2.y < CUDART_INF) A *= exp_small(av * anc2.y); else A = exp2(av * anc);
-          }
-          double* dst = sMT + (size_t)meta.x * 32 + lane;
-          const uint32_t hist_s = smem_u32(hist);
-          const double2* recA = reinterpret_cast<const double2*>(stp + L::rec);
-          const double2* recB = recA + n_obs;
-          const double2* recC = recB + n_obs;
+          double* dst = sMT + (size_t)s * KP * 32 + lane;
+          const double2* recA = reinterpret_cast<const double2*>(gsm + (size_t)slot * L::bytes + L::rec);
+          const double2* recB = recA + KP;
+          const double2* recC = recB + KP;
           // one observed pixel for this lane's walker; every shared-memory operand is the same address in all
           // lanes (one-wavefront broadcasts)
           auto pixel = [&](auto poly, int k, double& rm_out) -> double {
@@ -654,26 +452,31 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             double flo = 0.0, fhi = 0.0;
 #pragma unroll
             for (int stx = 0; stx < NS; ++stx) {
-              const double2 b0 = *reinterpret_cast<const double2*>(stB + (stx * NR) * BROWB + k * 16);
-              double l = cf[stx * NR] * b0.x, u = cf[stx * NR] * b0.y;
+              const double2 b0 = *reinterpret_cast<const double2*>(stB + stx * L::box + k * 16);
+              double l = __dmul_rn(cf[stx * NR], b0.x), u = __dmul_rn(cf[stx * NR], b0.y);
 #pragma unroll
               for (int r = 1; r < NR; ++r) {
-                const double2 b = *reinterpret_cast<const double2*>(stB + (stx * NR + r) * BROWB + k * 16);
+                const double2 b = *reinterpret_cast<const double2*>(stB + stx * L::box + r * L::rowb + k * 16);
                 l = fma(cf[stx * NR + r], b.x, l); u = fma(cf[stx * NR + r], b.y, u);
               }
-              flo = (stx == 0) ? l : flo + l; fhi = (stx == 0) ? u : fhi + u;        // mft6.py:744
+              flo = (stx == 0) ? l : __dadd_rn(flo, l); fhi = (stx == 0) ? u : __dadd_rn(fhi, u);        // mft6.py:744
             }
             double elo, ehi, scale_a = A;
             if constexpr (decltype(poly)::value) {
-              elo = exp_small(av * ra.y); ehi = exp_small(av * xhi);
+              elo = exp_small(__dmul_rn(av, ra.y)); ehi = exp_small(__dmul_rn(av, xhi));
             } else {
-              // exponent too large for the polynomial: exp2 of the whole exponent (1/ln 2 = 1.4426950408889634)
-              elo = exp2(av * fma(ra.y, 1.4426950408889634, anc));
-              ehi = exp2(av * fma(xhi, 1.4426950408889634, anc));
-              scale_a = 1.0;
+              // some lane's exponent is too large for the polynomial: those lanes take exp2 of the whole exponent
+              // (1/ln 2 = 1.4426950408889634), the others the same arithmetic as on the fast path
+              const double e2lo = exp2(av * fma(ra.y, 1.4426950408889634, anc));
+              const double e2hi = exp2(av * fma(xhi, 1.4426950408889634, anc));
+              elo = lane_poly ? exp_small(__dmul_rn(av, ra.y)) : e2lo;
+              ehi = lane_poly ? exp_small(__dmul_rn(av, xhi)) : e2hi;
+              scale_a = lane_poly ? A : 1.0;
             }
-            const double ylo = flo * elo, yhi = fhi * ehi;                 // extinct() at both brackets, mft6.py:1162
-            const double m = scale_a * fma(yhi - ylo, ra.x, ylo);          // interp1d onto the observed pixel, mft6.py:1169
+            // every product and sum is spelled out (no mul/add pair is left for the assembler to fuse or not): a walker's
+            // value must not depend on the kernel variant
+            const double ylo = __dmul_rn(flo, elo), yhi = __dmul_rn(fhi, ehi);     // extinct() at both brackets, mft6.py:1162
+            const double m = __dmul_rn(scale_a, fma(__dsub_rn(yhi, ylo), ra.x, ylo));   // interp1d onto the observed pixel, mft6.py:1169
             rm_out = fast_rcp(m);
             return m;
           };
@@ -689,8 +492,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
           };
           auto run = [&](auto poly) {
             // quadruple q of the stage (pixels 4q .. 4q+3) belongs to partial sum (qrot + q) mod VW: the quadruples are
-            // dealt round robin along the whole vector, so the warps' shares even out over the stages whatever the number
-            // of observed pixels per stage; this warp carries the partials wj, wj + NWW, ...
+            // dealt round robin along the whole vector, so the warps' shares even out over the stages; this warp
+            // carries the partials wj, wj + NWW, ...
             for (int q0 = -qrot; q0 * PIX < n_obs; q0 += VW) {
 #pragma unroll
               for (int v = 0; v < NV; ++v) {
@@ -710,7 +513,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         }
         qrot = (qrot + (n_obs + PIX - 1) / PIX) % VW;
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_done[cslot]));
+        if (lane == 0) mbar_arrive(smem_u32(&s_done[slot]));
       }
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
@@ -719,7 +522,6 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       }
       s_kmin[wj][lane] = kmin; s_kmax[wj][lane] = kmax;
       asm volatile("fence.proxy.async;" ::: "memory");                  // the model values are read back by bulk copies
-      GDBG_REPORT("walker")
     }
     it0 += (unsigned)n_stages;
     GTIME(1)
@@ -744,7 +546,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         if (lane == 0) bulk_g2s(dstb, GT.drec2 + (size_t)c * CHI_CHUNK * 4, npx * 32u, smem_u32(&s_cfull[slot]));
         else if (lane == 1) bulk_g2s(dstb + CHI_CHUNK * 32, sMT + (size_t)c * CHI_CHUNK * 32, npx * 256u, smem_u32(&s_cfull[slot]));
       }
-    } else if (wj >= 0) {
+    } else {
       // ================================================================= walker warps, phase B: lane = walker
       GDBG_DECL
       // ---- the walker's sums over all its pixels, combined in a fixed order (every warp ends up with the same values)
@@ -797,7 +599,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       // histogram of those keys (the next HBITS key bits) and the smallest key above the bin.  The per-pixel records
       // {q1, q2, d, 1/e^2} arrive through the ring (bulk copies by the producer warp), the model values are read one
       // block ahead.  Branch free: eight independent pixels are in flight per lane.
-      const double a0q0 = mom[0] * T.basis[0], a1 = mom[1], a2 = mom[2];
+      const double a0q0 = __dmul_rn(mom[0], T.basis[0]), a1 = mom[1], a2 = mom[2];
       double chiv[NV];
 #pragma unroll
       for (int v = 0; v < NV; ++v) chiv[v] = 0.0;
@@ -838,8 +640,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
                   const double m = mch[pp * 32];
                   const dbl4 r4 = rec[pp];                                  // same address in every lane
                   const double pfit = fma(a2, r4.y, fma(a1, r4.x, a0q0));
-                  const double r = m - r4.z * fast_rcp(pfit);
-                  res[v][u] = valid ? (r * r) * r4.w : 0.0;
+                  const double r = fma(-r4.z, fast_rcp(pfit), m);
+                  res[v][u] = valid ? __dmul_rn(__dmul_rn(r, r), r4.w) : 0.0;
                   mval[v][u] = m;
                 }
               }
@@ -850,7 +652,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
               for (int v = 0; v < NV; ++v) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                  chiv[v] += res[v][u];
+                  chiv[v] = __dadd_rn(chiv[v], res[v][u]);
                   const bool valid = (wj + v * NWW) * U + u < npx;
                   bool hit;
                   if constexpr (HI32) {
@@ -916,7 +718,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       // ---- second level: every warp locates the sub-bin in the summed second-level histograms, then filters its own
       // list into a small candidate buffer
       // [NWW][CAND][32], on the ring: every walker warp is past the chi-square pass, its chunks are consumed
-      static_assert(NWW * CAND * 32 * 8 <= L::bytes, "the candidate buffers fit the ring");
+      static_assert(NWW * CAND * 32 * 8 <= L::ring, "the candidate buffers fit the ring");
       unsigned long long* const cand_all = reinterpret_cast<unsigned long long*>(gsm);
       unsigned long long* const cand = cand_all + (size_t)wj * CAND * 32;
       LaneSel S2 = S;
@@ -1061,8 +863,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             for (int r = 0; r < NR; ++r) a = fma(cf[stx * NR + r], s_band[f * NROW + stx * NR + r], a);
             fl[stx] = a;
           }
-          const double m0 = -2.5 * log10(fl[0]), m1 = -2.5 * log10(fl[1]);
-          const double con = m1 - m0;                                        // mft6.py:741
+          const double m0 = __dmul_rn(-2.5, log10(fl[0])), m1 = __dmul_rn(-2.5, log10(fl[1]));
+          const double con = __dsub_rn(m1, m0);                              // mft6.py:741
           const double d = con - T.c_mag[f];
           icontrast += (d * d) / (T.c_err[f] * T.c_err[f]);
           if (live && parts.contrast) parts.contrast[w * T.n_contrast + f] = con;
@@ -1077,15 +879,15 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             for (int r = 0; r < NR; ++r) a = fma(cf[stx * NR + r], s_band[(MS_MAX_CONTRAST + f) * NROW + stx * NR + r], a);
             tot += a;
           }
-          double mag = -2.5 * log10(tot * T.p_norm[f]);                     // mft6.py:780-782
-          mag += av * T.p_ext[f];                                           // mft6.py:1163 (av == 0 when skipped)
+          double mag = __dmul_rn(-2.5, log10(__dmul_rn(tot, T.p_norm[f])));   // mft6.py:780-782
+          mag = __dadd_rn(mag, __dmul_rn(av, T.p_ext[f]));                  // mft6.py:1163 (av == 0 when skipped)
           const double d = mag - T.p_mag[f];
           iphot += (d * d) / (T.p_err[f] * T.p_err[f]);
           if (live && parts.phot) parts.phot[w * T.n_phot + f] = mag;
         }
         if (live) {
           const WalkerPlan& p = plans[w];
-          const double init_cs = iic * (double)(T.n_contrast + T.n_phot) + icontrast + iphot;   // mft6.py:1191
+          const double init_cs = __dadd_rn(__dadd_rn(__dmul_rn(iic, (double)(T.n_contrast + T.n_phot)), icontrast), iphot);   // mft6.py:1191
           const double lnl = (init_cs != init_cs) ? -CUDART_INF : -0.5 * init_cs;                // mft6.py:1202-1205
           double out = p.lp + lnl;
           if (out != out) out = -CUDART_INF;
@@ -1102,7 +904,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
     cit0 += (unsigned)n_chunks;
   }
 #ifdef MS_GROUP_TIMING
-  if (blockIdx.x < 8 && lane == 0 && (warp <= 1 || wj == 0 || wj == NWW - 1))
+  if (blockIdx.x < 8 && lane == 0 && (warp == 0 || wj == 0 || wj == NWW - 1))
     printf("cta %d warp %d groups %d: idle %lld A %lld sync %lld B: locate %lld chi %lld lists %lld bar %lld finish %lld | mbarrier waits A %lld B %lld\n", blockIdx.x, warp,
            gt_groups, gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[6], gt_acc[7], gt_acc[3], gt_acc[4], gt_acc[5], gt_wait_a, gt_wait);
 #endif

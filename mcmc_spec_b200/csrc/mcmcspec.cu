@@ -53,21 +53,11 @@ namespace cg = cooperative_groups;
 #ifndef MS_GROUP_WALKERS
 #define MS_GROUP_WALKERS 8                           // walkers (walker warps) per CTA of the group kernel
 #endif
-#ifndef MS_GROUP_WSLOTS
-#define MS_GROUP_WSLOTS 4                            // passbands that may overlap on one 128-pixel stage
+#ifndef MS_GROUP_VW
+#define MS_GROUP_VW 14                               // partial sums per walker of the group kernel = walker warps with one CTA per SM
 #endif
-#ifndef MS_GROUP_NWW
-#define MS_GROUP_NWW 6                               // walker warps of the group kernel with two CTAs per SM ...
-#endif
-#ifndef MS_GROUP_NSV
-#define MS_GROUP_NSV 2                               // ... and its service warps (2 or 4)
-#endif
-#ifndef MS_GROUP_NWW_WIDE
-#define MS_GROUP_NWW_WIDE 12                         // walker warps of the variant with one CTA per SM (four service warps)
-#endif
-#ifndef MS_GROUP_RCAP
-#define MS_GROUP_RCAP 64                             // observed pixels per 128-pixel stage the ring is sized for
-#endif
+#define MS_GROUP_NWW_WIDE MS_GROUP_VW
+#define MS_GROUP_NWW (MS_GROUP_VW / 2)               // walker warps with two CTAs per SM
 
 namespace msd {   // types shared by the translation units (external linkage)
 
@@ -1675,6 +1665,7 @@ struct ms_handle {
   CUtensorMap grid_map{};         // (pixel, Teff, log g) view of the device grid for the group kernel's row boxes
   bool group_ok = false;         // the tables fit the kernel's shared-memory ring (weight slots, records per stage)
   int group_mode = -1;           // -1 automatic (large posterior batches), 0 never, 1 whenever possible
+  int group_variant = 0;         // 0 by the number of groups, 1 always one CTA per SM, 2 always two (MCMCSPEC_GROUP_VARIANT, tests)
   bool group_now = false;        // decided per call
   long long group_min_walkers = 1024;
   grp::GroupDesc* groups = nullptr; long long groups_cap = 0;
@@ -1886,31 +1877,31 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
     h->ev_used += 2; h->timed_walkers += nw;
     CK(cudaEventRecord(e0, h->stream));
   }
-  // Few groups (at most one per SM): one CTA per SM with twelve walker warps per group shortens the time a group takes;
-  // otherwise two CTAs per SM with six walker warps each.  The number of groups depends on how the walkers spread over
+  // Few groups (at most one per SM): one CTA per SM with fourteen walker warps per group shortens the time a group takes;
+  // otherwise two CTAs per SM with seven walker warps each.  The number of groups depends on how the walkers spread over
   // the grid cells and is only known on the device: the count of a recent call of the same batch size (copied back
   // asynchronously, never waited for) stands in for it -- successive half steps of a chain look alike.
   const long long min_groups = (nw + grp::GMAX - 1) / grp::GMAX;
   const long long max_groups = min_groups + std::min<long long>(h->T.n_cells, nw);
-  const size_t ring = (size_t)grp::StageLayout<4>::bytes;
+  const size_t ring = (size_t)grp::StageLayout<4>::ring;
   const int seen = *reinterpret_cast<volatile int*>(h->h_n_groups);
   const long long seen_nw = *reinterpret_cast<volatile int*>(h->h_n_groups + 1);
   const long long expect_groups = (seen > 0 && seen_nw == nw) ? (long long)seen : min_groups + min_groups / 3;
-  if (expect_groups <= h->num_sms) {
-    constexpr int NWW = MS_GROUP_NWW_WIDE, NSV = 4;
-    auto kern = grp::lnprob_group_kernel<4, NWW, NSV, 1>;
+  if (h->group_variant == 1 || (h->group_variant == 0 && expect_groups <= h->num_sms)) {
+    constexpr int NWW = MS_GROUP_NWW_WIDE;
+    auto kern = grp::lnprob_group_kernel<4, NWW, 1>;
     const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned ctas = (unsigned)std::min<long long>(h->num_sms, max_groups);
-    kern<<<ctas, (NWW + NSV) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
+    kern<<<ctas, (NWW + 1) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
                                                                h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
   } else {
-    constexpr int NWW = MS_GROUP_NWW, NSV = MS_GROUP_NSV;
-    auto kern = grp::lnprob_group_kernel<4, NWW, NSV, 2>;
+    constexpr int NWW = MS_GROUP_NWW;
+    auto kern = grp::lnprob_group_kernel<4, NWW, 2>;
     const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned ctas = (unsigned)std::min<long long>(h->group_ctas, max_groups);
-    kern<<<ctas, (NWW + NSV) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
+    kern<<<ctas, (NWW + 1) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
                                                                h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
   }
   CK(cudaGetLastError());
@@ -2268,91 +2259,34 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     T.bracket = d_br; T.bandsum = d_bs;
   }
 
-  // ---- group kernel tables (group_kernel.cuh): 128-pixel stages
+  // ---- group kernel tables (group_kernel.cuh): stages of KP observed pixels over the bracket table
   {
     using namespace grp;
     const int n = cfg->n_data;
-    const int n_stages = (cfg->n_reg + TP - 1) / TP;
+    const int n_stages = (n + KP - 1) / KP;
     const double LN2 = 0.69314718055994530942;
-    bool ok = (cfg->nspec == 2) && (T.n_cells > 1) && (cfg->n_data <= 65535);     // uint16 histogram counts
-    // observed pixels per stage (rebin_hi ascending): [sd[s], sd[s+1])
-    std::vector<int> sd((size_t)n_stages + 1);
-    {
-      int i = 0;
-      for (int s = 0; s <= n_stages; ++s) {
-        while (i < n && cfg->rebin_hi[i] < s * TP) ++i;
-        sd[s] = i;
-      }
-      for (int s = 0; s < n_stages; ++s) ok = ok && (sd[s + 1] - sd[s] <= RCAP);
-    }
-    // tight stage range of every band (first / last non-zero weight), then one weight slot per band such that
-    // bands overlapping on a stage sit in different slots (interval colouring in order of first stage)
-    struct Band { int col, s_lo, s_hi, slot; };
-    std::vector<Band> bands;
-    auto add_band = [&](int col, const double* w, int lo_t, int hi_t) {
-      long long first = -1, last = -1;
-      const long long len = (long long)(hi_t - lo_t) * TILE;
-      for (long long k = 0; k < len; ++k) if (w[k] != 0.0) { if (first < 0) first = k; last = k; }
-      if (first < 0) return;
-      const long long p_lo = (long long)lo_t * TILE + first, p_hi = (long long)lo_t * TILE + last + 1;
-      Band b; b.col = col; b.s_lo = (int)(p_lo / TP); b.s_hi = std::min((int)((p_hi + TP - 1) / TP), n_stages); b.slot = -1;
-      if (b.s_hi > b.s_lo) bands.push_back(b);
-    };
-    for (int f = 0; f < cfg->n_contrast; ++f) add_band(f, cfg->c_weights + cfg->c_offset[f], cfg->c_tile_lo[f], cfg->c_tile_hi[f]);
-    for (int f = 0; f < cfg->n_phot; ++f) add_band(MS_MAX_CONTRAST + f, cfg->p_weights + cfg->p_offset[f], cfg->p_tile_lo[f], cfg->p_tile_hi[f]);
-    std::sort(bands.begin(), bands.end(), [](const Band& a, const Band& b) { return a.s_lo < b.s_lo || (a.s_lo == b.s_lo && a.col < b.col); });
-    {
-      int free_at[WS];
-      for (int q = 0; q < WS; ++q) free_at[q] = 0;
-      for (auto& b : bands) {
-        for (int q = 0; q < WS && b.slot < 0; ++q) if (free_at[q] <= b.s_lo) { b.slot = q; free_at[q] = b.s_hi; }
-        if (b.slot < 0) ok = false;
-      }
-    }
-    std::vector<int4> meta((size_t)n_stages);
-    for (int s = 0; s < n_stages; ++s) meta[s] = make_int4(sd[s], sd[s + 1] - sd[s], -1, 0);
-    if (ok) {
-      for (const auto& b : bands) {
-        for (int s = b.s_lo; s < b.s_hi; ++s) {
-          unsigned z = (unsigned)meta[s].z;
-          z = (z & ~(0xffu << (8 * b.slot))) | ((unsigned)b.col << (8 * b.slot));
-          meta[s].z = (int)z;
-        }
-        meta[b.s_hi - 1].w |= 1 << b.slot;
-      }
-    }
+    bool ok = cfg->nspec == 2 && T.n_cells > 1 && n <= 65535 && n >= 1;
     // records, one block per stage: x = (ext - anchor of the stage) ln 2; d q_k(x) of norm_spec's orthonormal
-    // quadratic basis; tile-local upper bracket
-    std::vector<double> anchor((size_t)n_stages + 32, 0.0);
+    // quadratic basis
     std::vector<double2> anchor2((size_t)n_stages + 32, make_double2(0.0, std::numeric_limits<double>::infinity()));
-    double dxmax = 0.0;
-    int n_nonempty = 0, prev_nonempty = -1;
-    std::vector<unsigned char> blk;
+    std::vector<double2> blk((size_t)n_stages * 3 * KP + 8, make_double2(0.0, 0.0));
     std::vector<double> dr2(4 * (size_t)n);
-    double xmax = 0.0;
+    double xmax = 0.0, dxmax = 0.0;
     for (int s = 0; s < n_stages; ++s) {
-      const int d0 = sd[s], ns_ = sd[s + 1] - sd[s];
-      const size_t off = blk.size();
-      meta[s].x = d0; meta[s].y = ns_;
-      meta[s].w = (meta[s].w & 0xff) | (int)((off / 16) << 8);
-      if (ns_ == 0) continue;
-      anchor[s] = 0.5 * (cfg->ext_lo[d0] + cfg->ext_hi[d0 + ns_ - 1]);
-      // the stage's common factor exp2(av * anchor) follows from the previous non-empty stage's by exp(av * step); every
+      const int d0 = s * KP, ns_ = std::min(KP, n - d0);
+      const double anc = 0.5 * (cfg->ext_lo[d0] + cfg->ext_hi[d0 + ns_ - 1]);
+      // the stage's common factor exp2(av * anchor) follows from the previous stage's by exp(av * step); every
       // ANCHOR_REFRESH-th one is taken exactly (step = +inf)
-      anchor2[s].x = anchor[s];
-      if (prev_nonempty >= 0 && n_nonempty % grp::ANCHOR_REFRESH != 0) {
-        anchor2[s].y = (anchor[s] - anchor[prev_nonempty]) * LN2;
+      anchor2[s].x = anc;
+      if (s % ANCHOR_REFRESH != 0) {
+        anchor2[s].y = (anc - anchor2[s - 1].x) * LN2;
         dxmax = std::max(dxmax, std::fabs(anchor2[s].y));
       }
-      prev_nonempty = s; ++n_nonempty;
-      const size_t bytes = ((size_t)ns_ * 52 + 15) & ~(size_t)15;
-      blk.resize(off + bytes, 0);
-      double2* pa = reinterpret_cast<double2*>(blk.data() + off);
-      double2* pb = pa + ns_; double2* pc = pb + ns_;
-      int* ph = reinterpret_cast<int*>(pc + ns_);
+      double2* pa = blk.data() + (size_t)s * 3 * KP;
+      double2* pb = pa + KP; double2* pc = pb + KP;
       for (int k = 0; k < ns_; ++k) {
         const int i = d0 + k;
-        const double xlo = (cfg->ext_lo[i] - anchor[s]) * LN2, xhi = (cfg->ext_hi[i] - anchor[s]) * LN2;
+        const double xlo = (cfg->ext_lo[i] - anc) * LN2, xhi = (cfg->ext_hi[i] - anc) * LN2;
         xmax = std::max(xmax, std::max(std::fabs(xlo), std::fabs(xhi)));
         const double x = cfg->data_x[i], d = cfg->data_flux[i];
         const double q0 = T.basis[0], q1 = std::fma(T.basis[4], x, T.basis[3]);
@@ -2360,21 +2294,16 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
         pa[k] = make_double2(cfg->rebin_t[i], xlo);
         pb[k] = make_double2(xhi, d * q0);
         pc[k] = make_double2(d * q1, d * q2);
-        ph[k] = cfg->rebin_hi[i] - s * TP;
         dr2[4 * (size_t)i] = q1; dr2[4 * (size_t)i + 1] = q2; dr2[4 * (size_t)i + 2] = d;
         dr2[4 * (size_t)i + 3] = 1.0 / (cfg->data_err[i] * cfg->data_err[i]);
       }
     }
-    if (blk.size() / 16 >= (1u << 23)) ok = false;
-    blk.resize(blk.size() + 64, 0);
     grp::GroupTables& GT = h->GT;
     GT.n_stages = n_stages; GT.xmax = xmax; GT.dxmax = dxmax; GT.n_teff = cfg->n_teff;
-    CKC(upload(h, meta.data(), meta.size(), &GT.stage_meta));
     CKC(upload(h, blk.data(), blk.size(), &GT.recblk));
     CKC(upload(h, anchor2.data(), anchor2.size(), &GT.anchor));
     CKC(upload(h, dr2.data(), dr2.size(), &GT.drec2));
-    for (int c = 0; c < BAND_COLS; ++c) GT.wbase[c] = (c < MS_MAX_CONTRAST) ? T.c_wbase[c] : T.p_wbase[c - MS_MAX_CONTRAST];
-    // (pixel, Teff, log g) tensor map of the device grid: one box = the 2 x 2 bracketing rows of a star
+    // (bracket pair, Teff, log g) tensor map of the bracket table: one box = KP pixels of the 2 x 2 bracketing rows of a star
     if (ok && cfg->n_feh == 1 && cfg->n_teff >= 2 && cfg->n_logg >= 2) {
       typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -2385,20 +2314,21 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
           qres != cudaDriverEntryPointSuccess) {
         ok = false;
       } else {
-        const cuuint64_t gdim[3] = {(cuuint64_t)T.stride, (cuuint64_t)cfg->n_teff, (cuuint64_t)cfg->n_logg};
-        const cuuint64_t gstr[2] = {(cuuint64_t)T.stride * 8, (cuuint64_t)T.stride * 8 * (cuuint64_t)cfg->n_teff};
-        const cuuint32_t box[3] = {(cuuint32_t)ROWPX, 2u, 2u};
-        const cuuint32_t estr[3] = {1u, 1u, 1u};
-        const CUresult cr = reinterpret_cast<EncodeFn>(fn)(&h->grid_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(T.grid),
-                                                          gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const cuuint64_t gdim[3] = {(cuuint64_t)2 * (cuuint64_t)n, (cuuint64_t)cfg->n_teff, (cuuint64_t)cfg->n_logg};
+        const cuuint64_t gstr[2] = {(cuuint64_t)n * 16, (cuuint64_t)n * 16 * (cuuint64_t)cfg->n_teff};
+        const cuuint32_t box[3] = {(cuuint32_t)(2 * KP), 2, 2};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult cr = reinterpret_cast<EncodeFn>(fn)(&h->grid_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                                                          const_cast<double2*>(T.bracket), gdim, gstr, box, estr,
+                                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) ok = false;
       }
     } else {
       ok = false;
     }
     h->group_ok = ok;
+    if (const char* v = std::getenv("MCMCSPEC_GROUP_VARIANT")) h->group_variant = (v[0] == 'w') ? 1 : (v[0] == 'n') ? 2 : 0;
     // persistent CTAs, two per SM
     h->group_ctas = 2 * h->num_sms;
     CKH(cudaMalloc((void**)&h->cell_start, ((size_t)T.n_cells + 1) * sizeof(unsigned)));
