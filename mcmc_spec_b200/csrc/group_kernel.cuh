@@ -9,12 +9,14 @@
 // same linear combination of the row integrals as its spectrum is of the rows, mft6.py:507-519, :689-700).  The
 // bracket rows are streamed ONCE per group, KP observed pixels (one stage) at a time, through a shared-memory ring:
 //
-//   warp 0      producer   -- per stage ONE 3-D tiled tensor copy per star (cp.async.bulk.tensor, SASS UTMALDG: box =
+//   copies                 -- per stage ONE 3-D tiled tensor copy per star (cp.async.bulk.tensor, SASS UTMALDG: box =
 //                             KP bracket pairs x 2 Teff nodes x 2 log g nodes = the star's four bracketing rows) and one
 //                             bulk copy (UBLKCP) of the stage's per-observed-pixel records; completion is counted in
-//                             bytes on the stage's `full` mbarrier, `done` mbarriers hand slots back.  After the stream:
-//                             bulk copies of the chi-square pass's inputs through the same ring.
-//   warps 1..   walkers    -- LANE = WALKER: lane l of every walker warp serves walker l of the group and keeps its
+//                             bytes on the slot's `full` mbarrier.  There is no producer warp: the walker warps count
+//                             themselves out of a slot (one shared-memory atomic per warp and stage) and the last one
+//                             out issues the copies of the stage NST ahead into it.  The chi-square pass's per-pixel
+//                             records go through the same ring in the same way.
+//   all warps   walkers    -- LANE = WALKER: lane l of every walker warp serves walker l of the group and keeps its
 //                             eight row coefficients and Av in registers; the warps split the observed pixels of
 //                             each stage between them.  The staged table and the records are the same for all lanes, so
 //                             every shared-memory read is a one-wavefront broadcast.  Per pixel and lane: composite at
@@ -29,7 +31,7 @@
 //                             magnitudes, priors, final sum (mft6.py:1182-1205).  No shuffles, no atomics.
 //
 // Extinction: exp2(Av * ext(p)) = A_s * exp(Av * x_p) with A_s = exp2(Av * anchor_s) per stage and walker and a
-// 7th-order polynomial on |Av * x_p| <= 0.02 (x^8/8! < 7e-19); walkers with larger exponents take exp2 of the whole exponent.  A_s
+// 8th-order polynomial on |Av * x_p| <= 0.045 (x^9/9! < 2.1e-18); walkers with larger exponents take exp2 of the whole exponent.  A_s
 // itself is taken exactly on every 8th stage and follows from the previous stage's by the same polynomial in between.
 
 namespace grp {
@@ -48,18 +50,18 @@ namespace grp {
 #define GDBG_REPORT(name)
 
 #ifndef MS_GROUP_KP
-#define MS_GROUP_KP 32
+#define MS_GROUP_KP 64
 #endif
 #ifndef MS_GROUP_NST
-#define MS_GROUP_NST 10
+#define MS_GROUP_NST 5
 #endif
 #ifndef MS_GROUP_VW
-#define MS_GROUP_VW 14
+#define MS_GROUP_VW 16
 #endif
 constexpr int KP = MS_GROUP_KP;            // observed pixels per stage
 constexpr int NST = MS_GROUP_NST;          // ring slots: stages in flight ahead of the walker warps
 constexpr int ANCHOR_REFRESH = 8;          // the stage's common extinction factor is taken exactly on every 8th stage
-constexpr int NWW_MAX = MS_GROUP_VW;       // walker warps per CTA (template parameter NWW: 7 with two CTAs per SM, 14 with
+constexpr int NWW_MAX = MS_GROUP_VW;       // walker warps per CTA (template parameter NWW: 8 with two CTAs per SM, 16 with
                                            // one): they split the observed pixels of the group's 32 walkers
 constexpr int GMAX = 32;                   // walkers per group (one per lane)
 constexpr int HBITS = 6;
@@ -70,11 +72,12 @@ constexpr int VW = MS_GROUP_VW;            // partial sums per walker: the quadr
                                            // walker warps, so that a walker's value does not depend on the kernel variant
 constexpr int PIX = 4;                     // observed pixels a walker lane keeps in flight (independent FMA chains)
 constexpr int CHI_U = 4;                   // observed pixels per block of the chi-square pass
-constexpr int CHI_CHUNK = VW * CHI_U;      // observed pixels per chunk of the chi-square pass: 32-byte records + the group's
-                                           // model values [pixel][lane]
-constexpr int CHI_BYTES = CHI_CHUNK * (32 + 256);
+constexpr int CHI_SB = VW * CHI_U;         // a super-block: one block for every partial sum
+constexpr int CHI_NSB = 7;
+constexpr int CHI_CHUNK = CHI_NSB * CHI_SB;   // observed pixels per chunk of the chi-square pass's 32-byte records
+constexpr int CHI_BYTES = CHI_CHUNK * 32;
 constexpr int CAND = 8;                    // keys of the median's second-level bin per lane and walker warp (fast finish)
-constexpr double POLY_XMAX = 0.02;
+constexpr double POLY_XMAX = 0.045;
 static_assert(KP % PIX == 0, "a stage is a whole number of quadruples");
 
 // One ring slot: the bracket table of the stage {star 0: [log g][Teff][KP] double2 | star 1} and its records.
@@ -165,13 +168,13 @@ __device__ __forceinline__ void store_if(unsigned long long* p, double v, bool p
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f64 [%0], %1;\n\t}" :: "l"(p), "d"(v), "r"((unsigned)pred));
 }
 
-// exp(y) for |y| <= POLY_XMAX: Taylor to y^7 (remainder y^8/40320 < 7e-19 relative).  The coefficients sit in constant
-// memory so that every FMA takes its coefficient as a constant-bank operand (no register moves to build 64-bit immediates).
-__constant__ double EXP_C[6] = {1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+// exp(y) for |y| <= POLY_XMAX: Taylor to y^8 (remainder y^9/9! < 2.1e-18 relative at 0.045).  The coefficients sit in
+// constant memory so that every FMA takes its coefficient as a constant-bank operand.
+__constant__ double EXP_C[7] = {1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
 __device__ __forceinline__ double exp_small(double y) {
   double p = fma(y, EXP_C[0], EXP_C[1]);
-  p = fma(p, y, EXP_C[2]); p = fma(p, y, EXP_C[3]); p = fma(p, y, EXP_C[4]);
-  p = fma(p, y, EXP_C[5]); p = fma(p, y, 1.0); p = fma(p, y, 1.0);
+  p = fma(p, y, EXP_C[2]); p = fma(p, y, EXP_C[3]); p = fma(p, y, EXP_C[4]); p = fma(p, y, EXP_C[5]);
+  p = fma(p, y, EXP_C[6]); p = fma(p, y, 1.0); p = fma(p, y, 1.0);
   return p;
 }
 
@@ -272,15 +275,22 @@ __device__ __forceinline__ void lane_locate_merged(const unsigned short* hist_al
   }
 }
 
+// ++counter in shared memory, release (the warp's reads of the slot come first) + acquire (the last one out sees everybody's)
+__device__ __forceinline__ unsigned count_out(uint32_t addr) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+  return old;
+}
+
 template <int NWW>
 __device__ __forceinline__ void walker_bar() { asm volatile("bar.sync 1, %0;" :: "n"(NWW * 32) : "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // NR: grid rows per star (4; 8 with [Fe/H] is not instantiated yet).  Binaries, posterior mode.
-// NWW walker warps per CTA + the producer warp.
+// NWW walker warps per CTA.
 // ------------------------------------------------------------------------------------------
 template <int NR, int NWW, int CTAS_PER_SM>
-__global__ void __launch_bounds__((NWW + 1) * 32, CTAS_PER_SM)
+__global__ void __launch_bounds__(NWW * 32, CTAS_PER_SM)
 lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__ GroupTables GT,
                     const __grid_constant__ CUtensorMap bracket_map, const WalkerPlan* __restrict__ plans,
                     const int* __restrict__ order, const GroupDesc* __restrict__ groups, const int* __restrict__ n_groups,
@@ -288,14 +298,15 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
                     double* __restrict__ scratch, unsigned long long* __restrict__ list_scratch) {
   constexpr int NS = 2;
   constexpr int NROW = NS * NR;
-  constexpr int NTHREADS = (NWW + 1) * 32;
+  constexpr int NTHREADS = NWW * 32;
   static_assert(NWW <= NWW_MAX && VW % NWW == 0, "scratch is sized for NWW_MAX walker warps; partial sums are dealt to the warps");
   constexpr int NV = VW / NWW;                                     // partial sums a walker warp carries
   using L = StageLayout<NR>;
   constexpr int CSLOTS = L::cslots;
   extern __shared__ __align__(128) unsigned char gsm[];
   unsigned short* const hist_all = reinterpret_cast<unsigned short*>(gsm + L::ring);   // [NWW][HBINS][32]
-  __shared__ __align__(8) unsigned long long s_full[NST], s_done[NST], s_cfull[CSLOTS], s_cempty[CSLOTS];
+  __shared__ __align__(8) unsigned long long s_full[NST], s_cfull[CSLOTS];
+  __shared__ unsigned s_out[NST], s_cout[CSLOTS];        // walker warps through with the slot's stage / chunk
   __shared__ double s_band[BAND_COLS * NROW];            // row integrals through every band
   __shared__ double s_part[VW][4][32];                   // per partial sum and lane: three moments / chi-square
   __shared__ unsigned long long s_above[NWW][32];
@@ -305,11 +316,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < NST; ++s) {
-      mbar_init(smem_u32(&s_full[s]), 1);
-      mbar_init(smem_u32(&s_done[s]), (unsigned)NWW);              // every walker warp is through with the stage
-    }
-    for (int s = 0; s < CSLOTS; ++s) { mbar_init(smem_u32(&s_cfull[s]), 1); mbar_init(smem_u32(&s_cempty[s]), (unsigned)NWW); }
+    for (int s = 0; s < NST; ++s) { mbar_init(smem_u32(&s_full[s]), 1); s_out[s] = 0u; }
+    for (int s = 0; s < CSLOTS; ++s) { mbar_init(smem_u32(&s_cfull[s]), 1); s_cout[s] = 0u; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const int n_stages = GT.n_stages;
@@ -317,12 +325,12 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
   const int n_chunks = (n + CHI_CHUNK - 1) / CHI_CHUNK;
   const int total_groups = *n_groups;
   const uint32_t ring = smem_u32(gsm);
-  const int wj = warp - 1;                                         // walker warp index, < 0 for the producer
+  const int wj = warp;                                             // walker warp index
   // the CTA's scratch, reused by every group it takes: model values [pixel][lane], key lists [warp][slot][lane]
   double* const sMT = scratch + (size_t)blockIdx.x * (size_t)n * 32;
   unsigned long long* const list0 = list_scratch + (size_t)blockIdx.x * (NWW + 1) * (size_t)LISTCAP * 32;       // + a spare list
-  unsigned long long* const listT = list0 + (size_t)max(wj, 0) * LISTCAP * 32;
-  unsigned short* const hist = hist_all + (size_t)max(wj, 0) * HBINS * 32;
+  unsigned long long* const listT = list0 + (size_t)wj * LISTCAP * 32;
+  unsigned short* const hist = hist_all + (size_t)wj * HBINS * 32;
   unsigned it0 = 0, cit0 = 0;               // ring uses so far (stages / chi-square chunks): slot and mbarrier parity go on
 
 #ifdef MS_GROUP_TIMING
@@ -384,26 +392,25 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
     for (int r = 0; r < NROW; ++r) cf[r] = 0.0;
     double av = 0.0;
 
-    if (warp == 0) {
-      // ================================================================= producer
-      // box origin of each star: its lower (Teff, log g) nodes (the plan's corners are in box order)
-      const int t0[NS] = {s_row[0] % GT.n_teff, s_row[NR] % GT.n_teff};
-      const int g0[NS] = {s_row[0] / GT.n_teff, s_row[NR] / GT.n_teff};
-      for (int s = 0; s < n_stages; ++s) {
-        const unsigned gs = it0 + (unsigned)s;
-        const int slot = (int)(gs % NST);
-        GDBG_WAIT(mbar_wait(smem_u32(&s_done[slot]), ((gs / NST) & 1u) ^ 1u))     // the walker warps are through with stage gs - NST
-        const uint32_t st = ring + (uint32_t)slot * L::bytes;
-        const uint32_t bar = smem_u32(&s_full[slot]);
-        if (lane == 0) mbar_expect_tx(bar, (unsigned)L::bytes);         // pixels past the end of the spectrum are zero-filled
-        __syncwarp();
-        if (lane < NS) {
-          tensor_g2s_3d(st + L::B + lane * L::box, &bracket_map, 2 * KP * s, t0[lane], g0[lane], bar);
-        } else if (lane == NS) {
-          bulk_g2s(st + L::rec, GT.recblk + (size_t)s * 3 * KP, KP * 48, bar);
-        }
+    // the copies of stage s into its ring slot (one thread): the two stars' bracket boxes and the record block
+    auto issue_stage = [&](int s) {
+      const unsigned gs = it0 + (unsigned)s;
+      const int slot = (int)(gs % NST);
+      const uint32_t st = ring + (uint32_t)slot * L::bytes;
+      const uint32_t bar = smem_u32(&s_full[slot]);
+      mbar_expect_tx(bar, (unsigned)L::bytes);                        // pixels past the end of the spectrum are zero-filled
+#pragma unroll
+      for (int stx = 0; stx < NS; ++stx) {
+        // box origin: the star's lower (Teff, log g) nodes (the plan's corners are in box order)
+        const int row0 = s_row[stx * NR];
+        tensor_g2s_3d(st + L::B + stx * L::box, &bracket_map, 2 * KP * s, row0 % GT.n_teff, row0 / GT.n_teff, bar);
       }
-    } else {
+      bulk_g2s(st + L::rec, GT.recblk + (size_t)s * 3 * KP, KP * 48, bar);
+    };
+    if (tid == 0) {
+      for (int s = 0; s < min(NST, n_stages); ++s) issue_stage(s);
+    }
+    {
       // ================================================================= walker warps, phase A: lane = walker
       double momv[NV][3];
 #pragma unroll
@@ -513,7 +520,11 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         }
         qrot = (qrot + (n_obs + PIX - 1) / PIX) % VW;
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_done[slot]));
+        // count this warp out of the slot; the last one out refills it with the stage NST ahead
+        if (lane == 0 && count_out(smem_u32(&s_out[slot])) == (unsigned)(NWW - 1)) {
+          s_out[slot] = 0u;
+          if (s + NST < n_stages) issue_stage(s + NST);
+        }
       }
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
@@ -521,7 +532,6 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         for (int c = 0; c < 3; ++c) s_part[wj + v * NWW][c][lane] = momv[v][c];
       }
       s_kmin[wj][lane] = kmin; s_kmax[wj][lane] = kmax;
-      asm volatile("fence.proxy.async;" ::: "memory");                  // the model values are read back by bulk copies
     }
     it0 += (unsigned)n_stages;
     GTIME(1)
@@ -532,21 +542,19 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
     __syncthreads();          // band integrals and the walker warps' partial sums complete
     GTIME(2)
 
-    // ================================================================= the chi-square pass's inputs through the ring: per
-    // chunk of 64 observed pixels the records {q1, q2, d, 1/e^2} and the group's model values [pixel][lane]
-    if (warp == 0) {
-      for (int c = 0; c < n_chunks; ++c) {
-        const unsigned gs = cit0 + (unsigned)c;
-        const int slot = (int)(gs % CSLOTS);
-        mbar_wait(smem_u32(&s_cempty[slot]), ((gs / CSLOTS) & 1u) ^ 1u);
-        const unsigned npx = (unsigned)min(CHI_CHUNK, n - c * CHI_CHUNK);
-        const uint32_t dstb = ring + (uint32_t)slot * CHI_BYTES;
-        if (lane == 0) mbar_expect_tx(smem_u32(&s_cfull[slot]), npx * (32u + 256u));
-        __syncwarp();
-        if (lane == 0) bulk_g2s(dstb, GT.drec2 + (size_t)c * CHI_CHUNK * 4, npx * 32u, smem_u32(&s_cfull[slot]));
-        else if (lane == 1) bulk_g2s(dstb + CHI_CHUNK * 32, sMT + (size_t)c * CHI_CHUNK * 32, npx * 256u, smem_u32(&s_cfull[slot]));
-      }
-    } else {
+    // ================================================================= the chi-square pass's records {q1, q2, d, 1/e^2}
+    // through the ring, CHI_CHUNK observed pixels per slot (the model values are read straight from the scratch)
+    auto issue_chunk = [&](int c) {
+      const unsigned gs = cit0 + (unsigned)c;
+      const int slot = (int)(gs % CSLOTS);
+      const unsigned npx = (unsigned)min(CHI_CHUNK, n - c * CHI_CHUNK);
+      mbar_expect_tx(smem_u32(&s_cfull[slot]), npx * 32u);
+      bulk_g2s(ring + (uint32_t)slot * CHI_BYTES, GT.drec2 + (size_t)c * CHI_CHUNK * 4, npx * 32u, smem_u32(&s_cfull[slot]));
+    };
+    if (tid == 0) {
+      for (int c = 0; c < min(CSLOTS, n_chunks); ++c) issue_chunk(c);
+    }
+    {
       // ================================================================= walker warps, phase B: lane = walker
       GDBG_DECL
       // ---- the walker's sums over all its pixels, combined in a fixed order (every warp ends up with the same values)
@@ -594,11 +602,10 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         lane_narrow<true>(sMT, (unsigned)n, S2, hist, lane);
         if (S.cnt > (unsigned)LISTCAP && S.bits < 64) S = S2;
       }
-      // ---- one pass over the model vector, split between the warps in blocks of 8 pixels: chi-square terms
-      // (mft6.py:196, :120 on the unscaled model) + the keys of the median's bin into the warp's list, a second-level
-      // histogram of those keys (the next HBITS key bits) and the smallest key above the bin.  The per-pixel records
-      // {q1, q2, d, 1/e^2} arrive through the ring (bulk copies by the producer warp), the model values are read one
-      // block ahead.  Branch free: eight independent pixels are in flight per lane.
+      // ---- one pass over the model vector, split between the warps in blocks of 4 pixels: chi-square terms
+      // (mft6.py:196, :120 on the unscaled model) + the keys of the median's bin into the warp's list and the smallest
+      // key above the bin.  The per-pixel records {q1, q2, d, 1/e^2} arrive through the ring (bulk copies), the model
+      // values are read one super-block ahead.  Branch free: eight independent pixels are in flight per lane.
       const double a0q0 = __dmul_rn(mom[0], T.basis[0]), a1 = mom[1], a2 = mom[2];
       double chiv[NV];
 #pragma unroll
@@ -620,29 +627,46 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
           const unsigned himask_h = (unsigned)(himask >> 32), prefix_h = (unsigned)(prefix >> 32);
           const unsigned bound_h = prefix_h | ~himask_h;                   // high word of the bin's largest key
           unsigned above_h = 0xffffffffu;
+          // this warp's pixels of super-block sb: blocks wj, wj + NWW, ... (block b belongs to partial sum b); the model
+          // values are read from the scratch one super-block ahead (coalesced: the lanes' walkers are adjacent)
+          auto load_m = [&](int sb, double (&mv)[NV][U]) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const int px = min(sb * CHI_SB + (wj + v * NWW) * U + u, n - 1);
+                mv[v][u] = __ldcg(sMT + (size_t)px * 32 + lane);
+              }
+            }
+          };
+          double mnext[NV][U];
+          load_m(0, mnext);
           for (int c = 0; c < n_chunks; ++c) {
             const unsigned gs = cit0 + (unsigned)c;
             const int slot = (int)(gs % CSLOTS);
             GDBG_WAIT(mbar_wait(smem_u32(&s_cfull[slot]), (gs / CSLOTS) & 1u))
             const dbl4* rec = reinterpret_cast<const dbl4*>(gsm + (size_t)slot * CHI_BYTES);
-            const double* mch = reinterpret_cast<const double*>(gsm + (size_t)slot * CHI_BYTES + CHI_CHUNK * 32) + lane;
             const int npx = min(CHI_CHUNK, n - c * CHI_CHUNK);
-            // block b of the chunk (pixels b * U ...) belongs to partial sum b; this warp's blocks: wj, wj + NWW, ...
-            if (wj * U < npx) {                                              // warp-uniform
+            for (int j = 0; j < CHI_NSB && j * CHI_SB < npx; ++j) {
+              const int sb = c * CHI_NSB + j;
               double res[NV][U], mval[NV][U];
 #pragma unroll
               for (int v = 0; v < NV; ++v) {
 #pragma unroll
+                for (int u = 0; u < U; ++u) mval[v][u] = mnext[v][u];
+              }
+              load_m(sb + 1, mnext);                                         // clamped past the end, never used there
+#pragma unroll
+              for (int v = 0; v < NV; ++v) {
+#pragma unroll
                 for (int u = 0; u < U; ++u) {
-                  const int px = (wj + v * NWW) * U + u;
+                  const int px = j * CHI_SB + (wj + v * NWW) * U + u;        // within the chunk
                   const bool valid = px < npx;
-                  const int pp = min(px, npx - 1);
-                  const double m = mch[pp * 32];
-                  const dbl4 r4 = rec[pp];                                  // same address in every lane
+                  const dbl4 r4 = rec[min(px, npx - 1)];                    // same address in every lane
+                  const double m = mval[v][u];
                   const double pfit = fma(a2, r4.y, fma(a1, r4.x, a0q0));
                   const double r = fma(-r4.z, fast_rcp(pfit), m);
                   res[v][u] = valid ? __dmul_rn(__dmul_rn(r, r), r4.w) : 0.0;
-                  mval[v][u] = m;
                 }
               }
               // keys of the median's bin: predicated stores of the raw values to the lane's list column, no branch
@@ -653,7 +677,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                   chiv[v] = __dadd_rn(chiv[v], res[v][u]);
-                  const bool valid = (wj + v * NWW) * U + u < npx;
+                  const bool valid = j * CHI_SB + (wj + v * NWW) * U + u < npx;
                   bool hit;
                   if constexpr (HI32) {
                     const unsigned hk = hi_key(mval[v][u]);
@@ -669,7 +693,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
                 }
               }
               // smallest key above the bin (the upper median of an even-sized vector when the lower one is the bin's
-              // largest key): the running minimum rarely changes, one warp-uniform branch per chunk
+              // largest key): the running minimum rarely changes, one warp-uniform branch per super-block
               if (__any_sync(0xffffffffu, touch)) {
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
@@ -679,14 +703,18 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
                     bool over;
                     if constexpr (HI32) over = (unsigned)(key >> 32) > bound_h;
                     else over = (key & himask) != prefix && key > prefix;
-                    if ((wj + v * NWW) * U + u < npx && over) above = min(above, key);
+                    if (j * CHI_SB + (wj + v * NWW) * U + u < npx && over) above = min(above, key);
                   }
                 }
                 above_h = (unsigned)(above >> 32);
               }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_cempty[slot]));
+            // count this warp out of the chunk's slot; the last one out refills it
+            if (lane == 0 && count_out(smem_u32(&s_cout[slot])) == (unsigned)(NWW - 1)) {
+              s_cout[slot] = 0u;
+              if (c + CSLOTS < n_chunks) issue_chunk(c + CSLOTS);
+            }
           }
         };
         if (__all_sync(0xffffffffu, S.bits <= 32)) chi_pass(std::true_type{}); else chi_pass(std::false_type{});
@@ -904,7 +932,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
     cit0 += (unsigned)n_chunks;
   }
 #ifdef MS_GROUP_TIMING
-  if (blockIdx.x < 8 && lane == 0 && (warp == 0 || wj == 0 || wj == NWW - 1))
+  if (blockIdx.x < 8 && lane == 0 && (wj == 0 || wj == NWW - 1))
     printf("cta %d warp %d groups %d: idle %lld A %lld sync %lld B: locate %lld chi %lld lists %lld bar %lld finish %lld | mbarrier waits A %lld B %lld\n", blockIdx.x, warp,
            gt_groups, gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[6], gt_acc[7], gt_acc[3], gt_acc[4], gt_acc[5], gt_wait_a, gt_wait);
 #endif

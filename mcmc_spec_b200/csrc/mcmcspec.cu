@@ -54,7 +54,7 @@ namespace cg = cooperative_groups;
 #define MS_GROUP_WALKERS 8                           // walkers (walker warps) per CTA of the group kernel
 #endif
 #ifndef MS_GROUP_VW
-#define MS_GROUP_VW 14                               // partial sums per walker of the group kernel = walker warps with one CTA per SM
+#define MS_GROUP_VW 16                               // partial sums per walker of the group kernel = walker warps with one CTA per SM
 #endif
 #define MS_GROUP_NWW_WIDE MS_GROUP_VW
 #define MS_GROUP_NWW (MS_GROUP_VW / 2)               // walker warps with two CTAs per SM
@@ -1877,8 +1877,8 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
     h->ev_used += 2; h->timed_walkers += nw;
     CK(cudaEventRecord(e0, h->stream));
   }
-  // Few groups (at most one per SM): one CTA per SM with fourteen walker warps per group shortens the time a group takes;
-  // otherwise two CTAs per SM with seven walker warps each.  The number of groups depends on how the walkers spread over
+  // Few groups (at most one per SM): one CTA per SM with sixteen walker warps per group shortens the time a group takes;
+  // otherwise two CTAs per SM with eight walker warps each.  The number of groups depends on how the walkers spread over
   // the grid cells and is only known on the device: the count of a recent call of the same batch size (copied back
   // asynchronously, never waited for) stands in for it -- successive half steps of a chain look alike.
   const long long min_groups = (nw + grp::GMAX - 1) / grp::GMAX;
@@ -1893,7 +1893,7 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
     const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned ctas = (unsigned)std::min<long long>(h->num_sms, max_groups);
-    kern<<<ctas, (NWW + 1) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
+    kern<<<ctas, NWW * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
                                                                h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
   } else {
     constexpr int NWW = MS_GROUP_NWW;
@@ -1901,7 +1901,7 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
     const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned ctas = (unsigned)std::min<long long>(h->group_ctas, max_groups);
-    kern<<<ctas, (NWW + 1) * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
+    kern<<<ctas, NWW * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
                                                                h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
   }
   CK(cudaGetLastError());
