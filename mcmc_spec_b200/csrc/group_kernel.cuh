@@ -505,13 +505,18 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
 #pragma unroll
               for (int v = 0; v < NV; ++v) {
                 const int k = (q0 + wj + v * NWW) * PIX;
-                if (k >= 0 && k < n_obs) {                                   // warp-uniform
+                if (k >= 0 && k + PIX <= n_obs) {                            // warp-uniform: a whole quadruple
                   double mv[PIX], rmv[PIX];
 #pragma unroll
-                  for (int u = 0; u < PIX; ++u) mv[u] = pixel(poly, min(k + u, n_obs - 1), rmv[u]);   // no branch: the chains interleave
+                  for (int u = 0; u < PIX; ++u) mv[u] = pixel(poly, k + u, rmv[u]);      // no branch: the chains interleave
 #pragma unroll
-                  for (int u = 0; u < PIX; ++u)
-                    if (k + u < n_obs) tally(k + u, mv[u], rmv[u], momv[v]);
+                  for (int u = 0; u < PIX; ++u) tally(k + u, mv[u], rmv[u], momv[v]);
+                } else if (k >= 0 && k < n_obs) {                            // the last, partial quadruple of the vector
+                  for (int u = 0; k + u < n_obs; ++u) {
+                    double rm;
+                    const double m = pixel(poly, k + u, rm);
+                    tally(k + u, m, rm, momv[v]);
+                  }
                 }
               }
             }
@@ -626,18 +631,57 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
           const unsigned long long prefix = S.prefix;
           const unsigned himask_h = (unsigned)(himask >> 32), prefix_h = (unsigned)(prefix >> 32);
           const unsigned bound_h = prefix_h | ~himask_h;                   // high word of the bin's largest key
+          // a lane that does not collect (its bin is too large or empty: the slow path below) never hits
+          const unsigned long long hitmask = collect ? himask : 0ull, hitprefix = collect ? prefix : 1ull;
+          const unsigned hitmask_h = collect ? himask_h : 0u, hitprefix_h = collect ? prefix_h : 1u;
           unsigned above_h = 0xffffffffu;
+          unsigned long long* lp = listT + lane;                            // next free slot of the lane's list column
           // this warp's pixels of super-block sb: blocks wj, wj + NWW, ... (block b belongs to partial sum b); the model
           // values are read from the scratch one super-block ahead (coalesced: the lanes' walkers are adjacent)
           auto load_m = [&](int sb, double (&mv)[NV][U]) {
+            if (sb * CHI_SB + CHI_SB <= n) {
+              const double* mp = sMT + ((size_t)sb * CHI_SB + wj * U) * 32 + lane;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
+              for (int v = 0; v < NV; ++v) {
 #pragma unroll
-              for (int u = 0; u < U; ++u) {
-                const int px = min(sb * CHI_SB + (wj + v * NWW) * U + u, n - 1);
-                mv[v][u] = __ldcg(sMT + (size_t)px * 32 + lane);
+                for (int u = 0; u < U; ++u) mv[v][u] = __ldcg(mp + (v * NWW * U + u) * 32);
+              }
+            } else {
+#pragma unroll
+              for (int v = 0; v < NV; ++v) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                  const int px = min(sb * CHI_SB + (wj + v * NWW) * U + u, n - 1);
+                  mv[v][u] = __ldcg(sMT + (size_t)px * 32 + lane);
+                }
               }
             }
+          };
+          // one pixel after its chi-square term: a key of the median's bin goes to the list by a predicated store (no branch:
+          // a pixel is a hit for a few lanes at most; a branch would run its body once per hit with one lane on); `touch`:
+          // a value between the bin and `above` was seen
+          auto collect_px = [&](double m, bool valid, bool& touch) {
+            bool hit;
+            if constexpr (HI32) {
+              const unsigned hk = hi_key(m);
+              hit = valid && (hk & hitmask_h) == hitprefix_h;
+              touch = touch || (valid && hk > bound_h && hk <= above_h);
+            } else {
+              const unsigned long long key = ordered_key(m);
+              hit = valid && (key & hitmask) == hitprefix;
+              touch = touch || (valid && (key & himask) != prefix && key > prefix && key < above);
+            }
+            store_if(lp, m, hit);
+            lp += hit ? 32 : 0;
+          };
+          // smallest key above the bin (the upper median of an even-sized vector when the lower one is the bin's largest
+          // key): the running minimum rarely changes, one warp-uniform branch per super-block
+          auto above_px = [&](double m, bool valid) {
+            const unsigned long long key = ordered_key(m);
+            bool over;
+            if constexpr (HI32) over = (unsigned)(key >> 32) > bound_h;
+            else over = (key & himask) != prefix && key > prefix;
+            if (valid && over) above = min(above, key);
           };
           double mnext[NV][U];
           load_m(0, mnext);
@@ -645,68 +689,73 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             const unsigned gs = cit0 + (unsigned)c;
             const int slot = (int)(gs % CSLOTS);
             GDBG_WAIT(mbar_wait(smem_u32(&s_cfull[slot]), (gs / CSLOTS) & 1u))
-            const dbl4* rec = reinterpret_cast<const dbl4*>(gsm + (size_t)slot * CHI_BYTES);
+            const double2* rec = reinterpret_cast<const double2*>(gsm + (size_t)slot * CHI_BYTES);   // {q1, q2}, {d, 1/e^2} per pixel
             const int npx = min(CHI_CHUNK, n - c * CHI_CHUNK);
             for (int j = 0; j < CHI_NSB && j * CHI_SB < npx; ++j) {
               const int sb = c * CHI_NSB + j;
-              double res[NV][U], mval[NV][U];
+              double mval[NV][U];
 #pragma unroll
               for (int v = 0; v < NV; ++v) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) mval[v][u] = mnext[v][u];
               }
               load_m(sb + 1, mnext);                                         // clamped past the end, never used there
-#pragma unroll
-              for (int v = 0; v < NV; ++v) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                  const int px = j * CHI_SB + (wj + v * NWW) * U + u;        // within the chunk
-                  const bool valid = px < npx;
-                  const dbl4 r4 = rec[min(px, npx - 1)];                    // same address in every lane
-                  const double m = mval[v][u];
-                  const double pfit = fma(a2, r4.y, fma(a1, r4.x, a0q0));
-                  const double r = fma(-r4.z, fast_rcp(pfit), m);
-                  res[v][u] = valid ? __dmul_rn(__dmul_rn(r, r), r4.w) : 0.0;
-                }
-              }
-              // keys of the median's bin: predicated stores of the raw values to the lane's list column, no branch
-              // (a pixel is a hit for a few lanes at most; a branch would run its body once per hit with one lane on)
-              bool touch = false;                                         // a value between the bin and `above` was seen
-#pragma unroll
-              for (int v = 0; v < NV; ++v) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                  chiv[v] = __dadd_rn(chiv[v], res[v][u]);
-                  const bool valid = j * CHI_SB + (wj + v * NWW) * U + u < npx;
-                  bool hit;
-                  if constexpr (HI32) {
-                    const unsigned hk = hi_key(mval[v][u]);
-                    hit = valid && (hk & himask_h) == prefix_h;
-                    touch = touch || (valid && hk > bound_h && hk <= above_h);
-                  } else {
-                    const unsigned long long key = ordered_key(mval[v][u]);
-                    hit = valid && (key & himask) == prefix;
-                    touch = touch || (valid && !hit && key > prefix && key < above);
-                  }
-                  store_if(listT + (size_t)nl * 32 + lane, mval[v][u], hit && collect);
-                  nl += hit ? 1u : 0u;
-                }
-              }
-              // smallest key above the bin (the upper median of an even-sized vector when the lower one is the bin's
-              // largest key): the running minimum rarely changes, one warp-uniform branch per super-block
-              if (__any_sync(0xffffffffu, touch)) {
+              bool touch = false;
+              if ((j + 1) * CHI_SB <= npx) {
+                // a whole super-block (all but the last one of the vector): the reciprocals of the fits first, eight
+                // independent chains, then the terms
+                const double2* rq = rec + 2 * (j * CHI_SB + wj * U);
+                double rcv[NV][U];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
 #pragma unroll
                   for (int u = 0; u < U; ++u) {
-                    const unsigned long long key = ordered_key(mval[v][u]);
-                    bool over;
-                    if constexpr (HI32) over = (unsigned)(key >> 32) > bound_h;
-                    else over = (key & himask) != prefix && key > prefix;
-                    if (j * CHI_SB + (wj + v * NWW) * U + u < npx && over) above = min(above, key);
+                    const double2 q = rq[2 * (v * NWW * U + u)];            // same address in every lane
+                    rcv[v][u] = fast_rcp(fma(a2, q.y, fma(a1, q.x, a0q0)));
                   }
                 }
-                above_h = (unsigned)(above >> 32);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+#pragma unroll
+                  for (int u = 0; u < U; ++u) {
+                    const double2 dw = rq[2 * (v * NWW * U + u) + 1];
+                    const double r = fma(-dw.x, rcv[v][u], mval[v][u]);
+                    chiv[v] = __dadd_rn(chiv[v], __dmul_rn(__dmul_rn(r, r), dw.y));
+                    collect_px(mval[v][u], true, touch);
+                  }
+                }
+                if (__any_sync(0xffffffffu, touch)) {
+#pragma unroll
+                  for (int v = 0; v < NV; ++v) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) above_px(mval[v][u], true);
+                  }
+                  above_h = (unsigned)(above >> 32);
+                }
+              } else {
+                // the last, partial super-block: pixel by pixel
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+#pragma unroll
+                  for (int u = 0; u < U; ++u) {
+                    const int px = j * CHI_SB + (wj + v * NWW) * U + u;      // within the chunk
+                    const bool valid = px < npx;
+                    const int pp = min(px, npx - 1);
+                    const double2 q = rec[2 * pp], dw = rec[2 * pp + 1];
+                    const double m = mval[v][u];
+                    const double r = fma(-dw.x, fast_rcp(fma(a2, q.y, fma(a1, q.x, a0q0))), m);
+                    chiv[v] = __dadd_rn(chiv[v], valid ? __dmul_rn(__dmul_rn(r, r), dw.y) : 0.0);
+                    collect_px(m, valid, touch);
+                  }
+                }
+                if (__any_sync(0xffffffffu, touch)) {
+#pragma unroll
+                  for (int v = 0; v < NV; ++v) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) above_px(mval[v][u], j * CHI_SB + (wj + v * NWW) * U + u < npx);
+                  }
+                  above_h = (unsigned)(above >> 32);
+                }
               }
             }
             __syncwarp();
@@ -716,6 +765,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
               if (c + CSLOTS < n_chunks) issue_chunk(c + CSLOTS);
             }
           }
+          nl = (unsigned)((lp - (listT + lane)) >> 5);
         };
         if (__all_sync(0xffffffffu, S.bits <= 32)) chi_pass(std::true_type{}); else chi_pass(std::false_type{});
       }
@@ -743,8 +793,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       for (int v = 0; v < NV; ++v) s_part[wj + v * NWW][3][lane] = chiv[v];
       s_nl[wj][lane] = collect ? nl : 0u;
       walker_bar<NWW>();
-      // ---- second level: every warp locates the sub-bin in the summed second-level histograms, then filters its own
-      // list into a small candidate buffer
+      // ---- second and third level: every warp locates the sub-bin in the summed histograms of its level, then filters
+      // its own list into a small candidate buffer
       // [NWW][CAND][32], on the ring: every walker warp is past the chi-square pass, its chunks are consumed
       static_assert(NWW * CAND * 32 * 8 <= L::ring, "the candidate buffers fit the ring");
       unsigned long long* const cand_all = reinterpret_cast<unsigned long long*>(gsm);
@@ -758,9 +808,32 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         S2.rank = S.rank - below; S2.cnt = in_bin;
         S2.prefix = S.prefix | (((unsigned long long)bin) << shift2);
         S2.bits = S.bits + width2;
-        const unsigned long long hm2 = (S2.bits >= 64) ? ~0ull : (~0ull << (64 - S2.bits));
         const unsigned nl_eff = collect ? nl : 0u;
         const unsigned nmax = __reduce_max_sync(0xffffffffu, nl_eff);
+        {
+          // ---- third level: the same once more on the next key bits (a spectrum's values crowd around the continuum,
+          // the median's second-level bin may still hold dozens of keys; after this one it holds one or two)
+          const unsigned long long hmb = (S2.bits >= 64) ? ~0ull : (~0ull << (64 - S2.bits));
+          const int width3 = min(HBITS, 64 - S2.bits);
+          const int shift3 = max(64 - S2.bits - width3, 0);
+          walker_bar<NWW>();                                               // every warp has read the second-level histograms
+          lane_hist_zero(hist, lane);
+          for (unsigned t0 = 0; t0 < nmax; t0 += 8) {
+            unsigned long long kb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) kb[u] = (t0 + u < nl_eff) ? listT[(size_t)(t0 + u) * 32 + lane] : 0ull;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (t0 + u < nl_eff && (kb[u] & hmb) == S2.prefix)
+                hist[(unsigned)((kb[u] >> shift3) & ((1u << width3) - 1u)) * 32 + lane] += 1;
+          }
+          walker_bar<NWW>();
+          lane_locate_merged<NWW>(hist_all, lane, 0u, S2.rank, bin, below, in_bin);
+          S2.rank -= below; S2.cnt = in_bin;
+          S2.prefix |= ((unsigned long long)bin) << shift3;
+          S2.bits += width3;
+        }
+        const unsigned long long hm2 = (S2.bits >= 64) ? ~0ull : (~0ull << (64 - S2.bits));
         for (unsigned t0 = 0; t0 < nmax; t0 += 8) {                        // eight loads in flight
           unsigned long long kb[8];
 #pragma unroll
@@ -874,6 +947,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             v1 = key_value(r1); v2 = key_value(r2);
           }
         }
+        GTIME(8)
         const double med = has_nan ? CUDART_NAN : ((n & 1) ? v1 : (v1 + v2) / 2.0);   // np.median, mft6.py:1173
         const double chi_un = has_nan ? CUDART_NAN : chi;
         const double scale = T.data_median / med;
@@ -933,8 +1007,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
   }
 #ifdef MS_GROUP_TIMING
   if (blockIdx.x < 8 && lane == 0 && (wj == 0 || wj == NWW - 1))
-    printf("cta %d warp %d groups %d: idle %lld A %lld sync %lld B: locate %lld chi %lld lists %lld bar %lld finish %lld | mbarrier waits A %lld B %lld\n", blockIdx.x, warp,
-           gt_groups, gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[6], gt_acc[7], gt_acc[3], gt_acc[4], gt_acc[5], gt_wait_a, gt_wait);
+    printf("cta %d warp %d groups %d: idle %lld A %lld sync %lld B: locate %lld chi %lld lists %lld bar %lld rank %lld finish %lld | mbarrier waits A %lld B %lld\n", blockIdx.x, warp,
+           gt_groups, gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[6], gt_acc[7], gt_acc[3], gt_acc[4], gt_acc[8], gt_acc[5], gt_wait_a, gt_wait);
 #endif
 }
 
