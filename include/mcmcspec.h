@@ -266,6 +266,21 @@ int ms_stretch_halfstep(ms_handle* h, double* state, int32_t* naccepted, const i
                         int64_t gid0, double* q, double* logfac, double* lnp_q, double* packed);
 
 /*
+ * The same half step in two calls, for N processes that each hold the whole ensemble and share the evaluation by
+ * groups (ms_set_group_shard): ms_stretch_evaluate proposes for all n_s walkers of the half and evaluates this
+ * rank's groups (lnp_q is 0 for the other ranks' walkers: the caller sums lnp_q over the ranks, one all-reduce);
+ * ms_stretch_accept_inplace then applies the acceptance test to all n_s walkers in place on every rank -- the ranks'
+ * ensembles stay identical, no positions are exchanged.  MS_ERR_UNSUPPORTED when a shard is set and the batch does
+ * not take the group kernel (ms_group_will_run).
+ */
+int ms_stretch_evaluate(ms_handle* h, const double* state, const int64_t* s_idx, int64_t n_s, const int64_t* c_idx, int64_t n_c,
+                        double a, uint64_t seed, uint64_t iteration, int32_t split, int64_t gid0, double* q, double* logfac,
+                        double* lnp_q);
+int ms_stretch_accept_inplace(ms_handle* h, double* state, int32_t* naccepted, const int64_t* s_idx, int64_t n_s, const double* q,
+                              const double* lnp_q, const double* logfac, uint64_t seed, uint64_t iteration, int32_t split,
+                              int64_t gid0);
+
+/*
  * One whole ensemble iteration (both half steps) for a single-rank ensemble of at most 2048 walkers, enqueued
  * from one call: the iteration's red/blue split (hashed keys sorted in one CTA; randomize_split = 0 gives
  * evens/odds), then per half: propose, evaluate (prep + streaming kernel), accept, scatter -- in place on
@@ -336,11 +351,17 @@ int ms_set_cell_order(ms_handle* h, int mode);
  * integrals), and a walker's value does not depend on which other walkers share its group.
  * mode: -1 (default) automatic -- batches of at least `min_walkers` (default 1024; <= 0 keeps the current
  * threshold) on handles whose tables fit the ring; 0 never; 1 whenever the tables fit.
- * ms_group_supported: 1 when this handle's tables fit (at most 4 passbands overlapping on a 128-pixel stage, at
- * most 64 observed pixels per stage, nspec = 2, no [Fe/H] axis).
+ * ms_group_supported: 1 when this handle can take it (nspec = 2, a 2-D (Teff, log g) grid with at least two nodes per
+ * axis, more than one grid cell, at most 65 535 observed pixels).
+ * ms_set_group_shard: this handle evaluates the groups rank, rank + world, ... of every batch and leaves the other
+ * walkers' lnprob at 0 -- N processes that hold the same ensemble each evaluate 1/N of the groups of the WHOLE half
+ * (whole groups per GPU instead of 1/N of every cell's walkers) and sum the results (one all-reduce).  Only
+ * ms_stretch_evaluate honours it.  ms_group_will_run: whether a posterior batch of nw walkers takes the group kernel.
  */
 int ms_set_group(ms_handle* h, int mode, int64_t min_walkers);
 int ms_group_supported(const ms_handle* h);
+int ms_set_group_shard(ms_handle* h, int rank, int world);
+int ms_group_will_run(const ms_handle* h, int64_t nw);
 
 /*
  * Evaluations that were cut short before any grid row was read (outside the prior box, off the isochrone or the

@@ -104,6 +104,7 @@ struct GroupTables {
   double dxmax;                 // max |step|
   int n_stages;
   int n_teff;
+  int shard_rank, shard_world;  // this launch evaluates the groups shard_rank, shard_rank + shard_world, ... (ms_set_group_shard)
 };
 
 struct GroupDesc { int start, count; };
@@ -340,7 +341,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
 #endif
   // Persistent CTA: groups are handed out by an atomic counter (reset by group_scan_kernel).
   while (true) {
-    if (tid == 0) s_group = atomicAdd(group_counter, 1);
+    if (tid == 0) s_group = atomicAdd(group_counter, 1) * GT.shard_world + GT.shard_rank;
     __syncthreads();                                                // also: the previous group is completely done
     const int g = s_group;
     GTIME(0)

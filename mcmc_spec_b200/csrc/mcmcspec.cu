@@ -22,6 +22,9 @@
 
 #include <cooperative_groups.h>
 #include <cuda.h>
+#if !defined(MS_TU) || MS_TU == 0 || MS_TU == 1
+#include <cub/device/device_radix_sort.cuh>
+#endif
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <nvtx3/nvToolsExt.h>
@@ -595,6 +598,12 @@ __global__ void __launch_bounds__(1024) cell_scan_kernel(unsigned* __restrict__ 
     if (tid == 1023) carry = before + v;
     __syncthreads();
   }
+}
+
+__global__ void cell_keys_kernel(const WalkerPlan* __restrict__ plans, long long nw, unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  keys[w] = (unsigned)plans[w].cell; vals[w] = (int)w;
 }
 
 __global__ void cell_scatter_kernel(const WalkerPlan* __restrict__ plans, long long nw, unsigned* __restrict__ offsets,
@@ -1643,6 +1652,9 @@ struct ms_handle {
   size_t smem_bytes = 0;
   // per-call buffers
   WalkerPlan* plans = nullptr; long long plans_cap = 0;
+  // canonical cell order (ms_stretch_evaluate with a group shard: every rank must form the same groups)
+  unsigned* sort_keys = nullptr; unsigned* sort_keys_out = nullptr; int* sort_vals = nullptr; void* sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0; long long sort_cap = 0;
   int* order = nullptr; unsigned* cell_hist = nullptr; bool use_order = false;
   int pairing = MS_PAIRING_DEFAULT;  // 0: one walker per CTA, 1: two cell-mates per CTA for large batches, -1: automatic
   bool pair_now = false;         // decided per call (evaluate_device)
@@ -1665,6 +1677,8 @@ struct ms_handle {
   CUtensorMap grid_map{};         // (pixel, Teff, log g) view of the device grid for the group kernel's row boxes
   bool group_ok = false;         // the tables fit the kernel's shared-memory ring (weight slots, records per stage)
   int group_mode = -1;           // -1 automatic (large posterior batches), 0 never, 1 whenever possible
+  int shard_rank = 0, shard_world = 1;   // ms_set_group_shard: this handle evaluates every shard_world-th group ...
+  bool shard_active = false;             // ... of the batches of ms_stretch_evaluate (set for the duration of that call)
   int group_variant = 0;         // 0 by the number of groups, 1 always one CTA per SM, 2 always two (MCMCSPEC_GROUP_VARIANT, tests)
   bool group_now = false;        // decided per call
   long long group_min_walkers = 1024;
@@ -1886,14 +1900,18 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
   const size_t ring = (size_t)grp::StageLayout<4>::ring;
   const int seen = *reinterpret_cast<volatile int*>(h->h_n_groups);
   const long long seen_nw = *reinterpret_cast<volatile int*>(h->h_n_groups + 1);
-  const long long expect_groups = (seen > 0 && seen_nw == nw) ? (long long)seen : min_groups + min_groups / 3;
+  const long long expect_all = (seen > 0 && seen_nw == nw) ? (long long)seen : min_groups + min_groups / 3;
+  const int sworld = h->shard_active ? h->shard_world : 1, srank = h->shard_active ? h->shard_rank : 0;
+  const long long expect_groups = (expect_all + sworld - 1) / sworld;      // this rank's share
+  grp::GroupTables GTs = h->GT;
+  GTs.shard_rank = srank; GTs.shard_world = sworld;
   if (h->group_variant == 1 || (h->group_variant == 0 && expect_groups <= h->num_sms)) {
     constexpr int NWW = MS_GROUP_NWW_WIDE;
     auto kern = grp::lnprob_group_kernel<4, NWW, 1>;
     const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned ctas = (unsigned)std::min<long long>(h->num_sms, max_groups);
-    kern<<<ctas, NWW * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
+    kern<<<ctas, NWW * 32, smem, h->stream>>>(h->T, GTs, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
                                                                h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
   } else {
     constexpr int NWW = MS_GROUP_NWW;
@@ -1901,7 +1919,7 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
     const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned ctas = (unsigned)std::min<long long>(h->group_ctas, max_groups);
-    kern<<<ctas, NWW * 32, smem, h->stream>>>(h->T, h->GT, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
+    kern<<<ctas, NWW * 32, smem, h->stream>>>(h->T, GTs, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
                                                                h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
   }
   CK(cudaGetLastError());
@@ -1920,6 +1938,10 @@ int ensure_plans(ms_handle* h, long long nw) {
   if (nw <= h->plans_cap) return MS_OK;
   if (h->plans) cudaFree(h->plans);
   if (h->order) cudaFree(h->order);
+  if (h->sort_keys) cudaFree(h->sort_keys);
+  if (h->sort_keys_out) cudaFree(h->sort_keys_out);
+  if (h->sort_vals) cudaFree(h->sort_vals);
+  if (h->sort_tmp) cudaFree(h->sort_tmp);
   h->plans = nullptr; h->order = nullptr; h->plans_cap = 0;
   long long cap = nw + nw / 4 + 64;
   CK(cudaMalloc((void**)&h->plans, (size_t)cap * sizeof(WalkerPlan)));
@@ -1981,7 +2003,32 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
     }
     grp::group_scan_kernel<<<1, 1024, 0, h->stream>>>(h->cell_hist, h->T.n_cells, h->cell_start, h->group_off, h->n_groups,
                                                       h->group_counter);
-    cell_scatter_kernel<<<pg, pb, 0, h->stream>>>(h->plans, nw, h->cell_hist, h->order);
+    if (h->shard_active) {
+      // the ranks that share this half must form the same groups: walkers in cell order, by index within a cell (a
+      // stable radix sort on the cell number) instead of the order the scatter's atomics happen to give
+      if (nw > h->sort_cap) {
+        if (h->sort_keys) cudaFree(h->sort_keys);
+        if (h->sort_keys_out) cudaFree(h->sort_keys_out);
+        if (h->sort_vals) cudaFree(h->sort_vals);
+        if (h->sort_tmp) cudaFree(h->sort_tmp);
+        h->sort_keys = h->sort_keys_out = nullptr; h->sort_vals = nullptr; h->sort_tmp = nullptr; h->sort_cap = 0;
+        const long long cap = nw + nw / 4 + 64;
+        CK(cudaMalloc((void**)&h->sort_keys, (size_t)cap * sizeof(unsigned)));
+        CK(cudaMalloc((void**)&h->sort_keys_out, (size_t)cap * sizeof(unsigned)));
+        CK(cudaMalloc((void**)&h->sort_vals, (size_t)cap * sizeof(int)));
+        size_t bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->sort_keys, h->sort_keys_out, h->sort_vals, h->order, (int)cap, 0, 32, h->stream));
+        CK(cudaMalloc(&h->sort_tmp, bytes));
+        h->sort_tmp_bytes = bytes; h->sort_cap = cap;
+      }
+      int bits = 1;
+      while ((1ll << bits) < (long long)h->T.n_cells + 1 && bits < 32) ++bits;
+      cell_keys_kernel<<<pg, pb, 0, h->stream>>>(h->plans, nw, h->sort_keys, h->sort_vals);
+      size_t bytes = h->sort_tmp_bytes;
+      CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, bytes, h->sort_keys, h->sort_keys_out, h->sort_vals, h->order, (int)nw, 0, bits, h->stream));
+    } else {
+      cell_scatter_kernel<<<pg, pb, 0, h->stream>>>(h->plans, nw, h->cell_hist, h->order);
+    }
     grp::group_table_kernel<<<pg, pb, 0, h->stream>>>(h->plans, h->order, nw, h->cell_start, h->group_off, h->groups);
     CK(cudaGetLastError());
     h->launches += 3;
@@ -2433,6 +2480,19 @@ int ms_set_group(ms_handle* h, int mode, int64_t min_walkers) {
 
 int ms_group_supported(const ms_handle* h) { return (h && h->group_ok && h->corners == 4) ? 1 : 0; }
 
+int ms_set_group_shard(ms_handle* h, int rank, int world) {
+  if (!h) return MS_ERR_INVALID;
+  if (world < 1 || rank < 0 || rank >= world) { set_err(h, "ms_set_group_shard: need 0 <= rank < world"); return MS_ERR_INVALID; }
+  h->shard_rank = rank; h->shard_world = world;
+  return MS_OK;
+}
+
+int ms_group_will_run(const ms_handle* h, int64_t nw) {
+  if (!h) return 0;
+  return (h->group_ok && h->group_mode != 0 && !h->fast && h->cluster <= 1 && h->corners == 4 &&
+          (h->group_mode > 0 || nw >= h->group_min_walkers)) ? 1 : 0;
+}
+
 int ms_set_cell_order(ms_handle* h, int mode) {
   if (!h) return MS_ERR_INVALID;
   h->cell_order = mode < 0 ? -1 : (mode != 0);
@@ -2819,6 +2879,42 @@ int ms_stretch_halfstep(ms_handle* h, double* state, int32_t* naccepted, const i
     stretch_accept_inplace_kernel<<<g, 128, 0, h->stream>>>(state, naccepted, (const long long*)s_idx, q, lnp_q, logfac, n_s, ndim,
                                                             seed, iteration, split, gid0);
   }
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return MS_OK;
+}
+
+int ms_stretch_evaluate(ms_handle* h, const double* state, const int64_t* s_idx, int64_t n_s, const int64_t* c_idx, int64_t n_c,
+                        double a, uint64_t seed, uint64_t iteration, int32_t split, int64_t gid0, double* q, double* logfac,
+                        double* lnp_q) {
+  NvtxRange nvtx_range("ms_stretch_evaluate");
+  if (!h) return MS_ERR_INVALID;
+  if (n_s < 0 || n_c < 1 || !state || !s_idx || !c_idx || !q || !logfac || !lnp_q) {
+    set_err(h, "ms_stretch_evaluate: invalid argument"); return MS_ERR_INVALID;
+  }
+  if (n_s == 0) return MS_OK;
+  CK(cudaSetDevice(h->device));
+  if (h->shard_world > 1) {
+    if (!ms_group_will_run(h, n_s)) { set_err(h, "ms_stretch_evaluate: a group shard is set but this batch does not take the group kernel"); return MS_ERR_UNSUPPORTED; }
+    CK(cudaMemsetAsync(lnp_q, 0, (size_t)n_s * sizeof(double), h->stream));        // the other ranks' groups: summed in by the caller
+  }
+  const ProposeIn prop{state, (const long long*)s_idx, (const long long*)c_idx, n_c, a, seed, iteration, split, (long long)gid0, q, logfac};
+  const PartsOut none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  h->shard_active = h->shard_world > 1;
+  const int rc = evaluate_device(h, q, n_s, lnp_q, none, -1, OptIn{nullptr, nullptr, nullptr, nullptr, nullptr}, prop);
+  h->shard_active = false;
+  return rc;
+}
+
+int ms_stretch_accept_inplace(ms_handle* h, double* state, int32_t* naccepted, const int64_t* s_idx, int64_t n_s, const double* q,
+                              const double* lnp_q, const double* logfac, uint64_t seed, uint64_t iteration, int32_t split,
+                              int64_t gid0) {
+  if (!h) return MS_ERR_INVALID;
+  if (n_s < 0 || !state || !s_idx || !q || !lnp_q || !logfac) { set_err(h, "ms_stretch_accept_inplace: invalid argument"); return MS_ERR_INVALID; }
+  if (n_s == 0) return MS_OK;
+  CK(cudaSetDevice(h->device));
+  stretch_accept_inplace_kernel<<<(unsigned)((n_s + 127) / 128), 128, 0, h->stream>>>(state, naccepted, (const long long*)s_idx, q, lnp_q,
+                                                                                     logfac, n_s, h->T.ncol, seed, iteration, split, gid0);
   CK(cudaGetLastError());
   h->launches += 1;
   return MS_OK;

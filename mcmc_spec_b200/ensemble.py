@@ -78,6 +78,23 @@ class CudaBackend:
                                      c_idx.shape[0], a, seed, iteration, split, gid0, q.data_ptr(), logfac.data_ptr(),
                                      lnp_q.data_ptr(), None if packed is None else packed.data_ptr())
 
+    def set_shard(self, rank, world):
+        self.engine.set_group_shard(rank, world)
+
+    def group_will_run(self, n):
+        return self.engine.group_will_run(n)
+
+    def evaluate(self, state, s_idx, c_idx, a, seed, iteration, split, gid0, q, logfac, lnp_q):
+        """Propose for the whole half, evaluate this rank's groups (lnp_q is 0 for the other ranks' walkers)."""
+        self._bind()
+        self.engine.stretch_evaluate(state.data_ptr(), s_idx.data_ptr(), s_idx.shape[0], c_idx.data_ptr(), c_idx.shape[0], a, seed,
+                                     iteration, split, gid0, q.data_ptr(), logfac.data_ptr(), lnp_q.data_ptr())
+
+    def accept_inplace(self, state, naccepted, s_idx, q, lnp_q, logfac, seed, iteration, split, gid0):
+        self._bind()
+        self.engine.stretch_accept_inplace(state.data_ptr(), naccepted.data_ptr(), s_idx.data_ptr(), s_idx.shape[0], q.data_ptr(),
+                                           lnp_q.data_ptr(), logfac.data_ptr(), seed, iteration, split, gid0)
+
     FUSED_MAX_WALKERS = 2048
 
     def iteration(self, state, naccepted, a, seed, iteration, randomize_split):
@@ -117,6 +134,8 @@ class EnsembleSampler:
         self._full = self._packed if world_size == 1 else torch.empty((self.half, ndim + 2), **f64)
         self._fixed = [torch.arange(0, nwalkers, 2, device=self.device), torch.arange(1, nwalkers, 2, device=self.device)]
         self._side, self._next = None, None
+        self._by_group = None                   # N > 1: shard the evaluation by groups of cell mates (decided at the first step)
+        self.shard_by_group = True
         self.fused = True                       # allow the one-call iteration where the backend offers it
         self._stored, self._iter0 = None, 0
 
@@ -198,8 +217,31 @@ class EnsembleSampler:
             self.iteration += 1
             return
         halves = self._halves()
+        if self._by_group is None:
+            # Several ranks and a backend with the group kernel: every rank holds the whole ensemble, proposes for the whole
+            # half and evaluates every world_size-th GROUP of cell mates (whole 32-walker groups per GPU instead of 1/N of
+            # every cell's walkers, which leaves most groups part filled); the log-probs are summed over the ranks (each
+            # walker's is non-zero on exactly one) and every rank applies the same acceptance test: no positions travel.
+            # It pays once a rank's 1/N of the half no longer fills the GPU with groups of its own (one group per SM,
+            # 32 walkers each): below that the part-filled groups of a walker shard cost a second round of CTAs, above
+            # it the replicated preparation and the all-reduce cost more than the fuller groups save.
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == 'cuda' else 0
+            self._by_group = bool(self.world_size > 1 and self.shard_by_group and hasattr(be, 'evaluate')
+                                  and self.shard <= 32 * sms and be.group_will_run(self.half))
+            if self._by_group:
+                be.set_shard(self.rank, self.world_size)
+                f64 = dict(dtype=torch.float64, device=self.device)
+                self._qh = torch.empty((self.half, self.ndim), **f64)
+                self._lfh = torch.empty(self.half, **f64)
+                self._lnph = torch.empty(self.half, **f64)
         for split in (0, 1):
             s_idx, c_idx = halves[split], halves[1 - split]
+            if self._by_group:
+                be.evaluate(self.state, s_idx, c_idx, self.a, self.seed, self.iteration, split, 0, self._qh, self._lfh, self._lnph)
+                dist.all_reduce(self._lnph, op=dist.ReduceOp.SUM, group=self.group)
+                be.accept_inplace(self.state, self.naccepted, s_idx, self._qh, self._lnph, self._lfh, self.seed, self.iteration,
+                                  split, 0)
+                continue
             lo = self.rank * self.shard
             mine = s_idx[lo:lo + self.shard]
             if hasattr(be, 'halfstep'):

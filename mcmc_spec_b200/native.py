@@ -23,7 +23,7 @@ _LIB_PATH = os.environ.get('MCMCSPEC_LIB') or os.path.join(os.path.dirname(os.pa
 
 EXPORTS = ['ms_config_size', 'ms_abi_version', 'ms_create', 'ms_create_shared', 'ms_destroy', 'ms_last_error', 'ms_stream',
            'ms_device', 'ms_lnprob', 'ms_lnprob_parts', 'ms_model_spectrum', 'ms_component_mags', 'ms_set_optimizer_data', 'ms_optimizer_chisq', 'ms_broaden_rows', 'ms_build_grid',
-           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_stretch_halfstep', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_fast', 'ms_set_cell_order', 'ms_set_group', 'ms_group_supported', 'ms_short_circuited', 'ms_set_timing',
+           'ms_split_keys', 'ms_stretch_propose', 'ms_stretch_accept', 'ms_stretch_scatter', 'ms_stretch_iteration', 'ms_stretch_halfstep', 'ms_stretch_evaluate', 'ms_stretch_accept_inplace', 'ms_set_group_shard', 'ms_group_will_run', 'ms_launch_count', 'ms_set_stream', 'ms_use_own_stream', 'ms_set_cluster', 'ms_set_pairing', 'ms_set_fast', 'ms_set_cell_order', 'ms_set_group', 'ms_group_supported', 'ms_short_circuited', 'ms_set_timing',
            'ms_kernel_time']
 
 _dp = C.POINTER(C.c_double)
@@ -109,6 +109,11 @@ def load_library(path=None):
     lib.ms_set_fast.argtypes = [vp, C.c_int]
     lib.ms_set_cell_order.argtypes = [vp, C.c_int]
     lib.ms_set_group.argtypes = [vp, C.c_int, C.c_int64]
+    lib.ms_set_group_shard.argtypes = [vp, C.c_int, C.c_int]
+    lib.ms_group_will_run.argtypes = [vp, C.c_int64]
+    lib.ms_stretch_evaluate.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, C.c_double, C.c_uint64, C.c_uint64, C.c_int32,
+                                        C.c_int64, vp, vp, vp]
+    lib.ms_stretch_accept_inplace.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64]
     lib.ms_group_supported.argtypes = [vp]
     lib.ms_short_circuited.argtypes = [vp, C.POINTER(C.c_int64), C.c_int]
     lib.ms_set_timing.argtypes = [vp, C.c_int]
@@ -370,6 +375,22 @@ class Engine:
         self._check(self.lib.ms_stretch_halfstep(self._h, state_ptr, naccepted_ptr, s_idx_ptr, n_s, c_idx_ptr, n_c, a, seed,
                                                  iteration, split, gid0, q_ptr, logfac_ptr, lnp_ptr, packed_ptr),
                     'ms_stretch_halfstep')
+
+    def set_group_shard(self, rank, world):
+        """This engine evaluates the groups rank, rank + world, ... of every ms_stretch_evaluate batch (ms_set_group_shard)."""
+        self._check(self.lib.ms_set_group_shard(self._h, int(rank), int(world)), 'ms_set_group_shard')
+
+    def group_will_run(self, nw):
+        return bool(self.lib.ms_group_will_run(self._h, int(nw)))
+
+    def stretch_evaluate(self, state_ptr, s_idx_ptr, n_s, c_idx_ptr, n_c, a, seed, iteration, split, gid0, q_ptr, logfac_ptr, lnp_ptr):
+        """Proposal for all n_s walkers + evaluation of this rank's groups (ms_stretch_evaluate)."""
+        self._check(self.lib.ms_stretch_evaluate(self._h, state_ptr, s_idx_ptr, n_s, c_idx_ptr, n_c, a, seed, iteration, split, gid0,
+                                                 q_ptr, logfac_ptr, lnp_ptr), 'ms_stretch_evaluate')
+
+    def stretch_accept_inplace(self, state_ptr, naccepted_ptr, s_idx_ptr, n_s, q_ptr, lnp_ptr, logfac_ptr, seed, iteration, split, gid0):
+        self._check(self.lib.ms_stretch_accept_inplace(self._h, state_ptr, naccepted_ptr, s_idx_ptr, n_s, q_ptr, lnp_ptr, logfac_ptr,
+                                                       seed, iteration, split, gid0), 'ms_stretch_accept_inplace')
 
     def stretch_scatter(self, state_ptr, naccepted_ptr, idx_ptr, packed_ptr, n):
         self._check(self.lib.ms_stretch_scatter(self._h, state_ptr, naccepted_ptr, idx_ptr, packed_ptr, n, self.ndim),

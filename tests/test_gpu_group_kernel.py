@@ -1,7 +1,8 @@
-"""The group kernel (lnprob_group_kernel: cell-mates share one TMA-staged stream of their grid rows, lane = walker)
+"""The group kernel (lnprob_group_kernel: cell-mates share one TMA-staged stream of their rows' bracket pairs, lane = walker)
 against the oracle and against the one-CTA-per-walker kernel, on the cases where its own code paths differ: exact
 median over odd / even / tiny / ragged sizes and many equal keys (per-lane histogram + key lists), partial groups,
-walkers outside the prior box, both kernel variants (4 / 8 walker warps), intermediate outputs, determinism.
+walkers outside the prior box, both kernel variants (8 / 16 walker warps), evaluation sharded by groups over ranks,
+intermediate outputs, determinism.
 
 Bar: identical -inf sets, 1e-9 relative against the oracle (tolerance of north_star), 1e-11 between the two device
 paths (they differ in the summation order of the band integrals and the moments).
@@ -48,7 +49,7 @@ def test_median_sizes_through_the_group_kernel(native_lib, n_data):
 
 def test_equal_keys_and_huge_av_through_the_group_kernel(native_lib):
     """Flat rows: every model value equal (Av = 0) or a smooth ramp (Av > 0); Av far beyond the polynomial's range
-    takes the exp2 path of the whole warp."""
+    takes the exp2 path (those walkers only)."""
     from mcmc_spec_b200 import synthetic
     from mcmc_spec_b200.posterior import LogPosterior
     from oracle_adapter import to_oracle
@@ -57,7 +58,7 @@ def test_equal_keys_and_huge_av_through_the_group_kernel(native_lib):
     lp = LogPosterior(p)
     theta = synthetic.sample_prior_box(p, 96, seed=5)
     theta[:16, 2] = 0.0
-    theta[16:24, 2] = 9.5                                         # |Av x| >> 0.02
+    theta[16:24, 2] = 9.5                                         # |Av x| >> 0.045
     g, s = _both(lp, theta)
     lp.close()
     assert _rel(g, to_oracle(p).lnprob_batch(theta)) <= 1e-9
@@ -89,7 +90,7 @@ def test_parts_and_model_through_the_group_kernel(small_problem, small_oracle, n
 
 
 def test_both_kernel_variants_give_the_same_bits(native_lib):
-    """Few groups -> eight walker warps per group on one CTA per SM, many groups -> four on two CTAs per SM; a
+    """Few groups -> sixteen walker warps per group on one CTA per SM, many groups -> eight on two CTAs per SM; a
     walker's value must not depend on the variant, the batch it arrives in or its companions in the group (the
     sharded chain then walks the same path on any number of GPUs)."""
     from mcmc_spec_b200 import synthetic
@@ -109,3 +110,51 @@ def test_both_kernel_variants_give_the_same_bits(native_lib):
     lp.close()
     assert np.array_equal(big, small)
     assert np.array_equal(big[perm], shuffled)
+
+
+def test_group_shards_sum_to_the_whole_half_step(native_lib):
+    """ms_set_group_shard: N ranks that hold the same ensemble each evaluate every N-th group of the whole half; the
+    sum of their log-probs (each walker non-zero on exactly one rank) is bit for bit what one rank computes alone,
+    the proposals are the same on every rank, and the in-place acceptance gives the single-rank ensemble."""
+    import torch
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.ensemble import CudaBackend
+    from mcmc_spec_b200.posterior import LogPosterior
+    p = synthetic.make_problem_small()
+    lp = LogPosterior(p)
+    lp.engine.set_group(True)
+    be = CudaBackend(lp.engine)
+    rng = np.random.default_rng(11)
+    nw = 4096
+    theta = np.asarray(p.truth) * (1 + 0.02 * rng.standard_normal((nw, 6)))
+    theta[:, 2] = np.abs(theta[:, 2])
+    state = torch.tensor(np.concatenate([theta, lp(theta)[:, None]], axis=1), device='cuda')
+    s_idx = torch.arange(0, nw, 2, device='cuda'); c_idx = torch.arange(1, nw, 2, device='cuda')
+    n_s = s_idx.shape[0]
+    f64 = dict(dtype=torch.float64, device='cuda')
+
+    def evaluate(rank, world):
+        q = torch.empty((n_s, 6), **f64); lf = torch.empty(n_s, **f64); lnp = torch.full((n_s,), 123.0, **f64)
+        be.set_shard(rank, world)
+        be.evaluate(state, s_idx, c_idx, 2.0, 5, 3, 0, 0, q, lf, lnp)
+        return q, lf, lnp
+
+    q1, lf1, whole = evaluate(0, 1)
+    parts = [evaluate(r, 3) for r in range(3)]
+    be.set_shard(0, 1)
+    for q, lf, _ in parts:
+        assert torch.equal(q, q1) and torch.equal(lf, lf1)
+    nonzero = torch.stack([(l != 0) for _, _, l in parts]).sum(dim=0)
+    assert int(nonzero.max()) == 1 and int((nonzero == 0).sum()) == 0          # every walker on exactly one rank (no lnprob is 0 here)
+    total = parts[0][2] + parts[1][2] + parts[2][2]
+    assert torch.equal(total, whole)
+    for _, _, l in parts:
+        assert 0.2 < float((l != 0).double().mean()) < 0.5                     # roughly a third of the groups each
+    # acceptance in place == the one-call half step
+    st_a = state.clone(); st_b = state.clone()
+    na = torch.zeros(nw, dtype=torch.int32, device='cuda'); nb = torch.zeros(nw, dtype=torch.int32, device='cuda')
+    be.accept_inplace(st_a, na, s_idx, q1, total, lf1, 5, 3, 0, 0)
+    q = torch.empty((n_s, 6), **f64); lf = torch.empty(n_s, **f64); lnp = torch.empty(n_s, **f64)
+    be.halfstep(st_b, nb, s_idx, c_idx, 2.0, 5, 3, 0, 0, q, lf, lnp)
+    assert torch.equal(st_a, st_b) and torch.equal(na, nb) and int(na.sum()) > 0
+    lp.close()
