@@ -276,10 +276,13 @@ __device__ __forceinline__ void lane_locate_merged(const unsigned short* hist_al
   }
 }
 
-// ++counter in shared memory, release (the warp's reads of the slot come first) + acquire (the last one out sees everybody's)
+// ++counter in shared memory.  Relaxed: what must come first are the warp's READS of the slot, and those have returned
+// their values (they were consumed by the arithmetic before this point); a release fence would also wait for the warp's
+// global stores of the model values, hundreds of cycles per stage.  The counter is never reset (the NWW-th, 2 NWW-th, ...
+// arrival is the last one out of a stage).
 __device__ __forceinline__ unsigned count_out(uint32_t addr) {
   unsigned old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+  asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
   return old;
 }
 
@@ -313,6 +316,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
   __shared__ unsigned long long s_above[NWW][32];
   __shared__ unsigned s_kmin[NWW][32], s_kmax[NWW][32], s_nl[NWW][32], s_nc[NWW][32];
   __shared__ int s_row[NROW];
+  __shared__ int s_box[NS][2];                           // (Teff, log g) origin of each star's box in the bracket table
   __shared__ int s_group, s_status;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -359,6 +363,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       for (int st = 0; st < NS; ++st) {
 #pragma unroll
         for (int r = 0; r < NR; ++r) s_row[st * NR + r] = p.row[st][r];
+        // box origin: the star's lower (Teff, log g) nodes (the plan's corners are in box order)
+        s_box[st][0] = p.row[st][0] % GT.n_teff; s_box[st][1] = p.row[st][0] / GT.n_teff;
       }
     }
     __syncthreads();
@@ -401,16 +407,11 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       const uint32_t bar = smem_u32(&s_full[slot]);
       mbar_expect_tx(bar, (unsigned)L::bytes);                        // pixels past the end of the spectrum are zero-filled
 #pragma unroll
-      for (int stx = 0; stx < NS; ++stx) {
-        // box origin: the star's lower (Teff, log g) nodes (the plan's corners are in box order)
-        const int row0 = s_row[stx * NR];
-        tensor_g2s_3d(st + L::B + stx * L::box, &bracket_map, 2 * KP * s, row0 % GT.n_teff, row0 / GT.n_teff, bar);
-      }
+      for (int stx = 0; stx < NS; ++stx)
+        tensor_g2s_3d(st + L::B + stx * L::box, &bracket_map, 2 * KP * s, s_box[stx][0], s_box[stx][1], bar);
       bulk_g2s(st + L::rec, GT.recblk + (size_t)s * 3 * KP, KP * 48, bar);
     };
-    if (tid == 0) {
-      for (int s = 0; s < min(NST, n_stages); ++s) issue_stage(s);
-    }
+    if (lane == 0 && wj < min(NST, n_stages)) issue_stage(wj);       // the first NST stages, one per warp
     {
       // ================================================================= walker warps, phase A: lane = walker
       double momv[NV][3];
@@ -527,8 +528,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         qrot = (qrot + (n_obs + PIX - 1) / PIX) % VW;
         __syncwarp();
         // count this warp out of the slot; the last one out refills it with the stage NST ahead
-        if (lane == 0 && count_out(smem_u32(&s_out[slot])) == (unsigned)(NWW - 1)) {
-          s_out[slot] = 0u;
+        if (lane == 0 && count_out(smem_u32(&s_out[slot])) % NWW == (unsigned)(NWW - 1)) {
           if (s + NST < n_stages) issue_stage(s + NST);
         }
       }
@@ -557,9 +557,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       mbar_expect_tx(smem_u32(&s_cfull[slot]), npx * 32u);
       bulk_g2s(ring + (uint32_t)slot * CHI_BYTES, GT.drec2 + (size_t)c * CHI_CHUNK * 4, npx * 32u, smem_u32(&s_cfull[slot]));
     };
-    if (tid == 0) {
-      for (int c = 0; c < min(CSLOTS, n_chunks); ++c) issue_chunk(c);
-    }
+    if (lane == 0 && wj < min(CSLOTS, n_chunks)) issue_chunk(wj);
     {
       // ================================================================= walker warps, phase B: lane = walker
       GDBG_DECL
@@ -761,8 +759,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             }
             __syncwarp();
             // count this warp out of the chunk's slot; the last one out refills it
-            if (lane == 0 && count_out(smem_u32(&s_cout[slot])) == (unsigned)(NWW - 1)) {
-              s_cout[slot] = 0u;
+            if (lane == 0 && count_out(smem_u32(&s_cout[slot])) % NWW == (unsigned)(NWW - 1)) {
               if (c + CSLOTS < n_chunks) issue_chunk(c + CSLOTS);
             }
           }
@@ -1007,7 +1004,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
     cit0 += (unsigned)n_chunks;
   }
 #ifdef MS_GROUP_TIMING
-  if (blockIdx.x < 8 && lane == 0 && (wj == 0 || wj == NWW - 1))
+  if (blockIdx.x < 4 && lane == 0)
     printf("cta %d warp %d groups %d: idle %lld A %lld sync %lld B: locate %lld chi %lld lists %lld bar %lld rank %lld finish %lld | mbarrier waits A %lld B %lld\n", blockIdx.x, warp,
            gt_groups, gt_acc[0], gt_acc[1], gt_acc[2], gt_acc[6], gt_acc[7], gt_acc[3], gt_acc[4], gt_acc[8], gt_acc[5], gt_wait_a, gt_wait);
 #endif
