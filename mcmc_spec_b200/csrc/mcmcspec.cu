@@ -53,9 +53,6 @@ namespace cg = cooperative_groups;
 #define MS_HAS_NR4_WIDE (MS_TU == 0 || MS_TU == 2)
 #define MS_HAS_NR8 (MS_TU == 0 || MS_TU == 3)
 #define MS_HAS_GROUP (MS_TU == 0 || MS_TU == 4)      // lnprob_group_kernel (group_kernel.cuh)
-#ifndef MS_GROUP_WALKERS
-#define MS_GROUP_WALKERS 8                           // walkers (walker warps) per CTA of the group kernel
-#endif
 #ifndef MS_GROUP_VW
 #define MS_GROUP_VW 16                               // partial sums per walker of the group kernel = walker warps with one CTA per SM
 #endif
@@ -1888,7 +1885,7 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
       for (int k = 0; k < 2; ++k) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
     }
     e0 = h->ev_pool[h->ev_used]; e1 = h->ev_pool[h->ev_used + 1];
-    h->ev_used += 2; h->timed_walkers += nw;
+    h->ev_used += 2; h->timed_walkers += h->shard_active ? nw / h->shard_world : nw;      // walkers this launch evaluates
     CK(cudaEventRecord(e0, h->stream));
   }
   // Few groups (at most one per SM): one CTA per SM with sixteen walker warps per group shortens the time a group takes;
