@@ -78,6 +78,7 @@ constexpr int CHI_CHUNK = CHI_NSB * CHI_SB;   // observed pixels per chunk of th
 constexpr int CHI_BYTES = CHI_CHUNK * 32;
 constexpr int CAND = 8;                    // keys of the median's second-level bin per lane and walker warp (fast finish)
 constexpr double POLY_XMAX = 0.045;
+constexpr double STEP_XMAX = 5.0e-4;
 static_assert(KP % PIX == 0, "a stage is a whole number of quadruples");
 
 // One ring slot: the bracket table of the stage {star 0: [log g][Teff][KP] double2 | star 1} and its records.
@@ -86,7 +87,7 @@ template <int NR> struct StageLayout {
   static constexpr int rowb = KP * 16;                     // one row of the stage
   static constexpr int box = NR * rowb;                    // one star's rows, written by one tensor copy
   static constexpr int B = 0;
-  static constexpr int rec = 2 * box;                      // {t, x_lo}[KP] | {x_hi, d q0}[KP] | {d q1, d q2}[KP]
+  static constexpr int rec = 2 * box;                      // {t, x_lo}[KP] | {x_hi - x_lo, d q0}[KP] | {d q1, d q2}[KP]
   static constexpr int bytes = rec + KP * 48;
   static constexpr int ring = NST * bytes;
   static_assert(box % 128 == 0 && bytes % 128 == 0, "bulk copies need aligned destinations");
@@ -96,12 +97,13 @@ template <int NR> struct StageLayout {
 
 // What the group kernel needs beyond DevTables (built once in ms_create).
 struct GroupTables {
-  const double2* recblk;        // per stage: {t, x_lo}[KP] | {x_hi, d q0}[KP] | {d q1, d q2}[KP]
+  const double2* recblk;        // per stage: {t, x_lo}[KP] | {x_hi - x_lo, d q0}[KP] | {d q1, d q2}[KP]
   const double2* anchor;        // [n_stages] {extinction exponent the stage's x values are relative to, (its step from the
                                 //  previous stage) ln 2, or +inf: take the exact factor here}
   const double* drec2;          // [n_data][4] {q1(x), q2(x), flux, 1/err^2}: phase B
   double xmax;                  // max |x| over all records (x = (ext - anchor) ln 2)
   double dxmax;                 // max |step|
+  double pxmax;                 // max |x_hi - x_lo| over all records
   int n_stages;
   int n_teff;
   int shard_rank, shard_world;  // this launch evaluates the groups shard_rank, shard_rank + shard_world, ... (ms_set_group_shard)
@@ -175,6 +177,13 @@ __constant__ double EXP_C[7] = {1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 
 __device__ __forceinline__ double exp_small(double y) {
   double p = fma(y, EXP_C[0], EXP_C[1]);
   p = fma(p, y, EXP_C[2]); p = fma(p, y, EXP_C[3]); p = fma(p, y, EXP_C[4]); p = fma(p, y, EXP_C[5]);
+  p = fma(p, y, EXP_C[6]); p = fma(p, y, 1.0); p = fma(p, y, 1.0);
+  return p;
+}
+
+// exp(y) for |y| <= STEP_XMAX = 5e-4: Taylor to y^4 (remainder y^5/120 < 2.7e-19 relative)
+__device__ __forceinline__ double exp_step(double y) {
+  double p = fma(y, 1.0 / 24.0, EXP_C[5]);
   p = fma(p, y, EXP_C[6]); p = fma(p, y, 1.0); p = fma(p, y, 1.0);
   return p;
 }
@@ -431,7 +440,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       // which form of the extinction factor a walker gets depends on its own Av only (never on its companions in the
       // group): the polynomial where it is accurate, exp2 of the whole exponent otherwise
       const bool lane_poly = av * GT.xmax <= POLY_XMAX, lane_inc = av * GT.dxmax <= POLY_XMAX;
-      const bool poly_ok = __all_sync(0xffffffffu, lane_poly);
+      const bool lane_step = av * GT.pxmax <= STEP_XMAX;             // the upper bracket's factor from the lower one's
+      const bool poly_ok = __all_sync(0xffffffffu, lane_poly && lane_step);
       double A = 1.0;
       double2 anc_next = __ldg(GT.anchor);
       int qrot = 0;                       // quadruples of the stages so far, mod VW: where this stage's first one is dealt
@@ -440,7 +450,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         const unsigned gs = it0 + (unsigned)s;
         const int slot = (int)(gs % NST);
         const double2 anc2 = anc_next;
-        anc_next = __ldg(GT.anchor + min(s + 1, n_stages - 1));           // in flight during this stage
+        // the next stage's anchor, in flight during this stage (volatile: issued here, not sunk to its use)
+        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(anc_next.x), "=d"(anc_next.y) : "l"(GT.anchor + min(s + 1, n_stages - 1)));
         // the stage's common extinction factor exp2(av * anchor): exact on every ANCHOR_REFRESH-th stage, from the
         // previous stage's by the polynomial in between (the same sequence in every warp and kernel variant)
         const double anc = anc2.x;
@@ -457,7 +468,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
           // lanes (one-wavefront broadcasts)
           auto pixel = [&](auto poly, int k, double& rm_out) -> double {
             const double2 ra = recA[k];                                      // t, x_lo
-            const double xhi = recB[k].x;
+            const double dx = recB[k].x;                                     // x_hi - x_lo
             double flo = 0.0, fhi = 0.0;
 #pragma unroll
             for (int stx = 0; stx < NS; ++stx) {
@@ -472,14 +483,16 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
             }
             double elo, ehi, scale_a = A;
             if constexpr (decltype(poly)::value) {
-              elo = exp_small(__dmul_rn(av, ra.y)); ehi = exp_small(__dmul_rn(av, xhi));
+              // the two bracketing model pixels are neighbours: exp(av x_hi) = exp(av x_lo) * exp(av dx), |av dx| <= 5e-4
+              elo = exp_small(__dmul_rn(av, ra.y)); ehi = __dmul_rn(elo, exp_step(__dmul_rn(av, dx)));
             } else {
               // some lane's exponent is too large for the polynomial: those lanes take exp2 of the whole exponent
               // (1/ln 2 = 1.4426950408889634), the others the same arithmetic as on the fast path
               const double e2lo = exp2(av * fma(ra.y, 1.4426950408889634, anc));
+              const double xhi = __dadd_rn(ra.y, dx);
               const double e2hi = exp2(av * fma(xhi, 1.4426950408889634, anc));
               elo = lane_poly ? exp_small(__dmul_rn(av, ra.y)) : e2lo;
-              ehi = lane_poly ? exp_small(__dmul_rn(av, xhi)) : e2hi;
+              ehi = lane_poly ? (lane_step ? __dmul_rn(elo, exp_step(__dmul_rn(av, dx))) : exp_small(__dmul_rn(av, xhi))) : e2hi;
               scale_a = lane_poly ? A : 1.0;
             }
             // every product and sum is spelled out (no mul/add pair is left for the assembler to fuse or not): a walker's

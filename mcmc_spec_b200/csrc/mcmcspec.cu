@@ -184,15 +184,13 @@ namespace {
 // Small device helpers
 // ------------------------------------------------------------------------------------------
 
-// 1/x to ~1 ulp for finite non-zero x (two Newton steps on the hardware seed); 0 -> inf, NaN -> NaN.
+// 1/x to ~1 ulp for finite non-zero x: one third-order step on the hardware seed (rcp.approx.ftz.f64 works from the
+// high word only, relative error e ~ 2^-20: r0 (1 + e + e^2) leaves e^3 ~ 2^-60); 0 -> inf, NaN -> NaN.
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
 }
 
 // Blackwell 256-bit global loads (LDG.E.256): four consecutive pixels per lane and instruction.
@@ -2315,7 +2313,7 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
     std::vector<double2> anchor2((size_t)n_stages + 32, make_double2(0.0, std::numeric_limits<double>::infinity()));
     std::vector<double2> blk((size_t)n_stages * 3 * KP + 8, make_double2(0.0, 0.0));
     std::vector<double> dr2(4 * (size_t)n);
-    double xmax = 0.0, dxmax = 0.0;
+    double xmax = 0.0, dxmax = 0.0, pxmax = 0.0;
     for (int s = 0; s < n_stages; ++s) {
       const int d0 = s * KP, ns_ = std::min(KP, n - d0);
       const double anc = 0.5 * (cfg->ext_lo[d0] + cfg->ext_hi[d0 + ns_ - 1]);
@@ -2336,14 +2334,15 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
         const double q0 = T.basis[0], q1 = std::fma(T.basis[4], x, T.basis[3]);
         const double q2 = std::fma(std::fma(T.basis[8], x, T.basis[7]), x, T.basis[6]);
         pa[k] = make_double2(cfg->rebin_t[i], xlo);
-        pb[k] = make_double2(xhi, d * q0);
+        pb[k] = make_double2((cfg->ext_hi[i] - cfg->ext_lo[i]) * LN2, d * q0);
+        pxmax = std::max(pxmax, std::fabs(pb[k].x));
         pc[k] = make_double2(d * q1, d * q2);
         dr2[4 * (size_t)i] = q1; dr2[4 * (size_t)i + 1] = q2; dr2[4 * (size_t)i + 2] = d;
         dr2[4 * (size_t)i + 3] = 1.0 / (cfg->data_err[i] * cfg->data_err[i]);
       }
     }
     grp::GroupTables& GT = h->GT;
-    GT.n_stages = n_stages; GT.xmax = xmax; GT.dxmax = dxmax; GT.n_teff = cfg->n_teff;
+    GT.n_stages = n_stages; GT.xmax = xmax; GT.dxmax = dxmax; GT.pxmax = pxmax; GT.n_teff = cfg->n_teff;
     CKC(upload(h, blk.data(), blk.size(), &GT.recblk));
     CKC(upload(h, anchor2.data(), anchor2.size(), &GT.anchor));
     CKC(upload(h, dr2.data(), dr2.size(), &GT.drec2));
