@@ -1048,14 +1048,21 @@ __global__ void __launch_bounds__(1024) group_scan_kernel(unsigned* __restrict__
                                                           int* __restrict__ n_groups, int* __restrict__ group_counter) {
   __shared__ unsigned wa[32], wb[32];
   __shared__ unsigned carry_a, carry_b;
+  constexpr int ITEMS = 8;                       // consecutive cells per thread: 8192 cells per pass
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { carry_a = 0; carry_b = 0; }
   __syncthreads();
-  for (int base = 0; base < n_cells; base += 1024) {
-    const int i = base + tid;
-    const unsigned v = (i < n_cells) ? hist_offsets[i] : 0u;
-    const unsigned g = (v + GMAX - 1) / GMAX;
-    unsigned ia = v, ib = g;
+  for (int base = 0; base < n_cells; base += 1024 * ITEMS) {
+    const int i0 = base + tid * ITEMS;
+    unsigned v[ITEMS], g[ITEMS];
+    unsigned sa = 0, sb = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      v[k] = (i0 + k < n_cells) ? hist_offsets[i0 + k] : 0u;
+      g[k] = (v[k] + GMAX - 1) / GMAX;
+      sa += v[k]; sb += g[k];
+    }
+    unsigned ia = sa, ib = sb;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
@@ -1073,11 +1080,15 @@ __global__ void __launch_bounds__(1024) group_scan_kernel(unsigned* __restrict__
       wa[lane] = xa; wb[lane] = xb;
     }
     __syncthreads();
-    const unsigned ea = carry_a + (warp ? wa[warp - 1] : 0u) + ia - v;
-    const unsigned eb = carry_b + (warp ? wb[warp - 1] : 0u) + ib - g;
-    if (i < n_cells) { hist_offsets[i] = ea; cell_start[i] = ea; group_off[i] = eb; }
+    unsigned ea = carry_a + (warp ? wa[warp - 1] : 0u) + ia - sa;       // exclusive prefix of this thread's first cell
+    unsigned eb = carry_b + (warp ? wb[warp - 1] : 0u) + ib - sb;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      if (i0 + k < n_cells) { hist_offsets[i0 + k] = ea; cell_start[i0 + k] = ea; group_off[i0 + k] = eb; }
+      ea += v[k]; eb += g[k];
+    }
     __syncthreads();
-    if (tid == 1023) { carry_a = ea + v; carry_b = eb + g; }
+    if (tid == 1023) { carry_a = ea; carry_b = eb; }
     __syncthreads();
   }
   if (tid == 0) { cell_start[n_cells] = carry_a; *n_groups = (int)carry_b; *group_counter = 0; }
