@@ -350,9 +350,11 @@ int ms_set_cell_order(ms_handle* h, int mode);
  * model pixel); values agree with the one-CTA-per-walker kernel to rounding (summation order of the band
  * integrals), and a walker's value does not depend on which other walkers share its group.
  * mode: -1 (default) automatic -- batches of at least `min_walkers` (default 1024; <= 0 keeps the current
- * threshold) on handles whose tables fit the ring; 0 never; 1 whenever the tables fit.
- * ms_group_supported: 1 when this handle can take it (nspec = 2, a 2-D (Teff, log g) grid with at least two nodes per
- * axis, more than one grid cell, at most 65 535 observed pixels).
+ * threshold), as long as the batch does not spread so thinly over the grid cells that a group holds fewer than ~6
+ * walkers (a group costs the same with 3 busy lanes as with 32; the count of the previous batch of the same size
+ * decides, with hysteresis); 0 never; 1 whenever the handle can take it.
+ * ms_group_supported: 1 when this handle can take it (nspec = 2, a (Teff, log g) or (Teff, log g, [Fe/H]) grid with at
+ * least two nodes per axis, more than one grid cell, at most 65 535 observed pixels).
  * ms_set_group_shard: this handle evaluates the groups rank, rank + world, ... of every batch and leaves the other
  * walkers' lnprob at 0 -- N processes that hold the same ensemble each evaluate 1/N of the groups of the WHOLE half
  * (whole groups per GPU instead of 1/N of every cell's walkers) and sum the results (one all-reduce).  Only

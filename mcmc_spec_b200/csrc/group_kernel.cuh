@@ -58,7 +58,9 @@ namespace grp {
 #ifndef MS_GROUP_VW
 #define MS_GROUP_VW 16
 #endif
-constexpr int KP = MS_GROUP_KP;            // observed pixels per stage
+constexpr int KP = MS_GROUP_KP;            // observed pixels per stage (2-D grids: 4 rows per star)
+constexpr int KP8 = MS_GROUP_KP / 2;       // ... with an [Fe/H] axis (8 rows per star): the same bytes per stage
+constexpr int kp_of(int nr) { return nr == 8 ? KP8 : KP; }
 constexpr int NST = MS_GROUP_NST;          // ring slots: stages in flight ahead of the walker warps
 constexpr int ANCHOR_REFRESH = 8;          // the stage's common extinction factor is taken exactly on every 8th stage
 constexpr int NWW_MAX = MS_GROUP_VW;       // walker warps per CTA (template parameter NWW: 8 with two CTAs per SM, 16 with
@@ -79,16 +81,17 @@ constexpr int CHI_BYTES = CHI_CHUNK * 32;
 constexpr int CAND = 8;                    // keys of the median's second-level bin per lane and walker warp (fast finish)
 constexpr double POLY_XMAX = 0.045;
 constexpr double STEP_XMAX = 5.0e-4;
-static_assert(KP % PIX == 0, "a stage is a whole number of quadruples");
+static_assert(KP % PIX == 0 && KP8 % PIX == 0, "a stage is a whole number of quadruples");
 
 // One ring slot: the bracket table of the stage {star 0: [log g][Teff][KP] double2 | star 1} and its records.
 template <int NR> struct StageLayout {
   static constexpr int NROW = 2 * NR;
-  static constexpr int rowb = KP * 16;                     // one row of the stage
+  static constexpr int kp = kp_of(NR);                     // observed pixels per stage
+  static constexpr int rowb = kp * 16;                     // one row of the stage
   static constexpr int box = NR * rowb;                    // one star's rows, written by one tensor copy
   static constexpr int B = 0;
   static constexpr int rec = 2 * box;                      // {t, x_lo}[KP] | {x_hi - x_lo, d q0}[KP] | {d q1, d q2}[KP]
-  static constexpr int bytes = rec + KP * 48;
+  static constexpr int bytes = rec + kp * 48;
   static constexpr int ring = NST * bytes;
   static_assert(box % 128 == 0 && bytes % 128 == 0, "bulk copies need aligned destinations");
   static constexpr int cslots = ring / CHI_BYTES;          // the chi-square pass cuts the same ring into chunk slots
@@ -105,7 +108,7 @@ struct GroupTables {
   double dxmax;                 // max |step|
   double pxmax;                 // max |x_hi - x_lo| over all records
   int n_stages;
-  int n_teff;
+  int n_teff, n_logg;
   int shard_rank, shard_world;  // this launch evaluates the groups shard_rank, shard_rank + shard_world, ... (ms_set_group_shard)
 };
 
@@ -136,6 +139,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// the same with a fourth coordinate ([Fe/H] node): the eight bracketing rows of one star in one request
+__device__ __forceinline__ void tensor_g2s_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               :: "r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 // 3-D tiled tensor copy (pixel, Teff node, log g node) global -> shared: the four bracketing rows of one star in
 // one request (TMA, SASS UTMALDG); out-of-range coordinates are filled with zeros
@@ -299,7 +307,7 @@ template <int NWW>
 __device__ __forceinline__ void walker_bar() { asm volatile("bar.sync 1, %0;" :: "n"(NWW * 32) : "memory"); }
 
 // ------------------------------------------------------------------------------------------
-// NR: grid rows per star (4; 8 with [Fe/H] is not instantiated yet).  Binaries, posterior mode.
+// NR: grid rows per star (4, or 8 with an [Fe/H] axis: a 4-D box per star).  Binaries, posterior mode.
 // NWW walker warps per CTA.
 // ------------------------------------------------------------------------------------------
 template <int NR, int NWW, int CTAS_PER_SM>
@@ -315,6 +323,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
   static_assert(NWW <= NWW_MAX && VW % NWW == 0, "scratch is sized for NWW_MAX walker warps; partial sums are dealt to the warps");
   constexpr int NV = VW / NWW;                                     // partial sums a walker warp carries
   using L = StageLayout<NR>;
+  constexpr int KPn = L::kp;
   constexpr int CSLOTS = L::cslots;
   extern __shared__ __align__(128) unsigned char gsm[];
   unsigned short* const hist_all = reinterpret_cast<unsigned short*>(gsm + L::ring);   // [NWW][HBINS][32]
@@ -325,7 +334,7 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
   __shared__ unsigned long long s_above[NWW][32];
   __shared__ unsigned s_kmin[NWW][32], s_kmax[NWW][32], s_nl[NWW][32], s_nc[NWW][32];
   __shared__ int s_row[NROW];
-  __shared__ int s_box[NS][2];                           // (Teff, log g) origin of each star's box in the bracket table
+  __shared__ int s_box[NS][3];                           // (Teff, log g, [Fe/H]) origin of each star's box in the bracket table
   __shared__ int s_group, s_status;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -373,7 +382,8 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
 #pragma unroll
         for (int r = 0; r < NR; ++r) s_row[st * NR + r] = p.row[st][r];
         // box origin: the star's lower (Teff, log g) nodes (the plan's corners are in box order)
-        s_box[st][0] = p.row[st][0] % GT.n_teff; s_box[st][1] = p.row[st][0] / GT.n_teff;
+        s_box[st][0] = p.row[st][0] % GT.n_teff; s_box[st][1] = (p.row[st][0] / GT.n_teff) % GT.n_logg;
+        s_box[st][2] = p.row[st][0] / (GT.n_teff * GT.n_logg);
       }
     }
     __syncthreads();
@@ -416,9 +426,13 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       const uint32_t bar = smem_u32(&s_full[slot]);
       mbar_expect_tx(bar, (unsigned)L::bytes);                        // pixels past the end of the spectrum are zero-filled
 #pragma unroll
-      for (int stx = 0; stx < NS; ++stx)
-        tensor_g2s_3d(st + L::B + stx * L::box, &bracket_map, 2 * KP * s, s_box[stx][0], s_box[stx][1], bar);
-      bulk_g2s(st + L::rec, GT.recblk + (size_t)s * 3 * KP, KP * 48, bar);
+      for (int stx = 0; stx < NS; ++stx) {
+        if constexpr (NR == 8)
+          tensor_g2s_4d(st + L::B + stx * L::box, &bracket_map, 2 * KPn * s, s_box[stx][0], s_box[stx][1], s_box[stx][2], bar);
+        else
+          tensor_g2s_3d(st + L::B + stx * L::box, &bracket_map, 2 * KPn * s, s_box[stx][0], s_box[stx][1], bar);
+      }
+      bulk_g2s(st + L::rec, GT.recblk + (size_t)s * 3 * KPn, KPn * 48, bar);
     };
     if (lane == 0 && wj < min(NST, n_stages)) issue_stage(wj);       // the first NST stages, one per warp
     {
@@ -456,14 +470,14 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
         // previous stage's by the polynomial in between (the same sequence in every warp and kernel variant)
         const double anc = anc2.x;
         if (lane_inc && anc2.y < CUDART_INF) A = __dmul_rn(A, exp_small(__dmul_rn(av, anc2.y))); else A = exp2(__dmul_rn(av, anc));
-        const int n_obs = min(KP, n - s * KP);
+        const int n_obs = min(KPn, n - s * KPn);
         GDBG_WAIT(mbar_wait(smem_u32(&s_full[slot]), (gs / NST) & 1u))
         const unsigned char* stB = gsm + (size_t)slot * L::bytes + L::B;
         {
-          double* dst = sMT + (size_t)s * KP * 32 + lane;
+          double* dst = sMT + (size_t)s * KPn * 32 + lane;
           const double2* recA = reinterpret_cast<const double2*>(gsm + (size_t)slot * L::bytes + L::rec);
-          const double2* recB = recA + KP;
-          const double2* recC = recB + KP;
+          const double2* recB = recA + KPn;
+          const double2* recC = recB + KPn;
           // one observed pixel for this lane's walker; every shared-memory operand is the same address in all
           // lanes (one-wavefront broadcasts)
           auto pixel = [&](auto poly, int k, double& rm_out) -> double {

@@ -53,6 +53,10 @@ namespace cg = cooperative_groups;
 #define MS_HAS_NR4_WIDE (MS_TU == 0 || MS_TU == 2)
 #define MS_HAS_NR8 (MS_TU == 0 || MS_TU == 3)
 #define MS_HAS_GROUP (MS_TU == 0 || MS_TU == 4)      // lnprob_group_kernel (group_kernel.cuh)
+#ifndef MS_GROUP_FILL_LO
+#define MS_GROUP_FILL_LO 6.0                         // walkers per group below which the per-walker kernel takes over ...
+#define MS_GROUP_FILL_HI 9.0                         // ... and above which the group kernel comes back
+#endif
 #ifndef MS_GROUP_VW
 #define MS_GROUP_VW 16                               // partial sums per walker of the group kernel = walker warps with one CTA per SM
 #endif
@@ -1676,6 +1680,8 @@ struct ms_handle {
   bool shard_active = false;             // ... of the batches of ms_stretch_evaluate (set for the duration of that call)
   int group_variant = 0;         // 0 by the number of groups, 1 always one CTA per SM, 2 always two (MCMCSPEC_GROUP_VARIANT, tests)
   bool group_now = false;        // decided per call
+  bool group_probe = false;      // group kernel possible but the groups are too thin: per-walker kernel, group count still refreshed
+  bool group_thin = false;       // sticky: the last counts said fewer than MS_GROUP_FILL_LO walkers per group
   long long group_min_walkers = 1024;
   grp::GroupDesc* groups = nullptr; long long groups_cap = 0;
   unsigned* cell_start = nullptr; unsigned* group_off = nullptr; int* n_groups = nullptr;
@@ -1892,7 +1898,6 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
   // asynchronously, never waited for) stands in for it -- successive half steps of a chain look alike.
   const long long min_groups = (nw + grp::GMAX - 1) / grp::GMAX;
   const long long max_groups = min_groups + std::min<long long>(h->T.n_cells, nw);
-  const size_t ring = (size_t)grp::StageLayout<4>::ring;
   const int seen = *reinterpret_cast<volatile int*>(h->h_n_groups);
   const long long seen_nw = *reinterpret_cast<volatile int*>(h->h_n_groups + 1);
   const long long expect_all = (seen > 0 && seen_nw == nw) ? (long long)seen : min_groups + min_groups / 3;
@@ -1900,23 +1905,26 @@ int ms_tu_launch_group(ms_handle* h, long long nw, double* d_lnp, const msd::Par
   const long long expect_groups = (expect_all + sworld - 1) / sworld;      // this rank's share
   grp::GroupTables GTs = h->GT;
   GTs.shard_rank = srank; GTs.shard_world = sworld;
-  if (h->group_variant == 1 || (h->group_variant == 0 && expect_groups <= h->num_sms)) {
-    constexpr int NWW = MS_GROUP_NWW_WIDE;
-    auto kern = grp::lnprob_group_kernel<4, NWW, 1>;
-    const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2);
+  const bool wide = h->group_variant == 1 || (h->group_variant == 0 && expect_groups <= h->num_sms);
+  auto launch = [&](auto kern, int nww, size_t ring, long long slots) -> int {
+    const int smem = (int)(ring + (size_t)nww * grp::HBINS * 32 * 2);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const unsigned ctas = (unsigned)std::min<long long>(h->num_sms, max_groups);
-    kern<<<ctas, NWW * 32, smem, h->stream>>>(h->T, GTs, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
-                                                               h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
+    const unsigned ctas = (unsigned)std::min<long long>(slots, max_groups);
+    kern<<<ctas, nww * 32, smem, h->stream>>>(h->T, GTs, h->grid_map, h->plans, h->order, h->groups, h->n_groups, h->group_counter,
+                                             d_lnp, parts, h->group_scratch, h->group_list);
+    return MS_OK;
+  };
+  int rc;
+  if (h->corners == 8) {
+    const size_t ring = (size_t)grp::StageLayout<8>::ring;
+    rc = wide ? launch(grp::lnprob_group_kernel<8, MS_GROUP_NWW_WIDE, 1>, MS_GROUP_NWW_WIDE, ring, h->num_sms)
+              : launch(grp::lnprob_group_kernel<8, MS_GROUP_NWW, 2>, MS_GROUP_NWW, ring, h->group_ctas);
   } else {
-    constexpr int NWW = MS_GROUP_NWW;
-    auto kern = grp::lnprob_group_kernel<4, NWW, 2>;
-    const int smem = (int)(ring + NWW * grp::HBINS * 32 * 2);
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const unsigned ctas = (unsigned)std::min<long long>(h->group_ctas, max_groups);
-    kern<<<ctas, NWW * 32, smem, h->stream>>>(h->T, GTs, h->grid_map, h->plans, h->order, h->groups, h->n_groups,
-                                                               h->group_counter, d_lnp, parts, h->group_scratch, h->group_list);
+    const size_t ring = (size_t)grp::StageLayout<4>::ring;
+    rc = wide ? launch(grp::lnprob_group_kernel<4, MS_GROUP_NWW_WIDE, 1>, MS_GROUP_NWW_WIDE, ring, h->num_sms)
+              : launch(grp::lnprob_group_kernel<4, MS_GROUP_NWW, 2>, MS_GROUP_NWW, ring, h->group_ctas);
   }
+  if (rc) return rc;
   CK(cudaGetLastError());
   if (h->timing) CK(cudaEventRecord(e1, h->stream));
   h->h_n_groups[1] = (int)std::min<long long>(nw, 0x7fffffff);
@@ -1977,8 +1985,23 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
   // Large posterior batches of binaries on a (Teff, log g) grid: groups of cell-mates share one stream of their
   // rows (group_kernel.cuh).  Needs the cell-sorted order and the group table.
   h->group_now = h->group_ok && h->group_mode != 0 && mode == MODE_POSTERIOR && !h->fast && h->cluster <= 1 &&
-                 h->corners == 4 && (h->group_mode > 0 || nw >= h->group_min_walkers);
-  if (h->group_now) { h->use_order = true; h->pair_now = false; }
+                 (h->group_mode > 0 || nw >= h->group_min_walkers);
+  h->group_probe = false;
+  if (h->group_now && h->group_mode < 0 && !h->shard_active) {
+    // A group costs the same whether 32 lanes or 3 are busy: when the batch spreads so thinly over the grid cells that a
+    // group holds only a few walkers (a chain far from convergence on a fine grid, C5's proposals), the per-walker kernel
+    // is faster.  The group count of the last call of this batch size decides (copied back asynchronously, never waited
+    // for), with hysteresis; the count keeps being refreshed on either path.  ms_set_group(1) forces the group kernel.
+    const int seen = *reinterpret_cast<volatile int*>(h->h_n_groups);
+    const long long seen_nw = *reinterpret_cast<volatile int*>(h->h_n_groups + 1);
+    if (seen > 0 && seen_nw == nw) {
+      const double fill = (double)nw / (double)seen;
+      if (fill < MS_GROUP_FILL_LO) h->group_thin = true;
+      else if (fill > MS_GROUP_FILL_HI) h->group_thin = false;
+    }
+    if (h->group_thin) { h->group_now = false; h->group_probe = true; }
+  }
+  if (h->group_now || h->group_probe) { h->use_order = true; h->pair_now = false; }
   if (h->use_order) CK(cudaMemsetAsync(h->cell_hist, 0, (size_t)h->T.n_cells * sizeof(unsigned), h->stream));
   const size_t prep_smem = (size_t)(3 * h->T.n_iso + h->T.n_teff + h->T.n_logg + h->T.n_feh + h->T.n_dm +
                                     h->T.n_dm * h->T.n_dust_samples) * sizeof(double);
@@ -2029,7 +2052,16 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
     h->launches += 3;
     return ms_tu_launch_group(h, nw, d_lnp, parts);
   }
-  if (h->use_order) {
+  if (h->group_probe) {
+    // per-walker kernel in cell order; the scan also counts the groups this batch would have made
+    grp::group_scan_kernel<<<1, 1024, 0, h->stream>>>(h->cell_hist, h->T.n_cells, h->cell_start, h->group_off, h->n_groups,
+                                                      h->group_counter);
+    cell_scatter_kernel<<<pg, pb, 0, h->stream>>>(h->plans, nw, h->cell_hist, h->order);
+    CK(cudaGetLastError());
+    h->h_n_groups[1] = (int)std::min<long long>(nw, 0x7fffffff);
+    CK(cudaMemcpyAsync(h->h_n_groups, h->n_groups, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    h->launches += 2;
+  } else if (h->use_order) {
     cell_scan_kernel<<<1, 1024, 0, h->stream>>>(h->cell_hist, h->T.n_cells);
     cell_scatter_kernel<<<pg, pb, 0, h->stream>>>(h->plans, nw, h->cell_hist, h->order);
     CK(cudaGetLastError());
@@ -2305,6 +2337,7 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
   {
     using namespace grp;
     const int n = cfg->n_data;
+    const int KP = kp_of(h->corners);                     // 64, or 32 with an [Fe/H] axis
     const int n_stages = (n + KP - 1) / KP;
     const double LN2 = 0.69314718055994530942;
     bool ok = cfg->nspec == 2 && T.n_cells > 1 && n <= 65535 && n >= 1;
@@ -2342,12 +2375,13 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
       }
     }
     grp::GroupTables& GT = h->GT;
-    GT.n_stages = n_stages; GT.xmax = xmax; GT.dxmax = dxmax; GT.pxmax = pxmax; GT.n_teff = cfg->n_teff;
+    GT.n_stages = n_stages; GT.xmax = xmax; GT.dxmax = dxmax; GT.pxmax = pxmax; GT.n_teff = cfg->n_teff; GT.n_logg = cfg->n_logg;
     CKC(upload(h, blk.data(), blk.size(), &GT.recblk));
     CKC(upload(h, anchor2.data(), anchor2.size(), &GT.anchor));
     CKC(upload(h, dr2.data(), dr2.size(), &GT.drec2));
-    // (bracket pair, Teff, log g) tensor map of the bracket table: one box = KP pixels of the 2 x 2 bracketing rows of a star
-    if (ok && cfg->n_feh == 1 && cfg->n_teff >= 2 && cfg->n_logg >= 2) {
+    // (bracket pair, Teff, log g[, Fe/H]) tensor map of the bracket table: one box = KP pixels of the 2 x 2 (x 2) bracketing
+    // rows of a star
+    if (ok && cfg->n_teff >= 2 && cfg->n_logg >= 2 && (cfg->n_feh == 1 || cfg->n_feh >= 2)) {
       typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -2357,11 +2391,13 @@ int ms_create_shared(const ms_config* cfg, const ms_handle* grid_owner, ms_handl
           qres != cudaDriverEntryPointSuccess) {
         ok = false;
       } else {
-        const cuuint64_t gdim[3] = {(cuuint64_t)2 * (cuuint64_t)n, (cuuint64_t)cfg->n_teff, (cuuint64_t)cfg->n_logg};
-        const cuuint64_t gstr[2] = {(cuuint64_t)n * 16, (cuuint64_t)n * 16 * (cuuint64_t)cfg->n_teff};
-        const cuuint32_t box[3] = {(cuuint32_t)(2 * KP), 2, 2};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        const CUresult cr = reinterpret_cast<EncodeFn>(fn)(&h->grid_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+        const int rank = (h->corners == 8) ? 4 : 3;
+        const cuuint64_t gdim[4] = {(cuuint64_t)2 * (cuuint64_t)n, (cuuint64_t)cfg->n_teff, (cuuint64_t)cfg->n_logg, (cuuint64_t)cfg->n_feh};
+        const cuuint64_t gstr[3] = {(cuuint64_t)n * 16, (cuuint64_t)n * 16 * (cuuint64_t)cfg->n_teff,
+                                    (cuuint64_t)n * 16 * (cuuint64_t)cfg->n_teff * (cuuint64_t)cfg->n_logg};
+        const cuuint32_t box[4] = {(cuuint32_t)(2 * KP), 2, 2, 2};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult cr = reinterpret_cast<EncodeFn>(fn)(&h->grid_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank,
                                                           const_cast<double2*>(T.bracket), gdim, gstr, box, estr,
                                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -2474,7 +2510,7 @@ int ms_set_group(ms_handle* h, int mode, int64_t min_walkers) {
   return MS_OK;
 }
 
-int ms_group_supported(const ms_handle* h) { return (h && h->group_ok && h->corners == 4) ? 1 : 0; }
+int ms_group_supported(const ms_handle* h) { return (h && h->group_ok) ? 1 : 0; }
 
 int ms_set_group_shard(ms_handle* h, int rank, int world) {
   if (!h) return MS_ERR_INVALID;
@@ -2485,7 +2521,7 @@ int ms_set_group_shard(ms_handle* h, int rank, int world) {
 
 int ms_group_will_run(const ms_handle* h, int64_t nw) {
   if (!h) return 0;
-  return (h->group_ok && h->group_mode != 0 && !h->fast && h->cluster <= 1 && h->corners == 4 &&
+  return (h->group_ok && h->group_mode != 0 && !h->fast && h->cluster <= 1 &&
           (h->group_mode > 0 || nw >= h->group_min_walkers)) ? 1 : 0;
 }
 

@@ -158,3 +158,25 @@ def test_group_shards_sum_to_the_whole_half_step(native_lib):
     be.halfstep(st_b, nb, s_idx, c_idx, 2.0, 5, 3, 0, 0, q, lf, lnp)
     assert torch.equal(st_a, st_b) and torch.equal(na, nb) and int(na.sum()) > 0
     lp.close()
+
+
+@pytest.mark.parametrize('feh_free', [False, True])
+def test_feh_axis_through_the_group_kernel(native_lib, feh_free):
+    """Grids with an [Fe/H] axis (BASELINE config C5): eight bracketing rows per star arrive as one 4-D tensor box;
+    fixed [Fe/H] (on and off a node) and [Fe/H] as a walker parameter (the cell key carries its bracket)."""
+    from mcmc_spec_b200 import synthetic
+    from mcmc_spec_b200.posterior import LogPosterior
+    from oracle_adapter import to_oracle
+    for feh in ((0.2,) if feh_free else (0.2, 0.0, -0.5)):
+        p = synthetic.make_problem_3d_small(feh_free=True) if feh_free else synthetic.make_problem_3d_small(feh=feh)
+        lp = LogPosterior(p)
+        assert lp.engine.group_supported
+        theta = synthetic.sample_prior_box(p, 320, seed=17)
+        t = np.asarray(p.truth, dtype=float)
+        dense = t[None, :] * (1 + 0.004 * np.random.default_rng(5).standard_normal((160, t.size)))     # one dense cell
+        dense[:, 2] = np.abs(dense[:, 2])
+        theta[160:, :t.size] = dense
+        g, s = _both(lp, theta)
+        lp.close()
+        assert _rel(g, to_oracle(p).lnprob_batch(theta)) <= 1e-9
+        assert _rel(g, s) <= 1e-11
