@@ -425,7 +425,12 @@ def test_c5_full_size_cell_ordered_launch(native_lib):
     lp = LogPosterior(p)
     assert lp.tables.n_data == 25000 and lp.tables.n_reg == 100000 and lp.tables.grid.nbytes > 400e6
     theta = synthetic.sample_prior_box(p, 2048, seed=5)
+    auto = lp(theta)                                             # >= 1024 walkers: the group kernel (4-D boxes) by default
+    lp.engine.set_group(False)                                   # the rest is about the per-walker kernel's launch order
     got = lp(theta)                                              # >= 1024 walkers: cell-ordered launch
+    assert np.array_equal(np.isfinite(auto), np.isfinite(got))
+    fin = np.isfinite(got)
+    assert np.max(np.abs(auto[fin] - got[fin]) / np.abs(got[fin])) <= 1e-11
     _compare(got[:12], to_oracle(p).lnprob_batch(theta[:12]))
     pieces = np.concatenate([lp(theta[k:k + 256]) for k in range(0, 2048, 256)])   # natural order
     assert np.array_equal(pieces, got)
@@ -438,6 +443,7 @@ def test_c5_full_size_cell_ordered_launch(native_lib):
     import dataclasses
     pf = dataclasses.replace(p, feh_free=True)
     lpf = LogPosterior(pf)
+    lpf.engine.set_group(False)
     th7 = synthetic.sample_prior_box(pf, 2048, seed=7)
     gotf = lpf(th7)
     _compare(gotf[:24], to_oracle(pf).lnprob_batch(th7[:24]))
