@@ -275,21 +275,20 @@ __device__ __forceinline__ unsigned lane_compact(unsigned long long* col, unsign
   return out;
 }
 
-// Sum of the NWW walker warps' histogram columns, scanned in the order first + t (mod HBINS).
+// The sum of the NWW walker warps' histograms, formed in place in warp 0's: warp wj adds up the bins [wj B, (wj + 1) B),
+// B = HBINS / NWW, over all warps and writes them to warp 0's columns (a lane's counts add up to at most n <= 65 535).
+// After a barrier every warp scans the one merged histogram (lane_locate) instead of NWW of them.
 template <int NWW>
-__device__ __forceinline__ void lane_locate_merged(const unsigned short* hist_all, int lane, unsigned first, unsigned rank,
-                                                   unsigned& bin_t, unsigned& below, unsigned& in_bin) {
-  unsigned cum = 0;
-  bool found = false;
-  bin_t = 0; below = 0; in_bin = 0;
-#pragma unroll 2
-  for (unsigned t = 0; t < (unsigned)HBINS; ++t) {
-    const unsigned b = (first + t) & (HBINS - 1);
+__device__ __forceinline__ void lane_merge(unsigned short* hist_all, int wj, int lane) {
+  static_assert(HBINS % NWW == 0, "bins are dealt evenly to the warps");
+  constexpr int BPW = HBINS / NWW;
+#pragma unroll
+  for (int k = 0; k < BPW; ++k) {
+    const int b = wj * BPW + k;
     unsigned c = 0;
 #pragma unroll
     for (int j = 0; j < NWW; ++j) c += hist_all[(j * HBINS + b) * 32 + lane];
-    if (!found && rank < cum + c) { found = true; bin_t = t; below = cum; in_bin = c; }
-    cum += c;
+    hist_all[b * 32 + lane] = (unsigned short)c;
   }
 }
 
@@ -611,11 +610,13 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       }
       const bool fast_hist = ((kmax >> 20) - (kmin >> 20)) < 8u && !suspicious;
       const bool all_fast = __all_sync(0xffffffffu, fast_hist);
+      lane_merge<NWW>(hist_all, wj, lane);
+      walker_bar<NWW>();
       if (all_fast) {
         constexpr int SH = 20 - (HBITS - 3);                                // hi-key bits below the histogram digit
         unsigned bin_t, below, in_bin;
         const unsigned first = (kmin >> SH) & ~((1u << (HBITS - 3)) - 1u);     // lowest binade, mantissa bits 0
-        lane_locate_merged<NWW>(hist_all, lane, first, S.rank, bin_t, below, in_bin);
+        lane_locate(hist_all, lane, first, S.rank, bin_t, below, in_bin);
         S.prefix = (unsigned long long)(first + bin_t) << (32 + SH); S.bits = 32 - SH;
         S.rank -= below; S.cnt = in_bin;
       }
@@ -829,7 +830,9 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       bool overflow = !collect;
       {
         unsigned bin, below, in_bin;
-        lane_locate_merged<NWW>(hist_all, lane, 0u, S.rank, bin, below, in_bin);
+        lane_merge<NWW>(hist_all, wj, lane);
+        walker_bar<NWW>();
+        lane_locate(hist_all, lane, 0u, S.rank, bin, below, in_bin);
         S2.rank = S.rank - below; S2.cnt = in_bin;
         S2.prefix = S.prefix | (((unsigned long long)bin) << shift2);
         S2.bits = S.bits + width2;
@@ -853,7 +856,9 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
                 hist[(unsigned)((kb[u] >> shift3) & ((1u << width3) - 1u)) * 32 + lane] += 1;
           }
           walker_bar<NWW>();
-          lane_locate_merged<NWW>(hist_all, lane, 0u, S2.rank, bin, below, in_bin);
+          lane_merge<NWW>(hist_all, wj, lane);
+          walker_bar<NWW>();
+          lane_locate(hist_all, lane, 0u, S2.rank, bin, below, in_bin);
           S2.rank -= below; S2.cnt = in_bin;
           S2.prefix |= ((unsigned long long)bin) << shift3;
           S2.bits += width3;
