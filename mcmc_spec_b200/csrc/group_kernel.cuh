@@ -9,8 +9,9 @@
 // same linear combination of the row integrals as its spectrum is of the rows, mft6.py:507-519, :689-700).  The
 // bracket rows are streamed ONCE per group, KP observed pixels (one stage) at a time, through a shared-memory ring:
 //
-//   copies                 -- per stage ONE 3-D tiled tensor copy per star (cp.async.bulk.tensor, SASS UTMALDG: box =
-//                             KP bracket pairs x 2 Teff nodes x 2 log g nodes = the star's four bracketing rows) and one
+//   copies                 -- per stage ONE tiled tensor copy per star (cp.async.bulk.tensor, SASS UTMALDG: 3-D box =
+//                             KP bracket pairs x 2 Teff nodes x 2 log g nodes = the star's four bracketing rows; 4-D
+//                             with two [Fe/H] nodes = its eight rows on grids with that axis) and one
 //                             bulk copy (UBLKCP) of the stage's per-observed-pixel records; completion is counted in
 //                             bytes on the slot's `full` mbarrier.  There is no producer warp: the walker warps count
 //                             themselves out of a slot (one shared-memory atomic per warp and stage) and the last one
@@ -28,17 +29,21 @@
 //                             warps split one pass over the scratch for the chi-square (mft6.py:1178-1179) that also
 //                             collects the keys of the median's histogram bin, and the first walker warp finishes:
 //                             exact selection on those keys (mft6.py:1173, np.median convention), contrasts,
-//                             magnitudes, priors, final sum (mft6.py:1182-1205).  No shuffles, no atomics.
+//                             magnitudes, priors, final sum (mft6.py:1182-1205).  No shuffles; the only atomics
+//                             are the slot counters.
 //
-// Extinction: exp2(Av * ext(p)) = A_s * exp(Av * x_p) with A_s = exp2(Av * anchor_s) per stage and walker and a
-// 8th-order polynomial on |Av * x_p| <= 0.045 (x^9/9! < 2.1e-18); walkers with larger exponents take exp2 of the whole exponent.  A_s
-// itself is taken exactly on every 8th stage and follows from the previous stage's by the same polynomial in between.
+// Extinction: exp2(Av * ext(p)) = A_s * exp(Av * x_p) with A_s = exp2(Av * anchor_s) per stage and walker and an
+// 8th-order polynomial on |Av * x_p| <= 0.045 (x^9/9! < 2.1e-18); walkers with larger exponents take exp2 of the whole
+// exponent.  The upper bracket's factor is the lower one's times a 4th-order series in Av (x_hi - x_lo) (neighbouring
+// model pixels).  A_s itself is taken exactly on every 8th stage and follows from the previous stage's by the
+// polynomial in between.  Every product / sum whose fusion is optional is spelled out, so that all instantiations
+// round alike.
 
 namespace grp {
 
-// -DMS_GROUP_TIMING: the first eight CTAs print, when they run out of groups, where the producer's and the first and
-// last walker warps' cycles went: waiting for a group, phase A, the barrier after it, phase B (bin of the median,
-// chi-square pass, lists), the finish (first warp only), and the time inside mbarrier waits
+// -DMS_GROUP_TIMING: every warp of the first four CTAs prints, when its CTA runs out of groups, where its cycles went:
+// waiting for a group, phase A, the barrier after it, phase B (bin of the median, chi-square pass, lists), candidate
+// ranking and final sum (first warp only), and the time inside mbarrier waits
 #ifdef MS_GROUP_TIMING
 #define GTIME(i) { const long long t__ = clock64(); gt_acc[i] += t__ - gt_last; gt_last = t__; }
 #define GDBG_WAIT(stmt) { const long long t__ = clock64(); stmt; gt_wait += clock64() - t__; }

@@ -1,3 +1,4 @@
+# The single-GPU measurements behind profiles/bench_r2_*.json, r2_launches.csv and r2_ncu_group_kernel.txt (run under gpurun from the repo root).
 set -x
 python bench.py --steps 20 --warmup 3 > gpurun_out/f_n1.json 2> gpurun_out/f_n1.err
 python bench.py --steps 20 --warmup 3 --init box --no-cpu-baseline > gpurun_out/f_n1_box.json 2>/dev/null
