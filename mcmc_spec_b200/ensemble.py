@@ -135,7 +135,7 @@ class EnsembleSampler:
         self._fixed = [torch.arange(0, nwalkers, 2, device=self.device), torch.arange(1, nwalkers, 2, device=self.device)]
         self._side, self._next = None, None
         self._by_group = None                   # N > 1: shard the evaluation by groups of cell mates (decided at the first step)
-        self.shard_by_group = True
+        self.shard_by_group = True              # True: by the shard size (see step()); False: never; 'always': whenever possible
         self.fused = True                       # allow the one-call iteration where the backend offers it
         self._stored, self._iter0 = None, 0
 
@@ -226,8 +226,9 @@ class EnsembleSampler:
             # 32 walkers each): below that the part-filled groups of a walker shard cost a second round of CTAs, above
             # it the replicated preparation and the all-reduce cost more than the fuller groups save.
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == 'cuda' else 0
+            small = self.shard_by_group == 'always' or self.shard <= 32 * sms
             self._by_group = bool(self.world_size > 1 and self.shard_by_group and hasattr(be, 'evaluate')
-                                  and self.shard <= 32 * sms and be.group_will_run(self.half))
+                                  and small and be.group_will_run(self.half))
             if self._by_group:
                 be.set_shard(self.rank, self.world_size)
                 f64 = dict(dtype=torch.float64, device=self.device)

@@ -87,3 +87,41 @@ class NumpyBackend:
         nd = self.ndim
         state[idx] = packed[:, :nd + 1]
         naccepted[idx] += packed[:, nd + 1].to(torch.int32)
+
+
+class GroupShardedNumpyBackend(NumpyBackend):
+    """The numpy backend with the entry points of the evaluation sharded by groups (CudaBackend.evaluate /
+    accept_inplace / set_shard / group_will_run): every rank proposes for the whole half, evaluates the walkers of
+    every world-th block of 4 ("groups"), leaves the others at 0; the sampler sums over the ranks."""
+
+    GROUP = 4
+
+    def __init__(self, lnprob_fn, ndim):
+        super().__init__(lnprob_fn, ndim)
+        self.rank, self.world = 0, 1
+
+    def set_shard(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def group_will_run(self, n):
+        return True
+
+    def evaluate(self, state, s_idx, c_idx, a, seed, iteration, split, gid0, q, logfac, lnp_q):
+        self.propose(state, s_idx, c_idx, a, seed, iteration, split, gid0, q, logfac)
+        n = q.shape[0]
+        mine = (np.arange(n) // self.GROUP) % self.world == self.rank
+        out = np.zeros(n)
+        if mine.any():
+            out[mine] = np.asarray(self.fn(q.numpy()[mine].copy()), dtype=np.float64)
+        lnp_q.copy_(torch.from_numpy(out))
+
+    def accept_inplace(self, state, naccepted, s_idx, q, lnp_q, logfac, seed, iteration, split, gid0):
+        nd = self.ndim
+        idx = s_idx.numpy()
+        cur = state.numpy()[idx]
+        m = accept_mask(cur[:, nd], lnp_q.numpy(), logfac.numpy(), seed, iteration, split, gid0)
+        st = state.numpy()
+        rows = idx[m]
+        st[rows, :nd] = q.numpy()[m]; st[rows, nd] = lnp_q.numpy()[m]
+        naccepted.numpy()[rows] += 1
+

@@ -70,11 +70,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, nw, nsteps, out):
+def _worker(rank, world, port, nw, nsteps, out, by_group=False):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    s = EnsembleSampler(nw, NDIM, sr.NumpyBackend(gauss_lnprob, NDIM), seed=5, group=None, rank=rank, world_size=world)
+    backend = (sr.GroupShardedNumpyBackend if by_group else sr.NumpyBackend)(gauss_lnprob, NDIM)
+    s = EnsembleSampler(nw, NDIM, backend, seed=5, group=None, rank=rank, world_size=world)
+    if by_group:
+        s.shard_by_group = 'always'
     s.initialize(_p0(nw))
     s.run_mcmc(nsteps)
     if rank == 0:
@@ -85,6 +88,7 @@ def _worker(rank, world, port, nw, nsteps, out):
     full = [torch.empty_like(s.state) for _ in range(world)]
     dist.all_gather(full, s.state)
     assert all(torch.equal(f, full[0]) for f in full)
+    assert bool(s._by_group) == bool(by_group)
     dist.destroy_process_group()
 
 
@@ -97,6 +101,21 @@ def test_two_rank_gloo_chain_is_bit_identical_to_single_process(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), nw, nsteps, out), nprocs=2, join=True)
     got = np.load(out)
     assert np.array_equal(got[:, :NDIM + 1], single.state.numpy())        # independent of the number of ranks
+    assert np.array_equal(got[:, NDIM + 1], single.naccepted.numpy())
+
+
+def test_two_rank_gloo_chain_sharded_by_groups_is_the_same_chain(tmp_path):
+    """The other way N ranks share a half step (ensemble.py): every rank holds the ensemble,
+    proposes for the whole half, evaluates every N-th group, the log-probs are summed by one all-reduce and every
+    rank accepts in place.  Same chain as one process, same state on both ranks."""
+    nw, nsteps = 48, 25
+    single = EnsembleSampler(nw, NDIM, sr.NumpyBackend(gauss_lnprob, NDIM), seed=5)
+    single.initialize(_p0(nw))
+    single.run_mcmc(nsteps)
+    out = str(tmp_path / 'state_g.npy')
+    mp.spawn(_worker, args=(2, _free_port(), nw, nsteps, out, True), nprocs=2, join=True)
+    got = np.load(out)
+    assert np.array_equal(got[:, :NDIM + 1], single.state.numpy())
     assert np.array_equal(got[:, NDIM + 1], single.naccepted.numpy())
 
 
