@@ -51,8 +51,6 @@ namespace grp {
 #define GTIME(i)
 #define GDBG_WAIT(stmt) stmt;
 #endif
-#define GDBG_DECL
-#define GDBG_REPORT(name)
 
 #ifndef MS_GROUP_KP
 #define MS_GROUP_KP 64
@@ -156,20 +154,6 @@ __device__ __forceinline__ void tensor_g2s_3d(uint32_t dst, const void* tmap, in
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                :: "r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
-__device__ __forceinline__ double2 lds128(uint32_t addr) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ double lds64(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, double2 v) {
-  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(addr), "d"(v.x), "d"(v.y) : "memory");
-}
-
 // ++(uint16 counter in shared memory), invisible to the compiler's alias analysis (the caller brackets the phase with
 // barriers that are compiler fences)
 __device__ __forceinline__ void hist_inc(uint32_t addr) {
@@ -591,7 +575,6 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
     if (lane == 0 && wj < min(CSLOTS, n_chunks)) issue_chunk(wj);
     {
       // ================================================================= walker warps, phase B: lane = walker
-      GDBG_DECL
       // ---- the walker's sums over all its pixels, combined in a fixed order (every warp ends up with the same values)
       double mom[3];
 #pragma unroll
@@ -894,7 +877,6 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
       GTIME(4)
       if (wj == 0) {
         // ---- the first walker warp finishes: merge, rank the candidates, final sum
-#pragma unroll
         double chi = s_part[0][3][lane];
 #pragma unroll
         for (int j = 1; j < VW; ++j) chi += s_part[j][3][lane];
@@ -1035,7 +1017,6 @@ lnprob_group_kernel(const __grid_constant__ DevTables T, const __grid_constant__
           if (parts.logg) for (int s = 0; s < NS; ++s) parts.logg[w * NS + s] = p.logg[s];
         }
       }
-      GDBG_REPORT("phaseB")
       GTIME(5)
     }
     cit0 += (unsigned)n_chunks;
