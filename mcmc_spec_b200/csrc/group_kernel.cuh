@@ -1047,33 +1047,39 @@ __global__ void group_table_kernel(const WalkerPlan* __restrict__ plans, const i
 }
 
 // Exclusive scans of the cell histogram (-> cell_start[n_cells + 1] and the mutable copy `offsets` the scatter
-// consumes) and of the per-cell group counts (-> group_off[n_cells], *n_groups).  One CTA.
+// consumes) and of the per-cell group counts (-> group_off[n_cells], *n_groups).  One CTA; each warp scans 256
+// consecutive cells per pass (coalesced rows of 32), then the warps' totals are scanned.
 __global__ void __launch_bounds__(1024) group_scan_kernel(unsigned* __restrict__ hist_offsets, int n_cells,
                                                           unsigned* __restrict__ cell_start, unsigned* __restrict__ group_off,
                                                           int* __restrict__ n_groups, int* __restrict__ group_counter) {
   __shared__ unsigned wa[32], wb[32];
   __shared__ unsigned carry_a, carry_b;
-  constexpr int ITEMS = 8;                       // consecutive cells per thread: 8192 cells per pass
+  constexpr int ROWS = 8;                        // 32-cell rows per warp and pass: 256 consecutive cells per warp, 8192 per pass
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { carry_a = 0; carry_b = 0; }
   __syncthreads();
-  for (int base = 0; base < n_cells; base += 1024 * ITEMS) {
-    const int i0 = base + tid * ITEMS;
-    unsigned v[ITEMS], g[ITEMS];
-    unsigned sa = 0, sb = 0;
+  for (int base = 0; base < n_cells; base += 1024 * ROWS) {
+    const int w0 = base + warp * 32 * ROWS;
+    unsigned v[ROWS], ea[ROWS], eb[ROWS];
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      v[k] = (i0 + k < n_cells) ? hist_offsets[i0 + k] : 0u;
-      g[k] = (v[k] + GMAX - 1) / GMAX;
-      sa += v[k]; sb += g[k];
+    for (int k = 0; k < ROWS; ++k) {               // coalesced, all in flight
+      const int i = w0 + k * 32 + lane;
+      v[k] = (i < n_cells) ? hist_offsets[i] : 0u;
     }
-    unsigned ia = sa, ib = sb;
+    unsigned run_a = 0, run_b = 0;                  // the warp's running totals
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-      if (lane >= o) { ia += ta; ib += tb; }
+    for (int k = 0; k < ROWS; ++k) {
+      const unsigned g = (v[k] + GMAX - 1) / GMAX;
+      unsigned ia = v[k], ib = g;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
+      }
+      ea[k] = run_a + ia - v[k]; eb[k] = run_b + ib - g;          // exclusive, within the warp's 256 cells
+      run_a += __shfl_sync(0xffffffffu, ia, 31); run_b += __shfl_sync(0xffffffffu, ib, 31);
     }
-    if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
+    if (lane == 31) { wa[warp] = run_a; wb[warp] = run_b; }
     __syncthreads();
     if (warp == 0) {
       unsigned xa = wa[lane], xb = wb[lane];
@@ -1082,18 +1088,17 @@ __global__ void __launch_bounds__(1024) group_scan_kernel(unsigned* __restrict__
         const unsigned ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
         if (lane >= o) { xa += ta; xb += tb; }
       }
-      wa[lane] = xa; wb[lane] = xb;
+      wa[lane] = xa; wb[lane] = xb;                 // inclusive over the warps
     }
     __syncthreads();
-    unsigned ea = carry_a + (warp ? wa[warp - 1] : 0u) + ia - sa;       // exclusive prefix of this thread's first cell
-    unsigned eb = carry_b + (warp ? wb[warp - 1] : 0u) + ib - sb;
+    const unsigned off_a = carry_a + (warp ? wa[warp - 1] : 0u), off_b = carry_b + (warp ? wb[warp - 1] : 0u);
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      if (i0 + k < n_cells) { hist_offsets[i0 + k] = ea; cell_start[i0 + k] = ea; group_off[i0 + k] = eb; }
-      ea += v[k]; eb += g[k];
+    for (int k = 0; k < ROWS; ++k) {
+      const int i = w0 + k * 32 + lane;
+      if (i < n_cells) { hist_offsets[i] = off_a + ea[k]; cell_start[i] = off_a + ea[k]; group_off[i] = off_b + eb[k]; }
     }
     __syncthreads();
-    if (tid == 1023) { carry_a = ea; carry_b = eb; }
+    if (tid == 0) { carry_a += wa[31]; carry_b += wb[31]; }
     __syncthreads();
   }
   if (tid == 0) { cell_start[n_cells] = carry_a; *n_groups = (int)carry_b; *group_counter = 0; }
