@@ -352,7 +352,8 @@ int ms_set_cell_order(ms_handle* h, int mode);
  * mode: -1 (default) automatic -- batches of at least `min_walkers` (default 1024; <= 0 keeps the current
  * threshold), as long as the batch does not spread so thinly over the grid cells that a group holds fewer than ~6
  * walkers (a group costs the same with 3 busy lanes as with 32; the count of the previous batch of the same size
- * decides, with hysteresis); 0 never; 1 whenever the handle can take it.
+ * decides, with hysteresis; the first batch of a size waits once for its own count); 0 never; 1 whenever the handle
+ * can take it.
  * ms_group_supported: 1 when this handle can take it (nspec = 2, a (Teff, log g) or (Teff, log g, [Fe/H]) grid with at
  * least two nodes per axis, more than one grid cell, at most 65 535 observed pixels).
  * ms_set_group_shard: this handle evaluates the groups rank, rank + world, ... of every batch and leaves the other

@@ -2010,7 +2010,7 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
                                                        h->short_circuited);
   CK(cudaGetLastError());
   h->launches += 1;
-  if (h->group_now) {
+  if (h->group_now || h->group_probe) {
     const long long max_groups = (nw + grp::GMAX - 1) / grp::GMAX + std::min<long long>(h->T.n_cells, nw);
     if (max_groups > h->groups_cap) {
       CK(cudaStreamSynchronize(h->stream));
@@ -2021,6 +2021,18 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
     }
     grp::group_scan_kernel<<<1, 1024, 0, h->stream>>>(h->cell_hist, h->T.n_cells, h->cell_start, h->group_off, h->n_groups,
                                                       h->group_counter);
+    h->launches += 1;
+    if (h->group_mode < 0 && !h->shard_active &&
+        !(*reinterpret_cast<volatile int*>(h->h_n_groups) > 0 && *reinterpret_cast<volatile int*>(h->h_n_groups + 1) == (int)std::min<long long>(nw, 0x7fffffff))) {
+      // first batch of this size: no earlier group count to go by -- wait for this one (once) before choosing the kernel
+      int ng = 0;
+      CK(cudaMemcpyAsync(&ng, h->n_groups, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      h->group_thin = ng > 0 && (double)nw / (double)ng < MS_GROUP_FILL_LO;
+      h->group_now = !h->group_thin; h->group_probe = h->group_thin;
+    }
+  }
+  if (h->group_now) {
     if (h->shard_active) {
       // the ranks that share this half must form the same groups: walkers in cell order, by index within a cell (a
       // stable radix sort on the cell number) instead of the order the scatter's atomics happen to give
@@ -2049,18 +2061,16 @@ int evaluate_device(ms_handle* h, const double* d_theta, long long nw, double* d
     }
     grp::group_table_kernel<<<pg, pb, 0, h->stream>>>(h->plans, h->order, nw, h->cell_start, h->group_off, h->groups);
     CK(cudaGetLastError());
-    h->launches += 3;
+    h->launches += 2;
     return ms_tu_launch_group(h, nw, d_lnp, parts);
   }
   if (h->group_probe) {
-    // per-walker kernel in cell order; the scan also counts the groups this batch would have made
-    grp::group_scan_kernel<<<1, 1024, 0, h->stream>>>(h->cell_hist, h->T.n_cells, h->cell_start, h->group_off, h->n_groups,
-                                                      h->group_counter);
+    // per-walker kernel in cell order; the scan above also counted the groups this batch would have made
     cell_scatter_kernel<<<pg, pb, 0, h->stream>>>(h->plans, nw, h->cell_hist, h->order);
     CK(cudaGetLastError());
     h->h_n_groups[1] = (int)std::min<long long>(nw, 0x7fffffff);
     CK(cudaMemcpyAsync(h->h_n_groups, h->n_groups, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    h->launches += 2;
+    h->launches += 1;
   } else if (h->use_order) {
     cell_scan_kernel<<<1, 1024, 0, h->stream>>>(h->cell_hist, h->T.n_cells);
     cell_scatter_kernel<<<pg, pb, 0, h->stream>>>(h->plans, nw, h->cell_hist, h->order);
