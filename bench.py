@@ -32,6 +32,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import multiprocessing as mp
 import os
 import subprocess
@@ -205,6 +206,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append((time.time(), [s.strip() for s in line.split(',')]))
 
+    def wait_ready(self, timeout):
+        t0 = time.time()
+        while self.proc and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc:
             self.proc.terminate()
@@ -313,11 +319,13 @@ def run_product_arm(args, rank, local_rank, world):
                 s_k.step()
             e = torch.cuda.Event(); e.record(streams[k]); work_stream.wait_event(e)
 
+    clocks = ClockSampler(local_rank) if rank == 0 else None        # nvidia-smi needs a moment to come up: start it before the warm-up
     for _ in range(args.warmup):
         step_all()
-    torch.cuda.synchronize(); barrier()
-
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    torch.cuda.synchronize()
+    if clocks:
+        clocks.wait_ready(3.0)
+    barrier()
     for l in lps:
         l.engine.set_timing(True); l.engine.kernel_time(); l.engine.short_circuited(reset=True)
     launches0 = sum(l.engine.launch_count for l in lps)
@@ -342,16 +350,29 @@ def run_product_arm(args, rank, local_rank, world):
         l.engine.set_timing(False)
     cut_short = sum(l.engine.short_circuited() for l in lps)
     launches = sum(l.engine.launch_count for l in lps) - launches0
-    clock_summary = None
-    if clocks:
-        time.sleep(0.12)
-        clocks.stop()
-        clock_summary = clocks.summary(t_wall0, t_wall1)
     acc_frac = float(np.mean([s.acceptance_fraction.mean() for s in samplers]))
     finite_frac = float(np.mean([torch.isfinite(s.log_prob).double().mean().item() for s in samplers]))
     checksum = 0
     for s in samplers:
         checksum = (checksum + s.checksum()) & 0xFFFFFFFFFFFFFFFF
+    # Clocks under load: nvidia-smi samples every 100 ms, a short timed region (K steps of a few ms) may see none.  The same
+    # loop then goes on untimed (every rank the same number of steps: total_s is the max over the ranks) until 0.4 s of
+    # load have been sampled; timers, counters and the checksum above are those of the K timed steps.
+    t_wall2 = t_wall1
+    if total_s < 0.4:
+        n_extra = min(2000, int(math.ceil((0.4 - total_s) / max(total_s / args.steps, 1e-6))))
+        for _ in range(n_extra):
+            flush.zero_()
+            step_all()
+        torch.cuda.synchronize(); barrier()
+        t_wall2 = time.time()
+    clock_summary = None
+    if clocks:
+        time.sleep(0.12)
+        clocks.stop()
+        clock_summary = clocks.summary(t_wall0, t_wall2)
+        if clock_summary is not None and t_wall2 > t_wall1:
+            clock_summary["window"] = "the timed steps + an untimed continuation of the same loop (0.4 s of load)"
 
     # ---- end-to-end through the host-buffer API (pinned staging + H2D + kernels + D2H per call)
     lp.engine.use_own_stream()
